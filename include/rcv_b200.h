@@ -1,0 +1,229 @@
+/*
+ * rcv_b200.h -- C ABI of librcv_b200.so: the B200 (sm_100a) implementation of
+ * RoboCupVision's one data-parallel hot path (encoder-decoder segmentation nets:
+ * conv / transposed conv / BatchNorm / ReLU / max-pool / skip add, weighted
+ * softmax cross-entropy, argmax + per-image confusion matrix, L1 + Adam tail).
+ *
+ * The reference has no FFI of its own: the arithmetic of this path lives behind
+ * torch.nn calls in /root/reference/model.py.  Every entry point below names the
+ * reference call site (file:line) whose arithmetic it replaces.  A maintainer
+ * binds these with ctypes; robocupvision_b200/_lib.py is
+ * that binding.
+ *
+ * Conventions
+ *   - plain C, POD structs, raw device pointers, sizes; no C++/torch types.
+ *   - all tensors are fp32, NCHW, contiguous, unless stated; labels int64.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     makes no hidden synchronisation and allocates no device memory: the
+ *     caller owns every buffer including workspaces.
+ *   - return value: 0 = RCV_OK, negative = rcv_status.  Nothing throws or exits.
+ *     rcv_last_error() returns a thread-local message for the last failure.
+ *   - no fallbacks: an unsupported geometry is RCV_ERR_UNSUPPORTED, never a
+ *     library/CPU path.
+ */
+#ifndef RCV_B200_H_
+#define RCV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCV_ABI_VERSION 1
+
+typedef enum rcv_status {
+  RCV_OK = 0,
+  RCV_ERR_BAD_ARG = -1,      /* null pointer / inconsistent sizes            */
+  RCV_ERR_UNSUPPORTED = -2,  /* geometry outside the hot path */
+  RCV_ERR_CUDA = -3,         /* launch / runtime error (message has detail)   */
+  RCV_ERR_WORKSPACE = -4     /* workspace too small                           */
+} rcv_status;
+
+/* Epilogue applied to v = conv(x, w)[+bias] before it is stored
+ * (model.py:116 `Conv`: bn(relu(conv)); model.py:175 `ConvPoolSimple` and
+ * model.py:191-193 `upSampleTransposeConv`: relu(bn(conv)); model.py:137-138
+ * `ConvPool`: relu(conv1)).  scale/shift are the folded eval-mode BatchNorm
+ * (gamma/sqrt(var+eps), beta-mean*scale). */
+typedef enum rcv_epilogue {
+  RCV_EPI_NONE = 0,         /* y = v                         */
+  RCV_EPI_RELU = 1,         /* y = max(v,0)                  */
+  RCV_EPI_RELU_AFFINE = 2,  /* y = scale*max(v,0)+shift      */
+  RCV_EPI_AFFINE_RELU = 3,  /* y = max(scale*v+shift,0)      */
+  RCV_EPI_AFFINE = 4        /* y = scale*v+shift             */
+} rcv_epilogue;
+
+/* Math mode of the GEMM-shaped kernels. */
+typedef enum rcv_math {
+  RCV_MATH_FP32 = 0,     /* fp32 FFMA on CUDA cores (always available)          */
+  RCV_MATH_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-term error-compensated split;  *
+                          * fp32-level accuracy; wide layers only               */
+  RCV_MATH_AUTO = 2      /* TF32X3 where the geometry supports it, else FP32     */
+} rcv_math;
+
+/* One convolution-type layer.  transposed=0: nn.Conv2d(Cin,Cout,ksize,stride,
+ * pad,dil) on x[N,Cin,H,W] (model.py:112,130-133,170,259,411,554).
+ * transposed=1: nn.ConvTranspose2d(Cin,Cout,3,stride=2,padding=1,
+ * output_padding=1) (model.py:186-187), x[N,Cin,H,W] -> y[N,Cout,2H,2W],
+ * weight layout (Cin,Cout,3,3).  Supported: ksize 1 (stride 1, pad 0) and
+ * ksize 3 with (stride,pad,dil) in {(1,1,1),(1,2,2),(2,1,1)}. */
+typedef struct rcv_conv_desc {
+  int32_t N, Cin, H, W; /* input tensor                                   */
+  int32_t Cout;
+  int32_t ksize, stride, pad, dil;
+  int32_t transposed;
+  int32_t epilogue;     /* rcv_epilogue (forward only)                    */
+  int32_t math;         /* rcv_math                                       */
+} rcv_conv_desc;
+
+int rcv_version(void);
+const char* rcv_last_error(void);
+
+/* Output spatial size of a layer (H_out, W_out). */
+int rcv_conv_out_hw(const rcv_conv_desc* d, int32_t* Ho, int32_t* Wo);
+
+/* ---- convolution family ------------------------------------------------- */
+
+/* y = EPI(conv(x,w) + bias) [+ residual].  bias, scale, shift, residual,
+ * stats may be NULL.  residual has the shape of y and is added after the
+ * epilogue (decoder skip: model.py:300-307, 509).  If stats != NULL it is a
+ * double[2*Cout] accumulator: stats[c] += sum(y_c), stats[Cout+c] += sum(y_c^2)
+ * over this call's outputs (train-mode BatchNorm batch statistics of the
+ * tensor BN consumes; caller zeroes it).
+ * Replaces F.conv2d / F.conv_transpose2d (+ relu + eval batch_norm + add). */
+int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float* w,
+                 const float* bias, const float* scale, const float* shift,
+                 const float* residual, float* y, double* stats, void* stream);
+
+/* dx = d(conv)/dx applied to dy (shape of y) [+ residual].  residual (may be
+ * NULL, may alias dx) has the shape of dx: the gradient arriving at the same
+ * tensor from a second consumer (the decoder skip), summed in the epilogue.
+ * Replaces convolution_backward's input gradient (+ autograd's add). */
+int rcv_conv_dgrad(const rcv_conv_desc* d, const float* dy, const float* w,
+                   const float* residual, float* dx, void* stream);
+
+/* dw += d(conv)/dw, dbias += sum(dy) (dbias may be NULL).  Split over pixels
+ * with fp32 atomic accumulation: the caller zeroes dw/dbias beforehand.
+ * Replaces convolution_backward's weight/bias gradients. */
+int rcv_conv_wgrad(const rcv_conv_desc* d, const float* x, const float* dy,
+                   float* dw, float* dbias, void* stream);
+
+/* ---- BatchNorm2d, training mode (model.py:113,134,171,188) --------------- */
+
+/* From stats (sum, sum of squares over count = N*H*W elements per channel):
+ * mean, biased var -> scale = gamma/sqrt(var+eps), shift = beta-mean*scale;
+ * running_mean = (1-m)*running_mean + m*mean, running_var likewise with the
+ * unbiased variance (either may be NULL); save_mean / save_invstd for the
+ * backward pass.  One tiny launch. */
+int rcv_bn_finalize(int32_t C, int64_t count, const double* stats,
+                    const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, float* scale,
+                    float* shift, float* save_mean, float* save_invstd,
+                    void* stream);
+
+/* Eval-mode fold (model.eval(), running statistics):
+ * scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
+int rcv_bn_fold(int32_t C, const float* gamma, const float* beta,
+                const float* mean, const float* var, float eps, float* scale,
+                float* shift, void* stream);
+
+/* y = act(scale_c*z + shift_c) [+ residual], act = relu if relu!=0.
+ * z,y: [N,C,HW]. */
+int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z,
+                 const float* scale, const float* shift, int relu,
+                 const float* residual, float* y, void* stream);
+
+/* Backward of y = act(scale*z+shift) composed with the producer's own ReLU.
+ * order = RCV_EPI_RELU_AFFINE: z = relu(conv), y = bn(z)      (model.py:116)
+ * order = RCV_EPI_AFFINE_RELU: z = conv,       y = relu(bn(z)) (model.py:175)
+ * Pass 1 (reduce): sums[c] += sum(g), sums[C+c] += sum(g*xhat) with
+ *   g = dy (RELU_AFFINE) or dy*[scale*z+shift>0] (AFFINE_RELU),
+ *   xhat = (z-mean)*invstd.  sums is double[2*C], caller zeroes.
+ * Pass 2 (apply): dz = scale*(g - sums[c]/cnt - xhat*sums[C+c]/cnt), then for
+ *   RELU_AFFINE dz *= [z>0]; writes dconv (gradient w.r.t. the conv output),
+ *   and accumulates dgamma[c] += sums[C+c], dbeta[c] += sums[c] (once, by the
+ *   first block), dbias[c] += sum(dconv) if dbias != NULL.
+ * Replaces native_batch_norm_backward + threshold_backward. */
+int rcv_bn_bwd_reduce(int32_t N, int32_t C, int64_t HW, int order,
+                      const float* dy, const float* z, const float* scale,
+                      const float* shift, const float* save_mean,
+                      const float* save_invstd, double* sums, void* stream);
+int rcv_bn_bwd_apply(int32_t N, int32_t C, int64_t HW, int order,
+                     const float* dy, const float* z, const float* scale,
+                     const float* shift, const float* save_mean,
+                     const float* save_invstd, const double* sums,
+                     float* dconv, float* dgamma, float* dbeta, float* dbias,
+                     void* stream);
+
+/* dx = dy * [y > 0] (threshold_backward for a stored ReLU output y). */
+int rcv_relu_bwd(int64_t n, const float* dy, const float* y, float* dx,
+                 void* stream);
+
+/* dbias[c] += sum over (n, hw) of dy[n,c,hw]. */
+int rcv_channel_sum(int32_t N, int32_t C, int64_t HW, const float* dy,
+                    float* dbias, void* stream);
+
+/* ---- MaxPool2d(2,2) (model.py:92-100) ----------------------------------- */
+/* y[N,C,H/2,W/2]; idx (may be NULL) = int64 flat index h*W+w inside the (n,c)
+ * plane, first maximum in row-major window order, NaN wins -- the convention
+ * of F.max_pool2d(return_indices=True); code (may be NULL) = uint8 window
+ * position 0..3 for the backward pass. */
+int rcv_maxpool2x2_fwd(int32_t N, int32_t C, int32_t H, int32_t W,
+                       const float* x, float* y, int64_t* idx, uint8_t* code,
+                       void* stream);
+/* dx[N,C,H,W] = scatter of dy through code (every dx element is written). */
+int rcv_maxpool2x2_bwd(int32_t N, int32_t C, int32_t H, int32_t W,
+                       const float* dy, const uint8_t* code, float* dx,
+                       void* stream);
+
+/* ---- weighted softmax cross-entropy + argmax + confusion ----------------- */
+/* CrossEntropyLoss2d (model.py:76-82), torch.max(pred,1) (train.py:70,128) and
+ * the per-image confusion loop (train.py:133-153) in one pass over the logits.
+ * logits [N,C,HW] (C <= 8), target int64 [N,HW] in [0,C), class_w [C] or NULL.
+ * loss_sums: double[2]: += sum_p w[y_p]*nll_p, += sum_p w[y_p]  (caller zeroes;
+ *   loss = loss_sums[0]/loss_sums[1]).
+ * argmax   : int64 [N,HW] or NULL; lowest class index among equal maxima.
+ * conf     : int64 [N,C,C] or NULL; conf[n,p,l] += #(argmax==p and target==l).
+ * correct  : int64[1] or NULL; += #(argmax==target).  */
+int rcv_ce_fwd(int32_t N, int32_t C, int64_t HW, const float* logits,
+               const int64_t* target, const float* class_w, double* loss_sums,
+               int64_t* argmax, int64_t* conf, int64_t* correct, void* stream);
+/* dlogits = gscale * w[y_p]*(softmax(z_p) - onehot(y_p)) / loss_sums[1];
+ * gscale (device float, may be NULL = 1) is the upstream gradient. */
+int rcv_ce_bwd(int32_t N, int32_t C, int64_t HW, const float* logits,
+               const int64_t* target, const float* class_w,
+               const double* loss_sums, const float* gscale, float* dlogits,
+               void* stream);
+/* conf[n,p,l] += #(pred==p and target==l) from two int64 label maps. */
+int rcv_confusion(int32_t N, int32_t C, int64_t HW, const int64_t* pred,
+                  const int64_t* target, int64_t* conf, void* stream);
+
+/* ---- train-step tail: L1 regulariser + pruning mask + Adam --------------- */
+/* One fused pass over a flat parameter range (train.py:23-27 l1reg, 59-65 grad
+ * mask, torch.optim.Adam defaults amsgrad=False, weight_decay=0):
+ *   g = grad_scale*g + l1_decay*sign(p); if mask && mask[i]: g = 0;
+ *   m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g*g;
+ *   p -= lr * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
+ * l1_sum (double[1], may be NULL) += sum |p| (before the update).  step = t>=1. */
+int rcv_adam_l1_step(int64_t n, float* p, const float* g, float* m, float* v,
+                     const uint8_t* mask, float lr, float beta1, float beta2,
+                     float eps, int32_t step, float l1_decay, float grad_scale,
+                     double* l1_sum, const int32_t* step_dev, const float* lr_dev,
+                     void* stream);
+/* *counter += inc on the stream (the device-resident Adam step count used when
+ * the train step is replayed from a CUDA graph: step_dev / lr_dev above, when
+ * non-NULL, override the host `step` / `lr`). */
+int rcv_counter_add(int32_t* counter, int32_t inc, void* stream);
+/* SGD with momentum/dampening=0/weight decay (trainer.py:182-184):
+ *   g = grad_scale*g + wd*p; masked -> 0; buf = mom*buf + g (buf = g at
+ *   first_step); p -= lr*buf. */
+int rcv_sgd_step(int64_t n, float* p, const float* g, float* buf,
+                 const uint8_t* mask, float lr, float momentum,
+                 float weight_decay, float grad_scale, int first_step,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCV_B200_H_ */

@@ -1,0 +1,170 @@
+"""Generate tests/golden/* FROM THE REFERENCE (run here, where /root/reference exists):
+
+    python -m oracle.make_golden
+
+  ckpt/<name>.npz        released checkpoints (weights are data, not source) as fp32 arrays
+  <name>_eval.npz        reference-class outputs on seeded synthetic frames (eval mode)
+  robo_train.npz         3 reference training steps (train.py:43-74 restated with the reference's
+                         own ROBO_UNet / CrossEntropyLoss2d / torch.optim.Adam): losses, grad norms
+  weightsLP_head.npz     first/last values + sha256 of weightsLP/weights.dat (paramSave.py format)
+Everything is produced by importing /root/reference/model.py unmodified (plus the LabelProp
+constructor shim of SURVEY.md section 8c, since the shipped constructor raises TypeError).
+"""
+from __future__ import annotations
+
+import hashlib
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+OUT = ROOT / "tests" / "golden"
+sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(REF))
+
+import model as REFM  # noqa: E402  (the reference)
+import synth  # noqa: E402
+
+
+def load_pth(name):
+    return torch.load(REF / "pth" / name, map_location="cpu", weights_only=False)
+
+
+def save_ckpt(name, sd):
+    np.savez_compressed(OUT / "ckpt" / (name + ".npz"), **{k: v.numpy() for k, v in sd.items()})
+
+
+def ref_labelprop():
+    """Reference LabelProp with the constructor's surplus 8th argument dropped."""
+    orig = REFM.ConvPoolSimple.__init__
+
+    def shim(self, inplanes, planes, size, stride, padding, dilation, bias, dropout=None):
+        orig(self, inplanes, planes, size, stride, padding, dilation, bias)
+
+    REFM.ConvPoolSimple.__init__ = shim
+    try:
+        return REFM.LabelProp(5, 32, 0)
+    finally:
+        REFM.ConvPoolSimple.__init__ = orig
+
+
+def labelprop_ref_forward(m, x):
+    """model.py:556-567 with line 565 written out of place (identical arithmetic)."""
+    top = m.pre(x)
+    middle = m.down1(top)
+    bottom = m.down2(middle)
+    a = m.conv3(m.conv2(m.conv1(m.down3(bottom))))
+    a = bottom + m.upConv1(a)
+    a = middle + m.upConv2(a)
+    a = m.upConv3(a)
+    a = torch.cat([a[:, 0:8] + top, a[:, 8:]], 1)
+    return m.classifier(a)
+
+
+def eval_golden(tag, model, fwd, shapes, num_classes=5, weights=synth.CLASS_WEIGHTS):
+    out = {}
+    crit = REFM.CrossEntropyLoss2d(torch.tensor(weights))
+    model.eval()
+    for i, (n, c, h, w) in enumerate(shapes):
+        x = synth.images(n, c, h, w, seed=1234 + i)
+        y = synth.labels_random(n, h, w, num_classes, seed=4321 + i)
+        with torch.no_grad():
+            logits = fwd(model, x)
+            loss = crit(logits, y)
+        pred = logits.argmax(1)
+        conf = np.zeros((n, num_classes, num_classes), dtype=np.int64)
+        for b in range(n):  # train.py:142-147
+            for l in range(num_classes):
+                for p in range(num_classes):
+                    conf[b, p, l] = int(((pred[b] == p) & (y[b] == l)).sum())
+        top2 = logits.topk(2, dim=1).values
+        out[f"shape{i}"] = np.array([n, c, h, w])
+        out[f"loss{i}"] = np.array(float(loss))
+        out[f"argmax{i}"] = pred.numpy().astype(np.uint8)
+        out[f"margin_min{i}"] = np.array(float((top2[:, 0] - top2[:, 1]).min()))
+        out[f"conf{i}"] = conf
+        lf = logits.reshape(-1)
+        out[f"logits_sub{i}"] = lf[::13].numpy().copy() if lf.numel() > 50000 else lf.numpy().copy()
+        out[f"logits_absmax{i}"] = np.array(float(logits.abs().max()))
+    np.savez_compressed(OUT / (tag + "_eval.npz"), **out)
+    print(tag, {k: v.shape for k, v in out.items() if k.startswith("logits_sub")})
+
+
+def main():
+    (OUT / "ckpt").mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(1)  # fixed accumulation order
+
+    # ---- PB_FCN checkpoints (legacy head name -> segmenter) ------------------------------
+    for name, no_scale, shapes in [
+        ("bestModelSeg", False, [(2, 3, 24, 32), (1, 3, 120, 160)]),
+        ("bestModelSegFinetunedPruned", False, [(2, 3, 24, 32), (4, 3, 120, 160)]),
+        ("bestModelSegVGA", True, [(1, 3, 48, 64), (1, 3, 480, 640)]),
+    ]:
+        sd = load_pth(name + ".pth")
+        save_ckpt(name, sd)
+        m = REFM.PB_FCN(32, 5, 1, no_scale, 0)
+        remapped = {("segmenter." + k[len("classifier."):] if k.startswith("classifier.classifier.") else k): v
+                    for k, v in sd.items()}
+        res = m.load_state_dict(remapped, strict=False)
+        assert not res.unexpected_keys, res
+        eval_golden(name, m, lambda mm, x: mm(x), shapes)
+
+    # ---- LabelProp ------------------------------------------------------------------------
+    sd = load_pth("bestModelLPFinetunedPruned.pth")
+    save_ckpt("bestModelLPFinetunedPruned", sd)
+    m = ref_labelprop()
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.endswith("num_batches_tracked") for k in res.missing_keys), res
+    eval_golden("bestModelLPFinetunedPruned", m, labelprop_ref_forward, [(2, 8, 24, 32), (2, 8, 120, 160)],
+                weights=synth.LP_CLASS_WEIGHTS)
+    # paramSave.py:5-17 wire format: float64 flatten of the state dict in key order
+    dat = np.fromfile(REF / "weightsLP" / "weights.dat", dtype=np.float64)
+    np.savez_compressed(OUT / "weightsLP_head.npz", n=np.array(dat.size), head=dat[:64], tail=dat[-64:],
+                        sha256=np.frombuffer(hashlib.sha256(dat.tobytes()).digest(), dtype=np.uint8))
+
+    # ---- ROBO_UNet variants, random init (train.py:332-337 seeds) -------------------------
+    for tag, kw in [("robo_default", {}), ("robo_unet_pool", dict(pool=True, levels=3, bellySize=0)),
+                    ("robo_noscale", dict(noScale=True))]:
+        torch.manual_seed(12345678)
+        m = REFM.ROBO_UNet(**kw)
+        # make eval-mode BN non-trivial: a few training forwards move the running stats
+        m.train()
+        with torch.no_grad():
+            for s in range(3):
+                m(synth.images(4, 3, 48, 64, seed=77 + s))
+        # (not saved as a checkpoint: tests rebuild it from the seed with the same three forwards)
+        full = (1, 3, 240, 320) if kw.get("noScale") else (1, 3, 120, 160)
+        eval_golden(tag, m, lambda mm, x: mm(x), [(2, 3, 48, 64), full])
+
+    # ---- 3 reference training steps ---------------------------------------------------------
+    torch.manual_seed(12345678)
+    m = REFM.ROBO_UNet()
+    crit = REFM.CrossEntropyLoss2d(torch.tensor(synth.CLASS_WEIGHTS))
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    m.train()
+    losses, regs, corrects, gnorms = [], [], [], []
+    for s in range(3):
+        x = synth.images(8, 3, 48, 64, seed=100 + s)
+        y = synth.labels_learnable(x)
+        opt.zero_grad()
+        pred = m(x)
+        loss = crit(pred, y)
+        reg = 1e-6 * sum(p.abs().sum() for p in m.parameters())  # train.py:23-27, 52-55
+        loss = loss + reg
+        loss.backward()
+        gnorms.append([float(p.grad.norm()) for p in m.parameters()])
+        opt.step()
+        losses.append(float(loss)); regs.append(float(reg))
+        corrects.append(int((pred.argmax(1) == y).sum()))
+    np.savez_compressed(OUT / "robo_train.npz", losses=np.array(losses), regs=np.array(regs),
+                        corrects=np.array(corrects), gnorms=np.array(gnorms),
+                        final_w0=m.state_dict()["downPart.Level0.layers.Conv0.conv.weight"].numpy(),
+                        final_rv=m.state_dict()["PB.PB_1.layers.Conv1.bn.running_var"].numpy())
+    print("losses", losses)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+"""ctypes binding of librcv_b200.so (include/rcv_b200.h).
+
+This is the only place the shared library is loaded.  There is no fallback: if the
+library is missing or fails to load, every op raises (``RcvLibraryError``) instead of
+silently running something else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "librcv_b200.so"
+
+
+class RcvLibraryError(RuntimeError):
+    pass
+
+
+class RcvError(RuntimeError):
+    """A librcv_b200 call returned a negative rcv_status."""
+
+    def __init__(self, fn: str, code: int, msg: str):
+        super().__init__(f"{fn} failed with rcv_status {code}: {msg}")
+        self.code = code
+
+
+# rcv_status
+RCV_OK, RCV_ERR_BAD_ARG, RCV_ERR_UNSUPPORTED, RCV_ERR_CUDA, RCV_ERR_WORKSPACE = 0, -1, -2, -3, -4
+# rcv_epilogue
+EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, EPI_AFFINE_RELU, EPI_AFFINE = 0, 1, 2, 3, 4
+# rcv_math
+MATH_FP32, MATH_TF32X3, MATH_AUTO = 0, 1, 2
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "N", "Cin", "H", "W", "Cout", "ksize", "stride", "pad", "dil", "transposed", "epilogue", "math")]
+
+
+_p = C.c_void_p
+_i32, _i64, _f32 = C.c_int32, C.c_int64, C.c_float
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+SIGNATURES = {
+    "rcv_version": [],
+    "rcv_last_error": [],
+    "rcv_conv_out_hw": [C.POINTER(ConvDesc), C.POINTER(_i32), C.POINTER(_i32)],
+    "rcv_conv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rcv_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
+    "rcv_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
+    "rcv_bn_finalize": [_i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p],
+    "rcv_bn_fold": [_i32, _p, _p, _p, _p, _f32, _p, _p, _p],
+    "rcv_bn_apply": [_i32, _i32, _i64, _p, _p, _p, C.c_int, _p, _p, _p],
+    "rcv_bn_bwd_reduce": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rcv_bn_bwd_apply": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rcv_relu_bwd": [_i64, _p, _p, _p, _p],
+    "rcv_channel_sum": [_i32, _i32, _i64, _p, _p, _p],
+    "rcv_maxpool2x2_fwd": [_i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
+    "rcv_maxpool2x2_bwd": [_i32, _i32, _i32, _i32, _p, _p, _p, _p],
+    "rcv_ce_fwd": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rcv_ce_bwd": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p],
+    "rcv_confusion": [_i32, _i32, _i64, _p, _p, _p, _p],
+    "rcv_adam_l1_step": [_i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _i32, _f32, _f32, _p, _p, _p, _p],
+    "rcv_counter_add": [_p, _i32, _p],
+    "rcv_sgd_step": [_i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, C.c_int, _p],
+}
+_RESTYPES = {"rcv_last_error": C.c_char_p}
+
+_lib = None
+
+
+def load(build_if_missing: bool = True) -> C.CDLL:
+    """Load (building first if the .so is absent and nvcc exists) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists() and build_if_missing and not os.environ.get("RCV_NO_BUILD"):
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise RcvLibraryError(
+                f"librcv_b200.so is missing and could not be built ({e}); "
+                "run `python -m robocupvision_b200.build`. There is no fallback path.") from e
+    if not LIB_PATH.exists():
+        raise RcvLibraryError(f"{LIB_PATH} not found; run `python -m robocupvision_b200.build`. "
+                              "There is no fallback path.")
+    try:
+        lib = C.CDLL(str(LIB_PATH))
+    except OSError as e:
+        raise RcvLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, argtypes in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise RcvLibraryError(f"{LIB_PATH} does not export {name}") from e
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    abi = lib.rcv_version()
+    if abi != 1:
+        raise RcvLibraryError(f"ABI version mismatch: library {abi}, binding 1")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    """Invoke an rcv_* entry point and raise RcvError on a negative status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RcvError(name, rc, lib.rcv_last_error().decode("utf-8", "replace"))

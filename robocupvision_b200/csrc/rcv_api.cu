@@ -1,0 +1,228 @@
+// extern "C" surface for the convolution family: validates an rcv_conv_desc and
+// maps conv / transposed-conv forward, dgrad and wgrad onto the two engines
+// (RcvIgemm, RcvWgrad).  See include/rcv_b200.h for the contract.
+#include <stdarg.h>
+#include <string.h>
+
+#include "rcv_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void rcv_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int rcv_version(void) { return RCV_ABI_VERSION; }
+extern "C" const char* rcv_last_error(void) { return g_err; }
+
+namespace {
+
+int validate(const rcv_conv_desc* d, const char* who) {
+  RCV_REQUIRE(d != nullptr, RCV_ERR_BAD_ARG, "%s: null desc", who);
+  RCV_REQUIRE(d->N > 0 && d->Cin > 0 && d->Cout > 0 && d->H > 0 && d->W > 0, RCV_ERR_BAD_ARG,
+              "%s: non-positive dimension", who);
+  RCV_REQUIRE(d->Cin <= 1024 && d->Cout <= 1024, RCV_ERR_UNSUPPORTED, "%s: channels > 1024", who);
+  if (d->transposed) {
+    RCV_REQUIRE(d->ksize == 3 && d->stride == 2 && d->pad == 1 && d->dil == 1, RCV_ERR_UNSUPPORTED,
+                "%s: transposed conv supports only k3 s2 p1 op1 (got k%d s%d p%d d%d)", who, d->ksize,
+                d->stride, d->pad, d->dil);
+  } else if (d->ksize == 1) {
+    RCV_REQUIRE(d->stride == 1 && d->pad == 0 && d->dil == 1, RCV_ERR_UNSUPPORTED,
+                "%s: 1x1 conv supports only s1 p0", who);
+  } else {
+    RCV_REQUIRE(d->ksize == 3, RCV_ERR_UNSUPPORTED, "%s: kernel size %d (supported 1, 3)", who, d->ksize);
+    const bool ok = (d->stride == 1 && d->pad == 1 && d->dil == 1) ||
+                    (d->stride == 1 && d->pad == 2 && d->dil == 2) ||
+                    (d->stride == 2 && d->pad == 1 && d->dil == 1);
+    RCV_REQUIRE(ok, RCV_ERR_UNSUPPORTED, "%s: 3x3 geometry s%d p%d d%d outside the hot path", who,
+                d->stride, d->pad, d->dil);
+  }
+  RCV_REQUIRE(d->math == RCV_MATH_FP32 || d->math == RCV_MATH_TF32X3 || d->math == RCV_MATH_AUTO,
+              RCV_ERR_BAD_ARG, "%s: bad math mode %d", who, d->math);
+  return RCV_OK;
+}
+
+void out_hw(const rcv_conv_desc* d, int* Ho, int* Wo) {
+  if (d->transposed) {
+    *Ho = 2 * d->H;
+    *Wo = 2 * d->W;
+  } else {
+    *Ho = (d->H + 2 * d->pad - d->dil * (d->ksize - 1) - 1) / d->stride + 1;
+    *Wo = (d->W + 2 * d->pad - d->dil * (d->ksize - 1) - 1) / d->stride + 1;
+  }
+}
+
+// taps of an ordinary (cross-correlation) conv: input offset ky*dil - pad
+void conv_taps(const rcv_conv_desc* d, RcvTapSet* t) {
+  t->n = d->ksize * d->ksize;
+  for (int ky = 0; ky < d->ksize; ++ky)
+    for (int kx = 0; kx < d->ksize; ++kx) {
+      const int i = ky * d->ksize + kx;
+      t->dy[i] = (int8_t)(ky * d->dil - d->pad);
+      t->dx[i] = (int8_t)(kx * d->dil - d->pad);
+      t->wi[i] = (int8_t)i;
+    }
+}
+
+// taps of the stride-1 input gradient: dx[y] = sum_ky dy[y + pad - ky*dil] w[ky]
+void flipped_taps(const rcv_conv_desc* d, RcvTapSet* t) {
+  t->n = d->ksize * d->ksize;
+  for (int ky = 0; ky < d->ksize; ++ky)
+    for (int kx = 0; kx < d->ksize; ++kx) {
+      const int i = ky * d->ksize + kx;
+      t->dy[i] = (int8_t)(d->pad - ky * d->dil);
+      t->dx[i] = (int8_t)(d->pad - kx * d->dil);
+      t->wi[i] = (int8_t)i;
+    }
+}
+
+// Parity classes of "fine[2i+a] += coarse[i + d] * w[k]" with fine = 2*coarse + k - 1
+// (k3 s2 p1): a=0 -> (k=1, d=0); a=1 -> (k=0, d=+1), (k=2, d=0).
+void parity_taps(RcvTapSet t[4]) {
+  static const int nk[2] = {1, 2};
+  static const int kk[2][2] = {{1, 1}, {0, 2}};
+  static const int dd[2][2] = {{0, 0}, {1, 0}};
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      RcvTapSet* s = &t[a * 2 + b];
+      s->n = 0;
+      for (int iy = 0; iy < nk[a]; ++iy)
+        for (int ix = 0; ix < nk[b]; ++ix) {
+          s->dy[s->n] = (int8_t)dd[a][iy];
+          s->dx[s->n] = (int8_t)dd[b][ix];
+          s->wi[s->n] = (int8_t)(kk[a][iy] * 3 + kk[b][ix]);
+          s->n++;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int rcv_conv_out_hw(const rcv_conv_desc* d, int32_t* Ho, int32_t* Wo) {
+  int rc = validate(d, "rcv_conv_out_hw");
+  if (rc) return rc;
+  RCV_REQUIRE(Ho && Wo, RCV_ERR_BAD_ARG, "rcv_conv_out_hw: null output");
+  int h, w;
+  out_hw(d, &h, &w);
+  *Ho = h;
+  *Wo = w;
+  return RCV_OK;
+}
+
+extern "C" int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float* w, const float* bias,
+                            const float* scale, const float* shift, const float* residual, float* y,
+                            double* stats, void* stream) {
+  int rc = validate(d, "rcv_conv_fwd");
+  if (rc) return rc;
+  RCV_REQUIRE(x && w && y, RCV_ERR_BAD_ARG, "rcv_conv_fwd: null tensor");
+  RCV_REQUIRE(d->epilogue >= RCV_EPI_NONE && d->epilogue <= RCV_EPI_AFFINE, RCV_ERR_BAD_ARG,
+              "rcv_conv_fwd: bad epilogue %d", d->epilogue);
+  const bool needs_affine = d->epilogue == RCV_EPI_RELU_AFFINE || d->epilogue == RCV_EPI_AFFINE_RELU ||
+                            d->epilogue == RCV_EPI_AFFINE;
+  RCV_REQUIRE(!needs_affine || (scale && shift), RCV_ERR_BAD_ARG,
+              "rcv_conv_fwd: affine epilogue needs scale and shift");
+  RCV_REQUIRE(d->math != RCV_MATH_TF32X3, RCV_ERR_UNSUPPORTED,
+              "rcv_conv_fwd: TF32X3 path not built in this version");
+  int Ho, Wo;
+  out_hw(d, &Ho, &Wo);
+  RCV_REQUIRE(Ho > 0 && Wo > 0, RCV_ERR_BAD_ARG, "rcv_conv_fwd: empty output");
+  RcvIgemm p;
+  memset(&p, 0, sizeof(p));
+  p.in = x; p.w = w; p.out = y; p.bias = bias; p.scale = scale; p.shift = shift;
+  p.residual = residual; p.stats = stats;
+  p.N = d->N; p.CA = d->Cin; p.CB = d->Cout;
+  p.Hin = d->H; p.Win = d->W; p.Hout = Ho; p.Wout = Wo;
+  p.epilogue = d->epilogue;
+  const int kk = d->ksize * d->ksize;
+  if (!d->transposed) {
+    p.Hg = Ho; p.Wg = Wo; p.gs = d->stride; p.ostep = 1; p.nclass = 1;
+    p.wsA = kk;            // weight (Cout, Cin, k, k): stride of the reduced channel (Cin)
+    p.wsB = d->Cin * kk;   // stride of the output channel
+    conv_taps(d, &p.taps[0]);
+  } else {
+    p.Hg = d->H; p.Wg = d->W; p.gs = 1; p.ostep = 2; p.nclass = 4;
+    p.wsA = d->Cout * 9;   // weight (Cin, Cout, 3, 3)
+    p.wsB = 9;
+    parity_taps(p.taps);
+  }
+  return rcv_launch_igemm(p, (cudaStream_t)stream);
+}
+
+extern "C" int rcv_conv_dgrad(const rcv_conv_desc* d, const float* dy, const float* w,
+                              const float* residual, float* dx, void* stream) {
+  int rc = validate(d, "rcv_conv_dgrad");
+  if (rc) return rc;
+  RCV_REQUIRE(dy && w && dx, RCV_ERR_BAD_ARG, "rcv_conv_dgrad: null tensor");
+  RCV_REQUIRE(d->math != RCV_MATH_TF32X3, RCV_ERR_UNSUPPORTED,
+              "rcv_conv_dgrad: TF32X3 path not built in this version");
+  int Ho, Wo;
+  out_hw(d, &Ho, &Wo);
+  RcvIgemm p;
+  memset(&p, 0, sizeof(p));
+  p.in = dy; p.w = w; p.out = dx;
+  p.residual = residual;
+  p.N = d->N; p.CA = d->Cout; p.CB = d->Cin;
+  p.Hin = Ho; p.Win = Wo; p.Hout = d->H; p.Wout = d->W;
+  p.epilogue = RCV_EPI_NONE;
+  const int kk = d->ksize * d->ksize;
+  if (d->transposed) {
+    // dx[ci,i,j] = sum dy[co, 2i+ky-1, 2j+kx-1] * w[ci,co,ky,kx]: a stride-2 conv over dy
+    p.Hg = d->H; p.Wg = d->W; p.gs = 2; p.ostep = 1; p.nclass = 1;
+    p.wsA = 9;             // weight (Cin, Cout, 3, 3): reduced channel = Cout
+    p.wsB = d->Cout * 9;
+    rcv_conv_desc s2 = *d;
+    s2.ksize = 3; s2.dil = 1; s2.pad = 1;
+    conv_taps(&s2, &p.taps[0]);
+  } else if (d->stride == 1) {
+    p.Hg = d->H; p.Wg = d->W; p.gs = 1; p.ostep = 1; p.nclass = 1;
+    p.wsA = d->Cin * kk;   // weight (Cout, Cin, k, k): reduced channel = Cout
+    p.wsB = kk;
+    flipped_taps(d, &p.taps[0]);
+  } else {
+    // stride-2 conv: the input gradient is a transposed conv = four parity classes
+    RCV_REQUIRE((d->H & 1) == 0 && (d->W & 1) == 0, RCV_ERR_UNSUPPORTED,
+                "rcv_conv_dgrad: stride-2 conv needs even H, W (got %dx%d)", d->H, d->W);
+    p.Hg = Ho; p.Wg = Wo; p.gs = 1; p.ostep = 2; p.nclass = 4;
+    p.wsA = d->Cin * 9;
+    p.wsB = 9;
+    parity_taps(p.taps);
+  }
+  return rcv_launch_igemm(p, (cudaStream_t)stream);
+}
+
+extern "C" int rcv_conv_wgrad(const rcv_conv_desc* d, const float* x, const float* dy, float* dw,
+                              float* dbias, void* stream) {
+  int rc = validate(d, "rcv_conv_wgrad");
+  if (rc) return rc;
+  RCV_REQUIRE(x && dy && dw, RCV_ERR_BAD_ARG, "rcv_conv_wgrad: null tensor");
+  int Ho, Wo;
+  out_hw(d, &Ho, &Wo);
+  RcvWgrad p;
+  memset(&p, 0, sizeof(p));
+  p.dw = dw;
+  p.N = d->N;
+  const int kk = d->ksize * d->ksize;
+  if (!d->transposed) {
+    p.src = x; p.row = dy; p.dbias = dbias;
+    p.CA = d->Cin; p.CB = d->Cout;
+    p.Hin = d->H; p.Win = d->W; p.Hg = Ho; p.Wg = Wo; p.gs = d->stride;
+    p.wsA = kk; p.wsB = d->Cin * kk;
+    conv_taps(d, &p.taps);
+  } else {
+    // dw[ci,co,ky,kx] = sum x[ci,i,j] * dy[co, 2i+ky-1, 2j+kx-1]
+    p.src = dy; p.row = x; p.dbias = nullptr;
+    p.CA = d->Cout; p.CB = d->Cin;
+    p.Hin = Ho; p.Win = Wo; p.Hg = d->H; p.Wg = d->W; p.gs = 2;
+    p.wsA = 9; p.wsB = d->Cout * 9;
+    rcv_conv_desc s2 = *d;
+    conv_taps(&s2, &p.taps);
+    if (dbias) {
+      rc = rcv_channel_sum(d->N, d->Cout, (int64_t)Ho * Wo, dy, dbias, stream);
+      if (rc) return rc;
+    }
+  }
+  return rcv_launch_wgrad(p, (cudaStream_t)stream);
+}

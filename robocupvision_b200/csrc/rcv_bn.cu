@@ -1,0 +1,332 @@
+// BatchNorm2d (training mode) pieces, ReLU backward and per-channel sums.
+// All are HBM-bound streaming kernels over [N, C, HW] fp32 tensors: float4
+// accesses along HW, one channel per blockIdx.x so per-channel constants live
+// in registers and the reductions finish with one double atomic per block.
+#include "rcv_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = l < (NT / 32) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in thread 0
+}
+
+__global__ void bn_finalize_kernel(int C, double count, const double* __restrict__ stats,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, float momentum, float eps,
+                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = stats[c] / count;
+  double var = stats[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - (float)mean * sc;
+  if (save_mean) save_mean[c] = (float)mean;
+  if (save_invstd) save_invstd[c] = invstd;
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_fold_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               float eps, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  // same operation order as ATen's eval batch_norm: invstd = 1/sqrt(var+eps)
+  const float invstd = 1.f / sqrtf(var[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = b - mean[c] * sc;
+}
+
+// y = act(sc*z+sh) + residual ; flat float4 grid-stride
+template <bool VEC>
+__global__ void __launch_bounds__(NT) bn_apply_kernel(int64_t total, int C, int64_t HW,
+                                                       const float* __restrict__ z,
+                                                       const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, int relu,
+                                                       const float* __restrict__ residual,
+                                                       float* __restrict__ y) {
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  if (VEC) {
+    const int64_t hw4 = HW >> 2, tot4 = total >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < tot4; i += stride) {
+      const int c = (int)((i / hw4) % C);
+      const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+      float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
+      v.x = fmaf(sc, v.x, sh); v.y = fmaf(sc, v.y, sh); v.z = fmaf(sc, v.z, sh); v.w = fmaf(sc, v.w, sh);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (residual) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(residual) + i);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+      const int c = (int)((i / HW) % C);
+      float v = fmaf(__ldg(scale + c), z[i], __ldg(shift + c));
+      if (relu) v = fmaxf(v, 0.f);
+      if (residual) v += residual[i];
+      y[i] = v;
+    }
+  }
+}
+
+// One channel per blockIdx.x, blockIdx.y splits the N*HW elements of the channel.
+// PASS 0: reduce (sum g, sum g*xhat).  PASS 1: apply + dbias.
+template <int PASS>
+__global__ void __launch_bounds__(NT) bn_bwd_kernel(int N, int C, int64_t HW, int order,
+                                                     const float* __restrict__ dy,
+                                                     const float* __restrict__ z,
+                                                     const float* __restrict__ scale,
+                                                     const float* __restrict__ shift,
+                                                     const float* __restrict__ save_mean,
+                                                     const float* __restrict__ save_invstd,
+                                                     double* sums, float* __restrict__ dconv,
+                                                     float* dgamma, float* dbeta, float* dbias) {
+  __shared__ double sh[NT / 32];
+  const int c = blockIdx.x;
+  const float sc = scale[c], sft = shift[c], mean = save_mean[c], invstd = save_invstd[c];
+  const int64_t E = (int64_t)N * HW;  // elements of this channel
+  const double cnt = (double)E;
+  float m1 = 0.f, m2 = 0.f;
+  if (PASS == 1) {
+    m1 = (float)(sums[c] / cnt);
+    m2 = (float)(sums[C + c] / cnt);
+  }
+  const bool vec = (HW & 3) == 0;
+  const int64_t per = (E + gridDim.y - 1) / gridDim.y;
+  int64_t beg = (int64_t)blockIdx.y * per;
+  beg = vec ? (beg & ~(int64_t)3) : beg;
+  int64_t end = (int64_t)(blockIdx.y + 1) * per;
+  end = vec ? (end & ~(int64_t)3) : end;
+  if (blockIdx.y == gridDim.y - 1) end = E;
+  if (end > E) end = E;
+  double s1 = 0.0, s2 = 0.0;
+  float fs1 = 0.f, fs2 = 0.f;
+
+  auto elem = [&](float g, float zz, float& out) {
+    if (order == RCV_EPI_AFFINE_RELU) g = (fmaf(sc, zz, sft) > 0.f) ? g : 0.f;
+    const float xh = (zz - mean) * invstd;
+    if (PASS == 0) {
+      fs1 += g;
+      fs2 += g * xh;
+    } else {
+      float d = sc * (g - m1 - xh * m2);
+      if (order == RCV_EPI_RELU_AFFINE) d = zz > 0.f ? d : 0.f;
+      out = d;
+      fs1 += d;
+    }
+  };
+
+  if (vec) {
+    const int step = NT * 4;
+    int iter = 0;
+    for (int64_t e = beg + (int64_t)threadIdx.x * 4; e < end; e += step) {
+      const int64_t n = e / HW, r = e - n * HW;
+      const size_t off = ((size_t)n * C + c) * HW + r;
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + off));
+      const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + off));
+      float4 o;
+      elem(g4.x, z4.x, o.x); elem(g4.y, z4.y, o.y); elem(g4.z, z4.z, o.z); elem(g4.w, z4.w, o.w);
+      if (PASS == 1) *reinterpret_cast<float4*>(dconv + off) = o;
+      if ((++iter & 15) == 0) { s1 += fs1; s2 += fs2; fs1 = fs2 = 0.f; }
+    }
+  } else {
+    int iter = 0;
+    for (int64_t e = beg + threadIdx.x; e < end; e += NT) {
+      const int64_t n = e / HW, r = e - n * HW;
+      const size_t off = ((size_t)n * C + c) * HW + r;
+      float o = 0.f;
+      elem(dy[off], z[off], o);
+      if (PASS == 1) dconv[off] = o;
+      if ((++iter & 63) == 0) { s1 += fs1; s2 += fs2; fs1 = fs2 = 0.f; }
+    }
+  }
+  s1 += fs1;
+  s2 += fs2;
+  const double t1 = block_sum(s1, sh);
+  if (PASS == 0) {
+    const double t2 = block_sum(s2, sh);
+    if (threadIdx.x == 0) {
+      atomicAdd(sums + c, t1);
+      atomicAdd(sums + C + c, t2);
+    }
+  } else if (threadIdx.x == 0) {
+    if (dbias) atomicAdd(dbias + c, (float)t1);
+    if (blockIdx.y == 0) {
+      if (dgamma) atomicAdd(dgamma + c, (float)(sums[C + c]));
+      if (dbeta) atomicAdd(dbeta + c, (float)(sums[c]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) relu_bwd_kernel(int64_t n, const float* __restrict__ dy,
+                                                       const float* __restrict__ y,
+                                                       float* __restrict__ dx) {
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += stride) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(y) + i);
+    float4 o;
+    o.x = v.x > 0.f ? g.x : 0.f; o.y = v.y > 0.f ? g.y : 0.f;
+    o.z = v.z > 0.f ? g.z : 0.f; o.w = v.w > 0.f ? g.w : 0.f;
+    reinterpret_cast<float4*>(dx)[i] = o;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += stride)
+    dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+__global__ void __launch_bounds__(NT) channel_sum_kernel(int N, int C, int64_t HW,
+                                                          const float* __restrict__ dy, float* dbias) {
+  __shared__ double sh[NT / 32];
+  const int c = blockIdx.x;
+  const int64_t E = (int64_t)N * HW;
+  const int64_t per = (E + gridDim.y - 1) / gridDim.y;
+  const int64_t beg = (int64_t)blockIdx.y * per;
+  int64_t end = beg + per;
+  if (end > E) end = E;
+  double s = 0.0;
+  float fs = 0.f;
+  int iter = 0;
+  for (int64_t e = beg + threadIdx.x; e < end; e += NT) {
+    const int64_t n = e / HW, r = e - n * HW;
+    fs += __ldg(dy + ((size_t)n * C + c) * HW + r);
+    if ((++iter & 63) == 0) { s += fs; fs = 0.f; }
+  }
+  s += fs;
+  const double t = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(dbias + c, (float)t);
+}
+
+int ew_blocks(int64_t work_items) {
+  int64_t b = (work_items + NT - 1) / NT;
+  const int64_t cap = 148 * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int chan_splits(int C, int64_t E) {
+  int s = rcv_cdiv(148 * 8, C);
+  const int64_t maxs = (E + NT * 16 - 1) / (NT * 16);
+  if (s > maxs) s = (int)maxs;
+  if (s < 1) s = 1;
+  if (s > 65535) s = 65535;
+  return s;
+}
+
+}  // namespace
+
+extern "C" int rcv_bn_finalize(int32_t C, int64_t count, const double* stats, const float* gamma,
+                               const float* beta, float* running_mean, float* running_var,
+                               float momentum, float eps, float* scale, float* shift,
+                               float* save_mean, float* save_invstd, void* stream) {
+  RCV_REQUIRE(C > 0 && count > 0 && stats && scale && shift, RCV_ERR_BAD_ARG, "bn_finalize: bad arg");
+  bn_finalize_kernel<<<rcv_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      C, (double)count, stats, gamma, beta, running_mean, running_var, momentum, eps, scale, shift,
+      save_mean, save_invstd);
+  RCV_CHECK_LAUNCH("bn_finalize");
+  return RCV_OK;
+}
+
+extern "C" int rcv_bn_fold(int32_t C, const float* gamma, const float* beta, const float* mean,
+                           const float* var, float eps, float* scale, float* shift, void* stream) {
+  RCV_REQUIRE(C > 0 && mean && var && scale && shift, RCV_ERR_BAD_ARG, "bn_fold: bad arg");
+  bn_fold_kernel<<<rcv_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, mean, var, eps,
+                                                                    scale, shift);
+  RCV_CHECK_LAUNCH("bn_fold");
+  return RCV_OK;
+}
+
+extern "C" int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z, const float* scale,
+                            const float* shift, int relu, const float* residual, float* y,
+                            void* stream) {
+  RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && z && scale && shift && y, RCV_ERR_BAD_ARG,
+              "bn_apply: bad arg");
+  const int64_t total = (int64_t)N * C * HW;
+  if ((HW & 3) == 0)
+    bn_apply_kernel<true><<<ew_blocks(total / 4), NT, 0, (cudaStream_t)stream>>>(
+        total, C, HW, z, scale, shift, relu, residual, y);
+  else
+    bn_apply_kernel<false><<<ew_blocks(total), NT, 0, (cudaStream_t)stream>>>(
+        total, C, HW, z, scale, shift, relu, residual, y);
+  RCV_CHECK_LAUNCH("bn_apply");
+  return RCV_OK;
+}
+
+extern "C" int rcv_bn_bwd_reduce(int32_t N, int32_t C, int64_t HW, int order, const float* dy,
+                                 const float* z, const float* scale, const float* shift,
+                                 const float* save_mean, const float* save_invstd, double* sums,
+                                 void* stream) {
+  RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && dy && z && scale && shift && save_mean && save_invstd && sums,
+              RCV_ERR_BAD_ARG, "bn_bwd_reduce: bad arg");
+  RCV_REQUIRE(order == RCV_EPI_RELU_AFFINE || order == RCV_EPI_AFFINE_RELU || order == RCV_EPI_AFFINE,
+              RCV_ERR_BAD_ARG, "bn_bwd_reduce: bad order %d", order);
+  dim3 grid(C, chan_splits(C, (int64_t)N * HW));
+  bn_bwd_kernel<0><<<grid, NT, 0, (cudaStream_t)stream>>>(N, C, HW, order, dy, z, scale, shift,
+                                                          save_mean, save_invstd, sums, nullptr,
+                                                          nullptr, nullptr, nullptr);
+  RCV_CHECK_LAUNCH("bn_bwd_reduce");
+  return RCV_OK;
+}
+
+extern "C" int rcv_bn_bwd_apply(int32_t N, int32_t C, int64_t HW, int order, const float* dy,
+                                const float* z, const float* scale, const float* shift,
+                                const float* save_mean, const float* save_invstd, const double* sums,
+                                float* dconv, float* dgamma, float* dbeta, float* dbias,
+                                void* stream) {
+  RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && dy && z && scale && shift && save_mean && save_invstd &&
+                  sums && dconv,
+              RCV_ERR_BAD_ARG, "bn_bwd_apply: bad arg");
+  RCV_REQUIRE(order == RCV_EPI_RELU_AFFINE || order == RCV_EPI_AFFINE_RELU || order == RCV_EPI_AFFINE,
+              RCV_ERR_BAD_ARG, "bn_bwd_apply: bad order %d", order);
+  dim3 grid(C, chan_splits(C, (int64_t)N * HW));
+  bn_bwd_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(N, C, HW, order, dy, z, scale, shift,
+                                                          save_mean, save_invstd,
+                                                          const_cast<double*>(sums), dconv, dgamma,
+                                                          dbeta, dbias);
+  RCV_CHECK_LAUNCH("bn_bwd_apply");
+  return RCV_OK;
+}
+
+extern "C" int rcv_relu_bwd(int64_t n, const float* dy, const float* y, float* dx, void* stream) {
+  RCV_REQUIRE(n > 0 && dy && y && dx, RCV_ERR_BAD_ARG, "relu_bwd: bad arg");
+  RCV_REQUIRE((((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) & 15) == 0, RCV_ERR_BAD_ARG,
+              "relu_bwd: pointers must be 16-byte aligned");
+  relu_bwd_kernel<<<ew_blocks(n / 4 + 1), NT, 0, (cudaStream_t)stream>>>(n, dy, y, dx);
+  RCV_CHECK_LAUNCH("relu_bwd");
+  return RCV_OK;
+}
+
+extern "C" int rcv_channel_sum(int32_t N, int32_t C, int64_t HW, const float* dy, float* dbias,
+                               void* stream) {
+  RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && dy && dbias, RCV_ERR_BAD_ARG, "channel_sum: bad arg");
+  dim3 grid(C, chan_splits(C, (int64_t)N * HW));
+  channel_sum_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(N, C, HW, dy, dbias);
+  RCV_CHECK_LAUNCH("channel_sum");
+  return RCV_OK;
+}

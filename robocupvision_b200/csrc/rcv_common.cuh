@@ -1,0 +1,76 @@
+// Shared internals of librcv_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "rcv_b200.h"
+
+void rcv_set_error(const char* fmt, ...);
+
+#define RCV_REQUIRE(cond, code, ...)      \
+  do {                                    \
+    if (!(cond)) {                        \
+      rcv_set_error(__VA_ARGS__);         \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+// Check the launch that was just enqueued (no sync: only launch-config errors).
+#define RCV_CHECK_LAUNCH(name)                                              \
+  do {                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                   \
+    if (e__ != cudaSuccess) {                                               \
+      rcv_set_error("%s: %s", (name), cudaGetErrorString(e__));             \
+      return RCV_ERR_CUDA;                                                  \
+    }                                                                       \
+  } while (0)
+
+static inline int rcv_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// Implicit-GEMM problem shared by conv forward, conv dgrad and the
+// transposed-conv family.  out[n, cb, oy, ox] = sum_{ca, t} in[n, ca, iy, ix] *
+// w[ca*wsA + cb*wsB + twi[t]] with (iy, ix) = (i*gs + tdy[t], j*gs + tdx[t])
+// and (oy, ox) = (i*ostep + a, j*ostep + b) for pixel-grid point (i, j) of
+// parity class (a, b) (ostep = 1: a single class).
+// ---------------------------------------------------------------------------
+struct RcvTapSet {
+  int32_t n;
+  int8_t dy[9], dx[9], wi[9];
+};
+
+struct RcvIgemm {
+  const float* in;
+  const float* w;
+  float* out;
+  const float* bias;
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  double* stats;
+  int32_t N, CA, CB;
+  int32_t Hin, Win, Hout, Wout, Hg, Wg;
+  int32_t gs, ostep;
+  int32_t wsA, wsB;
+  int32_t epilogue;
+  int32_t nclass;
+  RcvTapSet taps[4];
+};
+
+// Weight-gradient problem: dw[cb*wsB + ca*wsA + twi[t]] += sum over pixel-grid
+// points (n,i,j) of row[n,cb,i,j] * src[n,ca,i*gs+tdy[t], j*gs+tdx[t]].
+struct RcvWgrad {
+  const float* src;  // gathered (im2col) tensor [N, CA, Hin, Win]
+  const float* row;  // dense tensor [N, CB, Hg, Wg]
+  float* dw;
+  float* dbias;      // += sum of row over pixels (NULL to skip)
+  int32_t N, CA, CB;
+  int32_t Hin, Win, Hg, Wg;
+  int32_t gs;
+  int32_t wsA, wsB;
+  int32_t slab;      // pixels per split, multiple of 16
+  RcvTapSet taps;
+};
+
+int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st);
+int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st);

@@ -1,0 +1,320 @@
+"""Tensor-level wrappers over the C ABI (one function per rcv_* entry point).
+
+PyTorch is plumbing here: it owns device memory (caching allocator) and the current
+stream; every function below enqueues exactly the named librcv_b200 kernels on
+``torch.cuda.current_stream()``.  Inputs must be CUDA tensors -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO,
+                   MATH_FP32, MATH_TF32X3, ConvDesc)
+
+__all__ = [
+    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_fold", "bn_apply",
+    "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
+    "confusion", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
+    "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
+    "MATH_FP32", "MATH_TF32X3", "MATH_AUTO",
+]
+
+_launches = 0  # kernels enqueued through this module (bench.py's gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count() -> None:
+    global _launches
+    _launches = 0
+
+
+def _call(name: str, nkernels: int, *args) -> None:
+    global _launches
+    _launches += nkernels
+    _lib.call(name, *args)
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32, name: str = "tensor") -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"robocupvision_b200: {name} must be a CUDA tensor "
+                           "(there is no CPU path; the oracle lives in oracle/ for tests only)")
+    if t.dtype != dtype:
+        raise TypeError(f"robocupvision_b200: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ConvGeom:
+    """Geometry of one nn.Conv2d / nn.ConvTranspose2d on the hot path."""
+
+    __slots__ = ("cin", "cout", "k", "stride", "pad", "dil", "transposed")
+
+    def __init__(self, cin, cout, k=3, stride=1, pad=1, dil=1, transposed=False):
+        self.cin, self.cout, self.k = int(cin), int(cout), int(k)
+        self.stride, self.pad, self.dil = int(stride), int(pad), int(dil)
+        self.transposed = bool(transposed)
+
+    @staticmethod
+    def of(m: torch.nn.Module) -> "ConvGeom":
+        if isinstance(m, torch.nn.ConvTranspose2d):
+            if not (m.kernel_size == (3, 3) and m.stride == (2, 2) and m.padding == (1, 1)
+                    and m.output_padding == (1, 1) and m.dilation == (1, 1) and m.groups == 1):
+                raise NotImplementedError(f"unsupported ConvTranspose2d geometry: {m}")
+            return ConvGeom(m.in_channels, m.out_channels, 3, 2, 1, 1, True)
+        if isinstance(m, torch.nn.Conv2d):
+            k, s, p, d = m.kernel_size, m.stride, m.padding, m.dilation
+            if not (k[0] == k[1] and s[0] == s[1] and p[0] == p[1] and d[0] == d[1] and m.groups == 1
+                    and m.padding_mode == "zeros"):
+                raise NotImplementedError(f"unsupported Conv2d geometry: {m}")
+            return ConvGeom(m.in_channels, m.out_channels, k[0], s[0], p[0], d[0], False)
+        raise TypeError(f"not a convolution module: {type(m)}")
+
+    def out_hw(self, h: int, w: int) -> Tuple[int, int]:
+        if self.transposed:
+            return 2 * h, 2 * w
+        e = self.dil * (self.k - 1) + 1
+        return (h + 2 * self.pad - e) // self.stride + 1, (w + 2 * self.pad - e) // self.stride + 1
+
+    def weight_shape(self):
+        if self.transposed:
+            return (self.cin, self.cout, 3, 3)
+        return (self.cout, self.cin, self.k, self.k)
+
+    def desc(self, n: int, h: int, w: int, epilogue: int = EPI_NONE, math: int = MATH_FP32) -> ConvDesc:
+        return ConvDesc(n, self.cin, h, w, self.cout, self.k, self.stride, self.pad, self.dil,
+                        1 if self.transposed else 0, epilogue, math)
+
+
+# --------------------------------------------------------------------------- conv family
+def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=None, residual=None,
+             stats=None, math=MATH_FP32, out=None):
+    x = _chk(x, name="x")
+    w = _chk(w, name="weight")
+    n, cin, h, wd = x.shape
+    if cin != g.cin or tuple(w.shape) != g.weight_shape():
+        raise ValueError(f"conv_fwd: x {tuple(x.shape)} / w {tuple(w.shape)} do not match geometry")
+    ho, wo = g.out_hw(h, wd)
+    y = out if out is not None else torch.empty((n, g.cout, ho, wo), device=x.device, dtype=torch.float32)
+    if residual is not None:
+        residual = _chk(residual, name="residual")
+        if residual.shape != y.shape:
+            raise ValueError(f"conv_fwd: residual {tuple(residual.shape)} != output {tuple(y.shape)}")
+    for t, nm in ((bias, "bias"), (scale, "scale"), (shift, "shift")):
+        if t is not None and (t.numel() != g.cout or not t.is_cuda or t.dtype != torch.float32):
+            raise ValueError(f"conv_fwd: bad {nm}")
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 2 * g.cout):
+        raise ValueError("conv_fwd: stats must be float64[2*Cout]")
+    d = g.desc(n, h, wd, epilogue, math)
+    _call("rcv_conv_fwd", 1, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift),
+          _ptr(residual), _ptr(y), _ptr(stats), _stream())
+    return y
+
+
+def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=MATH_FP32, out=None):
+    """Input gradient; `residual` (shape of dx; may be `out`) is the gradient the same tensor
+    receives from a second consumer and is added in the kernel epilogue."""
+    dy = _chk(dy, name="dy")
+    w = _chk(w, name="weight")
+    n = dy.shape[0]
+    h, wd = in_hw
+    if tuple(dy.shape[1:]) != (g.cout, *g.out_hw(h, wd)):
+        raise ValueError(f"conv_dgrad: dy {tuple(dy.shape)} does not match geometry for input {in_hw}")
+    d = g.desc(n, h, wd, EPI_NONE, math)
+    dx = out if out is not None else torch.empty((n, g.cin, h, wd), device=dy.device, dtype=torch.float32)
+    if residual is not None:
+        residual = _chk(residual, name="residual")
+        if residual.shape != dx.shape:
+            raise ValueError("conv_dgrad: residual shape mismatch")
+    _call("rcv_conv_dgrad", 1, C.byref(d), _ptr(dy), _ptr(w), _ptr(residual), _ptr(dx), _stream())
+    return dx
+
+
+def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False):
+    """Weight (and bias) gradient, accumulated into dw/dbias (zero-filled if not given)."""
+    x = _chk(x, name="x")
+    dy = _chk(dy, name="dy")
+    n, _, h, wd = x.shape
+    if dw is None:
+        dw = torch.zeros(g.weight_shape(), device=x.device, dtype=torch.float32)
+    if dbias is None and want_bias:
+        dbias = torch.zeros(g.cout, device=x.device, dtype=torch.float32)
+    d = g.desc(n, h, wd)
+    _call("rcv_conv_wgrad", 2 if (g.transposed and dbias is not None) else 1, C.byref(d), _ptr(x),
+          _ptr(dy), _ptr(dw), _ptr(dbias), _stream())
+    return dw, dbias
+
+
+# --------------------------------------------------------------------------- batch norm
+def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps):
+    c = stats.numel() // 2
+    dev = stats.device
+    buf = torch.empty((4, c), device=dev, dtype=torch.float32)
+    scale, shift, mean, invstd = buf[0], buf[1], buf[2], buf[3]
+    _call("rcv_bn_finalize", 1, c, int(count), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+          _ptr(running_var), float(momentum), float(eps), _ptr(scale), _ptr(shift), _ptr(mean),
+          _ptr(invstd), _stream())
+    return scale, shift, mean, invstd
+
+
+def bn_fold(gamma, beta, mean, var, eps):
+    c = mean.numel()
+    buf = torch.empty((2, c), device=mean.device, dtype=torch.float32)
+    _call("rcv_bn_fold", 1, c, _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(var), float(eps), _ptr(buf[0]),
+          _ptr(buf[1]), _stream())
+    return buf[0], buf[1]
+
+
+def bn_apply(z, scale, shift, relu: bool, residual=None, out=None):
+    z = _chk(z, name="z")
+    n, c = z.shape[0], z.shape[1]
+    hw = z.numel() // (n * c)
+    y = out if out is not None else torch.empty_like(z)
+    if residual is not None:
+        residual = _chk(residual, name="residual")
+    _call("rcv_bn_apply", 1, n, c, hw, _ptr(z), _ptr(scale), _ptr(shift), 1 if relu else 0, _ptr(residual),
+          _ptr(y), _stream())
+    return y
+
+
+def bn_bwd(order: int, dy, z, scale, shift, mean, invstd, dgamma=None, dbeta=None, dbias=None,
+           want_dbias: bool = False, sums=None):
+    """-> (dconv, dgamma, dbeta, dbias|None).  Two passes: reduce, apply.  dgamma/dbeta/dbias are
+    accumulated into when given (zero-filled buffers otherwise); sums is float64[2C] zeros."""
+    dy = _chk(dy, name="dy")
+    z = _chk(z, name="z")
+    n, c = z.shape[0], z.shape[1]
+    hw = z.numel() // (n * c)
+    if sums is None:
+        sums = torch.zeros(2 * c, device=z.device, dtype=torch.float64)
+    if dgamma is None or dbeta is None or (want_dbias and dbias is None):
+        small = torch.zeros((3, c), device=z.device, dtype=torch.float32)
+        dgamma = small[0] if dgamma is None else dgamma
+        dbeta = small[1] if dbeta is None else dbeta
+        if want_dbias and dbias is None:
+            dbias = small[2]
+    dconv = torch.empty_like(z)
+    st = _stream()
+    _call("rcv_bn_bwd_reduce", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
+          _ptr(invstd), _ptr(sums), st)
+    _call("rcv_bn_bwd_apply", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
+          _ptr(invstd), _ptr(sums), _ptr(dconv), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), st)
+    return dconv, dgamma, dbeta, dbias
+
+
+def relu_bwd(dy, y):
+    dy = _chk(dy, name="dy")
+    y = _chk(y, name="y")
+    dx = torch.empty_like(dy)
+    _call("rcv_relu_bwd", 1, dy.numel(), _ptr(dy), _ptr(y), _ptr(dx), _stream())
+    return dx
+
+
+def channel_sum(dy, out=None):
+    dy = _chk(dy, name="dy")
+    n, c = dy.shape[0], dy.shape[1]
+    hw = dy.numel() // (n * c)
+    if out is None:
+        out = torch.zeros(c, device=dy.device, dtype=torch.float32)
+    _call("rcv_channel_sum", 1, n, c, hw, _ptr(dy), _ptr(out), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- pooling
+def maxpool2x2_fwd(x, want_idx=False, want_code=True):
+    x = _chk(x, name="x")
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, h // 2, w // 2), device=x.device, dtype=torch.float32)
+    idx = torch.empty(y.shape, device=x.device, dtype=torch.int64) if want_idx else None
+    code = torch.empty(y.shape, device=x.device, dtype=torch.uint8) if want_code else None
+    _call("rcv_maxpool2x2_fwd", 1, n, c, h, w, _ptr(x), _ptr(y), _ptr(idx), _ptr(code), _stream())
+    return y, idx, code
+
+
+def maxpool2x2_bwd(dy, code, in_hw):
+    dy = _chk(dy, name="dy")
+    n, c = dy.shape[0], dy.shape[1]
+    h, w = in_hw
+    dx = torch.empty((n, c, h, w), device=dy.device, dtype=torch.float32)
+    _call("rcv_maxpool2x2_bwd", 1, n, c, h, w, _ptr(dy), _ptr(code), _ptr(dx), _stream())
+    return dx
+
+
+# --------------------------------------------------------------------------- loss / metrics
+def ce_fwd(logits, target, class_w=None, want_argmax=False, want_conf=False, want_correct=False):
+    """-> (loss_sums float64[2], argmax|None, conf int64[N,C,C]|None, correct int64[1]|None)."""
+    logits = _chk(logits, name="logits")
+    target = _chk(target, torch.int64, "target")
+    n, c = logits.shape[0], logits.shape[1]
+    hw = logits.numel() // (n * c)
+    if target.numel() != n * hw:
+        raise ValueError(f"ce_fwd: target {tuple(target.shape)} does not match logits {tuple(logits.shape)}")
+    dev = logits.device
+    sums = torch.zeros(2, device=dev, dtype=torch.float64)
+    am = torch.empty((n, *logits.shape[2:]), device=dev, dtype=torch.int64) if want_argmax else None
+    conf = torch.zeros((n, c, c), device=dev, dtype=torch.int64) if want_conf else None
+    corr = torch.zeros(1, device=dev, dtype=torch.int64) if want_correct else None
+    if class_w is not None:
+        class_w = _chk(class_w, name="class_w")
+        if class_w.numel() != c:
+            raise ValueError("ce_fwd: class_w must have C entries")
+    _call("rcv_ce_fwd", 1, n, c, hw, _ptr(logits), _ptr(target), _ptr(class_w), _ptr(sums), _ptr(am),
+          _ptr(conf), _ptr(corr), _stream())
+    return sums, am, conf, corr
+
+
+def ce_bwd(logits, target, class_w, sums, gscale=None):
+    logits = _chk(logits, name="logits")
+    target = _chk(target, torch.int64, "target")
+    n, c = logits.shape[0], logits.shape[1]
+    hw = logits.numel() // (n * c)
+    dl = torch.empty_like(logits)
+    if gscale is not None:
+        gscale = _chk(gscale.reshape(1).to(torch.float32), name="gscale")
+    _call("rcv_ce_bwd", 1, n, c, hw, _ptr(logits), _ptr(target), _ptr(class_w), _ptr(sums), _ptr(gscale),
+          _ptr(dl), _stream())
+    return dl
+
+
+def confusion(pred, target, num_classes: int):
+    pred = _chk(pred, torch.int64, "pred")
+    target = _chk(target, torch.int64, "target")
+    n = pred.shape[0]
+    hw = pred.numel() // n
+    conf = torch.zeros((n, num_classes, num_classes), device=pred.device, dtype=torch.int64)
+    _call("rcv_confusion", 1, n, num_classes, hw, _ptr(pred), _ptr(target), _ptr(conf), _stream())
+    return conf
+
+
+# --------------------------------------------------------------------------- optimiser tail
+def adam_l1_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, l1_decay=0.0, grad_scale=1.0,
+                 mask=None, l1_sum=None, step_dev=None, lr_dev=None):
+    _call("rcv_adam_l1_step", 1, p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(mask), float(lr),
+          float(beta1), float(beta2), float(eps), int(step), float(l1_decay), float(grad_scale),
+          _ptr(l1_sum), _ptr(step_dev), _ptr(lr_dev), _stream())
+
+
+def sgd_step(p, g, buf, lr, momentum=0.0, weight_decay=0.0, grad_scale=1.0, mask=None, first_step=False):
+    _call("rcv_sgd_step", 1, p.numel(), _ptr(p), _ptr(g), _ptr(buf), _ptr(mask), float(lr), float(momentum),
+          float(weight_decay), float(grad_scale), 1 if first_step else 0, _stream())
+
+
+def counter_add(counter, inc=1):
+    _call("rcv_counter_add", 1, _ptr(counter), int(inc), _stream())
