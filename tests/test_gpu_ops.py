@@ -1,0 +1,281 @@
+"""Per-kernel parity: every rcv_* entry point (through the C ABI) against the ATen CPU op the
+reference delegates to, on seeded inputs.  fp32 tolerance: 1e-5 of the output range (the
+reference's own accumulation-order noise is 1.4e-5)."""
+import itertools
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+GEOMS = {  # name -> (k, stride, pad, dil, transposed)
+    "k3s1d1": (3, 1, 1, 1, False),
+    "k3s1d2": (3, 1, 2, 2, False),
+    "k3s2": (3, 2, 1, 1, False),
+    "k1": (1, 1, 0, 1, False),
+    "convT": (3, 2, 1, 1, True),
+}
+CHANS = [(3, 8), (8, 16), (16, 16), (32, 64), (64, 128), (128, 128), (128, 64), (16, 5), (24, 40)]
+
+
+def _mk(geom, cin, cout, n, h, w, seed=0):
+    from robocupvision_b200 import ops
+    k, s, p, d, tr = GEOMS[geom]
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wshape = (cin, cout, 3, 3) if tr else (cout, cin, k, k)
+    wt = torch.randn(wshape, generator=g) * (1.0 / (cin * k * k) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    return ops.ConvGeom(cin, cout, k, s, p, d, tr), x, wt, b
+
+
+def _ref_conv(geom, x, w, b):
+    k, s, p, d, tr = GEOMS[geom]
+    if tr:
+        return F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1)
+    return F.conv2d(x, w, b, s, p, d)
+
+
+@pytest.mark.parametrize("geom", list(GEOMS))
+@pytest.mark.parametrize("cin,cout", CHANS)
+def test_conv_fwd(geom, cin, cout):
+    from robocupvision_b200 import ops
+    g, x, w, b = _mk(geom, cin, cout, 3, 12, 20)
+    ref = _ref_conv(geom, x, w, b)
+    got = ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda())
+    assert_close(f"conv_fwd {geom} {cin}->{cout}", got, ref, 2e-6)
+
+
+@pytest.mark.parametrize("geom", ["k3s1d1", "k3s1d2", "k3s2", "k1", "convT"])
+@pytest.mark.parametrize("hw", [(9, 7), (5, 3), (15, 20), (1, 1), (2, 130)])
+def test_conv_fwd_ragged_sizes(geom, hw):
+    """odd extents (scalar store path), single pixels, M not a multiple of the tile."""
+    from robocupvision_b200 import ops
+    g, x, w, b = _mk(geom, 5, 7, 2, *hw, seed=3)
+    ref = _ref_conv(geom, x, w, None)
+    got = ops.conv_fwd(g, x.cuda(), w.cuda(), None)
+    assert_close(f"conv_fwd {geom} {hw}", got, ref, 2e-6)
+
+
+@pytest.mark.parametrize("epi", ["none", "relu", "relu_affine", "affine_relu", "affine"])
+@pytest.mark.parametrize("geom,cin,cout", [("k3s1d1", 8, 16), ("k3s1d2", 64, 128), ("convT", 32, 16), ("k3s2", 16, 32)])
+def test_conv_epilogues(epi, geom, cin, cout):
+    from robocupvision_b200 import ops
+    g, x, w, b = _mk(geom, cin, cout, 2, 12, 16, seed=1)
+    gen = torch.Generator().manual_seed(9)
+    sc, sh = torch.randn(cout, generator=gen), torch.randn(cout, generator=gen)
+    v = _ref_conv(geom, x, w, b)
+    res = torch.randn(v.shape, generator=gen)
+    A, B = sc.view(1, -1, 1, 1), sh.view(1, -1, 1, 1)
+    ref = {"none": v, "relu": F.relu(v), "relu_affine": A * F.relu(v) + B, "affine_relu": F.relu(A * v + B),
+           "affine": A * v + B}[epi] + res
+    code = {"none": ops.EPI_NONE, "relu": ops.EPI_RELU, "relu_affine": ops.EPI_RELU_AFFINE,
+            "affine_relu": ops.EPI_AFFINE_RELU, "affine": ops.EPI_AFFINE}[epi]
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    got = ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda(), epilogue=code, scale=sc.cuda(), shift=sh.cuda(),
+                       residual=res.cuda(), stats=stats)
+    assert_close(f"epilogue {epi} {geom}", got, ref, 3e-6)
+    rd = ref.double()
+    assert_close("stats sum", stats[:cout], rd.sum((0, 2, 3)), 1e-6, atol=1e-3)
+    assert_close("stats sumsq", stats[cout:], (rd * rd).sum((0, 2, 3)), 1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("geom", list(GEOMS))
+@pytest.mark.parametrize("cin,cout", [(3, 8), (8, 16), (32, 64), (128, 128), (64, 32), (16, 5)])
+def test_conv_dgrad_wgrad(geom, cin, cout):
+    from robocupvision_b200 import ops
+    g, x, w, b = _mk(geom, cin, cout, 3, 12, 20, seed=5)
+    x.requires_grad_(True); w.requires_grad_(True); b.requires_grad_(True)
+    y = _ref_conv(geom, x, w, b)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+    y.backward(dy)
+    dx = ops.conv_dgrad(g, dy.cuda(), w.detach().cuda(), (12, 20))
+    assert_close(f"dgrad {geom} {cin}->{cout}", dx, x.grad, 3e-6)
+    other = torch.randn(x.shape, generator=torch.Generator().manual_seed(7))
+    dx2 = ops.conv_dgrad(g, dy.cuda(), w.detach().cuda(), (12, 20), residual=other.cuda())
+    assert_close("dgrad+residual", dx2, x.grad + other, 3e-6)
+    dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True)
+    assert_close(f"wgrad {geom} {cin}->{cout}", dw, w.grad, 1e-5)
+    assert_close(f"bgrad {geom}", db, b.grad, 1e-5)
+
+
+@pytest.mark.parametrize("geom", ["k3s1d1", "k3s1d2", "k1"])
+def test_wgrad_ragged(geom):
+    """pixel count not a multiple of 4/16: scalar load path and slab tails."""
+    from robocupvision_b200 import ops
+    g, x, w, b = _mk(geom, 6, 10, 3, 7, 9, seed=8)
+    x.requires_grad_(True); w.requires_grad_(True); b.requires_grad_(True)
+    y = _ref_conv(geom, x, w, b)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+    y.backward(dy)
+    dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True)
+    assert_close("wgrad ragged", dw, w.grad, 1e-5)
+    assert_close("bgrad ragged", db, b.grad, 1e-5)
+    dx = ops.conv_dgrad(g, dy.cuda(), w.detach().cuda(), (7, 9))
+    assert_close("dgrad ragged", dx, x.grad, 3e-6)
+
+
+def test_conv_rejects_unsupported():
+    from robocupvision_b200 import ops, _lib
+    g = ops.ConvGeom(4, 4, 5, 1, 2, 1)
+    x = torch.zeros(1, 4, 8, 8, device="cuda")
+    w = torch.zeros(4, 4, 5, 5, device="cuda")
+    with pytest.raises(_lib.RcvError) as e:
+        ops.conv_fwd(g, x, w)
+    assert e.value.code == _lib.RCV_ERR_UNSUPPORTED
+    with pytest.raises(RuntimeError):
+        ops.conv_fwd(ops.ConvGeom(4, 4), x.cpu(), torch.zeros(4, 4, 3, 3))  # no CPU path
+
+
+@pytest.mark.parametrize("order", ["relu_affine", "affine_relu"])
+@pytest.mark.parametrize("shape", [(4, 8, 12, 20), (3, 128, 5, 4), (2, 5, 7, 9)])
+def test_bn_train_fwd_bwd(order, shape):
+    """conv-output statistics -> finalize -> apply, and the two-pass backward, against
+    F.batch_norm(training=True) composed with ReLU in the block's order."""
+    from robocupvision_b200 import ops
+    n, c, h, w = shape
+    gen = torch.Generator().manual_seed(11)
+    v = torch.randn(shape, generator=gen) * 2 + 0.3
+    gamma = torch.rand(c, generator=gen) + 0.5
+    beta = torch.randn(c, generator=gen)
+    rm, rv = torch.randn(c, generator=gen), torch.rand(c, generator=gen) + 0.5
+    res = torch.randn(shape, generator=gen)
+    dy = torch.randn(shape, generator=gen)
+    vr = v.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    if order == "relu_affine":
+        z_ref = F.relu(vr)
+        y_ref = F.batch_norm(z_ref, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5) + res
+    else:
+        z_ref = vr
+        y_ref = F.relu(F.batch_norm(z_ref, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5)) + res
+    y_ref.backward(dy)
+
+    z = z_ref.detach().cuda()
+    zd = z.double()
+    stats = torch.cat([zd.sum((0, 2, 3)), (zd * zd).sum((0, 2, 3))])
+    rm_g, rv_g = rm.cuda(), rv.cuda()
+    scale, shift, mean, invstd = ops.bn_finalize(stats, n * h * w, gamma.cuda(), beta.cuda(), rm_g, rv_g, 0.1, 1e-5)
+    y = ops.bn_apply(z, scale, shift, relu=(order == "affine_relu"), residual=res.cuda())
+    assert_close("bn y", y, y_ref, 3e-6)
+    assert_close("running_mean", rm_g, rm_ref, 1e-6)
+    assert_close("running_var", rv_g, rv_ref, 1e-6)
+    code = ops.EPI_RELU_AFFINE if order == "relu_affine" else ops.EPI_AFFINE_RELU
+    dconv, dgamma, dbeta, dbias = ops.bn_bwd(code, dy.cuda(), z, scale, shift, mean, invstd, want_dbias=True)
+    assert_close("bn dconv", dconv, vr.grad, 1e-5)
+    assert_close("bn dgamma", dgamma, gr.grad, 1e-5)
+    assert_close("bn dbeta", dbeta, br.grad, 1e-5)
+    assert_close("bn dbias", dbias, vr.grad.sum((0, 2, 3)), 1e-5, atol=1e-4)
+
+
+def test_bn_fold_eval():
+    from robocupvision_b200 import ops
+    gen = torch.Generator().manual_seed(2)
+    c = 37
+    gamma, beta, mean = (torch.randn(c, generator=gen) for _ in range(3))
+    var = torch.rand(c, generator=gen) * 1e-3  # released checkpoints have var << eps
+    x = torch.randn(2, c, 6, 10, generator=gen)
+    ref = F.batch_norm(x, mean, var, gamma, beta, False, 0.1, 1e-5)
+    sc, sh = ops.bn_fold(gamma.cuda(), beta.cuda(), mean.cuda(), var.cuda(), 1e-5)
+    got = ops.bn_apply(x.cuda(), sc, sh, relu=False)
+    assert_close("bn eval", got, ref, 3e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 12, 20), (3, 5, 6, 2), (1, 32, 30, 40)])
+def test_maxpool(shape):
+    from robocupvision_b200 import ops
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(shape, generator=gen)
+    x[0, 0, 0, 0:2] = 1.5  # tie inside a window: first wins
+    x[0, 0, 1, 0:2] = 1.5
+    x[-1, -1, 2, 1] = float("nan")
+    xr = x.clone().requires_grad_(True)
+    y_ref, idx_ref = F.max_pool2d(xr, 2, 2, return_indices=True)
+    dy = torch.randn(y_ref.shape, generator=gen)
+    y_ref.backward(dy)
+    y, idx, code = ops.maxpool2x2_fwd(x.cuda(), want_idx=True, want_code=True)
+    assert torch.equal(idx.cpu(), idx_ref), "pool indices must be bit-exact"
+    assert torch.equal(torch.nan_to_num(y.cpu(), nan=123.0), torch.nan_to_num(y_ref.detach(), nan=123.0))
+    dx = ops.maxpool2x2_bwd(dy.cuda(), code, shape[2:])
+    assert torch.equal(dx.cpu(), xr.grad)
+
+
+@pytest.mark.parametrize("c", [5, 4, 2, 8])
+@pytest.mark.parametrize("weighted", [True, False])
+def test_cross_entropy_argmax_confusion(c, weighted):
+    from robocupvision_b200 import ops
+    from oracle import ref_metrics, ref_model
+    gen = torch.Generator().manual_seed(21)
+    n, h, w = 3, 15, 20
+    logits = torch.randn(n, c, h, w, generator=gen) * 3
+    logits[0, :, 0, 0] = 0.25  # exact tie: argmax must be class 0
+    target = torch.randint(0, c, (n, h, w), generator=gen)
+    cw = (torch.rand(c, generator=gen) * 10 + 0.5) if weighted else None
+    lr = logits.clone().requires_grad_(True)
+    loss_ref = ref_model.cross_entropy_2d(lr, target, cw)
+    (loss_ref * 1.7).backward()
+    sums, am, conf, corr = ops.ce_fwd(logits.cuda(), target.cuda(), None if cw is None else cw.cuda(),
+                                      want_argmax=True, want_conf=True, want_correct=True)
+    loss = (sums[0] / sums[1]).item()
+    assert abs(loss - loss_ref.item()) <= 2e-6 * max(1, abs(loss_ref.item()))
+    am_ref = ref_metrics.argmax_first(logits.numpy())
+    assert (am.cpu().numpy() == am_ref).all()
+    conf_ref = ref_metrics.confusion_per_image(am_ref, target.numpy(), c)
+    assert (conf.cpu().numpy() == conf_ref).all()
+    assert int(corr) == int((am_ref == target.numpy()).sum())
+    conf2 = ops.confusion(am, target.cuda(), c)
+    assert (conf2.cpu().numpy() == conf_ref).all()
+    dl = ops.ce_bwd(logits.cuda(), target.cuda(), None if cw is None else cw.cuda(), sums,
+                    gscale=torch.tensor(1.7, device="cuda"))
+    assert_close("ce dlogits", dl, lr.grad, 1e-5, atol=1e-9)
+
+
+def test_adam_l1_matches_torch_adam():
+    from robocupvision_b200 import ops
+    gen = torch.Generator().manual_seed(31)
+    n = 10007
+    p0 = torch.randn(n, generator=gen)
+    p0[::17] = 0.0
+    mask = torch.rand(n, generator=gen) < 0.2
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p, m, v = p0.cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 6):
+        g = torch.randn(n, generator=gen)
+        opt.zero_grad()
+        loss = (p_ref * g).sum() + 1e-3 * p_ref.abs().sum()
+        loss.backward()
+        p_ref.grad[mask] = 0
+        l1_ref = float(p_ref.detach().abs().sum())
+        opt.step()
+        l1 = torch.zeros(1, dtype=torch.float64, device="cuda")
+        ops.adam_l1_step(p, g.cuda(), m, v, lr=1e-3, step=step, l1_decay=1e-3, mask=mask.cuda().to(torch.uint8),
+                         l1_sum=l1)
+        assert abs(float(l1) - l1_ref) <= 1e-5 * l1_ref
+        assert_close(f"adam step {step}", p, p_ref, 2e-6)
+    # device-resident step / lr (graph-replayable form)
+    step_dev = torch.tensor([6], dtype=torch.int32, device="cuda")
+    lr_dev = torch.tensor([1e-3], device="cuda")
+    g = torch.randn(n, generator=gen)
+    opt.zero_grad(); (p_ref * g).sum().backward(); opt.step()
+    ops.adam_l1_step(p, g.cuda(), m, v, lr=123.0, step=0, step_dev=step_dev, lr_dev=lr_dev)
+    assert_close("adam dev step", p, p_ref, 2e-6)
+
+
+def test_sgd_matches_torch_sgd():
+    from robocupvision_b200 import ops
+    gen = torch.Generator().manual_seed(32)
+    n = 5003
+    p0 = torch.randn(n, generator=gen)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([p_ref], lr=0.1, momentum=0.5, weight_decay=1e-3)  # trainer.py:182-184
+    p, buf = p0.cuda(), torch.zeros(n, device="cuda")
+    for step in range(4):
+        g = torch.randn(n, generator=gen)
+        opt.zero_grad(); (p_ref * g).sum().backward(); opt.step()
+        ops.sgd_step(p, g.cuda(), buf, lr=0.1, momentum=0.5, weight_decay=1e-3, first_step=(step == 0))
+        assert_close(f"sgd step {step}", p, p_ref, 2e-6)
