@@ -198,11 +198,14 @@ class TrainStep:
             self.plan.backward(saved, [dl], False, self.grad_views, node_done=hook)
 
     def step(self, x: torch.Tensor, y: torch.Tensor):
-        """One training step on device tensors x [B,Cin,H,W] fp32, y [B,H,W] int64.
+        """One training step on x [B,Cin,H,W] fp32, y [B,H,W] int64 (device tensors, or pinned
+        host tensors which are copied H2D straight into the step's static input buffers).
         Returns (loss_sums float64[2], l1_sum float64[1], correct int64[1]) device tensors:
         CE loss = loss_sums[0]/loss_sums[1]; total = CE + l1_decay*l1_sum."""
         self.model.train()
         if not self.use_graph:
+            x = x.to(self.dev, non_blocking=True)
+            y = y.to(self.dev, non_blocking=True)
             self.loss_sums, self.l1_sum, self.correct = self._step_impl(x, y)
             return self.loss_sums, self.l1_sum, self.correct
         if self.graph is None or self.static_x.shape != x.shape:
@@ -220,8 +223,8 @@ class TrainStep:
         """First call for a shape: one eager warm-up step on a side stream (lazy CUDA module
         loading / attribute setting must not happen inside capture), state restored, the step
         captured, then replayed once -- so this call still performs exactly one step."""
-        self.static_x = x.clone()
-        self.static_y = y.clone()
+        self.static_x = x.to(self.dev, copy=True)
+        self.static_y = y.to(self.dev, copy=True)
         snap = [t.clone() for t in self._state()]
         cur = torch.cuda.current_stream()
         s = torch.cuda.Stream(device=self.dev)

@@ -1,0 +1,168 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/rcv_b200.h declares (no
+compute calls without a GPU), argument validation returns rcv_status codes, and the host-side
+logic (plans, legacy checkpoint loading, train-step bookkeeping, gloo data-parallel averaging)."""
+import ctypes as C
+import os
+import re
+import socket
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared():
+    h = (ROOT / "include" / "rcv_b200.h").read_text()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcv_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_header_symbols_exported_and_bound():
+    from robocupvision_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in rcv_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.rcv_version() == 1
+
+
+def test_validation_without_gpu():
+    from robocupvision_b200 import _lib
+    lib = _lib.load()
+    ho, wo = C.c_int32(), C.c_int32()
+    d = _lib.ConvDesc(2, 3, 120, 160, 8, 3, 2, 1, 1, 0, 0, 0)
+    assert lib.rcv_conv_out_hw(C.byref(d), C.byref(ho), C.byref(wo)) == 0 and (ho.value, wo.value) == (60, 80)
+    d = _lib.ConvDesc(2, 64, 15, 20, 32, 3, 2, 1, 1, 1, 0, 0)
+    assert lib.rcv_conv_out_hw(C.byref(d), C.byref(ho), C.byref(wo)) == 0 and (ho.value, wo.value) == (30, 40)
+    bad = _lib.ConvDesc(2, 3, 120, 160, 8, 5, 1, 2, 1, 0, 0, 0)
+    assert lib.rcv_conv_out_hw(C.byref(bad), C.byref(ho), C.byref(wo)) == _lib.RCV_ERR_UNSUPPORTED
+    assert b"kernel size 5" in lib.rcv_last_error()
+    assert lib.rcv_conv_fwd(C.byref(d), None, None, None, None, None, None, None, None, None) == _lib.RCV_ERR_BAD_ARG
+    assert lib.rcv_ce_fwd(1, 9, 10, None, None, None, None, None, None, None, None) == _lib.RCV_ERR_BAD_ARG
+    assert lib.rcv_adam_l1_step(0, None, None, None, None, None, 0.1, 0.9, 0.999, 1e-8, 1, 0.0, 1.0, None, None,
+                                None, None) == _lib.RCV_ERR_BAD_ARG
+
+
+def test_no_cpu_fallback():
+    from robocupvision_b200.model import ROBO_UNet, CrossEntropyLoss2d
+    m = ROBO_UNet()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 24, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        CrossEntropyLoss2d()(torch.zeros(1, 5, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long))
+
+
+def test_product_never_imports_oracle():
+    for f in (ROOT / "robocupvision_b200").rglob("*.py"):
+        src = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_plans():
+    from robocupvision_b200.model import ROBO_UNet, PB_FCN, LabelProp, FCN
+    p = ROBO_UNet()._get_plan()
+    assert len(p.nodes) == 16 and len(p.params) == 62
+    assert [n.skip for n in p.nodes[12:15]] == [5, 3, 1]       # Up_i + downs[-(i+2)]  (model.py:509)
+    p = ROBO_UNet(pool=True, levels=3, bellySize=0)._get_plan()
+    assert [n.kind for n in p.nodes].count("pool") == 3
+    p = PB_FCN(32, 5, 1, True, 0)._get_plan()
+    assert len(p.nodes) == 18
+    assert all(not id(q) in {id(x) for x in p.params} for q in PB_FCN(32, 5, 1, True, 0).classifier.parameters())
+    p = LabelProp(5, 32, 0)._get_plan()
+    assert p.nodes[9].skip_mode == "partial" and p.nodes[9].skip_ch == 8
+    assert len(FCN()._get_plan().nodes) == 15
+    m = ROBO_UNet()
+    with pytest.raises(KeyError):
+        m.downPart[0]                      # reference quirk: add_module names, slices still work
+    assert len(list(m.downPart[0:2].parameters())) == 12
+
+
+def test_legacy_checkpoint_loading():
+    from robocupvision_b200.model import PB_FCN, LabelProp, load_legacy_state_dict
+    from util import load_ckpt
+    raw = load_ckpt("bestModelSeg")
+    assert "classifier.classifier.weight" in raw and "segmenter.classifier.weight" not in raw
+    m = PB_FCN(32, 5, 1, False, 0)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(raw)                                   # strict load fails, as in the reference
+    missing, unexpected = load_legacy_state_dict(m, raw)
+    assert not missing and not unexpected
+    assert torch.equal(m.segmenter.classifier.weight, raw["classifier.classifier.weight"])
+    with pytest.raises(RuntimeError):
+        load_legacy_state_dict(PB_FCN(32, 5, 1, True, 0), raw)   # VGA net needs conv_ext / up4
+    lp = LabelProp(5, 32, 0)
+    load_legacy_state_dict(lp, load_ckpt("bestModelLPFinetunedPruned"))
+    z = float((lp.conv2.conv.weight == 0).float().mean())
+    assert z > 0.5                                               # magnitude-pruned, dense shapes
+
+
+def test_pruning_helpers():
+    from robocupvision_b200.model import ROBO_UNet, pruneModelNew, count_zero_weights, getParamSize
+    torch.manual_seed(0)
+    m = ROBO_UNet()
+    with torch.no_grad():
+        masks = pruneModelNew(m.parameters(), ratio=0.2)
+    big = [p for p in m.parameters() if p.dim() > 1]
+    assert len(masks) == len(big) == 16
+    for p, mk in zip(big, masks):
+        assert mk.shape == p.shape and float(p[mk].abs().sum()) == 0.0
+    assert 0.1 < count_zero_weights(m) < 0.4
+    assert getParamSize(big[0]) == big[0].numel()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import synth
+    from oracle import ref_model as R
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.dp import bucket_ranges, allreduce_buckets
+    torch.manual_seed(12345678)
+    m = ROBO_UNet()
+    sd = R.leaf_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    # rank r owns samples [r*B, (r+1)*B) of the global batch; local BN statistics (no SyncBN)
+    B = 2
+    x = synth.images(B * world, 3, 24, 32, seed=5)[rank * B:(rank + 1) * B]
+    y = synth.labels_learnable(synth.images(B * world, 3, 24, 32, seed=5))[rank * B:(rank + 1) * B]
+    loss = R.cross_entropy_2d(R.robo_unet_forward(sd, x, training=True), y, torch.tensor(synth.CLASS_WEIGHTS))
+    loss.backward()
+    keys = R.param_keys(sd)
+    sizes = [sd[k].numel() for k in keys]
+    flat = torch.cat([sd[k].grad.reshape(-1) for k in keys])
+    local = flat.clone()
+    ranges = bucket_ranges(sizes, n_buckets=2)
+    allreduce_buckets(flat, ranges)
+    flat /= world
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    expect = sum(gathered) / world
+    ok = torch.allclose(flat, expect, rtol=0, atol=1e-7) and ranges[0][0] == 0 and ranges[-1][1] == flat.numel()
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_averaging_gloo():
+    """world_size-2 gloo: bucketed all-reduce of the flat gradient arena == mean of the per-rank
+    gradients (the N>1 exchange of TrainStep, on CPU)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

@@ -108,12 +108,15 @@ def _grad_check(tag, model, oracle_fwd, sd, x, y, weights, tol=2e-4):
     assert_close(f"{tag} train logits", pred, pred_ref, LOGIT_TOL)
     assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
     worst = 0.0
+    # a conv bias feeding BatchNorm has an exactly-zero true gradient: both sides hold rounding
+    # noise there, so the per-tensor scale is floored at 1e-3 of the largest gradient in the net
+    gmax = max(float(v.grad.abs().max()) for v in osd.values() if v.grad is not None)
     for k, p in model.named_parameters():
         gref = osd[k].grad
         assert p.grad is not None, k
         if gref is None:
             continue
-        scale = max(float(gref.abs().max()), 1e-6)
+        scale = max(float(gref.abs().max()), 1e-3 * gmax)
         err = float((p.grad.cpu() - gref).abs().max()) / scale
         worst = max(worst, err)
         assert err <= tol, f"{tag}: grad {k} rel err {err:.3e}"
@@ -154,12 +157,13 @@ def test_pb_fcn_backward():
     pred = m(x.cuda())
     CrossEntropyLoss2d(torch.tensor(synth.CLASS_WEIGHTS)).cuda()(pred, y.cuda()).backward()
     assert_close("pb_fcn train logits", pred, pred_ref, LOGIT_TOL)
+    gmax = max(float(v.grad.abs().max()) for v in o.values() if v.grad is not None)
     for k, p in m.named_parameters():
         if k.startswith("classifier."):
             assert p.grad is None
             continue
         gref = o[k].grad
-        scale = max(float(gref.abs().max()), 1e-6)
+        scale = max(float(gref.abs().max()), 1e-3 * gmax)
         err = float((p.grad.cpu() - gref).abs().max()) / scale
         assert err <= 5e-4, f"pb_fcn grad {k} rel err {err:.3e}"
 
@@ -234,7 +238,7 @@ def test_train_step_pruned_masks():
     for (k, p) in m.named_parameters():
         d = (p.detach().cpu() - oracle.sd[k].detach()).abs()
         assert float(d.max()) <= 2.05 * lr, f"{k}: {float(d.max()):.3e}"
-        assert float((d > 0.05 * lr).float().mean()) <= 0.02, f"{k}: too many weights disagree"
+        assert int((d > 0.05 * lr).sum()) <= max(4, 0.02 * d.numel()), f"{k}: too many weights disagree"
         if p.dim() > 1:
             if masks[i].any():
                 assert float(p.detach()[masks[i].cuda()].abs().max()) == 0.0

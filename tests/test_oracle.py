@@ -1,0 +1,214 @@
+"""CPU suite (no GPU): pins the oracle.
+
+1. oracle (functional, ATen CPU) == golden vectors the REFERENCE produced (tests/golden).
+2. where /root/reference exists (this container), oracle == imported reference classes, bit-exact.
+3. plain-C oracle (double accumulation) agrees with the ATen ops on small shapes.
+4. numpy metrics restatement against the reference's literal triple loop.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import synth
+from nets import ROBO_VARIANTS, pb_fcn_state, robo_state
+from oracle import c_ops, ref_metrics, ref_model as R
+from oracle.ref_train import OracleTrainer
+from util import GOLDEN, load_ckpt, load_golden, with_nbt
+
+REF_DIR = Path("/root/reference")
+has_ref = (REF_DIR / "model.py").exists()
+
+
+def _check_golden(fwd, golden, num_classes=5, weights=synth.CLASS_WEIGHTS, only_small=False):
+    i = 0
+    while f"shape{i}" in golden:
+        n, c, h, w = (int(v) for v in golden[f"shape{i}"])
+        if only_small and n * h * w > 40000:
+            i += 1
+            continue
+        x = synth.images(n, c, h, w, seed=1234 + i)
+        y = synth.labels_random(n, h, w, num_classes, seed=4321 + i)
+        with torch.no_grad():
+            logits = fwd(x)
+        lf = logits.reshape(-1)
+        sub = lf[::13] if lf.numel() > 50000 else lf
+        gsub = torch.from_numpy(golden[f"logits_sub{i}"])
+        # same ATen kernels; thread count may differ from the generator's single thread
+        assert float((sub - gsub).abs().max()) <= 2e-5 * max(1.0, float(gsub.abs().max()))
+        am = logits.argmax(1)
+        am_ref = torch.from_numpy(golden[f"argmax{i}"].astype(np.int64))
+        top2 = logits.topk(2, dim=1).values
+        near = (top2[:, 0] - top2[:, 1]) < 1e-4
+        assert not bool(((am != am_ref) & ~near).any())
+        loss = R.cross_entropy_2d(logits, y, torch.tensor(weights))
+        assert abs(float(loss) - float(golden[f"loss{i}"])) <= 1e-5 * max(1.0, abs(float(golden[f"loss{i}"])))
+        conf = ref_metrics.confusion_per_image(am_ref.numpy(), y.numpy(), num_classes)
+        assert (conf == golden[f"conf{i}"]).all()
+        i += 1
+    assert i > 0
+
+
+@pytest.mark.parametrize("name,no_scale", [("bestModelSeg", False), ("bestModelSegFinetunedPruned", False),
+                                           ("bestModelSegVGA", True)])
+def test_oracle_pb_fcn_vs_golden(name, no_scale):
+    osd, _ = pb_fcn_state(name)
+    _check_golden(lambda x: R.pb_fcn_forward(osd, x, no_scale), load_golden(name + "_eval"), only_small=no_scale)
+
+
+def test_oracle_labelprop_vs_golden():
+    osd = with_nbt(load_ckpt("bestModelLPFinetunedPruned"))
+    _check_golden(lambda x: R.labelprop_forward(osd, x), load_golden("bestModelLPFinetunedPruned_eval"),
+                  weights=synth.LP_CLASS_WEIGHTS)
+
+
+@pytest.mark.parametrize("tag", ["robo_default", "robo_unet_pool"])
+def test_oracle_robo_vs_golden(tag):
+    sd, kw, okw = robo_state(tag)
+    _check_golden(lambda x: R.robo_unet_forward(sd, x, **okw), load_golden(tag + "_eval"))
+
+
+def test_oracle_trainer_vs_golden_steps():
+    from robocupvision_b200.model import ROBO_UNet
+    gold = load_golden("robo_train")
+    torch.manual_seed(12345678)
+    sd0 = {k: v.clone() for k, v in ROBO_UNet().state_dict().items()}
+    tr = OracleTrainer(sd0, lambda s, x, training: R.robo_unet_forward(s, x, training=training),
+                       synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6)
+    for s in range(3):
+        x = synth.images(8, 3, 48, 64, seed=100 + s)
+        y = synth.labels_learnable(x)
+        loss, reg, correct, _, grads = tr.step(x, y)
+        assert abs(loss - float(gold["losses"][s])) <= 2e-5 * abs(float(gold["losses"][s]))
+        assert abs(reg - float(gold["regs"][s])) <= 1e-5 * abs(float(gold["regs"][s]))
+        gn = [float(grads[k].norm()) for k in tr.keys]
+        # step 0 is pinned tightly; later steps inherit Adam's sign-like first updates (chaotic)
+        assert np.allclose(gn, gold["gnorms"][s], rtol=1e-2 if s == 0 else 0.2, atol=1e-5)
+
+
+def test_weights_dat_wire_format():
+    """paramSave.py:5-17: float64 flatten of the state dict in key order; weightsLP/weights.dat is
+    that flatten of bestModelLPFinetunedPruned.pth (golden head/tail/size recorded from the file)."""
+    g = load_golden("weightsLP_head")
+    sd = load_ckpt("bestModelLPFinetunedPruned")
+    flat = np.concatenate([v.numpy().astype(np.float64).reshape(-1) for v in sd.values()])
+    assert flat.size == int(g["n"])
+    assert (flat[:64] == g["head"]).all() and (flat[-64:] == g["tail"]).all()
+    import hashlib
+    assert (np.frombuffer(hashlib.sha256(flat.tobytes()).digest(), dtype=np.uint8) == g["sha256"]).all()
+
+
+# ------------------------------------------------------------------ vs the imported reference
+@pytest.mark.skipif(not has_ref, reason="/root/reference not present on this box")
+def test_oracle_bit_exact_vs_reference_classes():
+    sys.path.insert(0, str(REF_DIR))
+    import model as REFM
+    torch.manual_seed(3)
+    x = synth.images(2, 3, 48, 64, seed=8)
+    for kw, okw in ROBO_VARIANTS.values():
+        m = REFM.ROBO_UNet(**kw)
+        for mode in (True, False):
+            m.train(mode)
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+            with torch.no_grad():
+                assert torch.equal(m(x), R.robo_unet_forward(sd, x, training=mode, **okw))
+            if mode:
+                for k, v in m.state_dict().items():
+                    assert torch.equal(v, sd[k]), k
+    for ns in (False, True):
+        m = REFM.PB_FCN(32, 5, 1, ns, 0).eval()
+        with torch.no_grad():
+            assert torch.equal(m(x), R.pb_fcn_forward(m.state_dict(), x, ns))
+    m = REFM.FCN().eval()
+    with torch.no_grad():
+        assert torch.equal(m(x), R.fcn_forward(m.state_dict(), x))
+    y = synth.labels_random(2, 48, 64)
+    w = torch.tensor(synth.CLASS_WEIGHTS)
+    lg = torch.randn(2, 5, 48, 64)
+    assert torch.equal(REFM.CrossEntropyLoss2d(w)(lg, y), R.cross_entropy_2d(lg, y, w))
+
+
+@pytest.mark.skipif(not has_ref, reason="/root/reference not present on this box")
+def test_dropin_module_tree_matches_reference():
+    """Same state_dict keys/shapes, parameter order and seeded init as the reference classes."""
+    sys.path.insert(0, str(REF_DIR))
+    import model as REFM
+    from robocupvision_b200 import model as M
+    cases = [(REFM.ROBO_UNet, M.ROBO_UNet, (), kw) for kw, _ in ROBO_VARIANTS.values()]
+    cases += [(REFM.ROBO_UNet, M.ROBO_UNet, (), dict(v2=True, levels=1, bellySize=9, classSize=3, bellyPlanes=64))]
+    cases += [(REFM.PB_FCN, M.PB_FCN, (32, 5, 1, ns, 0), {}) for ns in (False, True)]
+    cases += [(REFM.FCN, M.FCN, (), {}), (REFM.DownSampler, M.DownSampler, (32, False), {})]
+    for rc, mc, a, kw in cases:
+        torch.manual_seed(5); r = rc(*a, **kw)
+        torch.manual_seed(5); m = mc(*a, **kw)
+        sr, sm = r.state_dict(), m.state_dict()
+        assert list(sr.keys()) == list(sm.keys())
+        assert all(torch.equal(sr[k], sm[k]) for k in sr)
+        assert [n for n, _ in r.named_parameters()] == [n for n, _ in m.named_parameters()]
+    r = REFM.ROBO_UNet(); m = M.ROBO_UNet()
+    assert r.get_computations() == m.get_computations()
+    assert abs(sum(m.get_computations()) - 499.08e6) < 0.01e6
+
+
+# ------------------------------------------------------------------ plain-C oracle vs ATen
+@pytest.mark.parametrize("k,s,p,d", [(3, 1, 1, 1), (3, 1, 2, 2), (3, 2, 1, 1), (1, 1, 0, 1)])
+def test_c_conv2d(k, s, p, d):
+    g = torch.Generator().manual_seed(0)
+    x, w, b = torch.randn(2, 5, 9, 12, generator=g), torch.randn(7, 5, k, k, generator=g), torch.randn(7, generator=g)
+    ref = F.conv2d(x, w, b, s, p, d).numpy()
+    assert np.allclose(c_ops.conv2d(x.numpy(), w.numpy(), b.numpy(), s, p, d), ref, rtol=0, atol=2e-5)
+
+
+def test_c_conv_transpose_bn_pool_ce():
+    g = torch.Generator().manual_seed(1)
+    x, w, b = torch.randn(2, 6, 5, 7, generator=g), torch.randn(6, 4, 3, 3, generator=g), torch.randn(4, generator=g)
+    ref = F.conv_transpose2d(x, w, b, stride=2, padding=1, output_padding=1).numpy()
+    assert np.allclose(c_ops.conv_transpose2d(x.numpy(), w.numpy(), b.numpy()), ref, rtol=0, atol=2e-5)
+    ga, be = torch.rand(6, generator=g) + .5, torch.randn(6, generator=g)
+    rm, rv = torch.randn(6, generator=g), torch.rand(6, generator=g) + .5
+    rm_t, rv_t = rm.clone(), rv.clone()
+    yt = F.batch_norm(x, rm_t, rv_t, ga, be, True, 0.1, 1e-5).numpy()
+    y, crm, crv, _, _ = c_ops.bn_train(x.numpy(), ga.numpy(), be.numpy(), rm.numpy(), rv.numpy())
+    assert np.allclose(y, yt, atol=2e-5) and np.allclose(crm, rm_t.numpy(), atol=1e-6) and np.allclose(crv, rv_t.numpy(), atol=1e-6)
+    ye = F.batch_norm(x, rm, rv, ga, be, False, 0.1, 1e-5).numpy()
+    assert np.allclose(c_ops.bn_eval(x.numpy(), ga.numpy(), be.numpy(), rm.numpy(), rv.numpy()), ye, atol=2e-5)
+    xp = torch.randn(2, 3, 6, 8, generator=g); xp[0, 0, 0, :2] = 1.0; xp[0, 0, 1, :2] = 1.0
+    yr, ir = F.max_pool2d(xp, 2, 2, return_indices=True)
+    yc, ic = c_ops.maxpool2x2(xp.numpy())
+    assert (yc == yr.numpy()).all() and (ic == ir.numpy()).all()
+    lg = torch.randn(2, 5, 6, 8, generator=g, requires_grad=True)
+    t = torch.randint(0, 5, (2, 6, 8), generator=g)
+    cw = torch.tensor(synth.CLASS_WEIGHTS)
+    lr = R.cross_entropy_2d(lg, t, cw); lr.backward()
+    lc, dc = c_ops.weighted_ce(lg.detach().numpy(), t.numpy(), cw.numpy(), want_grad=True)
+    assert abs(lc - float(lr)) < 1e-5 and np.allclose(dc, lg.grad.numpy(), atol=1e-7)
+    am, conf, corr = c_ops.argmax_confusion(lg.detach().numpy(), t.numpy())
+    assert (am == ref_metrics.argmax_first(lg.detach().numpy())).all()
+    assert (conf == ref_metrics.confusion_per_image(am, t.numpy(), 5)).all() and corr == int((am == t.numpy()).sum())
+
+
+def test_metrics_vs_reference_literal_loop():
+    """train.py:133-163 written out literally (torch masks and the triple loop)."""
+    g = torch.Generator().manual_seed(2)
+    nC, B, H, W = 5, 3, 12, 16
+    pred = torch.randint(0, nC, (B, H, W), generator=g)
+    tgt = torch.randint(0, 4, (B, H, W), generator=g)   # class 4 absent from the labels: union==0 cases
+    pred[0][pred[0] == 4] = 0                            # ... and from one image's predictions
+    conf = torch.zeros(nC, nC); IoU = torch.zeros(nC); lab = torch.zeros(nC)
+    mp = torch.stack([(pred == c) for c in range(nC)]).long()
+    mt = torch.stack([(tgt == c) for c in range(nC)]).long()
+    for i in range(B):
+        for l in range(nC):
+            lab[l] += torch.sum(mt[l, i]).item()
+            for p in range(nC):
+                inter = torch.sum(mp[p, i] & mt[l, i]).item()
+                conf[(p, l)] += inter
+                if l == p:
+                    union = torch.sum(mp[p, i] | mt[l, i]).item()
+                    IoU[l] += 1 if union == 0 else inter / union
+    c_img = ref_metrics.confusion_per_image(pred.numpy(), tgt.numpy(), nC)
+    assert (c_img.sum(0) == conf.numpy()).all()
+    assert np.allclose(ref_metrics.iou_sums(c_img), IoU.numpy(), atol=1e-6)
