@@ -91,6 +91,13 @@ def test_robo_unet_eval(tag):
     _check_eval(tag, m, lambda x: R.robo_unet_forward(sd, x, **okw), load_golden(tag + "_eval"))
 
 
+def _bias_before_bn(model):
+    """Names of conv biases that feed a train-mode BatchNorm directly (upSampleTransposeConv,
+    model.py:191-193: relu(bn(convT(x)+b))): their true gradient is exactly zero."""
+    from robocupvision_b200.model import upSampleTransposeConv
+    return {f"{n}.conv.bias" for n, mod in model.named_modules() if isinstance(mod, upSampleTransposeConv)}
+
+
 def _grad_check(tag, model, oracle_fwd, sd, x, y, weights, tol=2e-4):
     """Autograd path of the drop-in module (model(x) -> criterion -> backward) against CPU
     autograd over the oracle: train-mode logits, loss, every parameter gradient, BN buffers."""
@@ -158,11 +165,17 @@ def test_pb_fcn_backward():
     CrossEntropyLoss2d(torch.tensor(synth.CLASS_WEIGHTS)).cuda()(pred, y.cuda()).backward()
     assert_close("pb_fcn train logits", pred, pred_ref, LOGIT_TOL)
     gmax = max(float(v.grad.abs().max()) for v in o.values() if v.grad is not None)
+    zero_true = _bias_before_bn(m)
     for k, p in m.named_parameters():
         if k.startswith("classifier."):
             assert p.grad is None
             continue
         gref = o[k].grad
+        if k in zero_true:
+            # analytically zero (bias followed directly by train-mode BN): both sides hold only
+            # rounding noise, amplified by this checkpoint's BN gains of up to 50x
+            assert float(p.grad.abs().max()) <= 1e-2 * gmax and float(gref.abs().max()) <= 1e-2 * gmax, k
+            continue
         scale = max(float(gref.abs().max()), 1e-3 * gmax)
         err = float((p.grad.cpu() - gref).abs().max()) / scale
         assert err <= 5e-4, f"pb_fcn grad {k} rel err {err:.3e}"
@@ -235,10 +248,12 @@ def test_train_step_pruned_masks():
     # |g| ~ eps.  Gate: masked weights stay exactly 0, no weight is off by more than one full
     # step in the opposite direction, and all but a sliver agree closely.
     lr, i = 5e-5, 0
+    zero_true = _bias_before_bn(m)
     for (k, p) in m.named_parameters():
         d = (p.detach().cpu() - oracle.sd[k].detach()).abs()
         assert float(d.max()) <= 2.05 * lr, f"{k}: {float(d.max()):.3e}"
-        assert int((d > 0.05 * lr).sum()) <= max(4, 0.02 * d.numel()), f"{k}: too many weights disagree"
+        if k not in zero_true:  # sign(noise) * lr on both sides where the true gradient is 0
+            assert int((d > 0.05 * lr).sum()) <= max(4, 0.02 * d.numel()), f"{k}: too many weights disagree"
         if p.dim() > 1:
             if masks[i].any():
                 assert float(p.detach()[masks[i].cuda()].abs().max()) == 0.0
