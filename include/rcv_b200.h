@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RCV_ABI_VERSION 1
+#define RCV_ABI_VERSION 2
 
 typedef enum rcv_status {
   RCV_OK = 0,
@@ -57,10 +57,18 @@ typedef enum rcv_epilogue {
 /* Math mode of the GEMM-shaped kernels. */
 typedef enum rcv_math {
   RCV_MATH_FP32 = 0,     /* fp32 FFMA on CUDA cores (always available)          */
-  RCV_MATH_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-term error-compensated split;  *
-                          * fp32-level accuracy; wide layers only               */
-  RCV_MATH_AUTO = 2      /* TF32X3 where the geometry supports it, else FP32     */
+  RCV_MATH_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-term error-compensated split,  *
+                          * TMEM accumulators: fp32-level accuracy (~1e-6 of the *
+                          * output range); needs packed weights (rcv_conv_pack)  */
+  RCV_MATH_AUTO = 2      /* TF32X3 where packed weights are given and the        *
+                          * reduction is long enough to pay, else FP32           */
 } rcv_math;
+
+/* Which operand a packed weight panel serves. */
+typedef enum rcv_pack_dir {
+  RCV_PACK_FWD = 0,      /* rcv_conv_fwd                                        */
+  RCV_PACK_DGRAD = 1     /* rcv_conv_dgrad                                      */
+} rcv_pack_dir;
 
 /* One convolution-type layer.  transposed=0: nn.Conv2d(Cin,Cout,ksize,stride,
  * pad,dil) on x[N,Cin,H,W] (model.py:112,130-133,170,259,411,554).
@@ -85,7 +93,23 @@ int rcv_conv_out_hw(const rcv_conv_desc* d, int32_t* Ho, int32_t* Wo);
 
 /* ---- convolution family ------------------------------------------------- */
 
-/* y = EPI(conv(x,w) + bias) [+ residual].  bias, scale, shift, residual,
+/* Weight panels for the tensor-core engine.  The nn.Conv2d / nn.ConvTranspose2d
+ * weight tensor w (model.py:112,186) is re-laid out once per forward as the
+ * engine's B operand: K-major rows in (tap, channel) order, split into tf32 hi
+ * and lo parts, in the 128-byte-swizzled shared-memory image a CTA copies in
+ * bulk.  packed must hold rcv_conv_packed_bytes(d, direction) bytes, 128-byte
+ * aligned; it depends on the layer geometry only, not on N, H, W.  One launch. */
+size_t rcv_conv_packed_bytes(const rcv_conv_desc* d, int direction);
+/* 1 if rcv_conv_fwd / rcv_conv_dgrad (per direction) would run this layer on
+ * the tensor cores under d->math when given packed weights, else 0: lets the
+ * caller skip packing layers that stay on CUDA cores under RCV_MATH_AUTO. */
+int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction);
+int rcv_conv_pack(const rcv_conv_desc* d, int direction, const float* w,
+                  void* packed, void* stream);
+
+/* y = EPI(conv(x,w) + bias) [+ residual].  wpacked (rcv_conv_pack of w,
+ * RCV_PACK_FWD) may be NULL: the call then runs on CUDA cores (RCV_MATH_TF32X3
+ * without it is RCV_ERR_BAD_ARG).  bias, scale, shift, residual,
  * stats may be NULL.  residual has the shape of y and is added after the
  * epilogue (decoder skip: model.py:300-307, 509).  If stats != NULL it is a
  * double[2*Cout] accumulator: stats[c] += sum(y_c), stats[Cout+c] += sum(y_c^2)
@@ -93,15 +117,18 @@ int rcv_conv_out_hw(const rcv_conv_desc* d, int32_t* Ho, int32_t* Wo);
  * tensor BN consumes; caller zeroes it).
  * Replaces F.conv2d / F.conv_transpose2d (+ relu + eval batch_norm + add). */
 int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float* w,
-                 const float* bias, const float* scale, const float* shift,
+                 const void* wpacked, const float* bias, const float* scale,
+                 const float* shift,
                  const float* residual, float* y, double* stats, void* stream);
 
 /* dx = d(conv)/dx applied to dy (shape of y) [+ residual].  residual (may be
  * NULL, may alias dx) has the shape of dx: the gradient arriving at the same
  * tensor from a second consumer (the decoder skip), summed in the epilogue.
+ * wpacked: rcv_conv_pack of w with RCV_PACK_DGRAD, or NULL (CUDA cores).
  * Replaces convolution_backward's input gradient (+ autograd's add). */
 int rcv_conv_dgrad(const rcv_conv_desc* d, const float* dy, const float* w,
-                   const float* residual, float* dx, void* stream);
+                   const void* wpacked, const float* residual, float* dx,
+                   void* stream);
 
 /* dw += d(conv)/dw, dbias += sum(dy) (dbias may be NULL).  Split over pixels
  * with fp32 atomic accumulation: the caller zeroes dw/dbias beforehand.

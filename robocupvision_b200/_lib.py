@@ -47,8 +47,11 @@ SIGNATURES = {
     "rcv_version": [],
     "rcv_last_error": [],
     "rcv_conv_out_hw": [C.POINTER(ConvDesc), C.POINTER(_i32), C.POINTER(_i32)],
-    "rcv_conv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p, _p],
-    "rcv_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
+    "rcv_conv_packed_bytes": [C.POINTER(ConvDesc), C.c_int],
+    "rcv_conv_uses_tensor_cores": [C.POINTER(ConvDesc), C.c_int],
+    "rcv_conv_pack": [C.POINTER(ConvDesc), C.c_int, _p, _p, _p],
+    "rcv_conv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rcv_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p],
     "rcv_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "rcv_bn_finalize": [_i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p],
     "rcv_bn_fold": [_i32, _p, _p, _p, _p, _f32, _p, _p, _p],
@@ -66,7 +69,9 @@ SIGNATURES = {
     "rcv_counter_add": [_p, _i32, _p],
     "rcv_sgd_step": [_i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, C.c_int, _p],
 }
-_RESTYPES = {"rcv_last_error": C.c_char_p}
+_RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t}
+PACK_FWD, PACK_DGRAD = 0, 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -99,8 +104,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
     abi = lib.rcv_version()
-    if abi != 1:
-        raise RcvLibraryError(f"ABI version mismatch: library {abi}, binding 1")
+    if abi != ABI_VERSION:
+        raise RcvLibraryError(f"ABI version mismatch: library {abi}, binding {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -112,30 +112,18 @@ extern "C" int rcv_conv_out_hw(const rcv_conv_desc* d, int32_t* Ho, int32_t* Wo)
   return RCV_OK;
 }
 
-extern "C" int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float* w, const float* bias,
-                            const float* scale, const float* shift, const float* residual, float* y,
-                            double* stats, void* stream) {
-  int rc = validate(d, "rcv_conv_fwd");
-  if (rc) return rc;
-  RCV_REQUIRE(x && w && y, RCV_ERR_BAD_ARG, "rcv_conv_fwd: null tensor");
-  RCV_REQUIRE(d->epilogue >= RCV_EPI_NONE && d->epilogue <= RCV_EPI_AFFINE, RCV_ERR_BAD_ARG,
-              "rcv_conv_fwd: bad epilogue %d", d->epilogue);
-  const bool needs_affine = d->epilogue == RCV_EPI_RELU_AFFINE || d->epilogue == RCV_EPI_AFFINE_RELU ||
-                            d->epilogue == RCV_EPI_AFFINE;
-  RCV_REQUIRE(!needs_affine || (scale && shift), RCV_ERR_BAD_ARG,
-              "rcv_conv_fwd: affine epilogue needs scale and shift");
-  RCV_REQUIRE(d->math != RCV_MATH_TF32X3, RCV_ERR_UNSUPPORTED,
-              "rcv_conv_fwd: TF32X3 path not built in this version");
+namespace {
+
+// Implicit-GEMM problem of the forward pass (tensor pointers left NULL).
+void fwd_problem(const rcv_conv_desc* d, RcvIgemm* pp) {
+  RcvIgemm& p = *pp;
+  memset(&p, 0, sizeof(p));
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
-  RCV_REQUIRE(Ho > 0 && Wo > 0, RCV_ERR_BAD_ARG, "rcv_conv_fwd: empty output");
-  RcvIgemm p;
-  memset(&p, 0, sizeof(p));
-  p.in = x; p.w = w; p.out = y; p.bias = bias; p.scale = scale; p.shift = shift;
-  p.residual = residual; p.stats = stats;
   p.N = d->N; p.CA = d->Cin; p.CB = d->Cout;
   p.Hin = d->H; p.Win = d->W; p.Hout = Ho; p.Wout = Wo;
   p.epilogue = d->epilogue;
+  p.math = d->math;
   const int kk = d->ksize * d->ksize;
   if (!d->transposed) {
     p.Hg = Ho; p.Wg = Wo; p.gs = d->stride; p.ostep = 1; p.nclass = 1;
@@ -148,25 +136,18 @@ extern "C" int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float*
     p.wsB = 9;
     parity_taps(p.taps);
   }
-  return rcv_launch_igemm(p, (cudaStream_t)stream);
 }
 
-extern "C" int rcv_conv_dgrad(const rcv_conv_desc* d, const float* dy, const float* w,
-                              const float* residual, float* dx, void* stream) {
-  int rc = validate(d, "rcv_conv_dgrad");
-  if (rc) return rc;
-  RCV_REQUIRE(dy && w && dx, RCV_ERR_BAD_ARG, "rcv_conv_dgrad: null tensor");
-  RCV_REQUIRE(d->math != RCV_MATH_TF32X3, RCV_ERR_UNSUPPORTED,
-              "rcv_conv_dgrad: TF32X3 path not built in this version");
+// Implicit-GEMM problem of the input gradient: reduces over Cout, produces Cin channels.
+int dgrad_problem(const rcv_conv_desc* d, RcvIgemm* pp) {
+  RcvIgemm& p = *pp;
+  memset(&p, 0, sizeof(p));
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
-  RcvIgemm p;
-  memset(&p, 0, sizeof(p));
-  p.in = dy; p.w = w; p.out = dx;
-  p.residual = residual;
   p.N = d->N; p.CA = d->Cout; p.CB = d->Cin;
   p.Hin = Ho; p.Win = Wo; p.Hout = d->H; p.Wout = d->W;
   p.epilogue = RCV_EPI_NONE;
+  p.math = d->math;
   const int kk = d->ksize * d->ksize;
   if (d->transposed) {
     // dx[ci,i,j] = sum dy[co, 2i+ky-1, 2j+kx-1] * w[ci,co,ky,kx]: a stride-2 conv over dy
@@ -190,6 +171,76 @@ extern "C" int rcv_conv_dgrad(const rcv_conv_desc* d, const float* dy, const flo
     p.wsB = 9;
     parity_taps(p.taps);
   }
+  return RCV_OK;
+}
+
+int pack_problem(const rcv_conv_desc* d, int direction, RcvIgemm* p, const char* who) {
+  int rc = validate(d, who);
+  if (rc) return rc;
+  RCV_REQUIRE(direction == RCV_PACK_FWD || direction == RCV_PACK_DGRAD, RCV_ERR_BAD_ARG,
+              "%s: bad direction %d", who, direction);
+  if (direction == RCV_PACK_FWD) {
+    fwd_problem(d, p);
+    return RCV_OK;
+  }
+  return dgrad_problem(d, p);
+}
+
+}  // namespace
+
+extern "C" size_t rcv_conv_packed_bytes(const rcv_conv_desc* d, int direction) {
+  RcvIgemm p;
+  if (pack_problem(d, direction, &p, "rcv_conv_packed_bytes")) return 0;
+  return rcv_umma_packed_bytes(p);
+}
+
+extern "C" int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction) {
+  RcvIgemm p;
+  if (pack_problem(d, direction, &p, "rcv_conv_uses_tensor_cores")) return 0;
+  if (d->math == RCV_MATH_FP32) return 0;
+  return (d->math == RCV_MATH_TF32X3 || rcv_umma_pays(p)) ? 1 : 0;
+}
+
+extern "C" int rcv_conv_pack(const rcv_conv_desc* d, int direction, const float* w, void* packed,
+                             void* stream) {
+  RcvIgemm p;
+  int rc = pack_problem(d, direction, &p, "rcv_conv_pack");
+  if (rc) return rc;
+  RCV_REQUIRE(w && packed, RCV_ERR_BAD_ARG, "rcv_conv_pack: null tensor");
+  p.w = w;
+  return rcv_launch_umma_pack(p, packed, (cudaStream_t)stream);
+}
+
+extern "C" int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float* w, const void* wpacked,
+                            const float* bias, const float* scale, const float* shift,
+                            const float* residual, float* y, double* stats, void* stream) {
+  int rc = validate(d, "rcv_conv_fwd");
+  if (rc) return rc;
+  RCV_REQUIRE(x && w && y, RCV_ERR_BAD_ARG, "rcv_conv_fwd: null tensor");
+  RCV_REQUIRE(d->epilogue >= RCV_EPI_NONE && d->epilogue <= RCV_EPI_AFFINE, RCV_ERR_BAD_ARG,
+              "rcv_conv_fwd: bad epilogue %d", d->epilogue);
+  const bool needs_affine = d->epilogue == RCV_EPI_RELU_AFFINE || d->epilogue == RCV_EPI_AFFINE_RELU ||
+                            d->epilogue == RCV_EPI_AFFINE;
+  RCV_REQUIRE(!needs_affine || (scale && shift), RCV_ERR_BAD_ARG,
+              "rcv_conv_fwd: affine epilogue needs scale and shift");
+  RcvIgemm p;
+  fwd_problem(d, &p);
+  RCV_REQUIRE(p.Hout > 0 && p.Wout > 0, RCV_ERR_BAD_ARG, "rcv_conv_fwd: empty output");
+  p.in = x; p.w = w; p.wpacked = wpacked; p.out = y; p.bias = bias; p.scale = scale; p.shift = shift;
+  p.residual = residual; p.stats = stats;
+  return rcv_launch_igemm(p, (cudaStream_t)stream);
+}
+
+extern "C" int rcv_conv_dgrad(const rcv_conv_desc* d, const float* dy, const float* w, const void* wpacked,
+                              const float* residual, float* dx, void* stream) {
+  int rc = validate(d, "rcv_conv_dgrad");
+  if (rc) return rc;
+  RCV_REQUIRE(dy && w && dx, RCV_ERR_BAD_ARG, "rcv_conv_dgrad: null tensor");
+  RcvIgemm p;
+  rc = dgrad_problem(d, &p);
+  if (rc) return rc;
+  p.in = dy; p.w = w; p.wpacked = wpacked; p.out = dx;
+  p.residual = residual;
   return rcv_launch_igemm(p, (cudaStream_t)stream);
 }
 

@@ -42,6 +42,7 @@ struct RcvTapSet {
 struct RcvIgemm {
   const float* in;
   const float* w;
+  const void* wpacked;  // rcv_conv_pack image of w for the tensor-core engine (may be NULL)
   float* out;
   const float* bias;
   const float* scale;
@@ -54,6 +55,7 @@ struct RcvIgemm {
   int32_t wsA, wsB;
   int32_t epilogue;
   int32_t nclass;
+  int32_t math;  // rcv_math
   RcvTapSet taps[4];
 };
 
@@ -72,5 +74,11 @@ struct RcvWgrad {
   RcvTapSet taps;
 };
 
-int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st);
+int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st);       // dispatch on p.math
+int rcv_launch_igemm_simt(const RcvIgemm& p, cudaStream_t st);  // fp32 FFMA, CUDA cores
+int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF32, TMEM accumulators
+bool rcv_umma_pays(const RcvIgemm& p);  // RCV_MATH_AUTO: is the reduction long enough for tensor cores
+bool rcv_umma_supported(const RcvIgemm& p);  // geometry within the tensor-core engine's limits
+size_t rcv_umma_packed_bytes(const RcvIgemm& p);
+int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st);
 int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st);

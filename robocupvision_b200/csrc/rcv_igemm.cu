@@ -282,7 +282,21 @@ int launch_cfg(const RcvIgemm& p, cudaStream_t st) {
 
 }  // namespace
 
+// AUTO: tensor cores wherever the reduction is long enough to amortise operand staging;
+// the 3-channel input layer and the 1x1 class head stay on CUDA cores (pure bandwidth).
+bool rcv_umma_pays(const RcvIgemm& p) {
+  int maxT = 0;
+  for (int c = 0; c < p.nclass; ++c) maxT = p.taps[c].n > maxT ? p.taps[c].n : maxT;
+  return p.CA * maxT >= 64 && p.CB >= 8 && rcv_umma_supported(p);
+}
+
 int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st) {
+  if (p.math == RCV_MATH_TF32X3 || (p.math == RCV_MATH_AUTO && p.wpacked != nullptr && rcv_umma_pays(p)))
+    return rcv_launch_igemm_umma(p, st);
+  return rcv_launch_igemm_simt(p, st);
+}
+
+int rcv_launch_igemm_simt(const RcvIgemm& p, cudaStream_t st) {
   if (p.CB > 64) return launch_cfg<128, 128, 8, 8>(p, st);
   if (p.CB > 32) return launch_cfg<128, 64, 4, 8>(p, st);
   if (p.CB > 16) return launch_cfg<256, 32, 4, 8>(p, st);

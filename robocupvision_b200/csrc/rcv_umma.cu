@@ -6,29 +6,37 @@
 //   M = pixel-grid points (n,i,j) of the whole batch, N = output channels,
 //   K = (tap, input channel)  -- tap-major so that a 32-wide K block touches few taps.
 //
-// One CTA = one 128 x BN output tile; 128 threads:
-//   * all four warps are PRODUCERS: thread t owns tile row t (one pixel).  Per K block of
-//     32 it gathers 32 activations straight from NCHW global memory (coalesced across the
-//     warp: lanes are consecutive pixels), splits them into tf32 hi / lo parts and writes
-//     both as the K-major, 128-byte-swizzled canonical UMMA layout (one 128 B row per
-//     pixel; 16 B chunk c of row r lives at chunk c ^ (r & 7)) -- conflict-free STS.128.
-//     The weight tile (BN rows) is staged the same way.  Next block's global loads are
-//     issued before this block's MMAs so they fly under the tensor-core work.
-//   * thread 0 ISSUES: 3 x tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per 8-wide K step,
-//     accumulating in TMEM; tcgen05.commit on an mbarrier frees the smem stage.
-//   * all four warps run the EPILOGUE: tcgen05.ld (32 lanes x 16 columns per warp), then
-//     bias / ReLU / folded-BN affine / residual, coalesced NCHW stores (lanes = pixels),
-//     and the train-mode BatchNorm per-channel sum / sum-of-squares via a shuffle
-//     transpose-reduce and one double atomic per channel per warp.
+// Weights are PRE-PACKED once per forward (rcv_conv_pack): for every (parity class, N tile,
+// K block) the exact shared-memory image of the B operand -- tf32 hi part and lo part, K-major
+// rows of 128 bytes with the 128-byte swizzle already applied -- so a stage of B is one
+// contiguous cp.async.bulk copy completing on an mbarrier.
+//
+// One CTA = one 128 x BN output tile, 160 threads:
+//   * warps 0-3, PRODUCERS: thread t owns tile row t (one pixel).  Per K block of 32 it gathers
+//     32 activations straight from NCHW global memory (coalesced across the warp: lanes are
+//     consecutive pixels), splits them into tf32 hi / lo parts and writes both in the K-major
+//     128B-swizzled canonical UMMA layout (16 B chunk c of row r at chunk c ^ (r & 7):
+//     conflict-free STS.128), then fence.proxy.async + one mbarrier arrive per warp.  The next
+//     block's global loads are issued before the arrive so they fly under the MMAs.
+//   * warp 4 lane 0, ISSUER: keeps SB bulk copies of B in flight, waits for a stage's A and B,
+//     issues 3 x tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per 8-wide K step -- the hi*hi
+//     product into one TMEM accumulator, the two correction products into a second one (the
+//     tensor core truncates when it accumulates; keeping the small terms apart keeps that error
+//     relative to THEIR magnitude) -- and tcgen05.commit's the stage's empty barriers.
+//   * warps 0-3, EPILOGUE: tcgen05.ld (32 lanes x 16 columns per warp) of both accumulators,
+//     bias / ReLU / folded-BN affine / residual, coalesced NCHW stores (lanes = pixels), and the
+//     train-mode BatchNorm per-channel sum / sum-of-squares via a shuffle transpose-reduce and
+//     one double atomic per channel per warp.
 #include "rcv_common.cuh"
 
 namespace {
 
-constexpr int NT = 128;
+constexpr int NPROD = 128;        // producer / epilogue threads
+constexpr int NT = NPROD + 32;    // + the issuer warp
 constexpr int BM = 128;
-constexpr int BK = 32;  // fp32 elements per K block: one 128-byte swizzle row
-constexpr int STAGES = 2;
+constexpr int BK = 32;            // fp32 elements per K block: one 128-byte swizzle row
 constexpr int MAXT = 9;
+constexpr int RCV_UMMA_MAX_TABLE_K = 2304;  // per-k gather table (channel counts that are not multiples of 32)
 
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -50,6 +58,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// contiguous global -> shared bulk copy (TMA engine, no tensor map); completes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -90,8 +111,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread = lane)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -100,9 +120,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -140,8 +160,8 @@ __device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh)
 __device__ __forceinline__ void warp_transpose_reduce16(float (&a)[16], int lane) {
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
-    const int half = 8 >> s;      // values kept per lane after this step
-    const int mask = 16 >> s;     // partner distance
+    const int half = 8 >> s;   // values kept per lane after this step
+    const int mask = 16 >> s;  // partner distance
     const bool up = (lane & mask) != 0;
 #pragma unroll
     for (int i = 0; i < half; ++i) {
@@ -153,31 +173,47 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&a)[16], int lane
   a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
-template <int BN>
-struct Smem {
-  static constexpr int A_BYTES = BM * 128;  // one hi or lo A tile
-  static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/;
+// Tile configuration per output-channel tile width.
+template <int BN_>
+struct Cfg {
+  static constexpr int BN = BN_;
+  static constexpr int SA = 2;                       // A ring depth (software gather)
+  static constexpr int SB = BN_ >= 64 ? (BN_ == 128 ? 4 : 2) : 3;  // B ring depth (bulk copies)
+  static constexpr int A_BYTES = BM * 128;           // one hi or lo A tile
+  static constexpr int A_STAGE = 2 * A_BYTES;
+  static constexpr int B_STAGE = BN_ * 256;          // hi rows then lo rows
+  static constexpr int TILE_BYTES = SA * A_STAGE + SB * B_STAGE;
+  static constexpr int FIXED = TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/;
+  // + the per-k gather table (8 B per k) when the channel count is not a multiple of 32
+  static constexpr int TCOLS = 2 * BN_ < 32 ? 32 : 2 * BN_;  // main + correction accumulators
 };
+
+__host__ __device__ inline int umma_bn(int CB) { return CB > 64 ? 128 : CB > 32 ? 64 : CB > 16 ? 32 : 16; }
+__host__ __device__ inline int max_taps(const RcvIgemm& p) {
+  int m = 0;
+  for (int c = 0; c < p.nclass; ++c) m = p.taps[c].n > m ? p.taps[c].n : m;
+  return m;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
-  using S = Smem<BN>;
-  constexpr int BCH = BN * 8 / NT;  // 16-byte weight chunks per thread per K block
-  static_assert(BCH >= 1, "BN too small");
-  constexpr int TCOLS = BN < 32 ? 32 : BN;
+  using C = Cfg<BN>;
+  constexpr int SA = C::SA, SB = C::SB;
 
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
   unsigned char* gen_tiles = smem_raw + (tiles - raw);
-  unsigned char* misc = gen_tiles + S::TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);               // [STAGES]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
-  int* s_toff = reinterpret_cast<int*>(misc + 128);                  // [MAXT] input offset of a tap
-  int* s_twi = s_toff + 16;                                          // [MAXT] weight offset of a tap
+  const uint32_t tilesB = tiles + SA * C::A_STAGE;
+  unsigned char* misc = gen_tiles + C::TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // afull[SA] emptyA[SA] bfull[SB] emptyB[SB] done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 120);
+  int* s_toff = reinterpret_cast<int*>(misc + 128);     // [MAXT] input offset of a tap
+  int2* s_ktab = reinterpret_cast<int2*>(misc + 256);   // [nkb*BK] per-k (offset, tap), non-uniform path
+  const uint32_t bar_afull = smem_u32(bars), bar_emptyA = bar_afull + 8 * SA;
+  const uint32_t bar_bfull = bar_emptyA + 8 * SA, bar_emptyB = bar_bfull + 8 * SB;
+  const uint32_t bar_done = bar_emptyB + 8 * SB;
+  static_assert(8 * (2 * SA + 2 * SB + 1) <= 120, "barrier area");
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -195,221 +231,321 @@ __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
   if (tid < MAXT) {
     const int t = tid < T ? tid : 0;
     s_toff[tid] = p.taps[cls].dy[t] * p.Win + p.taps[cls].dx[t];
-    s_twi[tid] = p.taps[cls].wi[t];
+  }
+  if ((CA % BK) != 0) {
+    for (int k = tid; k < nkb * BK; k += NT) {
+      const int tap = k / CA, ca = k - tap * CA;
+      s_ktab[k] = tap < T ? make_int2(ca * HWin + p.taps[cls].dy[tap] * p.Win + p.taps[cls].dx[tap], tap)
+                          : make_int2(0, 31);
+    }
   }
   if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(bar_afull + 8 * s, NPROD / 32);
+      mbar_init(bar_emptyA + 8 * s, 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_emptyB + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TCOLS);
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // ---- this thread's pixel (tile row) --------------------------------------------------
-  const int m = m0 + tid;
-  const bool mrow = m < M;
-  int pn = 0, pi = 0, pj = 0;
-  if (mrow) {
-    pn = m / HWg;
-    const int r = m - pn * HWg;
-    pi = r / p.Wg;
-    pj = r - pi * p.Wg;
-  }
-  const int gy0 = pi * p.gs, gx0 = pj * p.gs;
-  const float* gbase = p.in + (size_t)pn * CA * HWin + gy0 * p.Win + gx0;
-  uint32_t tapmask = 0;  // bit t: tap t reads inside the image for this pixel
-  if (mrow) {
-    for (int t = 0; t < T; ++t) {
-      const int iy = gy0 + p.taps[cls].dy[t], ix = gx0 + p.taps[cls].dx[t];
-      if ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) tapmask |= 1u << t;
-    }
-  }
-
-  float va[BK];
-  float vb[BCH * 4];
-
-  auto load_regs = [&](int kb) {
-    const int k0 = kb * BK;
-    {
-      int tap = k0 / CA;
-      int ca = k0 - tap * CA;
-#pragma unroll
-      for (int i = 0; i < BK; ++i) {
-        float v = 0.f;
-        if (tap < T && ((tapmask >> tap) & 1u)) v = __ldg(gbase + (size_t)ca * HWin + s_toff[tap]);
-        va[i] = v;
-        if (++ca == CA) { ca = 0; ++tap; }
+  if (warp == 4) {
+    // ================================ ISSUER ==========================================
+    if (lane == 0) {
+      const int kbmax = (CA * max_taps(p) + BK - 1) / BK;  // K blocks per (class, N tile) in the pack
+      const unsigned char* gB = reinterpret_cast<const unsigned char*>(p.wpacked) +
+                                ((size_t)(cls * gridDim.y + blockIdx.y) * kbmax) * C::B_STAGE;
+      auto issue_b = [&](int kb) {
+        const int sb = kb % SB, ub = kb / SB;
+        if (ub > 0) mbar_wait(bar_emptyB + 8 * sb, (uint32_t)((ub - 1) & 1));
+        mbar_expect_tx(bar_bfull + 8 * sb, C::B_STAGE);
+        bulk_g2s(tilesB + sb * C::B_STAGE, gB + (size_t)kb * C::B_STAGE, C::B_STAGE, bar_bfull + 8 * sb);
+      };
+      for (int kb = 0; kb < SB && kb < nkb; ++kb) issue_b(kb);
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int sa = kb % SA, ua = kb / SA, sb = kb % SB, ub = kb / SB;
+        mbar_wait(bar_afull + 8 * sa, (uint32_t)(ua & 1));
+        mbar_wait(bar_bfull + 8 * sb, (uint32_t)(ub & 1));
+        tc_fence_after();
+        const uint32_t abase = tiles + sa * C::A_STAGE, bbase = tilesB + sb * C::B_STAGE;
+        const uint64_t a_hi = make_desc(abase), a_lo = make_desc(abase + C::A_BYTES);
+        const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + BN * 128);
+        const int krem = K - kb * BK;
+        const int ksteps = krem >= BK ? BK / 8 : (krem + 7) / 8;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 2);  // 8 tf32 = 32 B = 2 x 16 B inside the swizzle row
+          const uint32_t acc = (kb | ks) != 0;
+          umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, acc);
+          umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, acc);
+        }
+        umma_commit(bar_emptyA + 8 * sa);
+        umma_commit(bar_emptyB + 8 * sb);
+        if (kb == nkb - 1) umma_commit(bar_done);
+        // refill the B slot of the previous block: its MMAs finish before this block's start
+        if (kb >= 1 && kb - 1 + SB < nkb) issue_b(kb - 1 + SB);
       }
     }
-#pragma unroll
-    for (int q = 0; q < BCH; ++q) {
-      const int ch = tid + q * NT;  // chunk id: row = ch % BN, 16-byte chunk = ch / BN
-      const int nrow = ch % BN, c = ch / BN;
-      const int co = n0 + nrow;
-      int k = k0 + c * 4;
-      int tap = k / CA;
-      int ca = k - tap * CA;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float v = 0.f;
-        if (tap < T && co < p.CB) v = __ldg(p.w + (size_t)co * p.wsB + (size_t)ca * p.wsA + s_twi[tap]);
-        vb[q * 4 + e] = v;
-        if (++ca == CA) { ca = 0; ++tap; }
+  } else {
+    // ================================ PRODUCERS =======================================
+    const int m = m0 + tid;
+    const bool mrow = m < M;
+    int pn = 0, pi = 0, pj = 0;
+    if (mrow) {
+      pn = m / HWg;
+      const int r = m - pn * HWg;
+      pi = r / p.Wg;
+      pj = r - pi * p.Wg;
+    }
+    const int gy0 = pi * p.gs, gx0 = pj * p.gs;
+    const float* gbase = p.in + (size_t)pn * CA * HWin + gy0 * p.Win + gx0;
+    uint32_t tapmask = 0;  // bit t: tap t reads inside the image for this pixel
+    if (mrow) {
+      for (int t = 0; t < T; ++t) {
+        const int iy = gy0 + p.taps[cls].dy[t], ix = gx0 + p.taps[cls].dx[t];
+        if ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) tapmask |= 1u << t;
       }
     }
-  };
+    const bool uni = (CA % BK) == 0;  // every K block lies inside one tap
 
-  auto store_smem = [&](int stage) {
-    unsigned char* st = gen_tiles + stage * S::STAGE_BYTES;
-    unsigned char* a_hi = st;
-    unsigned char* a_lo = st + S::A_BYTES;
-    unsigned char* b_hi = st + 2 * S::A_BYTES;
-    unsigned char* b_lo = b_hi + S::B_BYTES;
-    const int row = tid;
+    // Two K blocks of gathered activations live in registers: block kb is converted and stored
+    // while block kb+1 (issued one iteration earlier) is still landing.  The proxy fence that
+    // publishes the stores drains this thread's outstanding loads (MEMBAR), so a block's loads
+    // are issued only AFTER the previous block's fence + arrive.
+    float v0[BK], v1[BK];
+    auto load_regs = [&](int kb, float (&va)[BK]) {
+      const int k0 = kb * BK;
+      if (uni) {
+        const int tap = k0 / CA;
+        const int ca = k0 - tap * CA;
+        const bool ok = (tapmask >> tap) & 1u;
+        const float* src = gbase + (ca * HWin + s_toff[tap]);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float4 h, l;
-      split_tf32(va[4 * c + 0], h.x, l.x);
-      split_tf32(va[4 * c + 1], h.y, l.y);
-      split_tf32(va[4 * c + 2], h.z, l.z);
-      split_tf32(va[4 * c + 3], h.w, l.w);
-      const int off = row * 128 + ((c ^ (row & 7)) << 4);
-      *reinterpret_cast<float4*>(a_hi + off) = h;
-      *reinterpret_cast<float4*>(a_lo + off) = l;
-    }
+        for (int i = 0; i < BK; ++i) va[i] = ok ? __ldg(src + i * HWin) : 0.f;
+      } else {
 #pragma unroll
-    for (int q = 0; q < BCH; ++q) {
-      const int ch = tid + q * NT;
-      const int nrow = ch % BN, c = ch / BN;
-      float4 h, l;
-      split_tf32(vb[4 * q + 0], h.x, l.x);
-      split_tf32(vb[4 * q + 1], h.y, l.y);
-      split_tf32(vb[4 * q + 2], h.z, l.z);
-      split_tf32(vb[4 * q + 3], h.w, l.w);
-      const int off = nrow * 128 + ((c ^ (nrow & 7)) << 4);
-      *reinterpret_cast<float4*>(b_hi + off) = h;
-      *reinterpret_cast<float4*>(b_lo + off) = l;
-    }
-  };
-
-  constexpr uint32_t idesc = make_idesc(BM, BN);
-
-  // ---- main loop ------------------------------------------------------------------------
-  load_regs(0);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int stage = kb % STAGES;
-    const int use = kb / STAGES;  // how many times this stage has been filled before
-    if (use > 0) mbar_wait(smem_u32(&bars[stage]), (uint32_t)((use - 1) & 1));
-    store_smem(stage);
-    if (kb + 1 < nkb) load_regs(kb + 1);
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t sbase = tiles + stage * S::STAGE_BYTES;
-      const uint64_t a_hi = make_desc(sbase);
-      const uint64_t a_lo = make_desc(sbase + S::A_BYTES);
-      const uint64_t b_hi = make_desc(sbase + 2 * S::A_BYTES);
-      const uint64_t b_lo = make_desc(sbase + 2 * S::A_BYTES + S::B_BYTES);
-      const int krem = K - kb * BK;
-      const int ksteps = krem >= BK ? BK / 8 : (krem + 7) / 8;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 8 tf32 = 32 bytes along K inside the swizzle row
-        umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | ks) != 0);
-        umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
-        umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+        for (int i = 0; i < BK; ++i) {
+          const int2 e = s_ktab[k0 + i];  // (element offset, tap or 31 beyond K)
+          va[i] = ((tapmask >> e.y) & 1u) ? __ldg(gbase + e.x) : 0.f;
+        }
       }
-      umma_commit(smem_u32(&bars[stage]));
+    };
+    auto store_smem = [&](int sa, const float (&va)[BK]) {
+      unsigned char* a_hi = gen_tiles + sa * C::A_STAGE;
+      unsigned char* a_lo = a_hi + C::A_BYTES;
+      const int row = tid;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 h, l;
+        split_tf32(va[4 * c + 0], h.x, l.x);
+        split_tf32(va[4 * c + 1], h.y, l.y);
+        split_tf32(va[4 * c + 2], h.z, l.z);
+        split_tf32(va[4 * c + 3], h.w, l.w);
+        const int off = row * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<float4*>(a_hi + off) = h;
+        *reinterpret_cast<float4*>(a_lo + off) = l;
+      }
+    };
+    auto produce = [&](int kb, float (&va)[BK]) {
+      const int sa = kb % SA, ua = kb / SA;
+      if (ua > 0) mbar_wait(bar_emptyA + 8 * sa, (uint32_t)((ua - 1) & 1));
+      store_smem(sa, va);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
+      if (kb + 2 < nkb) load_regs(kb + 2, va);
+    };
+
+    load_regs(0, v0);
+    if (nkb > 1) load_regs(1, v1);
+    for (int kb = 0; kb < nkb; kb += 2) {
+      produce(kb, v0);
+      if (kb + 1 < nkb) produce(kb + 1, v1);
     }
-  }
-  {
-    const int last = nkb - 1;
-    mbar_wait(smem_u32(&bars[last % STAGES]), (uint32_t)((last / STAGES) & 1));
+
+    // ================================ EPILOGUE ========================================
+    mbar_wait(bar_done, 0);
     tc_fence_after();
-  }
-
-  // ---- epilogue -------------------------------------------------------------------------
-  const int epi = p.epilogue;
-  const int HWo = p.Hout * p.Wout;
-  size_t obase = 0;
-  if (mrow) {
-    const int ca_ = cls >> 1, cb_ = cls & 1;
-    const int oy = pi * p.ostep + ca_, ox = pj * p.ostep + cb_;
-    obase = (size_t)pn * p.CB * HWo + (size_t)oy * p.Wout + ox;
-  }
-  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 16) {
-    if (n0 + c0 >= p.CB) break;  // warp-uniform
-    float acc[16];
-    tmem_ld16(trow + c0, acc);
-    float s1[16], s2[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int co = n0 + c0 + j;
-      float v = 0.f;
-      if (mrow && co < p.CB) {
-        const float bi = p.bias ? __ldg(p.bias + co) : 0.f;
-        const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
-        const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
-        const size_t off = obase + (size_t)co * HWo;
-        v = apply_epi(acc[j] + bi, epi, sc, sh);
-        if (p.residual) v += __ldg(p.residual + off);
-        p.out[off] = v;
-      }
-      s1[j] = v;
-      s2[j] = v * v;
+    const int epi = p.epilogue;
+    const int HWo = p.Hout * p.Wout;
+    size_t obase = 0;
+    if (mrow) {
+      const int ca_ = cls >> 1, cb_ = cls & 1;
+      const int oy = pi * p.ostep + ca_, ox = pj * p.ostep + cb_;
+      obase = (size_t)pn * p.CB * HWo + (size_t)oy * p.Wout + ox;
     }
-    if (p.stats) {
-      warp_transpose_reduce16(s1, lane);
-      warp_transpose_reduce16(s2, lane);
-      const int co = n0 + c0 + (lane >> 1);
-      if ((lane & 1) == 0 && co < p.CB) {
-        atomicAdd(p.stats + co, (double)s1[0]);
-        atomicAdd(p.stats + p.CB + co, (double)s2[0]);
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (n0 + c0 >= p.CB) break;  // warp-uniform
+      uint32_t rm[16], rc[16];
+      tmem_ld16_nowait(trow + c0, rm);
+      tmem_ld16_nowait(trow + BN + c0, rc);
+      tmem_ld_wait();
+      float s1[16], s2[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int co = n0 + c0 + j;
+        float v = 0.f;
+        if (mrow && co < p.CB) {
+          const float bi = p.bias ? __ldg(p.bias + co) : 0.f;
+          const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
+          const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
+          const size_t off = obase + (size_t)co * HWo;
+          v = apply_epi(__uint_as_float(rm[j]) + __uint_as_float(rc[j]) + bi, epi, sc, sh);
+          if (p.residual) v += __ldg(p.residual + off);
+          p.out[off] = v;
+        }
+        s1[j] = v;
+        s2[j] = v * v;
+      }
+      if (p.stats) {
+        warp_transpose_reduce16(s1, lane);
+        warp_transpose_reduce16(s2, lane);
+        const int co = n0 + c0 + (lane >> 1);
+        if ((lane & 1) == 0 && co < p.CB) {
+          atomicAdd(p.stats + co, (double)s1[0]);
+          atomicAdd(p.stats + p.CB + co, (double)s2[0]);
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, C::TCOLS);
+  }
+}
+
+// One thread per 16-byte chunk of the packed image: 4 consecutive k of one weight row, split
+// into hi / lo and written at the swizzled position.
+__global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int ntiles, int kbmax,
+                                                   unsigned char* __restrict__ packed) {
+  const int64_t per_block = (int64_t)BN * 8;
+  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * per_block;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(q % BN);
+    const int c = (int)((q / BN) % 8);
+    int64_t blk = q / per_block;
+    const int kb = (int)(blk % kbmax);
+    blk /= kbmax;
+    const int tile = (int)(blk % ntiles);
+    const int cls = (int)(blk / ntiles);
+    const int T = p.taps[cls].n;
+    const int co = tile * BN + row;
+    int k = kb * BK + c * 4;
+    int tap = k / p.CA;
+    int ca = k - tap * p.CA;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[e] = 0.f;
+      if (tap < T && co < p.CB)
+        v[e] = __ldg(p.w + (size_t)co * p.wsB + (size_t)ca * p.wsA + p.taps[cls].wi[tap]);
+      if (++ca == p.CA) { ca = 0; ++tap; }
+    }
+    float4 h, l;
+    split_tf32(v[0], h.x, l.x);
+    split_tf32(v[1], h.y, l.y);
+    split_tf32(v[2], h.z, l.z);
+    split_tf32(v[3], h.w, l.w);
+    unsigned char* base = packed + ((size_t)(cls * ntiles + tile) * kbmax + kb) * ((size_t)BN * 256);
+    const int off = row * 128 + ((c ^ (row & 7)) << 4);
+    *reinterpret_cast<float4*>(base + off) = h;
+    *reinterpret_cast<float4*>(base + (size_t)BN * 128 + off) = l;
+  }
 }
 
 template <int BN>
 int launch_bn(const RcvIgemm& p, cudaStream_t st) {
-  using S = Smem<BN>;
+  using C = Cfg<BN>;
+  constexpr int MAX_SMEM = C::FIXED + RCV_UMMA_MAX_TABLE_K * 8;
+  static_assert(MAX_SMEM <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;  // benign race: idempotent
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(umma_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::TOTAL);
+                                         MAX_SMEM);
     if (e != cudaSuccess) {
-      rcv_set_error("umma_igemm: cannot reserve %d B of shared memory: %s", S::TOTAL, cudaGetErrorString(e));
+      rcv_set_error("umma_igemm: cannot reserve %d B of shared memory: %s", MAX_SMEM, cudaGetErrorString(e));
       return RCV_ERR_CUDA;
     }
     attr_done = true;
   }
+  const int kpad = rcv_cdiv((int64_t)p.CA * max_taps(p), BK) * BK;
+  const int smem = C::FIXED + ((p.CA % BK) != 0 ? kpad * 8 : 0);
+  RCV_REQUIRE((int64_t)p.N * p.CA * p.Hin * p.Win < (1ll << 31), RCV_ERR_UNSUPPORTED,
+              "umma_igemm: input tensor too large for 32-bit gather offsets");
   const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
   RCV_REQUIRE(M < (1ll << 31) && (int64_t)p.N * p.CB * p.Hout * p.Wout < (1ll << 40), RCV_ERR_UNSUPPORTED,
               "umma_igemm: problem too large");
   dim3 grid(rcv_cdiv(M, BM), rcv_cdiv(p.CB, BN), p.nclass);
   RCV_REQUIRE(grid.y <= 65535, RCV_ERR_UNSUPPORTED, "umma_igemm: too many output-channel tiles");
-  umma_igemm_kernel<BN><<<grid, NT, S::TOTAL, st>>>(p);
+  umma_igemm_kernel<BN><<<grid, NT, smem, st>>>(p);
   RCV_CHECK_LAUNCH("umma_igemm_kernel");
+  return RCV_OK;
+}
+
+int check_taps(const RcvIgemm& p) {
+  for (int c = 0; c < p.nclass; ++c)
+    RCV_REQUIRE(p.taps[c].n >= 1 && p.taps[c].n <= MAXT, RCV_ERR_UNSUPPORTED, "umma_igemm: %d taps",
+                p.taps[c].n);
+  RCV_REQUIRE(rcv_umma_supported(p), RCV_ERR_UNSUPPORTED,
+              "umma_igemm: %d reduced channels (not a multiple of 32) x %d taps exceeds the gather table",
+              p.CA, max_taps(p));
   return RCV_OK;
 }
 
 }  // namespace
 
+bool rcv_umma_supported(const RcvIgemm& p) {
+  return (p.CA % BK) == 0 || (int64_t)p.CA * max_taps(p) <= RCV_UMMA_MAX_TABLE_K;
+}
+
+size_t rcv_umma_packed_bytes(const RcvIgemm& p) {
+  const int BN = umma_bn(p.CB);
+  const int ntiles = rcv_cdiv(p.CB, BN);
+  const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), BK);
+  return (size_t)p.nclass * ntiles * kbmax * BN * 256;
+}
+
+int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st) {
+  int rc = check_taps(p);
+  if (rc) return rc;
+  RCV_REQUIRE(((uintptr_t)packed & 127) == 0, RCV_ERR_BAD_ARG, "conv_pack: packed buffer must be 128-byte aligned");
+  const int BN = umma_bn(p.CB);
+  const int ntiles = rcv_cdiv(p.CB, BN);
+  const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), BK);
+  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * 8;
+  int blocks = rcv_cdiv(total, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_kernel<<<blocks, 256, 0, st>>>(p, BN, ntiles, kbmax, reinterpret_cast<unsigned char*>(packed));
+  RCV_CHECK_LAUNCH("pack_kernel");
+  return RCV_OK;
+}
+
 int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st) {
-  for (int c = 0; c < p.nclass; ++c)
-    RCV_REQUIRE(p.taps[c].n >= 1 && p.taps[c].n <= MAXT, RCV_ERR_UNSUPPORTED, "umma_igemm: %d taps",
-                p.taps[c].n);
-  if (p.CB > 64) return launch_bn<128>(p, st);
-  if (p.CB > 32) return launch_bn<64>(p, st);
-  if (p.CB > 16) return launch_bn<32>(p, st);
-  return launch_bn<16>(p, st);
+  int rc = check_taps(p);
+  if (rc) return rc;
+  RCV_REQUIRE(p.wpacked != nullptr, RCV_ERR_BAD_ARG,
+              "tensor-core conv needs packed weights (rcv_conv_pack); none were given");
+  RCV_REQUIRE(((uintptr_t)p.wpacked & 127) == 0, RCV_ERR_BAD_ARG, "packed weights must be 128-byte aligned");
+  switch (umma_bn(p.CB)) {
+    case 128: return launch_bn<128>(p, st);
+    case 64: return launch_bn<64>(p, st);
+    case 32: return launch_bn<32>(p, st);
+    default: return launch_bn<16>(p, st);
+  }
 }

@@ -19,12 +19,20 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, ConvGeom
+from .ops import (EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO, MATH_FP32, PACK_DGRAD,
+                  PACK_FWD, ConvGeom)
+
+# Math mode of the conv engine for every plan: RCV_MATH_AUTO = tcgen05 3xTF32 tensor-core tiles
+# wherever the reduction is long enough, CUDA cores elsewhere.  RCV_B200_MATH=fp32 forces the
+# CUDA-core engine everywhere (A/B comparisons, bisecting a numerical difference).
+import os as _os
+
+DEFAULT_MATH = {"fp32": MATH_FP32, "auto": MATH_AUTO}[_os.environ.get("RCV_B200_MATH", "auto").lower()]
 
 
 class Node:
     __slots__ = ("kind", "src", "conv", "bn", "order", "skip", "skip_mode", "geom", "_fold_key",
-                 "_fold_val", "skip_ch")
+                 "_fold_val", "skip_ch", "_pack", "_pack_key", "_tc")
 
     def __init__(self, kind, src, conv=None, bn=None, order=EPI_NONE, skip=-1, skip_mode="add"):
         self.kind, self.src, self.conv, self.bn = kind, src, conv, bn
@@ -33,6 +41,9 @@ class Node:
         self._fold_key = None
         self._fold_val = None
         self.skip_ch = 0
+        self._pack = [None, None]      # persistent packed-weight buffers (fwd, dgrad)
+        self._pack_key = [None, None]
+        self._tc = [None, None]        # does this direction run on tensor cores
 
     def params(self) -> List[nn.Parameter]:
         out = []
@@ -44,10 +55,31 @@ class Node:
             out += [self.bn.weight, self.bn.bias]
         return out
 
-    def folded(self):
+    def packed(self, direction: int, epoch: int, fresh: bool, math: int):
+        """Weight panel of the tensor-core engine (None if this layer/direction stays on CUDA
+        cores).  Re-packed when `fresh` (training: weights change every step) or when the weight
+        tensor / the plan's epoch changed; the buffer itself is allocated once (CUDA-graph safe)."""
+        if math == MATH_FP32:
+            return None
+        if self._tc[direction] is None:
+            self._tc[direction] = ops.conv_uses_tensor_cores(self.geom, direction, math)
+        if not self._tc[direction]:
+            return None
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version, epoch)
+        buf = self._pack[direction]
+        if buf is not None and buf.device != w.device:
+            buf = None
+        if buf is None or fresh or key != self._pack_key[direction]:
+            buf = ops.conv_pack(self.geom, w.detach(), direction, out=buf)
+            self._pack[direction] = buf
+            self._pack_key[direction] = key
+        return buf
+
+    def folded(self, epoch: int = 0):
         bn = self.bn
         ts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
-        key = tuple((t.data_ptr(), t._version) for t in ts)
+        key = tuple((t.data_ptr(), t._version) for t in ts) + (epoch,)
         if key != self._fold_key:
             self._fold_val = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean,
                                          bn.running_var, bn.eps)
@@ -88,6 +120,10 @@ class Plan:
                 if id(p) not in seen:
                     seen.add(id(p))
                     self.params.append(p)
+        self.math = DEFAULT_MATH
+        # bumped whenever parameters / BN buffers may have been written behind torch's back (raw
+        # kernels of a training forward or of TrainStep): invalidates folded-BN and packed caches
+        self.epoch = 0
         self.n_stats = 0
         self._sum_off = {}
         for t, nd in enumerate(self.nodes):
@@ -108,6 +144,8 @@ class Plan:
         stats_arena = None
         soff = 0
         nbt = []
+        if training:
+            self.epoch += 1
         for t, nd in enumerate(self.nodes):
             src = acts[nd.src]
             if nd.kind == "pool":
@@ -119,8 +157,11 @@ class Plan:
             w = conv.weight.detach()
             b = conv.bias.detach() if conv.bias is not None else None
             skip = acts[nd.skip] if (nd.skip >= 0 and nd.skip_mode == "add") else None
+            wp = nd.packed(PACK_FWD, self.epoch, training, self.math)
+            if save and (nd.src != 0 or x.requires_grad):
+                nd.packed(PACK_DGRAD, self.epoch, training, self.math)
             if bn is None:
-                y = ops.conv_fwd(g, src, w, b, epilogue=nd.order)
+                y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, math=self.math, wpacked=wp)
                 saved[t] = (y if nd.order == EPI_RELU else None,)
             elif training and bn.training:
                 if stats_arena is None:
@@ -128,7 +169,7 @@ class Plan:
                 stats = stats_arena[soff:soff + 2 * g.cout]
                 soff += 2 * g.cout
                 z = ops.conv_fwd(g, src, w, b, epilogue=EPI_RELU if nd.order == EPI_RELU_AFFINE else EPI_NONE,
-                                 stats=stats)
+                                 stats=stats, math=self.math, wpacked=wp)
                 count = z.numel() // g.cout
                 if bn.momentum is None:
                     momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
@@ -143,8 +184,9 @@ class Plan:
                 if track and bn.num_batches_tracked is not None:
                     nbt.append(bn.num_batches_tracked)
             else:
-                scale, shift = nd.folded()
-                y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, scale=scale, shift=shift, residual=skip)
+                scale, shift = nd.folded(self.epoch)
+                y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, scale=scale, shift=shift, residual=skip,
+                                 math=self.math, wpacked=wp)
             if nd.skip >= 0 and nd.skip_mode == "partial":
                 y[:, :nd.skip_ch] += acts[nd.skip]
             elif nd.skip >= 0 and nd.skip_mode == "cat":
@@ -226,7 +268,9 @@ class Plan:
                 dconv = ops.relu_bwd(g, saved[t][0]) if nd.order == EPI_RELU else g
                 wg_bias = grad_views[id(conv.bias)] if has_bias else None
             if nd.src != 0 or x_needs_grad:
-                grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src])
+                wp = nd._pack[PACK_DGRAD] if (self.math != MATH_FP32 and nd._tc[PACK_DGRAD]) else None
+                grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
+                                               wpacked=wp)
             ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias)
 
 

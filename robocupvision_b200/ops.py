@@ -13,10 +13,10 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO,
-                   MATH_FP32, MATH_TF32X3, ConvDesc)
+                   MATH_FP32, MATH_TF32X3, PACK_DGRAD, PACK_FWD, ConvDesc)
 
 __all__ = [
-    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "bn_finalize", "bn_fold", "bn_apply",
+    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
     "confusion", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
@@ -104,10 +104,42 @@ class ConvGeom:
 
 
 # --------------------------------------------------------------------------- conv family
+def conv_packed_bytes(g: ConvGeom, direction: int) -> int:
+    d = g.desc(1, 2, 2)
+    n = _lib.load().rcv_conv_packed_bytes(C.byref(d), int(direction))
+    if n == 0:
+        raise _lib.RcvError("rcv_conv_packed_bytes", -1, _lib.load().rcv_last_error().decode())
+    return int(n)
+
+
+def conv_uses_tensor_cores(g: ConvGeom, direction: int, math: int = MATH_AUTO) -> bool:
+    d = g.desc(1, 2, 2, EPI_NONE, math)
+    return bool(_lib.load().rcv_conv_uses_tensor_cores(C.byref(d), int(direction)))
+
+
+def conv_pack(g: ConvGeom, w, direction: int, out=None):
+    """Weight panel of the tensor-core engine for `w` (one launch); `out` is reused when given."""
+    w = _chk(w, name="weight")
+    if tuple(w.shape) != g.weight_shape():
+        raise ValueError(f"conv_pack: w {tuple(w.shape)} does not match geometry")
+    if out is None:
+        out = torch.empty(conv_packed_bytes(g, direction), device=w.device, dtype=torch.uint8)
+    d = g.desc(1, 2, 2)
+    _call("rcv_conv_pack", 1, C.byref(d), int(direction), _ptr(w), _ptr(out), _stream())
+    return out
+
+
+def _packed_for(g, w, wpacked, math, direction):
+    if wpacked is None and math == MATH_TF32X3:
+        wpacked = conv_pack(g, w, direction)
+    return wpacked
+
+
 def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=None, residual=None,
-             stats=None, math=MATH_FP32, out=None):
+             stats=None, math=MATH_FP32, out=None, wpacked=None):
     x = _chk(x, name="x")
     w = _chk(w, name="weight")
+    wpacked = _packed_for(g, w, wpacked, math, PACK_FWD)
     n, cin, h, wd = x.shape
     if cin != g.cin or tuple(w.shape) != g.weight_shape():
         raise ValueError(f"conv_fwd: x {tuple(x.shape)} / w {tuple(w.shape)} do not match geometry")
@@ -123,16 +155,18 @@ def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 2 * g.cout):
         raise ValueError("conv_fwd: stats must be float64[2*Cout]")
     d = g.desc(n, h, wd, epilogue, math)
-    _call("rcv_conv_fwd", 1, C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(scale), _ptr(shift),
+    _call("rcv_conv_fwd", 1, C.byref(d), _ptr(x), _ptr(w), _ptr(wpacked), _ptr(bias), _ptr(scale), _ptr(shift),
           _ptr(residual), _ptr(y), _ptr(stats), _stream())
     return y
 
 
-def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=MATH_FP32, out=None):
+def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=MATH_FP32, out=None,
+               wpacked=None):
     """Input gradient; `residual` (shape of dx; may be `out`) is the gradient the same tensor
     receives from a second consumer and is added in the kernel epilogue."""
     dy = _chk(dy, name="dy")
     w = _chk(w, name="weight")
+    wpacked = _packed_for(g, w, wpacked, math, PACK_DGRAD)
     n = dy.shape[0]
     h, wd = in_hw
     if tuple(dy.shape[1:]) != (g.cout, *g.out_hw(h, wd)):
@@ -143,7 +177,7 @@ def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=M
         residual = _chk(residual, name="residual")
         if residual.shape != dx.shape:
             raise ValueError("conv_dgrad: residual shape mismatch")
-    _call("rcv_conv_dgrad", 1, C.byref(d), _ptr(dy), _ptr(w), _ptr(residual), _ptr(dx), _stream())
+    _call("rcv_conv_dgrad", 1, C.byref(d), _ptr(dy), _ptr(w), _ptr(wpacked), _ptr(residual), _ptr(dx), _stream())
     return dx
 
 

@@ -203,6 +203,7 @@ class TrainStep:
         Returns (loss_sums float64[2], l1_sum float64[1], correct int64[1]) device tensors:
         CE loss = loss_sums[0]/loss_sums[1]; total = CE + l1_decay*l1_sum."""
         self.model.train()
+        self.plan.epoch += 1  # parameters / BN buffers change under raw kernels (also on graph replay)
         if not self.use_graph:
             x = x.to(self.dev, non_blocking=True)
             y = y.to(self.dev, non_blocking=True)

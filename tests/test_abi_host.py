@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in rcv_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.rcv_version() == 1
+    assert lib.rcv_version() == 2
 
 
 def test_validation_without_gpu():
@@ -42,7 +42,8 @@ def test_validation_without_gpu():
     bad = _lib.ConvDesc(2, 3, 120, 160, 8, 5, 1, 2, 1, 0, 0, 0)
     assert lib.rcv_conv_out_hw(C.byref(bad), C.byref(ho), C.byref(wo)) == _lib.RCV_ERR_UNSUPPORTED
     assert b"kernel size 5" in lib.rcv_last_error()
-    assert lib.rcv_conv_fwd(C.byref(d), None, None, None, None, None, None, None, None, None) == _lib.RCV_ERR_BAD_ARG
+    assert lib.rcv_conv_fwd(C.byref(d), None, None, None, None, None, None, None, None, None, None) == _lib.RCV_ERR_BAD_ARG
+    assert lib.rcv_conv_packed_bytes(C.byref(d), 0) == 4 * 1 * 8 * 32 * 256  # 4 parity classes, K=64*4 -> 8 blocks, BN=32
     assert lib.rcv_ce_fwd(1, 9, 10, None, None, None, None, None, None, None, None) == _lib.RCV_ERR_BAD_ARG
     assert lib.rcv_adam_l1_step(0, None, None, None, None, None, 0.1, 0.9, 0.999, 1e-8, 1, 0.0, 1.0, None, None,
                                 None, None) == _lib.RCV_ERR_BAD_ARG

@@ -19,6 +19,9 @@ GEOMS = {  # name -> (k, stride, pad, dil, transposed)
     "convT": (3, 2, 1, 1, True),
 }
 CHANS = [(3, 8), (8, 16), (16, 16), (32, 64), (64, 128), (128, 128), (128, 64), (16, 5), (24, 40)]
+# engine -> (rcv_math, tolerance factor): "tc" = tcgen05 3xTF32 tiles with TMEM accumulators
+# (the tensor core truncates on accumulate: ~3e-6 of the output range at K = 1152)
+MATHS = {"simt": (0, 1.0), "tc": (1, 4.0)}
 
 
 def _mk(geom, cin, cout, n, h, w, seed=0):
@@ -39,31 +42,58 @@ def _ref_conv(geom, x, w, b):
     return F.conv2d(x, w, b, s, p, d)
 
 
+@pytest.mark.parametrize("engine", list(MATHS))
 @pytest.mark.parametrize("geom", list(GEOMS))
 @pytest.mark.parametrize("cin,cout", CHANS)
-def test_conv_fwd(geom, cin, cout):
+def test_conv_fwd(geom, cin, cout, engine):
     from robocupvision_b200 import ops
+    math, f = MATHS[engine]
     g, x, w, b = _mk(geom, cin, cout, 3, 12, 20)
     ref = _ref_conv(geom, x, w, b)
-    got = ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda())
-    assert_close(f"conv_fwd {geom} {cin}->{cout}", got, ref, 2e-6)
+    got = ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda(), math=math)
+    assert_close(f"conv_fwd {geom} {cin}->{cout}", got, ref, 2e-6 * f)
 
 
+@pytest.mark.parametrize("engine", list(MATHS))
 @pytest.mark.parametrize("geom", ["k3s1d1", "k3s1d2", "k3s2", "k1", "convT"])
 @pytest.mark.parametrize("hw", [(9, 7), (5, 3), (15, 20), (1, 1), (2, 130)])
-def test_conv_fwd_ragged_sizes(geom, hw):
+def test_conv_fwd_ragged_sizes(geom, hw, engine):
     """odd extents (scalar store path), single pixels, M not a multiple of the tile."""
     from robocupvision_b200 import ops
+    math, f = MATHS[engine]
     g, x, w, b = _mk(geom, 5, 7, 2, *hw, seed=3)
     ref = _ref_conv(geom, x, w, None)
-    got = ops.conv_fwd(g, x.cuda(), w.cuda(), None)
-    assert_close(f"conv_fwd {geom} {hw}", got, ref, 2e-6)
+    got = ops.conv_fwd(g, x.cuda(), w.cuda(), None, math=math)
+    assert_close(f"conv_fwd {geom} {hw}", got, ref, 2e-6 * f)
 
 
+def test_conv_wide_channel_tiles():
+    """Cout > 128: several N tiles per pixel tile on the tensor-core engine."""
+    from robocupvision_b200 import ops
+    g, x, w, b = _mk("k3s1d1", 40, 200, 2, 9, 11, seed=11)
+    ref = _ref_conv("k3s1d1", x, w, b)
+    got = ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda(), math=1)
+    assert_close("conv_fwd 40->200 tc", got, ref, 8e-6)
+
+
+def test_tc_requires_packed_weights():
+    """RCV_MATH_TF32X3 through the raw C ABI without a packed panel is an error, not a fallback."""
+    import ctypes as C
+    from robocupvision_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(1, 8, 4, 4, device="cuda"); w = torch.zeros(8, 8, 3, 3, device="cuda"); y = torch.zeros(1, 8, 4, 4, device="cuda")
+    d = _lib.ConvDesc(1, 8, 4, 4, 8, 3, 1, 1, 1, 0, 0, _lib.MATH_TF32X3)
+    rc = lib.rcv_conv_fwd(C.byref(d), C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), None, None, None, None,
+                          None, C.c_void_p(y.data_ptr()), None, None)
+    assert rc == _lib.RCV_ERR_BAD_ARG and b"packed" in lib.rcv_last_error()
+
+
+@pytest.mark.parametrize("engine", list(MATHS))
 @pytest.mark.parametrize("epi", ["none", "relu", "relu_affine", "affine_relu", "affine"])
 @pytest.mark.parametrize("geom,cin,cout", [("k3s1d1", 8, 16), ("k3s1d2", 64, 128), ("convT", 32, 16), ("k3s2", 16, 32)])
-def test_conv_epilogues(epi, geom, cin, cout):
+def test_conv_epilogues(epi, geom, cin, cout, engine):
     from robocupvision_b200 import ops
+    math, f = MATHS[engine]
     g, x, w, b = _mk(geom, cin, cout, 2, 12, 16, seed=1)
     gen = torch.Generator().manual_seed(9)
     sc, sh = torch.randn(cout, generator=gen), torch.randn(cout, generator=gen)
@@ -76,27 +106,29 @@ def test_conv_epilogues(epi, geom, cin, cout):
             "affine_relu": ops.EPI_AFFINE_RELU, "affine": ops.EPI_AFFINE}[epi]
     stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
     got = ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda(), epilogue=code, scale=sc.cuda(), shift=sh.cuda(),
-                       residual=res.cuda(), stats=stats)
-    assert_close(f"epilogue {epi} {geom}", got, ref, 3e-6)
+                       residual=res.cuda(), stats=stats, math=math)
+    assert_close(f"epilogue {epi} {geom}", got, ref, 3e-6 * f)
     rd = ref.double()
-    assert_close("stats sum", stats[:cout], rd.sum((0, 2, 3)), 1e-6, atol=1e-3)
-    assert_close("stats sumsq", stats[cout:], (rd * rd).sum((0, 2, 3)), 1e-6, atol=1e-3)
+    assert_close("stats sum", stats[:cout], rd.sum((0, 2, 3)), 1e-6 * f, atol=1e-3)
+    assert_close("stats sumsq", stats[cout:], (rd * rd).sum((0, 2, 3)), 1e-6 * f, atol=1e-3)
 
 
+@pytest.mark.parametrize("engine", list(MATHS))
 @pytest.mark.parametrize("geom", list(GEOMS))
 @pytest.mark.parametrize("cin,cout", [(3, 8), (8, 16), (32, 64), (128, 128), (64, 32), (16, 5)])
-def test_conv_dgrad_wgrad(geom, cin, cout):
+def test_conv_dgrad_wgrad(geom, cin, cout, engine):
     from robocupvision_b200 import ops
+    math, f = MATHS[engine]
     g, x, w, b = _mk(geom, cin, cout, 3, 12, 20, seed=5)
     x.requires_grad_(True); w.requires_grad_(True); b.requires_grad_(True)
     y = _ref_conv(geom, x, w, b)
     dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
     y.backward(dy)
-    dx = ops.conv_dgrad(g, dy.cuda(), w.detach().cuda(), (12, 20))
-    assert_close(f"dgrad {geom} {cin}->{cout}", dx, x.grad, 3e-6)
+    dx = ops.conv_dgrad(g, dy.cuda(), w.detach().cuda(), (12, 20), math=math)
+    assert_close(f"dgrad {geom} {cin}->{cout}", dx, x.grad, 3e-6 * f)
     other = torch.randn(x.shape, generator=torch.Generator().manual_seed(7))
-    dx2 = ops.conv_dgrad(g, dy.cuda(), w.detach().cuda(), (12, 20), residual=other.cuda())
-    assert_close("dgrad+residual", dx2, x.grad + other, 3e-6)
+    dx2 = ops.conv_dgrad(g, dy.cuda(), w.detach().cuda(), (12, 20), residual=other.cuda(), math=math)
+    assert_close("dgrad+residual", dx2, x.grad + other, 3e-6 * f)
     dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True)
     assert_close(f"wgrad {geom} {cin}->{cout}", dw, w.grad, 1e-5)
     assert_close(f"bgrad {geom}", db, b.grad, 1e-5)
