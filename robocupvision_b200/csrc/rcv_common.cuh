@@ -56,6 +56,7 @@ struct RcvIgemm {
   int32_t epilogue;
   int32_t nclass;
   int32_t math;  // rcv_math
+  int32_t debug; // timing experiments (RCV_UMMA_DEBUG), 0 in production
   RcvTapSet taps[4];
 };
 

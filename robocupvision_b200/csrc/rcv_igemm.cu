@@ -282,12 +282,13 @@ int launch_cfg(const RcvIgemm& p, cudaStream_t st) {
 
 }  // namespace
 
-// AUTO: tensor cores wherever the reduction is long enough to amortise operand staging;
-// the 3-channel input layer and the 1x1 class head stay on CUDA cores (pure bandwidth).
+// AUTO: tensor cores wherever the reduction is long enough to amortise operand staging
+// (measured on B200 at batch 64, tools/umma_probe.py: K >= 128 and >= 16 output channels);
+// the 3-/8-channel outer layers and the 1x1 class head stay on CUDA cores.
 bool rcv_umma_pays(const RcvIgemm& p) {
   int maxT = 0;
   for (int c = 0; c < p.nclass; ++c) maxT = p.taps[c].n > maxT ? p.taps[c].n : maxT;
-  return p.CA * maxT >= 64 && p.CB >= 8 && rcv_umma_supported(p);
+  return p.CA * maxT >= 128 && p.CB >= 16 && rcv_umma_supported(p);
 }
 
 int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st) {

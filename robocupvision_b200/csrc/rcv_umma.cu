@@ -11,30 +11,34 @@
 // rows of 128 bytes with the 128-byte swizzle already applied -- so a stage of B is one
 // contiguous cp.async.bulk copy completing on an mbarrier.
 //
-// One CTA = one 128 x BN output tile, 160 threads:
-//   * warps 0-3, PRODUCERS: thread t owns tile row t (one pixel).  Per K block of 32 it gathers
-//     32 activations straight from NCHW global memory (coalesced across the warp: lanes are
-//     consecutive pixels), splits them into tf32 hi / lo parts and writes both in the K-major
-//     128B-swizzled canonical UMMA layout (16 B chunk c of row r at chunk c ^ (r & 7):
-//     conflict-free STS.128), then fence.proxy.async + one mbarrier arrive per warp.  The next
-//     block's global loads are issued before the arrive so they fly under the MMAs.
-//   * warp 4 lane 0, ISSUER: keeps SB bulk copies of B in flight, waits for a stage's A and B,
+// One CTA = one 128 x BN output tile, G producer groups of 128 threads + one issuer warp:
+//   * PRODUCERS: group g fills K blocks g, g+G, g+2G, ... into A-ring stage g; thread t of a
+//     group owns tile row t (one pixel).  Per K block of 32 it gathers 32 activations straight
+//     from NCHW global memory (coalesced across the warp: lanes are consecutive pixels), splits
+//     them into tf32 hi / lo parts and writes both in the K-major 128B-swizzled canonical UMMA
+//     layout (16 B chunk c of row r at chunk c ^ (r & 7): conflict-free STS.128), then
+//     fence.proxy.async + one mbarrier arrive per warp.  The proxy fence is a full MEMBAR that
+//     drains the thread's outstanding loads, so a thread never prefetches across it; the global
+//     latency is hidden instead by the G groups working on G different K blocks at once.
+//   * last warp, lane 0, ISSUER: keeps SB bulk copies of B in flight, waits for a stage's A and B,
 //     issues 3 x tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per 8-wide K step -- the hi*hi
 //     product into one TMEM accumulator, the two correction products into a second one (the
 //     tensor core truncates when it accumulates; keeping the small terms apart keeps that error
 //     relative to THEIR magnitude) -- and tcgen05.commit's the stage's empty barriers.
-//   * warps 0-3, EPILOGUE: tcgen05.ld (32 lanes x 16 columns per warp) of both accumulators,
+//   * all producer warps, EPILOGUE (warp w: TMEM lanes 32*(w%4).., column group w/4):
+//     tcgen05.ld (32 lanes x 16 columns) of both accumulators,
 //     bias / ReLU / folded-BN affine / residual, coalesced NCHW stores (lanes = pixels), and the
 //     train-mode BatchNorm per-channel sum / sum-of-squares via a shuffle transpose-reduce and
 //     one double atomic per channel per warp.
+#include <stdlib.h>
+
 #include "rcv_common.cuh"
 
 namespace {
 
-constexpr int NPROD = 128;        // producer / epilogue threads
-constexpr int NT = NPROD + 32;    // + the issuer warp
-constexpr int BM = 128;
 constexpr int BK = 32;            // fp32 elements per K block: one 128-byte swizzle row
+constexpr int GTHREADS = 128;     // threads of one producer group: one per tile row
+constexpr int BM = 128;
 constexpr int MAXT = 9;
 constexpr int RCV_UMMA_MAX_TABLE_K = 2304;  // per-k gather table (channel counts that are not multiples of 32)
 
@@ -138,11 +142,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// x = hi + lo with hi on the tf32 grid (10 explicit mantissa bits, round-half-away by integer add:
+// 2 ALU ops; cvt.rna.tf32 expands to ~7) and lo = x - hi exact in fp32 (|lo| <= 2^-11 |x|); the
+// tensor core reads the upper 19 bits of lo, so hi + lo carries ~21 mantissa bits of x.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  lo = x - hi;  // exact in fp32; the tensor core reads its upper 19 bits
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
 }
 
 __device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh) {
@@ -174,11 +179,14 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&a)[16], int lane
 }
 
 // Tile configuration per output-channel tile width.
-template <int BN_>
+template <int BN_, int G_>
 struct Cfg {
   static constexpr int BN = BN_;
-  static constexpr int SA = 2;                       // A ring depth (software gather)
-  static constexpr int SB = BN_ >= 64 ? (BN_ == 128 ? 4 : 2) : 3;  // B ring depth (bulk copies)
+  static constexpr int G = G_;                       // producer groups
+  static constexpr int NPROD = G_ * GTHREADS;
+  static constexpr int NT = NPROD + 64;              // + the MMA-issuer warp + the B-loader warp
+  static constexpr int SA = G_;                      // A ring depth: one stage per group
+  static constexpr int SB = BN_ == 128 ? 2 : 3;      // B ring depth (bulk copies)
   static constexpr int A_BYTES = BM * 128;           // one hi or lo A tile
   static constexpr int A_STAGE = 2 * A_BYTES;
   static constexpr int B_STAGE = BN_ * 256;          // hi rows then lo rows
@@ -188,17 +196,27 @@ struct Cfg {
   static constexpr int TCOLS = 2 * BN_ < 32 ? 32 : 2 * BN_;  // main + correction accumulators
 };
 
-__host__ __device__ inline int umma_bn(int CB) { return CB > 64 ? 128 : CB > 32 ? 64 : CB > 16 ? 32 : 16; }
+static int g_bn_cap = 0, g_force_g = 0;  // experiments: RCV_UMMA_BNCAP / RCV_UMMA_G
+__host__ inline int umma_bn(int CB) {
+  if (g_bn_cap == 0) {
+    const char* e = getenv("RCV_UMMA_BNCAP");
+    g_bn_cap = e ? atoi(e) : 128;
+    e = getenv("RCV_UMMA_G");
+    g_force_g = e ? atoi(e) : -1;
+  }
+  const int bn = CB > 64 ? 128 : CB > 32 ? 64 : CB > 16 ? 32 : 16;
+  return bn > g_bn_cap ? g_bn_cap : bn;
+}
 __host__ __device__ inline int max_taps(const RcvIgemm& p) {
   int m = 0;
   for (int c = 0; c < p.nclass; ++c) m = p.taps[c].n > m ? p.taps[c].n : m;
   return m;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
-  using C = Cfg<BN>;
-  constexpr int SA = C::SA, SB = C::SB;
+template <int BN, int G>
+__global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const RcvIgemm p) {
+  using C = Cfg<BN, G>;
+  constexpr int SA = C::SA, SB = C::SB, NPROD = C::NPROD, NT = C::NT;
 
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -235,13 +253,13 @@ __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
   if ((CA % BK) != 0) {
     for (int k = tid; k < nkb * BK; k += NT) {
       const int tap = k / CA, ca = k - tap * CA;
-      s_ktab[k] = tap < T ? make_int2(ca * HWin + p.taps[cls].dy[tap] * p.Win + p.taps[cls].dx[tap], tap)
+      s_ktab[k] = tap < T ? make_int2(4 * (ca * HWin + p.taps[cls].dy[tap] * p.Win + p.taps[cls].dx[tap]), tap)
                           : make_int2(0, 31);
     }
   }
   if (tid == 0) {
     for (int s = 0; s < SA; ++s) {
-      mbar_init(bar_afull + 8 * s, NPROD / 32);
+      mbar_init(bar_afull + 8 * s, GTHREADS / 32);
       mbar_init(bar_emptyA + 8 * s, 1);
     }
     for (int s = 0; s < SB; ++s) {
@@ -251,54 +269,65 @@ __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
+  if (warp == NPROD / 32) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
-    // ================================ ISSUER ==========================================
-    if (lane == 0) {
+  if (warp == NPROD / 32 + 1) {
+    // ================================ B LOADER ========================================
+    // keeps up to SB bulk copies of packed weight blocks in flight, limited only by the ring
+    if (lane == 0 && !(p.debug & 16)) {
       const int kbmax = (CA * max_taps(p) + BK - 1) / BK;  // K blocks per (class, N tile) in the pack
       const unsigned char* gB = reinterpret_cast<const unsigned char*>(p.wpacked) +
                                 ((size_t)(cls * gridDim.y + blockIdx.y) * kbmax) * C::B_STAGE;
-      auto issue_b = [&](int kb) {
+      for (int kb = 0; kb < nkb; ++kb) {
         const int sb = kb % SB, ub = kb / SB;
         if (ub > 0) mbar_wait(bar_emptyB + 8 * sb, (uint32_t)((ub - 1) & 1));
         mbar_expect_tx(bar_bfull + 8 * sb, C::B_STAGE);
         bulk_g2s(tilesB + sb * C::B_STAGE, gB + (size_t)kb * C::B_STAGE, C::B_STAGE, bar_bfull + 8 * sb);
-      };
-      for (int kb = 0; kb < SB && kb < nkb; ++kb) issue_b(kb);
+      }
+    }
+  } else if (warp == NPROD / 32) {
+    // ================================ MMA ISSUER ======================================
+    if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       for (int kb = 0; kb < nkb; ++kb) {
         const int sa = kb % SA, ua = kb / SA, sb = kb % SB, ub = kb / SB;
         mbar_wait(bar_afull + 8 * sa, (uint32_t)(ua & 1));
-        mbar_wait(bar_bfull + 8 * sb, (uint32_t)(ub & 1));
+        if (!(p.debug & 16)) mbar_wait(bar_bfull + 8 * sb, (uint32_t)(ub & 1));
         tc_fence_after();
         const uint32_t abase = tiles + sa * C::A_STAGE, bbase = tilesB + sb * C::B_STAGE;
         const uint64_t a_hi = make_desc(abase), a_lo = make_desc(abase + C::A_BYTES);
         const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + BN * 128);
         const int krem = K - kb * BK;
         const int ksteps = krem >= BK ? BK / 8 : (krem + 7) / 8;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 2);  // 8 tf32 = 32 B = 2 x 16 B inside the swizzle row
-          const uint32_t acc = (kb | ks) != 0;
-          umma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, acc);
-          umma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-          umma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, acc);
+        if (!(p.debug & 1)) {
+          // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzled row per step
+          umma_tf32(d_corr, a_lo, b_hi, idesc, kb != 0);
+          umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+          umma_tf32(d_main, a_hi, b_hi, idesc, kb != 0);
+#pragma unroll
+          for (int ks = 1; ks < BK / 8; ++ks) {
+            if (ks < ksteps) {
+              umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+              umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+              umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+            }
+          }
         }
         umma_commit(bar_emptyA + 8 * sa);
         umma_commit(bar_emptyB + 8 * sb);
         if (kb == nkb - 1) umma_commit(bar_done);
-        // refill the B slot of the previous block: its MMAs finish before this block's start
-        if (kb >= 1 && kb - 1 + SB < nkb) issue_b(kb - 1 + SB);
       }
     }
   } else {
     // ================================ PRODUCERS =======================================
-    const int m = m0 + tid;
+    const int row = tid & (BM - 1);
+    const int grp = tid / GTHREADS;  // producer group (warp-uniform)
+    const int m = m0 + row;
     const bool mrow = m < M;
     int pn = 0, pi = 0, pj = 0;
     if (mrow) {
@@ -308,7 +337,10 @@ __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
       pj = r - pi * p.Wg;
     }
     const int gy0 = pi * p.gs, gx0 = pj * p.gs;
-    const float* gbase = p.in + (size_t)pn * CA * HWin + gy0 * p.Win + gx0;
+    // 32-bit byte offsets from the (uniform) tensor base keep the gather at ~4 instructions/load
+    const char* inb = reinterpret_cast<const char*>(p.in);
+    const uint32_t boff0 = 4u * (uint32_t)(pn * CA * HWin + gy0 * p.Win + gx0);
+    const uint32_t cstride = 4u * (uint32_t)HWin;
     uint32_t tapmask = 0;  // bit t: tap t reads inside the image for this pixel
     if (mrow) {
       for (int t = 0; t < T; ++t) {
@@ -317,33 +349,36 @@ __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
       }
     }
     const bool uni = (CA % BK) == 0;  // every K block lies inside one tap
+    unsigned char* a_hi = gen_tiles + grp * C::A_STAGE;
+    unsigned char* a_lo = a_hi + C::A_BYTES;
+    const uint32_t my_full = bar_afull + 8 * grp, my_empty = bar_emptyA + 8 * grp;
+    // (tap, channel) of this group's next K block on the uniform path
+    int tap = (grp * BK) / CA, ca = (grp * BK) % CA;
 
-    // Two K blocks of gathered activations live in registers: block kb is converted and stored
-    // while block kb+1 (issued one iteration earlier) is still landing.  The proxy fence that
-    // publishes the stores drains this thread's outstanding loads (MEMBAR), so a block's loads
-    // are issued only AFTER the previous block's fence + arrive.
-    float v0[BK], v1[BK];
-    auto load_regs = [&](int kb, float (&va)[BK]) {
-      const int k0 = kb * BK;
-      if (uni) {
-        const int tap = k0 / CA;
-        const int ca = k0 - tap * CA;
-        const bool ok = (tapmask >> tap) & 1u;
-        const float* src = gbase + (ca * HWin + s_toff[tap]);
+    for (int kb = grp, use = 0; kb < nkb; kb += G, ++use) {
+      float va[BK];
+      if (p.debug & 2) {
 #pragma unroll
-        for (int i = 0; i < BK; ++i) va[i] = ok ? __ldg(src + i * HWin) : 0.f;
+        for (int i = 0; i < BK; ++i) va[i] = 1.f;
+      } else if (uni) {
+        const bool ok = (tapmask >> tap) & 1u;
+        const uint32_t b = boff0 + 4u * (uint32_t)(ca * HWin + s_toff[tap]);
+#pragma unroll
+        for (int i = 0; i < BK; ++i)
+          va[i] = ok ? __ldg(reinterpret_cast<const float*>(inb + (b + (uint32_t)i * cstride))) : 0.f;
+        ca += G * BK;
+        while (ca >= CA) { ca -= CA; ++tap; }
       } else {
+        const int2* tab = s_ktab + kb * BK;
 #pragma unroll
         for (int i = 0; i < BK; ++i) {
-          const int2 e = s_ktab[k0 + i];  // (element offset, tap or 31 beyond K)
-          va[i] = ((tapmask >> e.y) & 1u) ? __ldg(gbase + e.x) : 0.f;
+          const int2 e = tab[i];  // (byte offset, tap or 31 beyond K)
+          va[i] = ((tapmask >> e.y) & 1u) ? __ldg(reinterpret_cast<const float*>(inb + (boff0 + (uint32_t)e.x)))
+                                          : 0.f;
         }
       }
-    };
-    auto store_smem = [&](int sa, const float (&va)[BK]) {
-      unsigned char* a_hi = gen_tiles + sa * C::A_STAGE;
-      unsigned char* a_lo = a_hi + C::A_BYTES;
-      const int row = tid;
+      if (use > 0) mbar_wait(my_empty, (uint32_t)((use - 1) & 1));
+      if (!(p.debug & 4))
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float4 h, l;
@@ -355,22 +390,9 @@ __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
         *reinterpret_cast<float4*>(a_hi + off) = h;
         *reinterpret_cast<float4*>(a_lo + off) = l;
       }
-    };
-    auto produce = [&](int kb, float (&va)[BK]) {
-      const int sa = kb % SA, ua = kb / SA;
-      if (ua > 0) mbar_wait(bar_emptyA + 8 * sa, (uint32_t)((ua - 1) & 1));
-      store_smem(sa, va);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_afull + 8 * sa);
-      if (kb + 2 < nkb) load_regs(kb + 2, va);
-    };
-
-    load_regs(0, v0);
-    if (nkb > 1) load_regs(1, v1);
-    for (int kb = 0; kb < nkb; kb += 2) {
-      produce(kb, v0);
-      if (kb + 1 < nkb) produce(kb + 1, v1);
+      if (lane == 0) mbar_arrive(my_full);
     }
 
     // ================================ EPILOGUE ========================================
@@ -384,10 +406,11 @@ __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
       const int oy = pi * p.ostep + ca_, ox = pj * p.ostep + cb_;
       obase = (size_t)pn * p.CB * HWo + (size_t)oy * p.Wout + ox;
     }
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // warps of different groups share TMEM lanes 32*(w%4)..+31 and interleave the 16-column chunks
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n0 + c0 >= p.CB) break;  // warp-uniform
+    for (int c0 = grp * 16; c0 < BN; c0 += G * 16) {
+      if (n0 + c0 >= p.CB || (p.debug & 32)) break;  // warp-uniform
       uint32_t rm[16], rc[16];
       tmem_ld16_nowait(trow + c0, rm);
       tmem_ld16_nowait(trow + BN + c0, rc);
@@ -423,7 +446,7 @@ __global__ void __launch_bounds__(NT) umma_igemm_kernel(const RcvIgemm p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NPROD / 32) {
     __syncwarp();
     tmem_dealloc(tmem_base, C::TCOLS);
   }
@@ -469,14 +492,14 @@ __global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int
   }
 }
 
-template <int BN>
+template <int BN, int G>
 int launch_bn(const RcvIgemm& p, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, G>;
   constexpr int MAX_SMEM = C::FIXED + RCV_UMMA_MAX_TABLE_K * 8;
   static_assert(MAX_SMEM <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;  // benign race: idempotent
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(umma_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_igemm_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          MAX_SMEM);
     if (e != cudaSuccess) {
       rcv_set_error("umma_igemm: cannot reserve %d B of shared memory: %s", MAX_SMEM, cudaGetErrorString(e));
@@ -486,14 +509,14 @@ int launch_bn(const RcvIgemm& p, cudaStream_t st) {
   }
   const int kpad = rcv_cdiv((int64_t)p.CA * max_taps(p), BK) * BK;
   const int smem = C::FIXED + ((p.CA % BK) != 0 ? kpad * 8 : 0);
-  RCV_REQUIRE((int64_t)p.N * p.CA * p.Hin * p.Win < (1ll << 31), RCV_ERR_UNSUPPORTED,
-              "umma_igemm: input tensor too large for 32-bit gather offsets");
+  RCV_REQUIRE((int64_t)p.N * p.CA * p.Hin * p.Win < (1ll << 30), RCV_ERR_UNSUPPORTED,
+              "umma_igemm: input tensor too large for 32-bit byte offsets");
   const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
   RCV_REQUIRE(M < (1ll << 31) && (int64_t)p.N * p.CB * p.Hout * p.Wout < (1ll << 40), RCV_ERR_UNSUPPORTED,
               "umma_igemm: problem too large");
   dim3 grid(rcv_cdiv(M, BM), rcv_cdiv(p.CB, BN), p.nclass);
   RCV_REQUIRE(grid.y <= 65535, RCV_ERR_UNSUPPORTED, "umma_igemm: too many output-channel tiles");
-  umma_igemm_kernel<BN><<<grid, NT, smem, st>>>(p);
+  umma_igemm_kernel<BN, G><<<grid, C::NT, smem, st>>>(p);
   RCV_CHECK_LAUNCH("umma_igemm_kernel");
   return RCV_OK;
 }
@@ -536,16 +559,27 @@ int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st) {
   return RCV_OK;
 }
 
-int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st) {
+int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
+  RcvIgemm p = p_in;
+  static int dbg = -1;  // RCV_UMMA_DEBUG: timing experiments only (results are wrong when set)
+  if (dbg < 0) {
+    const char* e = getenv("RCV_UMMA_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  p.debug = dbg;
   int rc = check_taps(p);
   if (rc) return rc;
   RCV_REQUIRE(p.wpacked != nullptr, RCV_ERR_BAD_ARG,
               "tensor-core conv needs packed weights (rcv_conv_pack); none were given");
   RCV_REQUIRE(((uintptr_t)p.wpacked & 127) == 0, RCV_ERR_BAD_ARG, "packed weights must be 128-byte aligned");
-  switch (umma_bn(p.CB)) {
-    case 128: return launch_bn<128>(p, st);
-    case 64: return launch_bn<64>(p, st);
-    case 32: return launch_bn<32>(p, st);
-    default: return launch_bn<16>(p, st);
+  // Long reductions: 4 producer groups (A ring of 4 stages, one CTA per SM).  Short ones (a few
+  // K blocks per tile): 2 groups so that 2-3 CTAs share an SM and overlap prologue / epilogue.
+  const int bn = umma_bn(p.CB);
+  const bool deep = g_force_g > 0 ? g_force_g == 4 : (int64_t)p.CA * max_taps(p) > 10 * BK;
+  switch (bn) {
+    case 128: return launch_bn<128, 4>(p, st);
+    case 64: return deep ? launch_bn<64, 4>(p, st) : launch_bn<64, 2>(p, st);
+    case 32: return deep ? launch_bn<32, 4>(p, st) : launch_bn<32, 2>(p, st);
+    default: return deep ? launch_bn<16, 4>(p, st) : launch_bn<16, 2>(p, st);
   }
 }

@@ -20,13 +20,26 @@ def ref_conv(geom, x, w, b):
 
 
 def timeit(fn, n=20):
+    """us per call, device time: n calls captured in a CUDA graph (the ctypes launch path costs
+    ~35 us of host time per call, more than the short kernels take)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        fn()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(n):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
@@ -34,6 +47,8 @@ def timeit(fn, n=20):
 
 def main():
     quick = "--quick" in sys.argv
+    if any(a.startswith("--layer=") for a in sys.argv):
+        return timing()
     cases = [("k3s1d1", 40, 200, 2, 9, 11), ("k3s1d1", 8, 16, 2, 12, 20), ("k3s1d1", 128, 128, 2, 15, 20), ("k3s1d2", 64, 128, 2, 15, 20),
              ("k3s2", 16, 32, 2, 12, 20), ("convT", 64, 32, 2, 15, 20), ("k1", 16, 5, 2, 12, 20),
              ("k3s1d1", 5, 7, 2, 9, 7), ("k3s1d1", 24, 40, 3, 12, 20), ("k3s1d1", 3, 8, 2, 12, 20)]
@@ -67,6 +82,10 @@ def main():
                 print(f"dgrad {geom:7s} {cin:3d}->{cout:3d} {nm:7s} FAILED {e}", flush=True)
     if quick:
         return
+    timing()
+
+
+def timing():
     # timing at the bench shapes (batch 64, ROBO-UNet 160x120 layer table)
     layers = [("k3s1d1", 3, 8, 120, 160), ("k3s2", 8, 16, 120, 160), ("k3s1d1", 16, 16, 60, 80),
               ("k3s2", 16, 32, 60, 80), ("k3s1d1", 32, 32, 30, 40), ("k3s2", 32, 64, 30, 40),
@@ -74,6 +93,9 @@ def main():
               ("k3s1d1", 128, 64, 15, 20), ("convT", 64, 32, 15, 20), ("convT", 32, 16, 30, 40),
               ("convT", 16, 8, 60, 80), ("k1", 8, 5, 120, 160)]
     B = 64
+    only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--layer=")]
+    if only:
+        layers = [layers[i] for i in only]
     for geom, cin, cout, h, w in layers:
         k, s, p, d, tr = GEOMS[geom]
         geo = ops.ConvGeom(cin, cout, k, s, p, d, tr)
