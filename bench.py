@@ -326,7 +326,14 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # NCCL communicators referenced by captured CUDA graphs can stall destroy_process_group()
+        # at interpreter teardown (seen on 2xB200: line printed, ranks never exited).  All ranks
+        # meet once more, drain their streams and leave without running the teardown.
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

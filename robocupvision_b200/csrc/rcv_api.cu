@@ -15,6 +15,11 @@ void rcv_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+long long* g_rcv_prof = nullptr;
+/* debug hook (not in the public header): device buffer of >= 4096 int64 that CTA 0 of the
+ * tensor-core kernels fills with clock64() samples per pipeline phase; NULL switches it off */
+extern "C" void rcv_debug_set_prof(void* buf) { g_rcv_prof = reinterpret_cast<long long*>(buf); }
+
 extern "C" int rcv_version(void) { return RCV_ABI_VERSION; }
 extern "C" const char* rcv_last_error(void) { return g_err; }
 
@@ -254,6 +259,7 @@ extern "C" int rcv_conv_wgrad(const rcv_conv_desc* d, const float* x, const floa
   RcvWgrad p;
   memset(&p, 0, sizeof(p));
   p.dw = dw;
+  p.math = d->math;
   p.N = d->N;
   const int kk = d->ksize * d->ksize;
   if (!d->transposed) {

@@ -57,6 +57,7 @@ struct RcvIgemm {
   int32_t nclass;
   int32_t math;  // rcv_math
   int32_t debug; // timing experiments (RCV_UMMA_DEBUG), 0 in production
+  long long* prof;  // per-phase clock64 samples of CTA 0 (rcv_debug_set_prof), NULL in production
   RcvTapSet taps[4];
 };
 
@@ -72,9 +73,12 @@ struct RcvWgrad {
   int32_t gs;
   int32_t wsA, wsB;
   int32_t slab;      // pixels per split, multiple of 16
+  int32_t math;      // rcv_math
+  long long* prof;   // see RcvIgemm::prof
   RcvTapSet taps;
 };
 
+extern long long* g_rcv_prof;  // debug: phase-timing buffer (rcv_debug_set_prof)
 int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st);       // dispatch on p.math
 int rcv_launch_igemm_simt(const RcvIgemm& p, cudaStream_t st);  // fp32 FFMA, CUDA cores
 int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF32, TMEM accumulators
@@ -82,4 +86,6 @@ bool rcv_umma_pays(const RcvIgemm& p);  // RCV_MATH_AUTO: is the reduction long 
 bool rcv_umma_supported(const RcvIgemm& p);  // geometry within the tensor-core engine's limits
 size_t rcv_umma_packed_bytes(const RcvIgemm& p);
 int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st);
-int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st);
+int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st);       // dispatch on p.math
+int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st);         // tcgen05 3xTF32
+bool rcv_umma_wgrad_pays(const RcvWgrad& p);

@@ -225,6 +225,8 @@ int launch_cfg(RcvWgrad p, cudaStream_t st) {
 }  // namespace
 
 int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st) {
+  if (p.math == RCV_MATH_TF32X3 || (p.math == RCV_MATH_AUTO && rcv_umma_wgrad_pays(p)))
+    return rcv_launch_wgrad_umma(p, st);
   if (p.CB > 64) return launch_cfg<128, 128, 8, 8>(p, st);
   if (p.CB > 32) return launch_cfg<64, 128, 4, 8>(p, st);
   if (p.CB > 16) return launch_cfg<32, 128, 4, 4>(p, st);

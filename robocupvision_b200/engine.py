@@ -271,7 +271,7 @@ class Plan:
                 wp = nd._pack[PACK_DGRAD] if (self.math != MATH_FP32 and nd._tc[PACK_DGRAD]) else None
                 grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
                                                wpacked=wp)
-            ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias)
+            ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math)
 
 
 class _PlanFn(torch.autograd.Function):

@@ -181,7 +181,7 @@ def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=M
     return dx
 
 
-def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False):
+def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False, math=MATH_FP32):
     """Weight (and bias) gradient, accumulated into dw/dbias (zero-filled if not given)."""
     x = _chk(x, name="x")
     dy = _chk(dy, name="dy")
@@ -190,7 +190,7 @@ def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False):
         dw = torch.zeros(g.weight_shape(), device=x.device, dtype=torch.float32)
     if dbias is None and want_bias:
         dbias = torch.zeros(g.cout, device=x.device, dtype=torch.float32)
-    d = g.desc(n, h, wd)
+    d = g.desc(n, h, wd, EPI_NONE, math)
     _call("rcv_conv_wgrad", 2 if (g.transposed and dbias is not None) else 1, C.byref(d), _ptr(x),
           _ptr(dy), _ptr(dw), _ptr(dbias), _stream())
     return dw, dbias

@@ -129,9 +129,25 @@ def test_conv_dgrad_wgrad(geom, cin, cout, engine):
     other = torch.randn(x.shape, generator=torch.Generator().manual_seed(7))
     dx2 = ops.conv_dgrad(g, dy.cuda(), w.detach().cuda(), (12, 20), residual=other.cuda(), math=math)
     assert_close("dgrad+residual", dx2, x.grad + other, 3e-6 * f)
-    dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True)
+    dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True, math=math)
     assert_close(f"wgrad {geom} {cin}->{cout}", dw, w.grad, 1e-5)
     assert_close(f"bgrad {geom}", db, b.grad, 1e-5)
+
+
+def test_wgrad_tc_split_and_tail():
+    """tensor-core wgrad: several pixel splits, k tiles with a ragged tail, pixel count not a multiple of 32."""
+    from robocupvision_b200 import ops
+    g, x, w, b = _mk("k3s1d1", 24, 40, 5, 18, 22, seed=12)
+    x.requires_grad_(True); w.requires_grad_(True); b.requires_grad_(True)
+    y = _ref_conv("k3s1d1", x, w, b)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+    y.backward(dy)
+    dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True, math=1)
+    assert_close("wgrad tc", dw, w.grad, 1e-5)
+    assert_close("bgrad tc", db, b.grad, 1e-5)
+    with pytest.raises(Exception, match="multiple of 4"):
+        g2, x2, w2, b2 = _mk("k3s1d1", 6, 10, 3, 7, 9, seed=8)
+        ops.conv_wgrad(g2, x2.cuda(), torch.zeros(3, 10, 7, 9, device="cuda"), math=1)
 
 
 @pytest.mark.parametrize("geom", ["k3s1d1", "k3s1d2", "k1"])

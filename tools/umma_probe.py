@@ -112,7 +112,9 @@ def timing():
             try:
                 tf = timeit(lambda: ops.conv_fwd(geo, x, wt, None, epilogue=ops.EPI_RELU, math=math, out=y))
                 tb = timeit(lambda: ops.conv_dgrad(geo, dy, wt, (h, w), math=math, out=dx))
-                row += f"  {nm}: fwd {tf:7.1f}us ({fl/tf/1e6:6.1f} TF/s) dgrad {tb:7.1f}us ({fl/tb/1e6:6.1f} TF/s)"
+                dw = torch.zeros_like(wt)
+                tw = timeit(lambda: ops.conv_wgrad(geo, x, dy, dw=dw, math=math))
+                row += f"  {nm}: fwd {tf:6.1f} dgrad {tb:6.1f} wgrad {tw:6.1f} us"
             except Exception as e:  # noqa: BLE001
                 row += f"  {nm}: FAILED {e}"
         print(row, flush=True)
