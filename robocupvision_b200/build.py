@@ -30,7 +30,7 @@ NVCC_FLAGS = [
     "-DRCV_BUILDING=1",
     f"-I{ROOT / 'include'}",
     f"-I{CSRC}",
-]
+] + (["-DRCV_PROF=1"] if os.environ.get("RCV_PROF") else [])  # phase-timing instrumentation (debug builds)
 
 
 def _nvcc() -> str:

@@ -45,6 +45,21 @@ constexpr int RCV_UMMA_MAX_TABLE_K = 2304;  // per-k gather table (channel count
 
 using namespace rcv_umma;
 
+// Phase-timing instrumentation (tools/umma_phases.py): compiled in only with -DRCV_PROF=1
+#ifndef RCV_PROF
+#define RCV_PROF 0
+#endif
+#if RCV_PROF
+#define RCV_PROF_ON(cond) (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (cond))
+#define RCV_PROF_I(e) do { if (RCV_PROF_ON(kb < 128)) p.prof[2048 + kb * 4 + (e)] = clock64(); } while (0)
+#define RCV_PROF_P(e) do { if (RCV_PROF_ON(row == 0 && kb < 128)) p.prof[kb * 8 + (e)] = clock64(); } while (0)
+#define RCV_PROF_E(e) do { if (RCV_PROF_ON(row == 0)) p.prof[4000 + grp * 4 + (e)] = clock64(); } while (0)
+#else
+#define RCV_PROF_I(e) do { } while (0)
+#define RCV_PROF_P(e) do { } while (0)
+#define RCV_PROF_E(e) do { } while (0)
+#endif
+
 __device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh) {
   switch (epi) {
     case RCV_EPI_RELU: return fmaxf(v, 0.f);
@@ -77,16 +92,15 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&a)[16], int lane
 template <int BN_, int G_>
 struct Cfg {
   static constexpr int BN = BN_;
-  static constexpr int G = G_;                       // producer groups
+  static constexpr int G = G_;                       // producer groups = ring depth
   static constexpr int NPROD = G_ * GTHREADS;
   static constexpr int NT = NPROD + 64;              // + the MMA-issuer warp + the B-loader warp
-  static constexpr int SA = G_;                      // A ring depth: one stage per group
-  static constexpr int SB = BN_ == 128 ? 2 : 3;      // B ring depth (bulk copies)
   static constexpr int A_BYTES = BM * 128;           // one hi or lo A tile
   static constexpr int A_STAGE = 2 * A_BYTES;
   static constexpr int B_STAGE = BN_ * 256;          // hi rows then lo rows
-  static constexpr int TILE_BYTES = SA * A_STAGE + SB * B_STAGE;
-  static constexpr int FIXED = TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/;
+  static constexpr int STAGE = A_STAGE + B_STAGE;    // one ring stage: A hi, A lo, B hi, B lo
+  static constexpr int TILE_BYTES = G_ * STAGE;
+  static constexpr int FIXED = TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/ + 3 * BN_ * 4;
   // + the per-k gather table (8 B per k) when the channel count is not a multiple of 32
   static constexpr int TCOLS = 2 * BN_ < 32 ? 32 : 2 * BN_;  // main + correction accumulators
 };
@@ -111,22 +125,20 @@ __host__ __device__ inline int max_taps(const RcvIgemm& p) {
 template <int BN, int G>
 __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const RcvIgemm p) {
   using C = Cfg<BN, G>;
-  constexpr int SA = C::SA, SB = C::SB, NPROD = C::NPROD, NT = C::NT;
+  constexpr int NPROD = C::NPROD, NT = C::NT;
 
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
   unsigned char* gen_tiles = smem_raw + (tiles - raw);
-  const uint32_t tilesB = tiles + SA * C::A_STAGE;
   unsigned char* misc = gen_tiles + C::TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // afull[SA] emptyA[SA] bfull[SB] emptyB[SB] done
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // full[G] empty[G] done
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 120);
   int* s_toff = reinterpret_cast<int*>(misc + 128);     // [MAXT] input offset of a tap
-  int2* s_ktab = reinterpret_cast<int2*>(misc + 256);   // [nkb*BK] per-k (offset, tap), non-uniform path
-  const uint32_t bar_afull = smem_u32(bars), bar_emptyA = bar_afull + 8 * SA;
-  const uint32_t bar_bfull = bar_emptyA + 8 * SA, bar_emptyB = bar_bfull + 8 * SB;
-  const uint32_t bar_done = bar_emptyB + 8 * SB;
-  static_assert(8 * (2 * SA + 2 * SB + 1) <= 120, "barrier area");
+  float* s_cst = reinterpret_cast<float*>(misc + 256);  // [3][BN] bias, scale, shift of this N tile
+  int2* s_ktab = reinterpret_cast<int2*>(misc + 256 + 3 * BN * 4);  // [nkb*BK] per-k (offset, tap), non-uniform path
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * G, bar_done = bar_empty + 8 * G;
+  static_assert(8 * (2 * G + 1) <= 120, "barrier area");
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -145,6 +157,13 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
     const int t = tid < T ? tid : 0;
     s_toff[tid] = p.taps[cls].dy[t] * p.Win + p.taps[cls].dx[t];
   }
+  for (int c = tid; c < BN; c += NT) {
+    const int co = n0 + c;
+    const bool in = co < p.CB;
+    s_cst[c] = (in && p.bias) ? __ldg(p.bias + co) : 0.f;
+    s_cst[BN + c] = (in && p.scale) ? __ldg(p.scale + co) : 1.f;
+    s_cst[2 * BN + c] = (in && p.shift) ? __ldg(p.shift + co) : 0.f;
+  }
   if ((CA % BK) != 0) {
     for (int k = tid; k < nkb * BK; k += NT) {
       const int tap = k / CA, ca = k - tap * CA;
@@ -153,13 +172,9 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < SA; ++s) {
-      mbar_init(bar_afull + 8 * s, GTHREADS / 32);
-      mbar_init(bar_emptyA + 8 * s, 1);
-    }
-    for (int s = 0; s < SB; ++s) {
-      mbar_init(bar_bfull + 8 * s, 1);
-      mbar_init(bar_emptyB + 8 * s, 1);
+    for (int s = 0; s < G; ++s) {
+      mbar_init(bar_full + 8 * s, GTHREADS / 32 + 1);  // 4 producer warps + the B loader's expect_tx
+      mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_done, 1);
     fence_barrier_init();
@@ -172,56 +187,65 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
 
   if (warp == NPROD / 32 + 1) {
     // ================================ B LOADER ========================================
-    // keeps up to SB bulk copies of packed weight blocks in flight, limited only by the ring
+    // one bulk copy of a packed weight block per ring stage, as soon as the stage is free
     if (lane == 0 && !(p.debug & 16)) {
       const int kbmax = (CA * max_taps(p) + BK - 1) / BK;  // K blocks per (class, N tile) in the pack
       const unsigned char* gB = reinterpret_cast<const unsigned char*>(p.wpacked) +
                                 ((size_t)(cls * gridDim.y + blockIdx.y) * kbmax) * C::B_STAGE;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int sb = kb % SB, ub = kb / SB;
-        if (ub > 0) mbar_wait(bar_emptyB + 8 * sb, (uint32_t)((ub - 1) & 1));
-        mbar_expect_tx(bar_bfull + 8 * sb, C::B_STAGE);
-        bulk_g2s(tilesB + sb * C::B_STAGE, gB + (size_t)kb * C::B_STAGE, C::B_STAGE, bar_bfull + 8 * sb);
+        const int st = kb % G, u = kb / G;
+        if (u > 0) mbar_wait(bar_empty + 8 * st, (uint32_t)((u - 1) & 1));
+        mbar_expect_tx(bar_full + 8 * st, C::B_STAGE);
+        bulk_g2s(tiles + st * C::STAGE + C::A_STAGE, gB + (size_t)kb * C::B_STAGE, C::B_STAGE,
+                 bar_full + 8 * st);
       }
+    } else if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) mbar_arrive(bar_full + 8 * (kb % G));  // timing experiments only
     }
   } else if (warp == NPROD / 32) {
     // ================================ MMA ISSUER ======================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int sa = kb % SA, ua = kb / SA, sb = kb % SB, ub = kb / SB;
-        const bool prof_w = p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && kb < 128;
-        if (prof_w) p.prof[2048 + kb * 4 + 3] = clock64();
-        mbar_wait(bar_afull + 8 * sa, (uint32_t)(ua & 1));
-        const bool prof_i = p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && kb < 128;
-        if (prof_i) p.prof[2048 + kb * 4 + 0] = clock64();
-        if (!(p.debug & 16)) mbar_wait(bar_bfull + 8 * sb, (uint32_t)(ub & 1));
-        if (prof_i) p.prof[2048 + kb * 4 + 1] = clock64();
-        tc_fence_after();
-        const uint32_t abase = tiles + sa * C::A_STAGE, bbase = tilesB + sb * C::B_STAGE;
-        const uint64_t a_hi = make_desc(abase), a_lo = make_desc(abase + C::A_BYTES);
-        const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + BN * 128);
-        const int krem = K - kb * BK;
-        const int ksteps = krem >= BK ? BK / 8 : (krem + 7) / 8;
-        if (!(p.debug & 1)) {
-          // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzled row per step
-          umma_tf32(d_corr, a_lo, b_hi, idesc, kb != 0);
-          umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
-          umma_tf32(d_main, a_hi, b_hi, idesc, kb != 0);
+      mbar_wait(bar_full, 0);
+      for (int kb0 = 0; kb0 < nkb; kb0 += G) {
+        const uint32_t par = (uint32_t)((kb0 / G) & 1);
 #pragma unroll
-          for (int ks = 1; ks < BK / 8; ++ks) {
-            if (ks < ksteps) {
-              umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
-              umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
-              umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+        for (int st = 0; st < G; ++st) {  // stage index is compile-time: descriptors fold to constants + base
+          const int kb = kb0 + st;
+          if (kb < nkb) {
+            RCV_PROF_I(0);
+            tc_fence_after();
+            const uint32_t abase = tiles + st * C::STAGE, bbase = abase + C::A_STAGE;
+            const uint64_t a_hi = make_desc(abase), a_lo = make_desc(abase + C::A_BYTES);
+            const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + BN * 128);
+            const int krem = K - kb * BK;
+            const int ksteps = krem >= BK ? BK / 8 : (krem + 7) / 8;
+            if (!(p.debug & 1)) {
+              // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzled row per step
+              umma_tf32(d_corr, a_lo, b_hi, idesc, kb != 0);
+              umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+              umma_tf32(d_main, a_hi, b_hi, idesc, kb != 0);
+#pragma unroll
+              for (int ks = 1; ks < BK / 8; ++ks) {
+                if (ks < ksteps) {
+                  umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+                  umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+                  umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+                }
+              }
             }
+            RCV_PROF_I(1);
+            // poll the next block's operands while this block's MMAs drain from the queue; the
+            // commit below frees a stage the next block does not depend on
+            if (kb + 1 < nkb)
+              mbar_wait(bar_full + 8 * ((st + 1) % G), st + 1 == G ? par ^ 1u : par);
+            RCV_PROF_I(2);
+            umma_commit(bar_empty + 8 * st);
+            if (kb == nkb - 1) umma_commit(bar_done);
+            RCV_PROF_I(3);
           }
         }
-        umma_commit(bar_emptyA + 8 * sa);
-        umma_commit(bar_emptyB + 8 * sb);
-        if (kb == nkb - 1) umma_commit(bar_done);
-        if (prof_i) p.prof[2048 + kb * 4 + 2] = clock64();
       }
     }
   } else {
@@ -250,16 +274,15 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
       }
     }
     const bool uni = (CA % BK) == 0;  // every K block lies inside one tap
-    unsigned char* a_hi = gen_tiles + grp * C::A_STAGE;
+    unsigned char* a_hi = gen_tiles + grp * C::STAGE;
     unsigned char* a_lo = a_hi + C::A_BYTES;
-    const uint32_t my_full = bar_afull + 8 * grp, my_empty = bar_emptyA + 8 * grp;
+    const uint32_t my_full = bar_full + 8 * grp, my_empty = bar_empty + 8 * grp;
     // (tap, channel) of this group's next K block on the uniform path
     int tap = (grp * BK) / CA, ca = (grp * BK) % CA;
 
-    const bool prof_p = p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && row == 0;
     for (int kb = grp, use = 0; kb < nkb; kb += G, ++use) {
       float va[BK];
-      if (prof_p && kb < 128) p.prof[kb * 8 + 0] = clock64();
+      RCV_PROF_P(0);
       if (p.debug & 2) {
 #pragma unroll
         for (int i = 0; i < BK; ++i) va[i] = 1.f;
@@ -280,9 +303,9 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
                                           : 0.f;
         }
       }
-      if (prof_p && kb < 128) p.prof[kb * 8 + 1] = clock64();
+      RCV_PROF_P(1);
       if (use > 0) mbar_wait(my_empty, (uint32_t)((use - 1) & 1));
-      if (prof_p && kb < 128) p.prof[kb * 8 + 2] = clock64();
+      RCV_PROF_P(2);
       if (!(p.debug & 4))
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -295,18 +318,18 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
         *reinterpret_cast<float4*>(a_hi + off) = h;
         *reinterpret_cast<float4*>(a_lo + off) = l;
       }
-      if (prof_p && kb < 128) p.prof[kb * 8 + 3] = clock64() + (long long)(va[0] == 12345.f);
+      RCV_PROF_P(3);
       fence_proxy_async_smem();
-      if (prof_p && kb < 128) p.prof[kb * 8 + 4] = clock64();
+      RCV_PROF_P(4);
       __syncwarp();
       if (lane == 0) mbar_arrive(my_full);
-      if (prof_p && kb < 128) p.prof[kb * 8 + 5] = clock64();
+      RCV_PROF_P(5);
     }
 
     // ================================ EPILOGUE ========================================
-    if (prof_p) p.prof[4000 + grp * 4 + 0] = clock64();
+    RCV_PROF_E(0);
     mbar_wait(bar_done, 0);
-    if (prof_p) p.prof[4000 + grp * 4 + 1] = clock64();
+    RCV_PROF_E(1);
     tc_fence_after();
     const int epi = p.epilogue;
     const int HWo = p.Hout * p.Wout;
@@ -318,44 +341,54 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
     }
     // warps of different groups share TMEM lanes 32*(w%4)..+31 and interleave the 16-column chunks
     const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const bool has_res = p.residual != nullptr, has_stats = p.stats != nullptr;
 #pragma unroll 1
     for (int c0 = grp * 16; c0 < BN; c0 += G * 16) {
       if (n0 + c0 >= p.CB || (p.debug & 32)) break;  // warp-uniform
       uint32_t rm[16], rc[16];
       tmem_ld16_nowait(trow + c0, rm);
       tmem_ld16_nowait(trow + BN + c0, rc);
+      const int nvalid = min(16, p.CB - (n0 + c0));  // channels of this chunk that exist
+      float* optr = p.out + obase + (size_t)(n0 + c0) * HWo;
+      const float* rptr = has_res ? p.residual + obase + (size_t)(n0 + c0) * HWo : nullptr;
+      float res[16];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) res[j] = (mrow && j < nvalid) ? __ldg(rptr + (size_t)j * HWo) : 0.f;
+      }
       tmem_ld_wait();
-      float s1[16], s2[16];
+      float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int co = n0 + c0 + j;
-        float v = 0.f;
-        if (mrow && co < p.CB) {
-          const float bi = p.bias ? __ldg(p.bias + co) : 0.f;
-          const float sc = p.scale ? __ldg(p.scale + co) : 1.f;
-          const float sh = p.shift ? __ldg(p.shift + co) : 0.f;
-          const size_t off = obase + (size_t)co * HWo;
-          v = apply_epi(__uint_as_float(rm[j]) + __uint_as_float(rc[j]) + bi, epi, sc, sh);
-          if (p.residual) v += __ldg(p.residual + off);
-          p.out[off] = v;
-        }
-        s1[j] = v;
-        s2[j] = v * v;
+        const float acc = __uint_as_float(rm[j]) + __uint_as_float(rc[j]) + s_cst[c0 + j];
+        float y = apply_epi(acc, epi, s_cst[BN + c0 + j], s_cst[2 * BN + c0 + j]);
+        if (has_res) y += res[j];
+        v[j] = (mrow && j < nvalid) ? y : 0.f;
       }
-      if (p.stats) {
-        warp_transpose_reduce16(s1, lane);
+      if (mrow) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) optr[(size_t)j * HWo] = v[j];
+      }
+      if (has_stats) {
+        float s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s2[j] = v[j] * v[j];
+        warp_transpose_reduce16(v, lane);
         warp_transpose_reduce16(s2, lane);
         const int co = n0 + c0 + (lane >> 1);
         if ((lane & 1) == 0 && co < p.CB) {
-          atomicAdd(p.stats + co, (double)s1[0]);
+          atomicAdd(p.stats + co, (double)v[0]);
           atomicAdd(p.stats + p.CB + co, (double)s2[0]);
         }
       }
     }
   }
 
+#if RCV_PROF
   if (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tid & 127) == 0 && tid < NPROD)
     p.prof[4000 + (tid >> 7) * 4 + 2] = clock64();
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == NPROD / 32) {
@@ -485,12 +518,12 @@ int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
   RCV_REQUIRE(p.wpacked != nullptr, RCV_ERR_BAD_ARG,
               "tensor-core conv needs packed weights (rcv_conv_pack); none were given");
   RCV_REQUIRE(((uintptr_t)p.wpacked & 127) == 0, RCV_ERR_BAD_ARG, "packed weights must be 128-byte aligned");
-  // Long reductions: 4 producer groups (A ring of 4 stages, one CTA per SM).  Short ones (a few
-  // K blocks per tile): 2 groups so that 2-3 CTAs share an SM and overlap prologue / epilogue.
+  // Ring depth = producer groups.  Long reductions: 3-4 stages, one CTA per SM.  Short ones (a few
+  // K blocks per tile): 2 stages so that 2 CTAs share an SM and overlap prologue / epilogue.
   const int bn = umma_bn(p.CB);
-  const bool deep = g_force_g > 0 ? g_force_g == 4 : (int64_t)p.CA * max_taps(p) > 10 * BK;
+  const bool deep = g_force_g > 0 ? g_force_g >= 3 : (int64_t)p.CA * max_taps(p) > 10 * BK;
   switch (bn) {
-    case 128: return launch_bn<128, 4>(p, st);
+    case 128: return launch_bn<128, 3>(p, st);
     case 64: return deep ? launch_bn<64, 4>(p, st) : launch_bn<64, 2>(p, st);
     case 32: return deep ? launch_bn<32, 4>(p, st) : launch_bn<32, 2>(p, st);
     default: return deep ? launch_bn<16, 4>(p, st) : launch_bn<16, 2>(p, st);

@@ -29,10 +29,10 @@ print("producer (row 0 of each group): kb: start loads_issued(+) wait_empty(+) s
 for kb in range(min(nkb, 128)):
     e = [int(v) for v in pr[kb * 8: kb * 8 + 6]]
     print(f"  kb {kb:3d}: {e[0]-t0:7d} " + " ".join(f"+{e[i+1]-e[i]:5d}" for i in range(5)))
-print("issuer: kb: start(before afull wait) afull_wait(+) bfull_wait(+) issue+commit(+)")
+print("issuer: kb: start  mma_issue(+) next_full_wait(+) commits(+)")
 for kb in range(min(nkb, 128)):
     e = [int(v) for v in pr[2048 + kb * 4: 2048 + kb * 4 + 4]]
-    print(f"  kb {kb:3d}: {e[3]-t0:7d} +{e[0]-e[3]:5d} +{e[1]-e[0]:5d} +{e[2]-e[1]:5d}")
+    print(f"  kb {kb:3d}: {e[0]-t0:7d} +{e[1]-e[0]:5d} +{e[2]-e[1]:5d} +{e[3]-e[2]:5d}")
 for g in range(4):
     e = [int(v) for v in pr[4000 + g * 4: 4000 + g * 4 + 3]]
     if e[0]:
