@@ -1,16 +1,17 @@
 // Weight gradient on the tensor cores (tcgen05 3xTF32, TMEM accumulators):
 //   dW[cb][k = (ca, tap)] = sum over pixels m of  row[m][cb] * gathered[m][k]
-// as a GEMM whose REDUCTION runs over pixels: D[128 x 128] += A[cb][32 px] * B[k][32 px]^T.
-// Both operands are pixel-contiguous in NCHW, i.e. naturally K-major for this GEMM:
-//   A rows = channels of the dense tensor (dy for a conv): float4 loads along pixels;
-//   B rows = (channel, tap) slices of the gathered tensor (x for a conv), shifted by the tap and
-//            zero outside the image: 4-byte loads, lanes along pixels.
-// A CTA owns one 128-wide k tile and a contiguous pixel range (split-K over pixels across the
-// grid); G producer groups of 128 threads each stage whole pixel chunks (hi / lo tf32 parts,
-// 128B-swizzled K-major tiles), one thread issues the MMAs, and the epilogue transposes the
-// accumulator through shared memory so that the fp32 RED atomics into dW are coalesced.
-// Bias gradient (sum of the dense tensor over pixels) is accumulated by the A loaders of the
-// first k tile.
+// as a GEMM whose REDUCTION runs over pixels:  D[k][cb] += A[k][32 px] * B[cb][32 px]^T
+//   A (MMA M = 128 rows) = (channel, tap) slices of the gathered tensor (x for a conv), shifted by
+//       the tap and zero outside the image: 4-byte loads, lanes along pixels;
+//   B (MMA N = BN rows)  = channels of the dense tensor (dy for a conv): float4 loads along pixels.
+// Both operands are pixel-contiguous in NCHW, i.e. naturally K-major for this GEMM.  Putting the
+// (channel, tap) rows on M keeps the tile full for every layer (N = 16..128 follows Cout), and makes
+// the accumulator rows consecutive weights: the epilogue's fp32 RED atomics (lanes = TMEM lanes =
+// consecutive k) are coalesced without a transposition.
+// A CTA owns one 128-row k tile x one BN-wide channel tile and a contiguous pixel range (split over
+// pixels across the grid); G producer groups of 128 threads each stage whole 32-pixel chunks
+// (hi / lo tf32 parts, 128B-swizzled K-major tiles), one thread issues the MMAs.  The bias
+// gradient (sum of the dense tensor over pixels) is accumulated by the B loaders of k tile 0.
 #include "rcv_common.cuh"
 #include "rcv_umma.cuh"
 
@@ -18,31 +19,41 @@ using namespace rcv_umma;
 
 namespace {
 
-constexpr int BM = 128;        // dense-tensor channels per tile (MMA M)
-constexpr int BN = 128;        // (channel, tap) rows per tile (MMA N)
+constexpr int BM = 128;        // (channel, tap) rows per tile (MMA M)
 constexpr int BK = 32;         // pixels per chunk: one 128-byte swizzle row
-constexpr int G = 3;           // producer groups = ring depth
 constexpr int GTHREADS = 128;
-constexpr int NPROD = G * GTHREADS;
-constexpr int NT = NPROD + 32; // + the MMA-issuer warp
-constexpr int TILE = BM * 128; // bytes of one hi or lo operand tile
-constexpr int STAGE = 4 * TILE;  // A hi, A lo, B hi, B lo
-constexpr int TILE_BYTES = G * STAGE;
-constexpr int SMEM = TILE_BYTES + 1024 + 2048;  // + alignment slack + barriers / tables
-constexpr int TCOLS = 2 * BN;
-constexpr int EPITCH = BN + 1;  // transposition buffer pitch (floats)
-static_assert(BM * EPITCH * 4 <= TILE_BYTES, "epilogue buffer fits in the ring");
+constexpr int MAXT = 9;
 
-__global__ void __launch_bounds__(NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
+template <int BN_>
+struct WCfg {
+  static constexpr int BN = BN_;                    // dense-tensor channels per tile (MMA N)
+  static constexpr int G = BN_ == 128 ? 3 : 4;      // producer groups = ring depth
+  static constexpr int NPROD = G * GTHREADS;
+  static constexpr int NT = NPROD + 32;             // + the MMA-issuer warp
+  static constexpr int A_TILE = BM * 128;           // bytes of the hi or lo gathered tile
+  static constexpr int B_TILE = BN_ * 128;
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;  // A hi, A lo, B hi, B lo
+  static constexpr int TILE_BYTES = G * STAGE;
+  static constexpr int SMEM = TILE_BYTES + 1024 + 2048;  // + alignment slack + barriers / tables
+  static constexpr int TCOLS = 2 * BN_ < 32 ? 32 : 2 * BN_;
+  static constexpr int BROWS = BN_ / 16;            // dense rows per loader thread
+};
+
+template <int BN>
+__global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
+  using C = WCfg<BN>;
+  constexpr int G = C::G, NPROD = C::NPROD, NT = C::NT;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
   unsigned char* gen_tiles = smem_raw + (tiles - raw);
-  unsigned char* misc = gen_tiles + TILE_BYTES;
+  unsigned char* misc = gen_tiles + C::TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // full[G] empty[G] done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 64);
-  int2* s_tab = reinterpret_cast<int2*>(misc + 128);    // [BN] (element offset, tap | 31)
-  int* s_wo = reinterpret_cast<int*>(misc + 128 + BN * 8);  // [BN] weight offset of row k, -1 beyond K
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 96);
+  int2* s_tab = reinterpret_cast<int2*>(misc + 128);    // [BM] (element offset, tap | 31)
+  int* s_wo = reinterpret_cast<int*>(misc + 128 + BM * 8);  // [BM] weight offset of row k, -1 beyond K
+  int* s_tdy = s_wo + BM;                               // [MAXT] tap offsets (avoids indexing the params)
+  int* s_tdx = s_tdy + 16;
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * G, bar_done = bar_empty + 8 * G;
 
   const int tid = threadIdx.x;
@@ -52,13 +63,13 @@ __global__ void __launch_bounds__(NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
   const int HWin = p.Hin * p.Win;
   const int HWg = p.Hg * p.Wg;
   const int M = p.N * HWg;
-  const int k0 = blockIdx.x * BN;
-  const int cb0 = blockIdx.y * BM;
+  const int k0 = blockIdx.x * BM;
+  const int cb0 = blockIdx.y * BN;
   const int mbeg = blockIdx.z * p.slab;
   const int mend = min(M, mbeg + p.slab);
   const int nchunks = (mend - mbeg + BK - 1) / BK;
 
-  for (int kl = tid; kl < BN; kl += NT) {
+  for (int kl = tid; kl < BM; kl += NT) {
     const int k = k0 + kl;
     if (k < K) {
       const int ca = k / T, t = k - ca * T;
@@ -69,11 +80,15 @@ __global__ void __launch_bounds__(NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
       s_wo[kl] = -1;
     }
   }
-  // rows of A beyond the dense tensor's channel count stay zero for the whole kernel
-  if (cb0 + BM > p.CB) {
+  if (tid < MAXT) {
+    s_tdy[tid] = tid < T ? p.taps.dy[tid] : 0;
+    s_tdx[tid] = tid < T ? p.taps.dx[tid] : 0;
+  }
+  // rows of B beyond the dense tensor's channel count stay zero for the whole kernel
+  if (cb0 + BN > p.CB) {
     for (int g = 0; g < G; ++g) {
-      float4* a = reinterpret_cast<float4*>(gen_tiles + g * STAGE);
-      for (int i = tid; i < 2 * TILE / 16; i += NT) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4* b = reinterpret_cast<float4*>(gen_tiles + g * C::STAGE + 2 * C::A_TILE);
+      for (int i = tid; i < 2 * C::B_TILE / 16; i += NT) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   if (tid == 0) {
@@ -84,7 +99,7 @@ __global__ void __launch_bounds__(NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == NPROD / 32) tmem_alloc(smem_u32(tmem_slot), TCOLS);
+  if (warp == NPROD / 32) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -93,63 +108,71 @@ __global__ void __launch_bounds__(NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
 
   if (warp == NPROD / 32) {
     // ================================ MMA ISSUER ======================================
-    if (lane == 0) {
+    if (lane == 0 && nchunks > 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % G, u = c / G;
-        mbar_wait(bar_full + 8 * s, (uint32_t)(u & 1));
-        tc_fence_after();
-        const uint32_t base = tiles + s * STAGE;
-        const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + TILE);
-        const uint64_t b_hi = make_desc(base + 2 * TILE), b_lo = make_desc(base + 3 * TILE);
-        umma_tf32(d_corr, a_lo, b_hi, idesc, c != 0);
-        umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
-        umma_tf32(d_main, a_hi, b_hi, idesc, c != 0);
+      mbar_wait(bar_full, 0);
+      for (int c0 = 0; c0 < nchunks; c0 += G) {
+        const uint32_t par = (uint32_t)((c0 / G) & 1);
 #pragma unroll
-        for (int ks = 1; ks < BK / 8; ++ks) {
-          umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
-          umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
-          umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+        for (int st = 0; st < G; ++st) {
+          const int c = c0 + st;
+          if (c < nchunks) {
+            tc_fence_after();
+            const uint32_t base = tiles + st * C::STAGE;
+            const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + C::A_TILE);
+            const uint64_t b_hi = make_desc(base + 2 * C::A_TILE), b_lo = make_desc(base + 2 * C::A_TILE + C::B_TILE);
+            umma_tf32(d_corr, a_lo, b_hi, idesc, c != 0);
+            umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_main, a_hi, b_hi, idesc, c != 0);
+#pragma unroll
+            for (int ks = 1; ks < BK / 8; ++ks) {
+              umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+              umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+              umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+            }
+            if (c + 1 < nchunks) mbar_wait(bar_full + 8 * ((st + 1) % G), st + 1 == G ? par ^ 1u : par);
+            umma_commit(bar_empty + 8 * st);
+            if (c == nchunks - 1) umma_commit(bar_done);
+          }
         }
-        umma_commit(bar_empty + 8 * s);
-        if (c == nchunks - 1) umma_commit(bar_done);
       }
     }
   } else {
     // ================================ PRODUCERS =======================================
     const int gt = tid & (GTHREADS - 1);
     const int grp = tid / GTHREADS;
-    unsigned char* st = gen_tiles + grp * STAGE;
+    unsigned char* st = gen_tiles + grp * C::STAGE;
+    unsigned char* sb = st + 2 * C::A_TILE;
     const uint32_t my_full = bar_full + 8 * grp, my_empty = bar_empty + 8 * grp;
-    // A loader mapping: 16-byte chunk ac of rows ar0 + 16*i (a warp covers 4 rows x 128 B)
-    const int ac = gt & 7, ar0 = gt >> 3;
-    // B loader mapping: pixel = lane, rows bw + 4*i
-    const int bw = gt >> 5;
+    // dense (B) loader mapping: 16-byte chunk bc of rows br0 + 16*i (a warp covers 4 rows x 128 B)
+    const int bc = gt & 7, br0 = gt >> 3;
+    // gathered (A) loader mapping: pixel = lane, rows aw + 4*i
+    const int aw = gt >> 5;
     const bool do_bias = p.dbias != nullptr && blockIdx.x == 0;
-    float bsum[8];
+    float bsum[C::BROWS];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+    for (int i = 0; i < C::BROWS; ++i) bsum[i] = 0.f;
 
     for (int c = grp, use = 0; c < nchunks; c += G, ++use) {
       const int mc = mbeg + c * BK;
-      // ---- A: dense tensor, rows = channels, float4 along pixels ----
-      float4 ra[8];
+      // ---- B: dense tensor, rows = channels, float4 along pixels ----
+      float4 rb[C::BROWS];
       {
-        const int m = mc + ac * 4;  // HWg % 4 == 0: a quad never straddles two images
+        const int m = mc + bc * 4;  // HWg % 4 == 0: a quad never straddles two images
         const bool ok = m < mend;
         int n = 0, r = 0;
         if (ok) { n = m / HWg; r = m - n * HWg; }
         const float* src = p.row + ((size_t)n * p.CB + cb0) * HWg + r;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rowc = ar0 + 16 * i;
-          ra[i] = (ok && cb0 + rowc < p.CB) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)rowc * HWg))
+        for (int i = 0; i < C::BROWS; ++i) {
+          const int rowc = br0 + 16 * i;
+          rb[i] = (ok && cb0 + rowc < p.CB) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)rowc * HWg))
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      // ---- B: gathered tensor, rows = (channel, tap), lanes along pixels ----
-      float rb[32];
+      // ---- A: gathered tensor, rows = (channel, tap), lanes along pixels ----
+      float ra[32];
       {
         const int m = mc + lane;
         const bool ok = m < mend;
@@ -164,41 +187,41 @@ __global__ void __launch_bounds__(NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
         uint32_t tapmask = 0;
         if (ok) {
           for (int t = 0; t < T; ++t) {
-            const int iy = gy0 + p.taps.dy[t], ix = gx0 + p.taps.dx[t];
+            const int iy = gy0 + s_tdy[t], ix = gx0 + s_tdx[t];
             if ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) tapmask |= 1u << t;
           }
         }
         const float* src = p.src + (size_t)n * p.CA * HWin + gy0 * p.Win + gx0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int2 e = s_tab[bw + 4 * i];
-          rb[i] = ((tapmask >> e.y) & 1u) ? __ldg(src + e.x) : 0.f;
+          const int2 e = s_tab[aw + 4 * i];
+          ra[i] = ((tapmask >> e.y) & 1u) ? __ldg(src + e.x) : 0.f;
         }
       }
       if (use > 0) mbar_wait(my_empty, (uint32_t)((use - 1) & 1));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rowc = ar0 + 16 * i;
+      for (int i = 0; i < C::BROWS; ++i) {
+        const int rowc = br0 + 16 * i;
         if (cb0 + rowc < p.CB) {
           float4 h, l;
-          split_tf32(ra[i].x, h.x, l.x);
-          split_tf32(ra[i].y, h.y, l.y);
-          split_tf32(ra[i].z, h.z, l.z);
-          split_tf32(ra[i].w, h.w, l.w);
-          const int off = rowc * 128 + ((ac ^ (rowc & 7)) << 4);
-          *reinterpret_cast<float4*>(st + off) = h;
-          *reinterpret_cast<float4*>(st + TILE + off) = l;
-          bsum[i] += (ra[i].x + ra[i].y) + (ra[i].z + ra[i].w);
+          split_tf32(rb[i].x, h.x, l.x);
+          split_tf32(rb[i].y, h.y, l.y);
+          split_tf32(rb[i].z, h.z, l.z);
+          split_tf32(rb[i].w, h.w, l.w);
+          const int off = rowc * 128 + ((bc ^ (rowc & 7)) << 4);
+          *reinterpret_cast<float4*>(sb + off) = h;
+          *reinterpret_cast<float4*>(sb + C::B_TILE + off) = l;
+          bsum[i] += (rb[i].x + rb[i].y) + (rb[i].z + rb[i].w);
         }
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int rowk = bw + 4 * i;
+        const int rowk = aw + 4 * i;
         float h, l;
-        split_tf32(rb[i], h, l);
+        split_tf32(ra[i], h, l);
         const int off = rowk * 128 + (((lane >> 2) ^ (rowk & 7)) << 4) + (lane & 3) * 4;
-        *reinterpret_cast<float*>(st + 2 * TILE + off) = h;
-        *reinterpret_cast<float*>(st + 3 * TILE + off) = l;
+        *reinterpret_cast<float*>(st + off) = h;
+        *reinterpret_cast<float*>(st + C::A_TILE + off) = l;
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -208,44 +231,36 @@ __global__ void __launch_bounds__(NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
     if (do_bias) {
       // the 8 lanes that share a row (chunks 0..7) are consecutive lanes
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < C::BROWS; ++i) {
         float s = bsum[i];
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
-        const int rowc = ar0 + 16 * i;
-        if (ac == 0 && cb0 + rowc < p.CB && s != 0.f) atomicAdd(p.dbias + cb0 + rowc, s);
+        const int rowc = br0 + 16 * i;
+        if (bc == 0 && cb0 + rowc < p.CB && s != 0.f) atomicAdd(p.dbias + cb0 + rowc, s);
       }
     }
 
     // ================================ EPILOGUE ========================================
+    // thread = accumulator row = one weight offset; consecutive lanes hit consecutive addresses
     if (nchunks > 0) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
-      float* ebuf = reinterpret_cast<float*>(gen_tiles);  // [BM][EPITCH], the ring is free now
-      const int lrow = (warp & 3) * 32 + lane;             // accumulator row = TMEM lane
+      const int lrow = (warp & 3) * 32 + lane;
+      const int wo = s_wo[lrow];
       const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
       for (int c0 = grp * 16; c0 < BN; c0 += G * 16) {
+        if (cb0 + c0 >= p.CB) break;  // warp-uniform
         uint32_t rm[16], rc[16];
         tmem_ld16_nowait(trow + c0, rm);
         tmem_ld16_nowait(trow + BN + c0, rc);
         tmem_ld_wait();
+        if (wo >= 0) {
+          float* dst = p.dw + (size_t)(cb0 + c0) * p.wsB + wo;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          ebuf[lrow * EPITCH + c0 + j] = __uint_as_float(rm[j]) + __uint_as_float(rc[j]);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
-      // coalesced RED: a warp walks the k columns of one accumulator row
-      const int pw = tid >> 5;  // producer warp 0 .. NPROD/32-1
-      for (int rowc = pw; rowc < BM; rowc += NPROD / 32) {
-        if (cb0 + rowc >= p.CB) break;
-        float* dst = p.dw + (size_t)(cb0 + rowc) * p.wsB;
-#pragma unroll
-        for (int q = 0; q < BN / 32; ++q) {
-          const int kl = q * 32 + lane;
-          const int wo = s_wo[kl];
-          if (wo >= 0) atomicAdd(dst + wo, ebuf[rowc * EPITCH + kl]);
+          for (int j = 0; j < 16; ++j)
+            if (cb0 + c0 + j < p.CB) atomicAdd(dst + (size_t)j * p.wsB, __uint_as_float(rm[j]) + __uint_as_float(rc[j]));
         }
       }
     }
@@ -255,34 +270,27 @@ __global__ void __launch_bounds__(NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
   __syncthreads();
   if (warp == NPROD / 32) {
     __syncwarp();
-    tmem_dealloc(tmem_base, TCOLS);
+    tmem_dealloc(tmem_base, C::TCOLS);
   }
 }
 
-}  // namespace
-
-bool rcv_umma_wgrad_pays(const RcvWgrad& p) {
-  const int K = p.CA * p.taps.n;
-  return ((p.Hg * p.Wg) & 3) == 0 && K >= 128 && p.CB >= 16 &&
-         (int64_t)p.N * p.CA * p.Hin * p.Win < (1ll << 31);
-}
-
-int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st) {
+template <int BN>
+int launch_w(RcvWgrad p, cudaStream_t st) {
+  using C = WCfg<BN>;
+  static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
   const int K = p.CA * p.taps.n;
   const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
-  RCV_REQUIRE(M < (1ll << 31), RCV_ERR_UNSUPPORTED, "wgrad: problem too large");
-  RCV_REQUIRE(((p.Hg * p.Wg) & 3) == 0, RCV_ERR_UNSUPPORTED,
-              "tensor-core wgrad needs a pixel count per image that is a multiple of 4 (got %d)", p.Hg * p.Wg);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t e =
+        cudaFuncSetAttribute(umma_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
     if (e != cudaSuccess) {
-      rcv_set_error("umma_wgrad: cannot reserve %d B of shared memory: %s", SMEM, cudaGetErrorString(e));
+      rcv_set_error("umma_wgrad: cannot reserve %d B of shared memory: %s", C::SMEM, cudaGetErrorString(e));
       return RCV_ERR_CUDA;
     }
     attr_done = true;
   }
-  const int tiles = rcv_cdiv(K, BN) * rcv_cdiv(p.CB, BM);
+  const int tiles = rcv_cdiv(K, BM) * rcv_cdiv(p.CB, BN);
   int splits = rcv_cdiv(148, tiles);
   const int max_splits = rcv_cdiv(M, BK * 4);
   if (splits > max_splits) splits = max_splits;
@@ -291,8 +299,28 @@ int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st) {
   slab = ((slab + BK - 1) / BK) * BK;
   splits = rcv_cdiv(M, slab);
   p.slab = slab;
-  dim3 grid(rcv_cdiv(K, BN), rcv_cdiv(p.CB, BM), splits);
-  umma_wgrad_kernel<<<grid, NT, SMEM, st>>>(p);
+  dim3 grid(rcv_cdiv(K, BM), rcv_cdiv(p.CB, BN), splits);
+  umma_wgrad_kernel<BN><<<grid, C::NT, C::SMEM, st>>>(p);
   RCV_CHECK_LAUNCH("umma_wgrad_kernel");
   return RCV_OK;
+}
+
+}  // namespace
+
+bool rcv_umma_wgrad_pays(const RcvWgrad& p) {
+  const int K = p.CA * p.taps.n;
+  return ((p.Hg * p.Wg) & 3) == 0 && K >= 64 && p.CB >= 8 &&
+         (int64_t)p.N * p.CA * p.Hin * p.Win < (1ll << 31);
+}
+
+int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st) {
+  const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
+  RCV_REQUIRE(M < (1ll << 31), RCV_ERR_UNSUPPORTED, "wgrad: problem too large");
+  RCV_REQUIRE(p.taps.n >= 1 && p.taps.n <= MAXT, RCV_ERR_UNSUPPORTED, "wgrad: %d taps", p.taps.n);
+  RCV_REQUIRE(((p.Hg * p.Wg) & 3) == 0, RCV_ERR_UNSUPPORTED,
+              "tensor-core wgrad needs a pixel count per image that is a multiple of 4 (got %d)", p.Hg * p.Wg);
+  if (p.CB > 64) return launch_w<128>(p, st);
+  if (p.CB > 32) return launch_w<64>(p, st);
+  if (p.CB > 16) return launch_w<32>(p, st);
+  return launch_w<16>(p, st);
 }
