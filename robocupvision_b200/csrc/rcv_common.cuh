@@ -81,6 +81,8 @@ struct RcvWgrad {
 extern long long* g_rcv_prof;  // debug: phase-timing buffer (rcv_debug_set_prof)
 int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st);       // dispatch on p.math
 int rcv_launch_igemm_simt(const RcvIgemm& p, cudaStream_t st);  // fp32 FFMA, CUDA cores
+int rcv_launch_direct(const RcvIgemm& p, cudaStream_t st);      // fp32 direct conv, <= 16 output channels
+bool rcv_direct_supported(const RcvIgemm& p);
 int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF32, TMEM accumulators
 bool rcv_umma_pays(const RcvIgemm& p);  // RCV_MATH_AUTO: is the reduction long enough for tensor cores
 bool rcv_umma_supported(const RcvIgemm& p);  // geometry within the tensor-core engine's limits

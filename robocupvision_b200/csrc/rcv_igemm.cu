@@ -12,6 +12,8 @@
 //
 // Epilogue (fused): + bias, ReLU / folded-BN affine in either order, + residual
 // (decoder skip), per-channel sum / sum-of-squares for train-mode BatchNorm.
+#include <stdlib.h>
+
 #include "rcv_common.cuh"
 
 namespace {
@@ -294,6 +296,13 @@ bool rcv_umma_pays(const RcvIgemm& p) {
 int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st) {
   if (p.math == RCV_MATH_TF32X3 || (p.math == RCV_MATH_AUTO && p.wpacked != nullptr && rcv_umma_pays(p)))
     return rcv_launch_igemm_umma(p, st);
+  // narrow layers: direct convolution (RCV_DIRECT=0 keeps the implicit-GEMM engine, for A/B runs)
+  static int use_direct = -1;
+  if (use_direct < 0) {
+    const char* e = getenv("RCV_DIRECT");
+    use_direct = e ? atoi(e) : 1;
+  }
+  if (use_direct && rcv_direct_supported(p)) return rcv_launch_direct(p, st);
   return rcv_launch_igemm_simt(p, st);
 }
 

@@ -202,6 +202,111 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const RcvWgrad p) {
   if (do_bias && cb0 + tid < p.CB) atomicAdd(p.dbias + cb0 + tid, bsum);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tiny weight gradients (<= 8 dense channels: the 3->8 input layer, the 8->5 class head): the
+// whole result is a few dozen numbers reduced over ~10^6 pixels, i.e. a streaming reduction.
+// One thread = one pixel at a time (lanes along pixels: coalesced), T x CBP x CAG accumulators in
+// registers for CAG gathered channels, then shuffle + shared-memory reduction and one atomic per
+// weight per CTA.  blockIdx.y walks the gathered channels in groups of CAG.
+template <int T, int CBP, int CAG>
+__global__ void __launch_bounds__(NT) small_wgrad_kernel(const RcvWgrad p) {
+  constexpr int NACC = CAG * T * CBP;
+  __shared__ float red[NT / 32][NACC + CBP];
+  const int tid = threadIdx.x;
+  const int HWin = p.Hin * p.Win;
+  const int HWg = p.Hg * p.Wg;
+  const int M = p.N * HWg;
+  const int ca0 = blockIdx.y * CAG;
+  const bool do_bias = p.dbias != nullptr && blockIdx.y == 0;
+  float acc[CAG][T][CBP];
+  float bs[CBP];
+#pragma unroll
+  for (int g = 0; g < CAG; ++g)
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int c = 0; c < CBP; ++c) acc[g][t][c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < CBP; ++c) bs[c] = 0.f;
+
+  for (int m = blockIdx.x * NT + tid; m < M; m += gridDim.x * NT) {
+    const int n = m / HWg, r = m - n * HWg;
+    const int i = r / p.Wg, j = r - i * p.Wg;
+    float dyv[CBP];
+#pragma unroll
+    for (int c = 0; c < CBP; ++c) {
+      dyv[c] = c < p.CB ? __ldg(p.row + ((size_t)n * p.CB + c) * HWg + r) : 0.f;
+      bs[c] += dyv[c];
+    }
+    const int gy0 = i * p.gs, gx0 = j * p.gs;
+#pragma unroll
+    for (int g = 0; g < CAG; ++g) {
+      const int ca = ca0 + g;
+      if (ca < p.CA) {
+        const float* src = p.src + ((size_t)n * p.CA + ca) * HWin;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int iy = gy0 + p.taps.dy[t], ix = gx0 + p.taps.dx[t];
+          const float x = ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win)
+                              ? __ldg(src + iy * p.Win + ix) : 0.f;
+#pragma unroll
+          for (int c = 0; c < CBP; ++c) acc[g][t][c] = fmaf(x, dyv[c], acc[g][t][c]);
+        }
+      }
+    }
+  }
+
+  const int lane = tid & 31, wi = tid >> 5;
+#pragma unroll
+  for (int g = 0; g < CAG; ++g)
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+      for (int c = 0; c < CBP; ++c) {
+        float v = acc[g][t][c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[wi][(g * T + t) * CBP + c] = v;
+      }
+#pragma unroll
+  for (int c = 0; c < CBP; ++c) {
+    float v = bs[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wi][NACC + c] = v;
+  }
+  __syncthreads();
+  for (int e = tid; e < NACC + CBP; e += NT) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) v += red[w][e];
+    if (e < NACC) {
+      const int c = e % CBP, t = (e / CBP) % T, g = e / (CBP * T);
+      const int ca = ca0 + g;
+      if (c < p.CB && ca < p.CA) atomicAdd(p.dw + (size_t)c * p.wsB + (size_t)ca * p.wsA + p.taps.wi[t], v);
+    } else if (do_bias) {
+      const int c = e - NACC;
+      if (c < p.CB) atomicAdd(p.dbias + c, v);
+    }
+  }
+}
+
+template <int T, int CBP, int CAG>
+int launch_small(const RcvWgrad& p, cudaStream_t st) {
+  const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
+  RCV_REQUIRE(M < (1ll << 31), RCV_ERR_UNSUPPORTED, "wgrad: problem too large");
+  const int ygroups = rcv_cdiv(p.CA, CAG);
+  int xblocks = rcv_cdiv(148 * 4, ygroups);
+  const int maxx = rcv_cdiv(M, NT);
+  if (xblocks > maxx) xblocks = maxx;
+  if (xblocks < 1) xblocks = 1;
+  dim3 grid(xblocks, ygroups);
+  small_wgrad_kernel<T, CBP, CAG><<<grid, NT, 0, st>>>(p);
+  RCV_CHECK_LAUNCH("small_wgrad_kernel");
+  return RCV_OK;
+}
+
 template <int BMW, int BNW, int TMW, int TNW>
 int launch_cfg(RcvWgrad p, cudaStream_t st) {
   const int K = p.CA * p.taps.n;
@@ -227,6 +332,8 @@ int launch_cfg(RcvWgrad p, cudaStream_t st) {
 int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st) {
   if (p.math == RCV_MATH_TF32X3 || (p.math == RCV_MATH_AUTO && rcv_umma_wgrad_pays(p)))
     return rcv_launch_wgrad_umma(p, st);
+  if (p.CB <= 8 && p.taps.n == 9 && p.CA <= 16) return launch_small<9, 8, 1>(p, st);
+  if (p.CB <= 8 && p.taps.n == 1 && p.CA <= 64) return launch_small<1, 8, 8>(p, st);
   if (p.CB > 64) return launch_cfg<128, 128, 8, 8>(p, st);
   if (p.CB > 32) return launch_cfg<64, 128, 4, 8>(p, st);
   if (p.CB > 16) return launch_cfg<32, 128, 4, 4>(p, st);
