@@ -134,6 +134,21 @@ def test_conv_dgrad_wgrad(geom, cin, cout, engine):
     assert_close(f"bgrad {geom}", db, b.grad, 1e-5)
 
 
+@pytest.mark.parametrize("geom,hw", [("k3s1d1", (18, 24)), ("k3s1d2", (18, 24)), ("k3s1d1", (7, 12)), ("k3s1d2", (5, 8))])
+def test_wgrad_tc_quad_gather(geom, hw):
+    """tensor-core wgrad, aligned-quad gather (stride-1 3x3, W % 4 == 0): row wraps inside a pixel chunk,
+    chunk-edge neighbour loads, several pixel splits, a partial last k tile (47 channels = 141 units)."""
+    from robocupvision_b200 import ops
+    g, x, w, b = _mk(geom, 47, 24, 5, *hw, seed=13)
+    x.requires_grad_(True); w.requires_grad_(True); b.requires_grad_(True)
+    y = _ref_conv(geom, x, w, b)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+    y.backward(dy)
+    dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True, math=1)
+    assert_close(f"wgrad quad {geom} {hw}", dw, w.grad, 1e-5)
+    assert_close("bgrad quad", db, b.grad, 1e-5)
+
+
 def test_wgrad_tc_split_and_tail():
     """tensor-core wgrad: several pixel splits, k tiles with a ragged tail, pixel count not a multiple of 32."""
     from robocupvision_b200 import ops

@@ -8,22 +8,28 @@ sys.path.insert(0, str(ROOT))
 import torch
 from robocupvision_b200 import _lib, ops
 
-cin, cout, h, w, B = (int(a) for a in sys.argv[1:6]) if len(sys.argv) > 5 else (128, 128, 15, 20, 64)
+mode = "wgrad" if "wgrad" in sys.argv else "fwd"
+nums = [a for a in sys.argv[1:] if a.isdigit()]
+cin, cout, h, w, B = (int(a) for a in nums[:5]) if len(nums) >= 5 else (128, 128, 15, 20, 64)
 lib = _lib.load()
 lib.rcv_debug_set_prof.argtypes = [C.c_void_p]
 lib.rcv_debug_set_prof.restype = None
 geo = ops.ConvGeom(cin, cout, 3, 1, 1, 1, False)
 x = torch.randn(B, cin, h, w, device="cuda"); wt = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
 wp = ops.conv_pack(geo, wt, ops.PACK_FWD)
+dy = torch.randn(B, cout, h, w, device="cuda"); dw = torch.zeros_like(wt)
+run = (lambda: ops.conv_wgrad(geo, x, dy, dw=dw, math=ops.MATH_TF32X3)) if mode == "wgrad" else \
+      (lambda: ops.conv_fwd(geo, x, wt, None, math=ops.MATH_TF32X3, wpacked=wp))
 for _ in range(3):
-    ops.conv_fwd(geo, x, wt, None, math=ops.MATH_TF32X3, wpacked=wp)
+    run()
 prof = torch.zeros(8192, dtype=torch.int64, device="cuda")
 lib.rcv_debug_set_prof(C.c_void_p(prof.data_ptr()))
-ops.conv_fwd(geo, x, wt, None, math=ops.MATH_TF32X3, wpacked=wp)
+run()
 torch.cuda.synchronize()
 lib.rcv_debug_set_prof(None)
 pr = prof.cpu().numpy()
-nkb = (cin * 9 + 31) // 32
+nkb = (cin * 9 + 31) // 32 if mode == 'fwd' else 48
+nkb = max([kb for kb in range(128) if pr[kb * 8]] + [0]) + 1
 t0 = min(int(pr[kb * 8]) for kb in range(min(nkb, 128)) if pr[kb * 8])
 print("producer (row 0 of each group): kb: start loads_issued(+) wait_empty(+) stores(+) fence(+) arrive(+)")
 for kb in range(min(nkb, 128)):
