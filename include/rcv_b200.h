@@ -107,6 +107,18 @@ int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction);
 int rcv_conv_pack(const rcv_conv_desc* d, int direction, const float* w,
                   void* packed, void* stream);
 
+/* Batched form: the panels of many layers in ONE launch (a train step re-packs every layer's
+ * weights each step).  The caller builds a job table on the host once -- the weight and panel
+ * device pointers must stay valid and unchanged -- copies it to device memory it owns
+ * (rcv_conv_pack_table_bytes(n) bytes), and runs it on a stream whenever the weights changed.
+ * njobs <= 128. */
+size_t rcv_conv_pack_table_bytes(int32_t njobs);
+int rcv_conv_pack_table_build(int32_t njobs, const rcv_conv_desc* descs,
+                              const int32_t* directions, const float* const* weights,
+                              void* const* packed, void* host_table, int64_t* total_chunks);
+int rcv_conv_pack_table_run(const void* device_table, int32_t njobs,
+                            int64_t total_chunks, void* stream);
+
 /* y = EPI(conv(x,w) + bias) [+ residual].  wpacked (rcv_conv_pack of w,
  * RCV_PACK_FWD) may be NULL: the call then runs on CUDA cores (RCV_MATH_TF32X3
  * without it is RCV_ERR_BAD_ARG).  bias, scale, shift, residual,
@@ -160,6 +172,15 @@ int rcv_bn_fold(int32_t C, const float* gamma, const float* beta,
 int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z,
                  const float* scale, const float* shift, int relu,
                  const float* residual, float* y, void* stream);
+
+/* rcv_bn_finalize + rcv_bn_apply in one launch (the train-mode forward of a BatchNorm node):
+ * every block derives scale/shift from stats; block 0 also writes scale, shift, save_mean,
+ * save_invstd (for the backward pass) and updates the running statistics. */
+int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const double* stats,
+                          const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, float momentum, float eps, const float* z,
+                          int relu, const float* residual, float* y, float* scale,
+                          float* shift, float* save_mean, float* save_invstd, void* stream);
 
 /* Backward of y = act(scale*z+shift) composed with the producer's own ReLU.
  * order = RCV_EPI_RELU_AFFINE: z = relu(conv), y = bn(z)      (model.py:116)

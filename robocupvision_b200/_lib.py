@@ -50,12 +50,18 @@ SIGNATURES = {
     "rcv_conv_packed_bytes": [C.POINTER(ConvDesc), C.c_int],
     "rcv_conv_uses_tensor_cores": [C.POINTER(ConvDesc), C.c_int],
     "rcv_conv_pack": [C.POINTER(ConvDesc), C.c_int, _p, _p, _p],
+    "rcv_conv_pack_table_bytes": [_i32],
+    "rcv_conv_pack_table_build": [_i32, C.POINTER(ConvDesc), C.POINTER(_i32), C.POINTER(_p), C.POINTER(_p), _p,
+                                  C.POINTER(_i64)],
+    "rcv_conv_pack_table_run": [_p, _i32, _i64, _p],
     "rcv_conv_fwd": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p],
     "rcv_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "rcv_bn_finalize": [_i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p],
     "rcv_bn_fold": [_i32, _p, _p, _p, _p, _f32, _p, _p, _p],
     "rcv_bn_apply": [_i32, _i32, _i64, _p, _p, _p, C.c_int, _p, _p, _p],
+    "rcv_bn_finalize_apply": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, C.c_int, _p, _p, _p, _p, _p,
+                              _p, _p],
     "rcv_bn_bwd_reduce": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_bn_bwd_apply": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_relu_bwd": [_i64, _p, _p, _p, _p],
@@ -69,7 +75,8 @@ SIGNATURES = {
     "rcv_counter_add": [_p, _i32, _p],
     "rcv_sgd_step": [_i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, C.c_int, _p],
 }
-_RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t}
+_RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t,
+             "rcv_conv_pack_table_bytes": C.c_size_t}
 PACK_FWD, PACK_DGRAD = 0, 1
 ABI_VERSION = 2
 

@@ -216,6 +216,39 @@ extern "C" int rcv_conv_pack(const rcv_conv_desc* d, int direction, const float*
   return rcv_launch_umma_pack(p, packed, (cudaStream_t)stream);
 }
 
+extern "C" size_t rcv_conv_pack_table_bytes(int32_t njobs) {
+  return njobs > 0 ? (size_t)njobs * sizeof(RcvPackJob) : 0;
+}
+
+extern "C" int rcv_conv_pack_table_build(int32_t njobs, const rcv_conv_desc* descs, const int32_t* directions,
+                                         const float* const* weights, void* const* packed, void* host_table,
+                                         int64_t* total_chunks) {
+  RCV_REQUIRE(njobs >= 1 && njobs <= RCV_PACK_MAX_JOBS, RCV_ERR_BAD_ARG, "pack table: %d jobs (1..%d)", njobs,
+              RCV_PACK_MAX_JOBS);
+  RCV_REQUIRE(descs && directions && weights && packed && host_table && total_chunks, RCV_ERR_BAD_ARG,
+              "pack table: null argument");
+  RcvPackJob* jobs = reinterpret_cast<RcvPackJob*>(host_table);
+  long long begin = 0;
+  for (int j = 0; j < njobs; ++j) {
+    RcvIgemm p;
+    int rc = pack_problem(&descs[j], directions[j], &p, "rcv_conv_pack_table_build");
+    if (rc) return rc;
+    RCV_REQUIRE(weights[j] && packed[j], RCV_ERR_BAD_ARG, "pack table: null tensor in job %d", j);
+    p.w = weights[j];
+    rc = rcv_umma_pack_job(p, packed[j], begin, &jobs[j]);
+    if (rc) return rc;
+    begin += jobs[j].chunks;
+  }
+  *total_chunks = begin;
+  return RCV_OK;
+}
+
+extern "C" int rcv_conv_pack_table_run(const void* device_table, int32_t njobs, int64_t total_chunks, void* stream) {
+  RCV_REQUIRE(device_table != nullptr, RCV_ERR_BAD_ARG, "pack table: null device table");
+  return rcv_launch_umma_pack_multi(reinterpret_cast<const RcvPackJob*>(device_table), njobs, total_chunks,
+                                    (cudaStream_t)stream);
+}
+
 extern "C" int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float* w, const void* wpacked,
                             const float* bias, const float* scale, const float* shift,
                             const float* residual, float* y, double* stats, void* stream) {

@@ -94,6 +94,65 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(int64_t total, int C, int6
   }
 }
 
+// bn_finalize fused into bn_apply: each block re-derives the per-channel scale / shift from the fp64
+// statistics (C <= 1024 values: negligible next to the streaming pass) into shared memory; block 0
+// publishes them for the backward pass and updates the running statistics.
+template <bool VEC>
+__global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
+    int64_t total, int C, int64_t HW, double count, const double* __restrict__ stats,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
+    float momentum, float eps, const float* __restrict__ z, int relu, const float* __restrict__ residual,
+    float* __restrict__ y, float* scale_out, float* shift_out, float* save_mean, float* save_invstd) {
+  extern __shared__ float s_ss[];  // [2][C]
+  for (int c = threadIdx.x; c < C; c += NT) {
+    const double mean = stats[c] / count;
+    double var = stats[C + c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float sc = g * invstd;
+    const float sh = b - (float)mean * sc;
+    s_ss[c] = sc;
+    s_ss[C + c] = sh;
+    if (blockIdx.x == 0) {
+      scale_out[c] = sc;
+      shift_out[c] = sh;
+      if (save_mean) save_mean[c] = (float)mean;
+      if (save_invstd) save_invstd[c] = invstd;
+      if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      if (running_var) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  if (VEC) {
+    const int64_t hw4 = HW >> 2, tot4 = total >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < tot4; i += stride) {
+      const int c = (int)((i / hw4) % C);
+      const float sc = s_ss[c], sh = s_ss[C + c];
+      float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
+      v.x = fmaf(sc, v.x, sh); v.y = fmaf(sc, v.y, sh); v.z = fmaf(sc, v.z, sh); v.w = fmaf(sc, v.w, sh);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (residual) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(residual) + i);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      reinterpret_cast<float4*>(y)[i] = v;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+      const int c = (int)((i / HW) % C);
+      float v = fmaf(s_ss[c], z[i], s_ss[C + c]);
+      if (relu) v = fmaxf(v, 0.f);
+      if (residual) v += residual[i];
+      y[i] = v;
+    }
+  }
+}
+
 // One channel per blockIdx.x, blockIdx.y splits the N*HW elements of the channel.
 // PASS 0: reduce (sum g, sum g*xhat).  PASS 1: apply + dbias.
 template <int PASS>
@@ -275,6 +334,29 @@ extern "C" int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z, co
     bn_apply_kernel<false><<<ew_blocks(total), NT, 0, (cudaStream_t)stream>>>(
         total, C, HW, z, scale, shift, relu, residual, y);
   RCV_CHECK_LAUNCH("bn_apply");
+  return RCV_OK;
+}
+
+extern "C" int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const double* stats, const float* gamma,
+                                     const float* beta, float* running_mean, float* running_var, float momentum,
+                                     float eps, const float* z, int relu, const float* residual, float* y,
+                                     float* scale, float* shift, float* save_mean, float* save_invstd,
+                                     void* stream) {
+  RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && stats && z && y && scale && shift, RCV_ERR_BAD_ARG,
+              "bn_finalize_apply: bad arg");
+  RCV_REQUIRE(C <= 4096, RCV_ERR_UNSUPPORTED, "bn_finalize_apply: C=%d > 4096", C);
+  const int64_t total = (int64_t)N * C * HW;
+  const double count = (double)N * (double)HW;
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  if ((HW & 3) == 0)
+    bn_finalize_apply_kernel<true><<<ew_blocks(total / 4), NT, smem, (cudaStream_t)stream>>>(
+        total, C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, y,
+        scale, shift, save_mean, save_invstd);
+  else
+    bn_finalize_apply_kernel<false><<<ew_blocks(total), NT, smem, (cudaStream_t)stream>>>(
+        total, C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, y,
+        scale, shift, save_mean, save_invstd);
+  RCV_CHECK_LAUNCH("bn_finalize_apply");
   return RCV_OK;
 }
 

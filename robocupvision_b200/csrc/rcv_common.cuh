@@ -79,6 +79,17 @@ struct RcvWgrad {
 };
 
 extern long long* g_rcv_prof;  // debug: phase-timing buffer (rcv_debug_set_prof)
+// One entry of the batched weight-pack table (rcv_conv_pack_table_*).
+constexpr int RCV_PACK_MAX_JOBS = 128;
+struct RcvPackJob {
+  RcvIgemm p;
+  unsigned char* packed;
+  long long chunk_begin, chunks;  // 16-byte chunks: prefix sum over the table, count of this job
+  int32_t BN, ntiles, kbmax, pad_;
+};
+int rcv_umma_pack_job(const RcvIgemm& p, void* packed, long long chunk_begin, RcvPackJob* job);
+int rcv_launch_umma_pack_multi(const RcvPackJob* dev_jobs, int njobs, long long total_chunks, cudaStream_t st);
+
 int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st);       // dispatch on p.math
 int rcv_launch_igemm_simt(const RcvIgemm& p, cudaStream_t st);  // fp32 FFMA, CUDA cores
 int rcv_launch_direct(const RcvIgemm& p, cudaStream_t st);      // fp32 direct conv, <= 16 output channels

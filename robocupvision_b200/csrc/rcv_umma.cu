@@ -399,12 +399,10 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
 
 // One thread per 16-byte chunk of the packed image: 4 consecutive k of one weight row, split
 // into hi / lo and written at the swizzled position.
-__global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int ntiles, int kbmax,
-                                                   unsigned char* __restrict__ packed) {
+__device__ __forceinline__ void pack_chunk(const RcvIgemm& p, int BN, int ntiles, int kbmax,
+                                           unsigned char* __restrict__ packed, int64_t q) {
   const int64_t per_block = (int64_t)BN * 8;
-  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * per_block;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
-       q += (int64_t)gridDim.x * blockDim.x) {
+  {
     const int row = (int)(q % BN);
     const int c = (int)((q / BN) % 8);
     int64_t blk = q / per_block;
@@ -434,6 +432,31 @@ __global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int
     const int off = row * 128 + ((c ^ (row & 7)) << 4);
     *reinterpret_cast<float4*>(base + off) = h;
     *reinterpret_cast<float4*>(base + (size_t)BN * 128 + off) = l;
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int ntiles, int kbmax,
+                                                   unsigned char* __restrict__ packed) {
+  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * 8;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+       q += (int64_t)gridDim.x * blockDim.x)
+    pack_chunk(p, BN, ntiles, kbmax, packed, q);
+}
+
+// All layers' panels in one launch: a device-resident job table (built once on the host, the
+// weight and panel pointers are stable) with the prefix sum of 16-byte chunks per job.
+__global__ void __launch_bounds__(256) pack_multi_kernel(const RcvPackJob* __restrict__ jobs, int njobs) {
+  __shared__ long long s_begin[RCV_PACK_MAX_JOBS + 1];
+  for (int j = threadIdx.x; j <= njobs; j += blockDim.x)
+    s_begin[j] = j < njobs ? jobs[j].chunk_begin : jobs[njobs - 1].chunk_begin + jobs[njobs - 1].chunks;
+  __syncthreads();
+  const long long total = s_begin[njobs];
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+       q += (long long)gridDim.x * blockDim.x) {
+    int j = 0;
+    while (q >= s_begin[j + 1]) ++j;
+    const RcvPackJob& jb = jobs[j];
+    pack_chunk(jb.p, jb.BN, jb.ntiles, jb.kbmax, jb.packed, q - s_begin[j]);
   }
 }
 
@@ -501,6 +524,31 @@ int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st) {
   if (blocks > 148 * 8) blocks = 148 * 8;
   pack_kernel<<<blocks, 256, 0, st>>>(p, BN, ntiles, kbmax, reinterpret_cast<unsigned char*>(packed));
   RCV_CHECK_LAUNCH("pack_kernel");
+  return RCV_OK;
+}
+
+int rcv_umma_pack_job(const RcvIgemm& p, void* packed, long long chunk_begin, RcvPackJob* job) {
+  int rc = check_taps(p);
+  if (rc) return rc;
+  RCV_REQUIRE(((uintptr_t)packed & 127) == 0, RCV_ERR_BAD_ARG, "conv_pack: packed buffer must be 128-byte aligned");
+  job->p = p;
+  job->BN = umma_bn(p.CB);
+  job->ntiles = rcv_cdiv(p.CB, job->BN);
+  job->kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), BK);
+  job->packed = reinterpret_cast<unsigned char*>(packed);
+  job->chunk_begin = chunk_begin;
+  job->chunks = (long long)p.nclass * job->ntiles * job->kbmax * job->BN * 8;
+  return RCV_OK;
+}
+
+int rcv_launch_umma_pack_multi(const RcvPackJob* dev_jobs, int njobs, long long total_chunks, cudaStream_t st) {
+  RCV_REQUIRE(njobs >= 1 && njobs <= RCV_PACK_MAX_JOBS, RCV_ERR_BAD_ARG, "pack_multi: %d jobs (1..%d)", njobs,
+              RCV_PACK_MAX_JOBS);
+  long long blocks = (total_chunks + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  pack_multi_kernel<<<(int)blocks, 256, 0, st>>>(dev_jobs, njobs);
+  RCV_CHECK_LAUNCH("pack_multi_kernel");
   return RCV_OK;
 }
 

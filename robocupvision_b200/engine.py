@@ -28,6 +28,7 @@ from .ops import (EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, MATH_AUT
 import os as _os
 
 DEFAULT_MATH = {"fp32": MATH_FP32, "auto": MATH_AUTO}[_os.environ.get("RCV_B200_MATH", "auto").lower()]
+WGRAD_SIDE_STREAM = _os.environ.get("RCV_B200_WGRAD_STREAM", "1") != "0"
 
 
 class Node:
@@ -55,26 +56,27 @@ class Node:
             out += [self.bn.weight, self.bn.bias]
         return out
 
-    def packed(self, direction: int, epoch: int, fresh: bool, math: int):
-        """Weight panel of the tensor-core engine (None if this layer/direction stays on CUDA
-        cores).  Re-packed when `fresh` (training: weights change every step) or when the weight
-        tensor / the plan's epoch changed; the buffer itself is allocated once (CUDA-graph safe)."""
-        if math == MATH_FP32:
-            return None
+    def uses_tc(self, direction: int, math: int) -> bool:
+        """Does this layer / direction run on the tensor-core engine (and so need a packed panel)."""
+        if math == MATH_FP32 or self.kind != "conv":
+            return False
         if self._tc[direction] is None:
             self._tc[direction] = ops.conv_uses_tensor_cores(self.geom, direction, math)
-        if not self._tc[direction]:
-            return None
+        return self._tc[direction]
+
+    def pack_buffer(self, direction: int) -> torch.Tensor:
+        """Persistent panel buffer (allocated once per device: CUDA-graph safe)."""
         w = self.conv.weight
-        key = (w.data_ptr(), w._version, epoch)
         buf = self._pack[direction]
-        if buf is not None and buf.device != w.device:
-            buf = None
-        if buf is None or fresh or key != self._pack_key[direction]:
-            buf = ops.conv_pack(self.geom, w.detach(), direction, out=buf)
+        if buf is None or buf.device != w.device:
+            buf = torch.empty(ops.conv_packed_bytes(self.geom, direction), device=w.device, dtype=torch.uint8)
             self._pack[direction] = buf
-            self._pack_key[direction] = key
+            self._pack_key[direction] = None
         return buf
+
+    def pack_key(self, epoch: int):
+        w = self.conv.weight
+        return (w.data_ptr(), w._version, epoch)
 
     def folded(self, epoch: int = 0):
         bn = self.bn
@@ -121,6 +123,8 @@ class Plan:
                     seen.add(id(p))
                     self.params.append(p)
         self.math = DEFAULT_MATH
+        self._wgrad_stream = None
+        self._pack_tables = {}
         # bumped whenever parameters / BN buffers may have been written behind torch's back (raw
         # kernels of a training forward or of TrainStep): invalidates folded-BN and packed caches
         self.epoch = 0
@@ -130,6 +134,25 @@ class Plan:
             if nd.bn is not None:
                 self._sum_off[t] = self.n_stats
                 self.n_stats += 2 * nd.geom.cout
+
+    def _ensure_packed(self, directions, fresh: bool, x_requires_grad: bool):
+        """Weight panels of every tensor-core layer, re-packed in ONE launch when `fresh` (training:
+        the weights change every step) or when any weight tensor / the plan epoch changed."""
+        jobs = [(nd, d) for nd in self.nodes if nd.kind == "conv" for d in directions
+                if nd.uses_tc(d, self.math) and not (d == PACK_DGRAD and nd.src == 0 and not x_requires_grad)]
+        if not jobs:
+            return
+        bufs = [nd.pack_buffer(d) for nd, d in jobs]
+        if not fresh and all(nd._pack_key[d] == nd.pack_key(self.epoch) for nd, d in jobs):
+            return
+        tkey = tuple((nd.conv.weight.data_ptr(), b.data_ptr()) for (nd, _), b in zip(jobs, bufs))
+        tbl = self._pack_tables.get(tuple(directions))
+        if tbl is None or tbl.key != tkey:
+            tbl = ops.PackTable([(nd.geom, d, nd.conv.weight.detach(), b) for (nd, d), b in zip(jobs, bufs)])
+            self._pack_tables[tuple(directions)] = tbl
+        tbl.run()
+        for nd, d in jobs:
+            nd._pack_key[d] = nd.pack_key(self.epoch)
 
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, training: bool, save: bool):
@@ -146,6 +169,7 @@ class Plan:
         nbt = []
         if training:
             self.epoch += 1
+        self._ensure_packed((PACK_FWD, PACK_DGRAD) if save else (PACK_FWD,), training, x.requires_grad)
         for t, nd in enumerate(self.nodes):
             src = acts[nd.src]
             if nd.kind == "pool":
@@ -157,9 +181,7 @@ class Plan:
             w = conv.weight.detach()
             b = conv.bias.detach() if conv.bias is not None else None
             skip = acts[nd.skip] if (nd.skip >= 0 and nd.skip_mode == "add") else None
-            wp = nd.packed(PACK_FWD, self.epoch, training, self.math)
-            if save and (nd.src != 0 or x.requires_grad):
-                nd.packed(PACK_DGRAD, self.epoch, training, self.math)
+            wp = nd._pack[PACK_FWD] if nd.uses_tc(PACK_FWD, self.math) else None
             if bn is None:
                 y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, math=self.math, wpacked=wp)
                 saved[t] = (y if nd.order == EPI_RELU else None,)
@@ -176,10 +198,10 @@ class Plan:
                 else:
                     momentum = bn.momentum
                 track = bn.track_running_stats and bn.running_mean is not None
-                scale, shift, mean, invstd = ops.bn_finalize(
-                    stats, count, bn.weight.detach(), bn.bias.detach(),
-                    bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps)
-                y = ops.bn_apply(z, scale, shift, relu=(nd.order == EPI_AFFINE_RELU), residual=skip)
+                y, scale, shift, mean, invstd = ops.bn_finalize_apply(
+                    z, stats, bn.weight.detach(), bn.bias.detach(),
+                    bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps,
+                    relu=(nd.order == EPI_AFFINE_RELU), residual=skip)
                 saved[t] = (z, scale, shift, mean, invstd)
                 if track and bn.num_batches_tracked is not None:
                     nbt.append(bn.num_batches_tracked)
@@ -221,13 +243,26 @@ class Plan:
             if g is not None:
                 add_to(oi, g)
         sums_arena = torch.zeros(max(self.n_stats, 1), device=dev, dtype=torch.float64)
+        # Weight gradients run on a side stream: dgrad(t) and wgrad(t) only share their input, so the
+        # wgrad CTAs fill the SMs a dgrad's partial last wave leaves idle (150 tiles on 148 SMs at
+        # 15x20) and overlap the next node's BatchNorm backward.  Tensors the side stream reads are
+        # kept alive until the streams join, so the caching allocator cannot hand them out early.
+        cur = torch.cuda.current_stream(dev)
+        if self._wgrad_stream is None or self._wgrad_stream.device != dev:
+            self._wgrad_stream = torch.cuda.Stream(device=dev)
+        side = self._wgrad_stream if WGRAD_SIDE_STREAM else None
+        keep: List[torch.Tensor] = []
         for t in range(len(self.nodes) - 1, -1, -1):
-            self._backward_node(t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to)
+            self._backward_node(t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side, keep)
             if node_done is not None:
                 node_done(t)
+        if side is not None:
+            cur.wait_stream(side)
+        keep.clear()
         return grads[0], grad_views
 
-    def _backward_node(self, t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to):
+    def _backward_node(self, t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side=None,
+                       keep=None):
         if True:
             nd = self.nodes[t]
             g = grads[t + 1]
@@ -268,10 +303,17 @@ class Plan:
                 dconv = ops.relu_bwd(g, saved[t][0]) if nd.order == EPI_RELU else g
                 wg_bias = grad_views[id(conv.bias)] if has_bias else None
             if nd.src != 0 or x_needs_grad:
-                wp = nd._pack[PACK_DGRAD] if (self.math != MATH_FP32 and nd._tc[PACK_DGRAD]) else None
+                wp = nd._pack[PACK_DGRAD] if nd.uses_tc(PACK_DGRAD, self.math) else None
                 grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
                                                wpacked=wp)
-            ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math)
+            if side is None:
+                ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math)
+            else:
+                cur = torch.cuda.current_stream(src.device)
+                side.wait_stream(cur)  # dconv (and every earlier write to the gradient arena) is ordered before
+                keep.append(dconv)
+                with torch.cuda.stream(side):
+                    ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math)
 
 
 class _PlanFn(torch.autograd.Function):

@@ -16,7 +16,7 @@ from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFF
                    MATH_FP32, MATH_TF32X3, PACK_DGRAD, PACK_FWD, ConvDesc)
 
 __all__ = [
-    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
+    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
     "confusion", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
@@ -127,6 +127,45 @@ def conv_pack(g: ConvGeom, w, direction: int, out=None):
     d = g.desc(1, 2, 2)
     _call("rcv_conv_pack", 1, C.byref(d), int(direction), _ptr(w), _ptr(out), _stream())
     return out
+
+
+class PackTable:
+    """Device-resident job table that re-packs the weight panels of many layers in one launch
+    (rcv_conv_pack_table_*).  Valid while every weight / panel pointer it was built from is."""
+
+    def __init__(self, jobs):
+        """jobs: list of (ConvGeom, direction, weight tensor, packed uint8 tensor)."""
+        n = len(jobs)
+        lib = _lib.load()
+        descs = (ConvDesc * n)(*[g.desc(1, 2, 2) for g, _, _, _ in jobs])
+        dirs = (C.c_int32 * n)(*[int(d) for _, d, _, _ in jobs])
+        ws = (C.c_void_p * n)(*[w.data_ptr() for _, _, w, _ in jobs])
+        ps = (C.c_void_p * n)(*[pk.data_ptr() for _, _, _, pk in jobs])
+        nbytes = int(lib.rcv_conv_pack_table_bytes(n))
+        host = torch.empty(nbytes, dtype=torch.uint8)
+        total = C.c_int64(0)
+        _lib.call("rcv_conv_pack_table_build", n, descs, dirs, ws, ps, C.c_void_p(host.data_ptr()), C.byref(total))
+        self.n, self.total = n, int(total.value)
+        self.key = tuple((w.data_ptr(), pk.data_ptr()) for _, _, w, pk in jobs)
+        self.table = host.to(jobs[0][2].device)
+
+    def run(self):
+        _call("rcv_conv_pack_table_run", 1, _ptr(self.table), self.n, self.total, _stream())
+
+
+def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum, eps, relu, residual=None):
+    """Train-mode BatchNorm forward in one launch -> (y, scale, shift, mean, invstd)."""
+    z = _chk(z, name="z")
+    n, c = z.shape[0], z.shape[1]
+    hw = z.numel() // (n * c)
+    buf = torch.empty((4, c), device=z.device, dtype=torch.float32)
+    y = torch.empty_like(z)
+    if residual is not None:
+        residual = _chk(residual, name="residual")
+    _call("rcv_bn_finalize_apply", 1, n, c, hw, _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean),
+          _ptr(running_var), float(momentum), float(eps), _ptr(z), 1 if relu else 0, _ptr(residual), _ptr(y),
+          _ptr(buf[0]), _ptr(buf[1]), _ptr(buf[2]), _ptr(buf[3]), _stream())
+    return y, buf[0], buf[1], buf[2], buf[3]
 
 
 def _packed_for(g, w, wpacked, math, direction):

@@ -165,6 +165,8 @@ class TrainStep:
             def hook(t):
                 if t == self.split_node:
                     self.comm_stream.wait_stream(cur)
+                    if self.plan._wgrad_stream is not None:  # weight gradients are produced on the side stream
+                        self.comm_stream.wait_stream(self.plan._wgrad_stream)
                     with torch.cuda.stream(self.comm_stream):
                         self._allreduce(self.grads[self.split_off:])
             self._backward(saved, dl, hook)

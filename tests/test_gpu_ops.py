@@ -76,6 +76,22 @@ def test_conv_wide_channel_tiles():
     assert_close("conv_fwd 40->200 tc", got, ref, 8e-6)
 
 
+def test_pack_table_matches_single_packs():
+    """rcv_conv_pack_table_* (all layers in one launch) writes the same panels as rcv_conv_pack."""
+    from robocupvision_b200 import ops
+    jobs, singles = [], []
+    for i, (geom, cin, cout, d) in enumerate([("k3s1d1", 128, 128, 0), ("k3s1d1", 128, 128, 1), ("convT", 64, 32, 0),
+                                              ("k3s2", 16, 32, 1), ("k3s1d2", 24, 40, 0), ("k1", 16, 5, 0)]):
+        g, x, w, b = _mk(geom, cin, cout, 1, 4, 4, seed=20 + i)
+        w = w.cuda()
+        singles.append(ops.conv_pack(g, w, d))
+        jobs.append((g, d, w, torch.zeros_like(singles[-1])))
+    tbl = ops.PackTable(jobs)
+    tbl.run()
+    for (g, d, w, pk), ref in zip(jobs, singles):
+        assert torch.equal(pk, ref)
+
+
 def test_tc_requires_packed_weights():
     """RCV_MATH_TF32X3 through the raw C ABI without a packed panel is an error, not a fallback."""
     import ctypes as C
@@ -227,6 +243,13 @@ def test_bn_train_fwd_bwd(order, shape):
     assert_close("bn y", y, y_ref, 3e-6)
     assert_close("running_mean", rm_g, rm_ref, 1e-6)
     assert_close("running_var", rv_g, rv_ref, 1e-6)
+    # the fused single-launch form must agree bit for bit with finalize + apply
+    rm_f, rv_f = rm.cuda(), rv.cuda()
+    y2, sc2, sh2, mean2, inv2 = ops.bn_finalize_apply(z, stats, gamma.cuda(), beta.cuda(), rm_f, rv_f, 0.1, 1e-5,
+                                                      relu=(order == "affine_relu"), residual=res.cuda())
+    assert torch.equal(y2, y) and torch.equal(sc2, scale) and torch.equal(sh2, shift)
+    assert torch.equal(mean2, mean) and torch.equal(inv2, invstd)
+    assert torch.equal(rm_f, rm_g) and torch.equal(rv_f, rv_g)
     code = ops.EPI_RELU_AFFINE if order == "relu_affine" else ops.EPI_AFFINE_RELU
     dconv, dgamma, dbeta, dbias = ops.bn_bwd(code, dy.cuda(), z, scale, shift, mean, invstd, want_dbias=True)
     assert_close("bn dconv", dconv, vr.grad, 1e-5)
