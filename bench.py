@@ -268,26 +268,28 @@ def main():
         launches = ops.launch_count() - k0
 
     # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----------------
-    hx = torch.empty_like(xs[0]); hy = torch.empty_like(ys[0])
-    loss_host = torch.empty(2, dtype=torch.float64).pin_memory()
-
-    def e2e_step(i):
-        if wl["train"]:
-            ts.step(xs_host[i % nbatches], ys_host[i % nbatches])  # H2D into the step's input buffers
-            loss_host.copy_(ts.loss_sums, non_blocking=True)
-        else:
-            hx.copy_(xs_host[i % nbatches], non_blocking=True)
-            hy.copy_(ys_host[i % nbatches], non_blocking=True)
-            r = ev(hx, hy)
-            loss_host[:1].copy_(r["loss"].reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the user reads the loss
-    for i in range(3):
-        e2e_step(i)
+    # The public pipelined API (TrainStep.step_async / EvalStep.run_async): step i's inputs are
+    # copied H2D on a copy stream while step i-1 still computes, and every step's loss is copied
+    # D2H behind it and read by the host one step later.  All copies happen inside the timed
+    # region, once per step.
+    def e2e_loop(n):
+        prev = None
+        for i in range(n):
+            if wl["train"]:
+                h = ts.step_async(xs_host[i % nbatches], ys_host[i % nbatches])
+                if prev is not None:
+                    prev.wait()
+            else:
+                h = ev.run_async(xs_host[i % nbatches], ys_host[i % nbatches])
+                if prev is not None:
+                    EvalStep.wait_host(prev)
+            prev = h
+        return prev.wait() if wl["train"] else EvalStep.wait_host(prev)
+    e2e_loop(4)
     barrier()
     e2e_steps = args.steps
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
+    e2e_loop(e2e_steps)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     if world > 1:
@@ -296,7 +298,7 @@ def main():
         e2e_ms = float(t)
     e2e_value = batch * world / (e2e_ms * 1e-3)
     h2d = xs_host[0].numel() * 4 + ys_host[0].numel() * 8
-    d2h = 16 if wl["train"] else 8
+    d2h = 32 if wl["train"] else 16
 
     # ---- roofline of the dominant kernel, measured live with CUDA events -----------------------
     pk = peaks()
@@ -363,13 +365,15 @@ def dominant_kernel_roofline(model, wl, batch, dev, pk):
     wt = best.conv.weight.detach()
     ho, wo = g.out_hw(best_in[1], best_in[2])
     y = torch.empty(batch, g.cout, ho, wo, device=dev)
+    on_tc = ops.conv_uses_tensor_cores(g, ops.PACK_FWD, ops.MATH_AUTO)
+    wp = ops.conv_pack(g, wt, ops.PACK_FWD) if on_tc else None
     flush = torch.empty(64 * 1024 * 1024, device=dev)  # 256 MB > L2
     times = []
     for i in range(13):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv_fwd(g, x, wt, None, epilogue=ops.EPI_RELU, out=y)
+        ops.conv_fwd(g, x, wt, None, epilogue=ops.EPI_RELU, out=y, math=ops.MATH_AUTO, wpacked=wp)
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -379,14 +383,23 @@ def dominant_kernel_roofline(model, wl, batch, dev, pk):
     bytes_alg = 4.0 * (x.numel() + y.numel() + wt.numel())
     intensity = flops / bytes_alg
     ridge = pk["tensor_sustained"] * 1e12 / (pk["hbm"] * 1e9)
-    if intensity >= ridge:
-        achieved, peak, unit, bound = flops / (ms * 1e-3) / 1e12, pk["tensor_sustained"], "TFLOP/s", "tensor"
+    tfl = flops / (ms * 1e-3) / 1e12
+    if intensity >= ridge * 0.5:
+        # the burst figure: this kernel is timed alone.  The fp32-parity mode spends three TF32 MMAs per
+        # product and TF32 runs at half the bf16 rate, so its ceiling is peak/6 (also reported).
+        achieved, peak, unit, bound = tfl, pk["tensor_burst"], "TFLOP/s", "tensor"
     else:
         achieved, peak, unit, bound = bytes_alg / (ms * 1e-3) / 1e9, pk["hbm"], "GB/s", "hbm"
-    return {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
-            "kernel": f"igemm conv fwd {g.cin}->{g.cout} k{g.k} s{g.stride} d{g.dil} @{best_in[1]}x{best_in[2]} batch {batch}",
-            "us_per_launch": ms * 1e3, "flop_per_byte": intensity, "math": "fp32 FFMA (CUDA cores)",
-            "achieved_tflops": flops / (ms * 1e-3) / 1e12, "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9}
+    out = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
+           "kernel": f"{'umma_igemm (tcgen05 3xTF32)' if on_tc else 'igemm (fp32 FFMA)'} conv fwd {g.cin}->{g.cout} "
+                     f"k{g.k} s{g.stride} d{g.dil} @{best_in[1]}x{best_in[2]} batch {batch}",
+           "us_per_launch": ms * 1e3, "flop_per_byte": intensity,
+           "math": "tcgen05 kind::tf32 x3 (fp32-level accuracy), TMEM accumulators" if on_tc else "fp32 FFMA (CUDA cores)",
+           "achieved_tflops": tfl, "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9, "peak_is": "measured bf16 dense (burst)"}
+    if on_tc:
+        out["tf32_mma_tflops"] = 3.0 * tfl
+        out["frac_of_tf32x3_ceiling"] = tfl / (pk["tensor_burst"] / 6.0)
+    return out
 
 
 if __name__ == "__main__":

@@ -115,6 +115,7 @@ class TrainStep:
         self.static_y = None
         self.kernels_per_step = 0
         self._warm = 0
+        self._pipe = None
 
     # ------------------------------------------------------------------ helpers
     def set_lr(self, lr: float):
@@ -219,6 +220,39 @@ class TrainStep:
             self.graph.replay()
         return self.loss_sums, self.l1_sum, self.correct
 
+    def step_async(self, x: torch.Tensor, y: torch.Tensor) -> "StepResult":
+        """Pipelined form of step() for a loop fed from pinned host memory: this step's inputs go
+        H2D on a copy stream into one of two staging buffers (overlapping the previous step, which
+        is still running), the main stream waits for them, moves them into the graph's input
+        buffers device-to-device and replays; the step's loss sums / L1 sum / correct count are
+        copied to pinned host memory right behind it.  Returns a handle whose wait() blocks until
+        THIS step's scalars have landed -- call it one step late to keep the pipe full."""
+        if self.graph is None or self.static_x.shape != x.shape or not self.use_graph or x.is_cuda:
+            self.step(x, y)
+            return StepResult.ready(self)
+        self.model.train()
+        self.plan.epoch += 1
+        if self._pipe is None:
+            self._pipe = _HostPipe(self.static_x, self.static_y, self.dev)
+        pipe = self._pipe
+        k = pipe.next_slot()
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(pipe.copy_stream):
+            pipe.copy_stream.wait_event(pipe.free[k])      # the D2D that last read this slot is done
+            pipe.sx[k].copy_(x, non_blocking=True)
+            pipe.sy[k].copy_(y, non_blocking=True)
+            pipe.loaded[k].record(pipe.copy_stream)
+        cur.wait_event(pipe.loaded[k])
+        self.static_x.copy_(pipe.sx[k], non_blocking=True)
+        self.static_y.copy_(pipe.sy[k], non_blocking=True)
+        pipe.free[k].record(cur)
+        self.graph.replay()
+        pipe.out_f[k][:2].copy_(self.loss_sums, non_blocking=True)
+        pipe.out_f[k][2:3].copy_(self.l1_sum, non_blocking=True)
+        pipe.out_i[k].copy_(self.correct, non_blocking=True)
+        pipe.done[k].record(cur)
+        return StepResult(pipe, k, self.l1_decay)
+
     def _state(self):
         return [self.arena, self.m, self.v, self.step_dev] + list(self.model.buffers())
 
@@ -256,6 +290,53 @@ class TrainStep:
         return ce + self.l1_decay * float(self.l1_sum)
 
 
+class _HostPipe:
+    """Two staging slots (device inputs + pinned host outputs) and the events that order them."""
+
+    def __init__(self, like_x, like_y, dev):
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.sx = [torch.empty_like(like_x) for _ in range(2)]
+        self.sy = [torch.empty_like(like_y) for _ in range(2)]
+        self.out_f = [torch.empty(3, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.out_i = [torch.empty(1, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.loaded = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
+        for e in self.free:
+            e.record(cur)
+        self.k = 1
+
+    def next_slot(self) -> int:
+        self.k ^= 1
+        return self.k
+
+
+class StepResult:
+    """Host-side view of one pipelined step's scalars (TrainStep.step_async)."""
+
+    def __init__(self, pipe, k, l1_decay):
+        self.pipe, self.k, self.l1_decay, self._ts = pipe, k, l1_decay, None
+
+    @staticmethod
+    def ready(ts):
+        """Result of a step that ran through step() (first call / device inputs): read now, the
+        device scalars are overwritten by the next replay."""
+        r = StepResult(None, 0, ts.l1_decay)
+        ce = float(ts.loss_sums[0] / ts.loss_sums[1])
+        r._ts = (ce, ce + ts.l1_decay * float(ts.l1_sum), int(ts.correct))
+        return r
+
+    def wait(self):
+        """-> (ce_loss, total_loss, correct) of that step, after its D2H copy has completed."""
+        if self._ts is not None:
+            return self._ts
+        self.pipe.done[self.k].synchronize()
+        f = self.pipe.out_f[self.k]
+        ce = float(f[0] / f[1])
+        return ce, ce + self.l1_decay * float(f[2]), int(self.pipe.out_i[self.k])
+
+
 class EvalStep:
     """Validation batch (train.py:114-153): logits, weighted CE, argmax, correct-pixel count,
     per-image confusion and IoU sums -- no host syncs (the reference does 3+25*B `.item()`s)."""
@@ -265,6 +346,39 @@ class EvalStep:
         dev = next(model.parameters()).device
         self.class_w = None if class_weights is None else torch.as_tensor(
             class_weights, dtype=torch.float32).to(dev)
+        self._pipe = None
+
+    @torch.no_grad()
+    def run_async(self, x_host, y_host):
+        """Pipelined validation batch fed from pinned host memory: H2D on a copy stream into one of
+        two staging slots (overlapping the previous batch's kernels), then __call__ on the slot."""
+        dev = next(self.model.parameters()).device
+        if self._pipe is None or self._pipe.sx[0].shape != x_host.shape:
+            self._pipe = _HostPipe(torch.empty(x_host.shape, device=dev, dtype=x_host.dtype),
+                                   torch.empty(y_host.shape, device=dev, dtype=y_host.dtype), dev)
+        pipe = self._pipe
+        k = pipe.next_slot()
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(pipe.copy_stream):
+            pipe.copy_stream.wait_event(pipe.free[k])
+            pipe.sx[k].copy_(x_host, non_blocking=True)
+            pipe.sy[k].copy_(y_host, non_blocking=True)
+            pipe.loaded[k].record(pipe.copy_stream)
+        cur.wait_event(pipe.loaded[k])
+        out = self(pipe.sx[k], pipe.sy[k])
+        pipe.free[k].record(cur)
+        pipe.out_f[k][:1].copy_(out["loss"].reshape(1), non_blocking=True)
+        pipe.out_i[k].copy_(out["correct"], non_blocking=True)
+        pipe.done[k].record(cur)
+        out["host"] = (pipe, k)
+        return out
+
+    @staticmethod
+    def wait_host(out):
+        """-> (loss, correct) of a run_async batch once its D2H copy has completed."""
+        pipe, k = out["host"]
+        pipe.done[k].synchronize()
+        return float(pipe.out_f[k][0]), int(pipe.out_i[k])
 
     @torch.no_grad()
     def __call__(self, x, y):

@@ -226,6 +226,41 @@ def test_train_step_matches_reference_steps():
                  torch.from_numpy(gold["final_rv"]), 1e-3)
 
 
+def test_step_async_matches_step():
+    """The pipelined host-fed API (H2D on a copy stream, staged D2D, D2H of the scalars) performs
+    exactly the same steps as step() on device-resident inputs."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import TrainStep
+    models, steps = [], []
+    for _ in range(2):
+        torch.manual_seed(12345678)
+        m = ROBO_UNet().cuda()
+        models.append(m)
+        steps.append(TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, use_graph=True))
+    xs = [synth.images(4, 3, 48, 64, seed=200 + s) for s in range(5)]
+    ys = [synth.labels_learnable(x) for x in xs]
+    ref_losses = []
+    for x, y in zip(xs, ys):
+        steps[0].step(x.cuda(), y.cuda())
+        ref_losses.append((steps[0].loss_value(), int(steps[0].correct)))
+    handles, got = [], []
+    prev = None
+    for x, y in zip(xs, ys):
+        h = steps[1].step_async(x.pin_memory(), y.pin_memory())
+        if prev is not None:
+            got.append(prev.wait())
+        prev = h
+    got.append(prev.wait())
+    # (fp32 RED atomics in the weight gradient make two runs agree to rounding, not bit for bit)
+    for (l0, c0), (ce, tot, c1) in zip(ref_losses, got):
+        assert abs(l0 - tot) <= 1e-6 * abs(l0) and abs(c0 - c1) <= 8
+    for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
+        if a.is_floating_point():
+            assert_close(k, a, b, 1e-4)
+        else:
+            assert torch.equal(a, b), k
+
+
 def test_train_step_pruned_masks():
     """Pruned finetune (train.py:59-65): masked weights receive zero gradient, no L1 term."""
     from robocupvision_b200.model import ROBO_UNet, pruneModelNew
