@@ -73,6 +73,7 @@ struct RcvWgrad {
   int32_t gs;
   int32_t wsA, wsB;
   int32_t slab;      // pixels per split, multiple of 16
+  int32_t qunits;    // tensor-core quad gather: (channel, tap-row) units per k tile
   int32_t math;      // rcv_math
   long long* prof;   // see RcvIgemm::prof
   RcvTapSet taps;

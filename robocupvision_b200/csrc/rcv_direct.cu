@@ -3,7 +3,7 @@
 // input gradients of their neighbours).  These layers are bandwidth-shaped (1.5-12 FLOP/B): the
 // implicit-GEMM engines pay more for staging operands than the arithmetic is worth.
 //
-// One thread = PIX pixel-grid points x ALL output channels in registers.  Lanes are consecutive
+// One thread = PIX (2 or 4) pixel-grid points x ALL output channels in registers.  Lanes are consecutive
 // pixels, so every activation load and every NCHW store is coalesced; the 9x tap re-use of the
 // input is served by L1.  Weights of the CTA's parity class live in shared memory as
 // [k = (channel, tap)][CBP] and are read as broadcast float4 (4 output channels per LDS.128).
@@ -14,7 +14,6 @@
 namespace {
 
 constexpr int NT = 256;
-constexpr int PIX = 2;
 
 __device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh) {
   switch (epi) {
@@ -26,7 +25,7 @@ __device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh)
   }
 }
 
-template <int CBP>
+template <int CBP, int PIX>
 __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cls = blockIdx.z;
@@ -36,6 +35,7 @@ __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
   int2* ktab = reinterpret_cast<int2*>(ws + (size_t)K * CBP);  // [K] (byte offset, tap)
   float* cst = reinterpret_cast<float*>(ktab + K);           // [3][CBP] bias, scale, shift
   __shared__ double red[2][NT / 32][CBP];
+  __shared__ int s_ext[4];  // min dy, max dy, min dx, max dx over the taps of this class
 
   const int tid = threadIdx.x;
   const int HWin = p.Hin * p.Win;
@@ -50,6 +50,14 @@ __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
   for (int k = tid; k < K; k += NT) {
     const int ca = k / T, t = k - ca * T;
     ktab[k] = make_int2(4 * (ca * HWin + p.taps[cls].dy[t] * p.Win + p.taps[cls].dx[t]), t);
+  }
+  if (tid == 0) {
+    int a = 127, b = -127, c = 127, d = -127;
+    for (int t = 0; t < T; ++t) {
+      a = min(a, (int)p.taps[cls].dy[t]); b = max(b, (int)p.taps[cls].dy[t]);
+      c = min(c, (int)p.taps[cls].dx[t]); d = max(d, (int)p.taps[cls].dx[t]);
+    }
+    s_ext[0] = a; s_ext[1] = b; s_ext[2] = c; s_ext[3] = d;
   }
   if (tid < CBP) {
     const bool in = tid < p.CB;
@@ -79,7 +87,11 @@ __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
     const int gy0 = pi * p.gs, gx0 = pj * p.gs;
     boff[q] = 4u * (uint32_t)(pn * p.CA * HWin + gy0 * p.Win + gx0);
     uint32_t tm = 0;
-    if (mrow[q]) {
+    const bool interior = mrow[q] && gy0 + s_ext[0] >= 0 && gy0 + s_ext[1] < p.Hin && gx0 + s_ext[2] >= 0 &&
+                          gx0 + s_ext[3] < p.Win;
+    if (interior) {
+      tm = 0xffffffffu;  // every tap reads inside the image (the common case: no per-tap tests)
+    } else if (mrow[q]) {
       for (int t = 0; t < T; ++t) {
         const int iy = gy0 + p.taps[cls].dy[t], ix = gx0 + p.taps[cls].dx[t];
         if ((unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win) tm |= 1u << t;
@@ -96,13 +108,12 @@ __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
 #pragma unroll
     for (int c = 0; c < CBP; ++c) acc[q][c] = 0.f;
 
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const int2 e = ktab[k];
-    float x[PIX];
+  bool all_in = true;
 #pragma unroll
-    for (int q = 0; q < PIX; ++q)
-      x[q] = ((tapmask[q] >> e.y) & 1u) ? __ldg(reinterpret_cast<const float*>(inb + (boff[q] + (uint32_t)e.x))) : 0.f;
+  for (int q = 0; q < PIX; ++q) all_in = all_in && tapmask[q] == 0xffffffffu;
+  const bool fast = __all_sync(0xffffffffu, all_in);  // warp-uniform: no divergence in the hot loop
+
+  auto fma_row = [&](int k, const float (&x)[PIX]) {
     const float4* wr = reinterpret_cast<const float4*>(ws + (size_t)k * CBP);
 #pragma unroll
     for (int c4 = 0; c4 < CBP / 4; ++c4) {
@@ -115,6 +126,29 @@ __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
         acc[q][4 * c4 + 3] = fmaf(x[q], w4.w, acc[q][4 * c4 + 3]);
       }
     }
+  };
+  if (fast) {
+    const char* b0[PIX];
+#pragma unroll
+    for (int q = 0; q < PIX; ++q) b0[q] = inb + boff[q];
+#pragma unroll 9
+    for (int k = 0; k < K; ++k) {
+      const int off = ktab[k].x;
+      float x[PIX];
+#pragma unroll
+      for (int q = 0; q < PIX; ++q) x[q] = __ldg(reinterpret_cast<const float*>(b0[q] + off));
+      fma_row(k, x);
+    }
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const int2 e = ktab[k];
+      float x[PIX];
+#pragma unroll
+      for (int q = 0; q < PIX; ++q)
+        x[q] = ((tapmask[q] >> e.y) & 1u) ? __ldg(reinterpret_cast<const float*>(inb + (boff[q] + (uint32_t)e.x))) : 0.f;
+      fma_row(k, x);
+    }
   }
 
   // ---------------- epilogue ----------------
@@ -122,19 +156,24 @@ __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
   float s1[CBP], s2[CBP];
 #pragma unroll
   for (int c = 0; c < CBP; ++c) s1[c] = s2[c] = 0.f;
+  const bool has_res = p.residual != nullptr;
+  const int ncb = p.CB;
 #pragma unroll
   for (int q = 0; q < PIX; ++q) {
     if (!mrow[q]) continue;
+    float* o = p.out + obase[q];
+    const float* rs = has_res ? p.residual + obase[q] : nullptr;
 #pragma unroll
     for (int c = 0; c < CBP; ++c) {
-      if (c < p.CB) {
-        const size_t off = obase[q] + (size_t)c * HWo;
+      if (c < ncb) {
         float v = apply_epi(acc[q][c] + cst[c], epi, cst[CBP + c], cst[2 * CBP + c]);
-        if (p.residual) v += __ldg(p.residual + off);
-        p.out[off] = v;
+        if (has_res) v += __ldg(rs);
+        *o = v;
         s1[c] += v;
         s2[c] += v * v;
       }
+      o += HWo;
+      if (has_res) rs += HWo;
     }
   }
   if (p.stats) {
@@ -161,7 +200,7 @@ __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
   }
 }
 
-template <int CBP>
+template <int CBP, int PIX>
 int launch_direct(const RcvIgemm& p, cudaStream_t st) {
   int maxT = 0;
   for (int c = 0; c < p.nclass; ++c) maxT = p.taps[c].n > maxT ? p.taps[c].n : maxT;
@@ -170,7 +209,7 @@ int launch_direct(const RcvIgemm& p, cudaStream_t st) {
   const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
   RCV_REQUIRE(M < (1ll << 31), RCV_ERR_UNSUPPORTED, "direct_conv: problem too large");
   dim3 grid(rcv_cdiv(M, NT * PIX), 1, p.nclass);
-  direct_conv_kernel<CBP><<<grid, NT, smem, st>>>(p);
+  direct_conv_kernel<CBP, PIX><<<grid, NT, smem, st>>>(p);
   RCV_CHECK_LAUNCH("direct_conv_kernel");
   return RCV_OK;
 }
@@ -188,5 +227,6 @@ bool rcv_direct_supported(const RcvIgemm& p) {
 
 int rcv_launch_direct(const RcvIgemm& p, cudaStream_t st) {
   RCV_REQUIRE(rcv_direct_supported(p), RCV_ERR_UNSUPPORTED, "direct_conv: geometry outside the kernel's limits");
-  return p.CB <= 8 ? launch_direct<8>(p, st) : launch_direct<16>(p, st);
+  // pixels per thread amortise the broadcast weight reads: 2 per thread (4 measured no faster on B200)
+  return p.CB <= 8 ? launch_direct<8, 2>(p, st) : launch_direct<16, 2>(p, st);
 }

@@ -47,7 +47,8 @@ struct WCfg {
   static constexpr int BROWS = BN_ / 16;            // dense rows per loader thread
 };
 
-constexpr int QUNITS = 42;  // (channel, tap-row) units per k tile in QUAD mode: 126 of the 128 rows
+constexpr int QUNITS = 42;  // most (channel, tap-row) units per k tile in QUAD mode: 126 of the 128 rows;
+                            // p.qunits <= 42 balances the units over the k tiles
 
 template <int BN, bool QUAD>
 __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
   const int HWin = p.Hin * p.Win;
   const int HWg = p.Hg * p.Wg;
   const int M = p.N * HWg;
-  const int k0 = QUAD ? blockIdx.x * (3 * QUNITS) : blockIdx.x * BM;  // QUAD: 42 units x 3 tap columns
+  const int k0 = QUAD ? blockIdx.x * (3 * p.qunits) : blockIdx.x * BM;  // QUAD: qunits units x 3 tap columns
   const int cb0 = blockIdx.y * BN;
   const int mbeg = blockIdx.z * p.slab;
   const int mend = min(M, mbeg + p.slab);
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
 
   for (int kl = tid; kl < BM; kl += NT) {
     const int k = k0 + kl;
-    if (k < K && (!QUAD || kl < 3 * QUNITS)) {
+    if (k < K && (!QUAD || kl < 3 * p.qunits)) {
       const int ca = k / T, t = k - ca * T;
       s_tab[kl] = make_int2(ca * HWin + p.taps.dy[t] * p.Win + p.taps.dx[t], t);
       s_wo[kl] = ca * p.wsA + p.taps.wi[t];
@@ -208,10 +209,10 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int u = qu0 + 16 * r;          // unit inside the tile
-          const int U = blockIdx.x * QUNITS + u;  // global unit = ca * 3 + tap row
+          const int U = blockIdx.x * p.qunits + u;  // global unit = ca * 3 + tap row
           const int ca = U / 3, ty = U - ca * 3;
           const int iy = i0 + (ty - 1) * d;
-          const bool uok = ok && u < QUNITS && ca < p.CA && (unsigned)iy < (unsigned)p.Hin;
+          const bool uok = ok && u < p.qunits && ca < p.CA && (unsigned)iy < (unsigned)p.Hin;
           const float* src = p.src + ((size_t)n * p.CA + ca) * HWin + iy * p.Win + j0;
           qv[r] = uok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
           // neighbours from the adjacent lanes (same unit, adjacent quad) ...
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           const int u = qu0 + 16 * r;
-          if (u < QUNITS) {
+          if (u < p.qunits) {
             const float4 v = qv[r];
             float4 row[3];
             row[1] = v;
@@ -382,7 +383,11 @@ int launch_w(RcvWgrad p, cudaStream_t st) {
     }
     attr_done = true;
   }
-  const int ktiles = QUAD ? rcv_cdiv(p.CA * 3, QUNITS) : rcv_cdiv(K, BM);
+  int ktiles = rcv_cdiv(K, BM);
+  if (QUAD) {
+    ktiles = rcv_cdiv(p.CA * 3, QUNITS);
+    p.qunits = rcv_cdiv(p.CA * 3, ktiles);  // balanced: every k tile gathers the same number of units
+  }
   const int tiles = ktiles * rcv_cdiv(p.CB, BN);
   int splits = 148 / tiles;  // one CTA per SM, never a second partial wave
   const int max_splits = rcv_cdiv(M, BK * 4);
