@@ -214,6 +214,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries the JSON line
         torch.distributed.init_process_group("nccl", device_id=dev)
     model = build_model(wl, dev)
     cw = class_weights(wl)
