@@ -398,6 +398,14 @@ def dominant_kernel_roofline(model, wl, batch, dev, pk):
            "us_per_launch": ms * 1e3, "flop_per_byte": intensity,
            "math": "tcgen05 kind::tf32 x3 (fp32-level accuracy), TMEM accumulators" if on_tc else "fp32 FFMA (CUDA cores)",
            "achieved_tflops": tfl, "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9, "peak_is": "measured bf16 dense (burst)"}
+    tfile = ROOT / "profiles" / "r1_traffic.json"
+    if tfile.exists():
+        key = f"conv fwd {g.cin}->{g.cout} k{g.k} s{g.stride} d{g.dil} @{best_in[1]}x{best_in[2]} batch {batch}"
+        ent = json.loads(tfile.read_text()).get(key)
+        if ent:
+            out["traffic"] = ent["bytes"]
+            out["traffic_source"] = ent["source"]
+            out["algorithmic_bytes"] = bytes_alg
     if on_tc:
         out["tf32_mma_tflops"] = 3.0 * tfl
         out["frac_of_tf32x3_ceiling"] = tfl / (pk["tensor_burst"] / 6.0)

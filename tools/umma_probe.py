@@ -92,7 +92,7 @@ def timing():
               ("k3s1d1", 64, 64, 15, 20), ("k3s1d1", 64, 128, 15, 20), ("k3s1d1", 128, 128, 15, 20),
               ("k3s1d1", 128, 64, 15, 20), ("convT", 64, 32, 15, 20), ("convT", 32, 16, 30, 40),
               ("convT", 16, 8, 60, 80), ("k1", 8, 5, 120, 160)]
-    B = 64
+    B = int(__import__("os").environ.get("PROBE_B", "64"))
     only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--layer=")]
     if only:
         layers = [layers[i] for i in only]
