@@ -247,6 +247,21 @@ int rcv_ce_bwd(int32_t N, int32_t C, int64_t HW, const float* logits,
 int rcv_confusion(int32_t N, int32_t C, int64_t HW, const int64_t* pred,
                   const int64_t* target, int64_t* conf, void* stream);
 
+/* ---- input-side label ops of the callers --------------------------------- */
+/* labels[i] = lut[labels[i]] in place for 0 <= labels[i] < nlut (nlut <= 64): maskLabel,
+ * transform.py:26-49 (the class-drop relabel is a permutation-with-merges of 0..4). */
+int rcv_label_lut(int64_t n, int64_t* labels, int32_t nlut, const int64_t* lut, void* stream);
+/* out[b,c,p] = labels[b,p]==c ? +1 : -1, float [B,C,HW]: labelToPred, transform.py:172-183. */
+int rcv_label_to_pred(int64_t B, int32_t C, int64_t HW, const int64_t* labels, float* out,
+                      void* stream);
+/* The two mirrored LabelProp samples of each of P frame pairs (labelPropTrain.py:178-193):
+ * inputs[2q]   = (Y_a, Y_b, Y_a-Y_b, labelToPred(lab_b)), targets[2q]   = lab_a
+ * inputs[2q+1] = (Y_b, Y_a, Y_b-Y_a, labelToPred(lab_a)), targets[2q+1] = lab_b
+ * ya, yb float [P,HW]; la, lb int64 [P,HW]; inputs float [2P,3+C,HW]; targets int64 [2P,HW]. */
+int rcv_lp_assemble(int64_t P, int32_t C, int64_t HW, const float* ya, const float* yb,
+                    const int64_t* la, const int64_t* lb, float* inputs, int64_t* targets,
+                    void* stream);
+
 /* ---- train-step tail: L1 regulariser + pruning mask + Adam --------------- */
 /* One fused pass over a flat parameter range (train.py:23-27 l1reg, 59-65 grad
  * mask, torch.optim.Adam defaults amsgrad=False, weight_decay=0):

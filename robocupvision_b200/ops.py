@@ -18,7 +18,7 @@ from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFF
 __all__ = [
     "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
-    "confusion", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
+    "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
     "MATH_FP32", "MATH_TF32X3", "MATH_AUTO",
 ]
@@ -374,6 +374,55 @@ def confusion(pred, target, num_classes: int):
     conf = torch.zeros((n, num_classes, num_classes), device=pred.device, dtype=torch.int64)
     _call("rcv_confusion", 1, n, num_classes, hw, _ptr(pred), _ptr(target), _ptr(conf), _stream())
     return conf
+
+
+# --------------------------------------------------------------------------- input-side label ops
+def mask_label_lut(nb: bool, nr: bool, ng: bool, nl: bool, num_classes: int = 5):
+    """Lookup table of maskLabel (transform.py:26-49): the relabel applied to class ids 0..C-1."""
+    lut = list(range(num_classes))
+    b, r, g, l = 1, 2, 3, 4
+
+    def drop(k, lut):
+        return [0 if v == k else (v - 1 if v > k else v) for v in lut]
+    if nb:
+        lut = drop(b, lut); r, g, l = 1, 2, 3
+    if nr:
+        lut = drop(r, lut); g, l = 1, 2
+    if ng:
+        lut = drop(g, lut); l = 1
+    if nl:
+        lut = [0 if v == l else v for v in lut]
+    return lut
+
+
+def mask_label_(label, nb, nr, ng, nl, num_classes: int = 5):
+    """In-place maskLabel on a CUDA int64 label tensor (one launch)."""
+    label = _chk(label, torch.int64, "label")
+    lut = torch.tensor(mask_label_lut(nb, nr, ng, nl, num_classes), dtype=torch.int64, device=label.device)
+    _call("rcv_label_lut", 1, label.numel(), _ptr(label), lut.numel(), _ptr(lut), _stream())
+    return label
+
+
+def label_to_pred(label, num_classes: int):
+    """labelToPred (transform.py:172-183): int64 [B,H,W] -> float [B,C,H,W] of +-1."""
+    label = _chk(label, torch.int64, "label")
+    b, h, w = label.shape
+    out = torch.empty((b, num_classes, h, w), device=label.device, dtype=torch.float32)
+    _call("rcv_label_to_pred", 1, b, num_classes, h * w, _ptr(label), _ptr(out), _stream())
+    return out
+
+
+def lp_assemble(ya, yb, la, lb, num_classes: int = 5):
+    """LabelProp batch assembly (labelPropTrain.py:178-193) for P frame pairs -> (inputs [2P,3+C,H,W],
+    targets [2P,H,W])."""
+    ya, yb = _chk(ya, name="ya"), _chk(yb, name="yb")
+    la, lb = _chk(la, torch.int64, "la"), _chk(lb, torch.int64, "lb")
+    p, h, w = ya.shape
+    inputs = torch.empty((2 * p, 3 + num_classes, h, w), device=ya.device, dtype=torch.float32)
+    targets = torch.empty((2 * p, h, w), device=ya.device, dtype=torch.int64)
+    _call("rcv_lp_assemble", 1, p, num_classes, h * w, _ptr(ya), _ptr(yb), _ptr(la), _ptr(lb), _ptr(inputs),
+          _ptr(targets), _stream())
+    return inputs, targets
 
 
 # --------------------------------------------------------------------------- optimiser tail

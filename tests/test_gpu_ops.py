@@ -365,3 +365,33 @@ def test_sgd_matches_torch_sgd():
         opt.zero_grad(); (p_ref * g).sum().backward(); opt.step()
         ops.sgd_step(p, g.cuda(), buf, lr=0.1, momentum=0.5, weight_decay=1e-3, first_step=(step == 0))
         assert_close(f"sgd step {step}", p, p_ref, 2e-6)
+
+
+def test_label_ops():
+    """maskLabel LUT kernel, labelToPred and the LabelProp batch assembly against the reference's own
+    tensor code restated on CPU (transform.py:26-49, 172-183; labelPropTrain.py:178-193)."""
+    from robocupvision_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    lab = torch.randint(0, 5, (3, 12, 20), generator=g)
+    for flags in [(False, False, False, False), (True, False, False, True), (False, True, True, False), (True, True, True, True)]:
+        ref = lab.clone()
+        lut = torch.tensor(ops.mask_label_lut(*flags))
+        got = ops.mask_label_(lab.clone().cuda(), *flags)
+        assert torch.equal(got.cpu(), lut[ref])
+    # labelToPred: ones.scatter_(1, label, -1) * -1, viewed [B,H,W,C] and permuted (transform.py:172-183)
+    B, H, W, C = 3, 12, 20, 5
+    ref = (torch.ones(B * H * W, C).scatter_(1, lab.view(-1, 1), -1.0) * (-1)).view(B, H, W, C).permute(0, 3, 1, 2)
+    assert torch.equal(ops.label_to_pred(lab.cuda(), C).cpu(), ref.contiguous())
+    # LabelProp assembly of P frame pairs
+    P = 4
+    ya, yb = torch.randn(P, H, W, generator=g), torch.randn(P, H, W, generator=g)
+    la, lb = torch.randint(0, 5, (P, H, W), generator=g), torch.randint(0, 5, (P, H, W), generator=g)
+    inp = torch.zeros(2 * P, 8, H, W); tgt = torch.zeros(2 * P, H, W, dtype=torch.long)
+    for q in range(P):
+        preds = (torch.ones(2 * H * W, C).scatter_(1, torch.stack([la[q], lb[q]]).view(-1, 1), -1.0) * (-1)) \
+            .view(2, H, W, C).permute(0, 3, 1, 2)
+        inp[2 * q] = torch.cat([ya[q][None], yb[q][None], (ya[q] - yb[q])[None], preds[1]])
+        inp[2 * q + 1] = torch.cat([yb[q][None], ya[q][None], (yb[q] - ya[q])[None], preds[0]])
+        tgt[2 * q], tgt[2 * q + 1] = la[q], lb[q]
+    gi, gt = ops.lp_assemble(ya.cuda(), yb.cuda(), la.cuda(), lb.cuda(), C)
+    assert torch.equal(gi.cpu(), inp) and torch.equal(gt.cpu(), tgt)

@@ -212,3 +212,39 @@ def test_metrics_vs_reference_literal_loop():
     c_img = ref_metrics.confusion_per_image(pred.numpy(), tgt.numpy(), nC)
     assert (c_img.sum(0) == conf.numpy()).all()
     assert np.allclose(ref_metrics.iou_sums(c_img), IoU.numpy(), atol=1e-6)
+
+
+def test_export_wire_format_matches_reference_file():
+    """robocupvision_b200.export.flatten_state_dict (paramSave.py:5-17) reproduces the reference's committed
+    weightsLP/weights.dat from the released LabelProp checkpoint: length, first / last 64 values, sha256."""
+    import hashlib
+    from collections import OrderedDict
+    from robocupvision_b200.export import flatten_state_dict
+    from util import load_ckpt, load_golden
+    gold = load_golden("weightsLP_head")
+    raw = load_ckpt("bestModelLPFinetunedPruned")          # npz keeps the checkpoint's key order
+    flat = flatten_state_dict(OrderedDict(raw))
+    assert flat.dtype == np.float64 and flat.size == int(gold["n"])
+    assert (flat[:64] == gold["head"]).all() and (flat[-64:] == gold["tail"]).all()
+    assert (np.frombuffer(hashlib.sha256(flat.tobytes()).digest(), dtype=np.uint8) == gold["sha256"]).all()
+
+
+def test_mask_label_lut_matches_reference_logic():
+    """ops.mask_label_lut against a literal restatement of maskLabel (transform.py:26-49) for all 16 flag sets."""
+    import itertools
+    from robocupvision_b200.ops import mask_label_lut
+
+    def ref_mask(label, nb, nr, ng, nl):  # transform.py:26-49, numpy instead of torch indexing
+        b, r, g, l = 1, 2, 3, 4
+        label = label.copy()
+        if nb:
+            label[label == b] = 0; label[label > b] -= 1; r, g, l = 1, 2, 3
+        if nr:
+            label[label == r] = 0; label[label > r] -= 1; g, l = 1, 2
+        if ng:
+            label[label == g] = 0; label[label > g] -= 1; l = 1
+        if nl:
+            label[label == l] = 0
+        return label
+    for flags in itertools.product([False, True], repeat=4):
+        assert mask_label_lut(*flags) == ref_mask(np.arange(5), *flags).tolist(), flags
