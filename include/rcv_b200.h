@@ -107,6 +107,18 @@ int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction);
 int rcv_conv_pack(const rcv_conv_desc* d, int direction, const float* w,
                   void* packed, void* stream);
 
+/* Which kernel family rcv_conv_fwd / rcv_conv_dgrad (per direction) dispatches this layer to
+ * under d->math, given 16-byte aligned tensors and packed weights (tests and profiles name the
+ * engine they measured).  Negative = rcv_status. */
+typedef enum rcv_engine {
+  RCV_ENGINE_SIMT = 0,    /* fp32 FFMA implicit GEMM (any geometry)                       */
+  RCV_ENGINE_DIRECT = 1,  /* fp32 direct conv through L1 (<= 16 output channels, any width) */
+  RCV_ENGINE_UMMA = 2,    /* tcgen05 3xTF32 implicit GEMM, TMEM accumulators               */
+  RCV_ENGINE_NARROW = 3   /* fp32 FFMA2 direct conv, TMA halo staging (<= 16 output        *
+                           * channels, widths that are multiples of 4)                     */
+} rcv_engine;
+int rcv_conv_engine(const rcv_conv_desc* d, int direction);
+
 /* Batched form: the panels of many layers in ONE launch (a train step re-packs every layer's
  * weights each step).  The caller builds a job table on the host once -- the weight and panel
  * device pointers must stay valid and unchanged -- copies it to device memory it owns

@@ -32,6 +32,8 @@ RCV_OK, RCV_ERR_BAD_ARG, RCV_ERR_UNSUPPORTED, RCV_ERR_CUDA, RCV_ERR_WORKSPACE = 
 EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, EPI_AFFINE_RELU, EPI_AFFINE = 0, 1, 2, 3, 4
 # rcv_math
 MATH_FP32, MATH_TF32X3, MATH_AUTO = 0, 1, 2
+# rcv_engine
+ENGINE_SIMT, ENGINE_DIRECT, ENGINE_UMMA, ENGINE_NARROW = 0, 1, 2, 3
 
 
 class ConvDesc(C.Structure):
@@ -50,6 +52,7 @@ SIGNATURES = {
     "rcv_conv_packed_bytes": [C.POINTER(ConvDesc), C.c_int],
     "rcv_conv_uses_tensor_cores": [C.POINTER(ConvDesc), C.c_int],
     "rcv_conv_pack": [C.POINTER(ConvDesc), C.c_int, _p, _p, _p],
+    "rcv_conv_engine": [C.POINTER(ConvDesc), C.c_int],
     "rcv_conv_pack_table_bytes": [_i32],
     "rcv_conv_pack_table_build": [_i32, C.POINTER(ConvDesc), C.POINTER(_i32), C.POINTER(_p), C.POINTER(_p), _p,
                                   C.POINTER(_i64)],

@@ -202,8 +202,14 @@ extern "C" size_t rcv_conv_packed_bytes(const rcv_conv_desc* d, int direction) {
 extern "C" int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction) {
   RcvIgemm p;
   if (pack_problem(d, direction, &p, "rcv_conv_uses_tensor_cores")) return 0;
-  if (d->math == RCV_MATH_FP32) return 0;
-  return (d->math == RCV_MATH_TF32X3 || rcv_umma_pays(p)) ? 1 : 0;
+  return rcv_pick_engine(p, true) == RCV_ENGINE_UMMA ? 1 : 0;
+}
+
+extern "C" int rcv_conv_engine(const rcv_conv_desc* d, int direction) {
+  RcvIgemm p;
+  int rc = pack_problem(d, direction, &p, "rcv_conv_engine");
+  if (rc) return rc;
+  return rcv_pick_engine(p, true);
 }
 
 extern "C" int rcv_conv_pack(const rcv_conv_desc* d, int direction, const float* w, void* packed,

@@ -95,6 +95,9 @@ int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st);       // dispatch on p
 int rcv_launch_igemm_simt(const RcvIgemm& p, cudaStream_t st);  // fp32 FFMA, CUDA cores
 int rcv_launch_direct(const RcvIgemm& p, cudaStream_t st);      // fp32 direct conv, <= 16 output channels
 bool rcv_direct_supported(const RcvIgemm& p);
+int rcv_launch_narrow(const RcvIgemm& p, cudaStream_t st);      // fp32 FFMA2 direct conv, TMA halo staging, <= 16 output channels
+bool rcv_narrow_supported(const RcvIgemm& p);
+int rcv_pick_engine(const RcvIgemm& p, bool have_packed);      // rcv_engine that rcv_launch_igemm dispatches to
 int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF32, TMEM accumulators
 bool rcv_umma_pays(const RcvIgemm& p);  // RCV_MATH_AUTO: is the reduction long enough for tensor cores
 bool rcv_umma_supported(const RcvIgemm& p);  // geometry within the tensor-core engine's limits

@@ -293,17 +293,31 @@ bool rcv_umma_pays(const RcvIgemm& p) {
   return p.CA * maxT >= 128 && p.CB >= 16 && rcv_umma_supported(p);
 }
 
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Which engine runs a problem (rcv_engine).  RCV_NARROW=0 / RCV_DIRECT=0 switch the two direct
+// engines off for A/B runs.
+int rcv_pick_engine(const RcvIgemm& p, bool have_packed) {
+  static const int use_narrow = env_flag("RCV_NARROW", 1);
+  static const int use_direct = env_flag("RCV_DIRECT", 1);
+  if (p.math == RCV_MATH_TF32X3) return RCV_ENGINE_UMMA;
+  // <= 16 output channels: TMA-staged FFMA2 direct convolution (exact fp32), whatever the reduction length
+  if (use_narrow && rcv_narrow_supported(p)) return RCV_ENGINE_NARROW;
+  if (p.math == RCV_MATH_AUTO && have_packed && rcv_umma_pays(p)) return RCV_ENGINE_UMMA;
+  if (use_direct && rcv_direct_supported(p)) return RCV_ENGINE_DIRECT;
+  return RCV_ENGINE_SIMT;
+}
+
 int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st) {
-  if (p.math == RCV_MATH_TF32X3 || (p.math == RCV_MATH_AUTO && p.wpacked != nullptr && rcv_umma_pays(p)))
-    return rcv_launch_igemm_umma(p, st);
-  // narrow layers: direct convolution (RCV_DIRECT=0 keeps the implicit-GEMM engine, for A/B runs)
-  static int use_direct = -1;
-  if (use_direct < 0) {
-    const char* e = getenv("RCV_DIRECT");
-    use_direct = e ? atoi(e) : 1;
+  switch (rcv_pick_engine(p, p.wpacked != nullptr)) {
+    case RCV_ENGINE_UMMA: return rcv_launch_igemm_umma(p, st);
+    case RCV_ENGINE_NARROW: return rcv_launch_narrow(p, st);
+    case RCV_ENGINE_DIRECT: return rcv_launch_direct(p, st);
+    default: return rcv_launch_igemm_simt(p, st);
   }
-  if (use_direct && rcv_direct_supported(p)) return rcv_launch_direct(p, st);
-  return rcv_launch_igemm_simt(p, st);
 }
 
 int rcv_launch_igemm_simt(const RcvIgemm& p, cudaStream_t st) {

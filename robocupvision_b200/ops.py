@@ -16,7 +16,7 @@ from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFF
                    MATH_FP32, MATH_TF32X3, PACK_DGRAD, PACK_FWD, ConvDesc)
 
 __all__ = [
-    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
+    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
     "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
@@ -115,6 +115,15 @@ def conv_packed_bytes(g: ConvGeom, direction: int) -> int:
 def conv_uses_tensor_cores(g: ConvGeom, direction: int, math: int = MATH_AUTO) -> bool:
     d = g.desc(1, 2, 2, EPI_NONE, math)
     return bool(_lib.load().rcv_conv_uses_tensor_cores(C.byref(d), int(direction)))
+
+
+def conv_engine(g: ConvGeom, n: int, h: int, w: int, direction: int = PACK_FWD, math: int = MATH_AUTO) -> int:
+    """rcv_engine the layer dispatches to at this size (ENGINE_SIMT / DIRECT / UMMA / NARROW)."""
+    d = g.desc(n, h, w, EPI_NONE, math)
+    e = _lib.load().rcv_conv_engine(C.byref(d), int(direction))
+    if e < 0:
+        raise _lib.RcvError("rcv_conv_engine", e, _lib.load().rcv_last_error().decode())
+    return int(e)
 
 
 def conv_pack(g: ConvGeom, w, direction: int, out=None):

