@@ -69,6 +69,7 @@ typedef enum rcv_pack_dir {
   RCV_PACK_FWD = 0,      /* rcv_conv_fwd                                        */
   RCV_PACK_DGRAD = 1     /* rcv_conv_dgrad                                      */
 } rcv_pack_dir;
+#define RCV_DIR_WGRAD 2  /* rcv_conv_engine only: the weight gradient (no panel) */
 
 /* One convolution-type layer.  transposed=0: nn.Conv2d(Cin,Cout,ksize,stride,
  * pad,dil) on x[N,Cin,H,W] (model.py:112,130-133,170,259,411,554).
@@ -107,15 +108,16 @@ int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction);
 int rcv_conv_pack(const rcv_conv_desc* d, int direction, const float* w,
                   void* packed, void* stream);
 
-/* Which kernel family rcv_conv_fwd / rcv_conv_dgrad (per direction) dispatches this layer to
- * under d->math, given 16-byte aligned tensors and packed weights (tests and profiles name the
+/* Which kernel family rcv_conv_fwd / rcv_conv_dgrad / rcv_conv_wgrad (direction RCV_PACK_FWD,
+ * RCV_PACK_DGRAD, RCV_DIR_WGRAD) dispatches this layer to under d->math, given 16-byte aligned tensors and packed weights (tests and profiles name the
  * engine they measured).  Negative = rcv_status. */
 typedef enum rcv_engine {
   RCV_ENGINE_SIMT = 0,    /* fp32 FFMA implicit GEMM (any geometry)                       */
   RCV_ENGINE_DIRECT = 1,  /* fp32 direct conv through L1 (<= 16 output channels, any width) */
   RCV_ENGINE_UMMA = 2,    /* tcgen05 3xTF32 implicit GEMM, TMEM accumulators               */
-  RCV_ENGINE_NARROW = 3   /* fp32 FFMA2 direct conv, TMA halo staging (<= 16 output        *
-                           * channels, widths that are multiples of 4)                     */
+  RCV_ENGINE_NARROW = 3   /* fp32 FFMA2 direct conv / register-accumulating wgrad, TMA     *
+                           * halo staging (<= 16 channels on the narrow side, widths that  *
+                           * are multiples of 4)                                           */
 } rcv_engine;
 int rcv_conv_engine(const rcv_conv_desc* d, int direction);
 

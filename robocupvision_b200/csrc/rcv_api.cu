@@ -205,7 +205,18 @@ extern "C" int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction)
   return rcv_pick_engine(p, true) == RCV_ENGINE_UMMA ? 1 : 0;
 }
 
+namespace {
+void wgrad_problem(const rcv_conv_desc* d, RcvWgrad* pp);
+}
+
 extern "C" int rcv_conv_engine(const rcv_conv_desc* d, int direction) {
+  if (direction == RCV_DIR_WGRAD) {
+    int rc = validate(d, "rcv_conv_engine");
+    if (rc) return rc;
+    RcvWgrad w;
+    wgrad_problem(d, &w);
+    return rcv_pick_wgrad_engine(w);
+  }
   RcvIgemm p;
   int rc = pack_problem(d, direction, &p, "rcv_conv_engine");
   if (rc) return rc;
@@ -288,35 +299,46 @@ extern "C" int rcv_conv_dgrad(const rcv_conv_desc* d, const float* dy, const flo
   return rcv_launch_igemm(p, (cudaStream_t)stream);
 }
 
-extern "C" int rcv_conv_wgrad(const rcv_conv_desc* d, const float* x, const float* dy, float* dw,
-                              float* dbias, void* stream) {
-  int rc = validate(d, "rcv_conv_wgrad");
-  if (rc) return rc;
-  RCV_REQUIRE(x && dy && dw, RCV_ERR_BAD_ARG, "rcv_conv_wgrad: null tensor");
+namespace {
+// Pixel-reduction problem of the weight gradient (tensor pointers left NULL; dbias handled by the caller).
+void wgrad_problem(const rcv_conv_desc* d, RcvWgrad* pp) {
+  RcvWgrad& p = *pp;
+  memset(&p, 0, sizeof(p));
   int Ho, Wo;
   out_hw(d, &Ho, &Wo);
-  RcvWgrad p;
-  memset(&p, 0, sizeof(p));
-  p.dw = dw;
   p.math = d->math;
   p.N = d->N;
   const int kk = d->ksize * d->ksize;
   if (!d->transposed) {
-    p.src = x; p.row = dy; p.dbias = dbias;
     p.CA = d->Cin; p.CB = d->Cout;
     p.Hin = d->H; p.Win = d->W; p.Hg = Ho; p.Wg = Wo; p.gs = d->stride;
     p.wsA = kk; p.wsB = d->Cin * kk;
     conv_taps(d, &p.taps);
   } else {
     // dw[ci,co,ky,kx] = sum x[ci,i,j] * dy[co, 2i+ky-1, 2j+kx-1]
-    p.src = dy; p.row = x; p.dbias = nullptr;
     p.CA = d->Cout; p.CB = d->Cin;
     p.Hin = Ho; p.Win = Wo; p.Hg = d->H; p.Wg = d->W; p.gs = 2;
     p.wsA = 9; p.wsB = d->Cout * 9;
     rcv_conv_desc s2 = *d;
     conv_taps(&s2, &p.taps);
+  }
+}
+}  // namespace
+
+extern "C" int rcv_conv_wgrad(const rcv_conv_desc* d, const float* x, const float* dy, float* dw,
+                              float* dbias, void* stream) {
+  int rc = validate(d, "rcv_conv_wgrad");
+  if (rc) return rc;
+  RCV_REQUIRE(x && dy && dw, RCV_ERR_BAD_ARG, "rcv_conv_wgrad: null tensor");
+  RcvWgrad p;
+  wgrad_problem(d, &p);
+  p.dw = dw;
+  if (!d->transposed) {
+    p.src = x; p.row = dy; p.dbias = dbias;
+  } else {
+    p.src = dy; p.row = x; p.dbias = nullptr;
     if (dbias) {
-      rc = rcv_channel_sum(d->N, d->Cout, (int64_t)Ho * Wo, dy, dbias, stream);
+      rc = rcv_channel_sum(d->N, d->Cout, (int64_t)p.Hin * p.Win, dy, dbias, stream);
       if (rc) return rc;
     }
   }

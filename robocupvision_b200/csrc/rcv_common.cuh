@@ -106,3 +106,6 @@ int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st);
 int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st);       // dispatch on p.math
 int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st);         // tcgen05 3xTF32
 bool rcv_umma_wgrad_pays(const RcvWgrad& p);
+int rcv_launch_narrow_wgrad(const RcvWgrad& p, cudaStream_t st);  // fp32 FFMA, TMA-staged, few row channels
+bool rcv_narrow_wgrad_supported(const RcvWgrad& p);
+int rcv_pick_wgrad_engine(const RcvWgrad& p);                  // rcv_engine that rcv_launch_wgrad dispatches to

@@ -20,17 +20,11 @@
 //     FMA arithmetic (no split, no tensor core): results match the ATen CPU path to rounding order.
 //   * Epilogue: bias, ReLU / folded-BN affine in either order, residual, float4 NCHW stores,
 //     train-mode BatchNorm sum / sum-of-squares (warp shuffle -> shared -> one fp64 atomic per channel).
-#include <cuda.h>
-#include <stdlib.h>
-
-#include <type_traits>
-#include <utility>
-
-#include "rcv_common.cuh"
-#include "rcv_umma.cuh"
+#include "rcv_narrow.cuh"
 
 namespace {
 using namespace rcv_umma;
+using namespace rcv_narrow;
 
 constexpr int PIX = 4;    // grid points per thread along x
 constexpr int HL = 2;     // window slots left of the first centre column (dx >= -2)
@@ -106,30 +100,12 @@ __host__ __device__ constexpr int window_rows() {
   return KindTraits<KIND>::PARITY ? KindTraits<KIND>::NR : KindTraits<KIND>::NR - (2 - SLOTS) * KindTraits<KIND>::GS;
 }
 
-template <int N, class F, int... I>
-__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
-  (f(std::integral_constant<int, I>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-  static_for_impl<N>(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
-}
-
 struct NarrowCfg {
   int32_t TR, SPR, RS, R, pitch, CC, nchunk, TWg, ctiles, KK, tiles_per_img, total_tiles;
   uint32_t stage_bytes;  // stage stride (128-byte multiple)
   uint32_t tx_bytes;     // bytes one box delivers
   uint64_t wmap;         // 4 bits per canonical tap position: index into the 3x3 (or 1x1) weight kernel, 15 = unused
 };
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
-      "%5}], [%6];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
-}
 
 // acc.xy += x * w.xy
 __device__ __forceinline__ void ffma2(unsigned long long& acc, float x, float wx, float wy) {
@@ -429,27 +405,6 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__(CBP <= 8 ? 1
 }
 
 // ---------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 // Does tap set `ts` equal the canonical structure of (KIND, Z, slot-0 view)?  Fills wmap.
 // A tap (dy, dx, wi) of an ordinary problem sits at window row dy - RYMIN (slot 0) and column dx + 2.
 template <int KIND, int Z>
@@ -582,18 +537,9 @@ bool plan(const RcvIgemm& p, NarrowCfg* out, int* kind_out, int* nthreads, size_
 
 template <int CBP, int KIND>
 int launch(const RcvIgemm& p, const NarrowCfg& cfg, int nthreads, size_t smem, cudaStream_t st) {
-  EncodeTiledFn enc = encode_fn();
-  RCV_REQUIRE(enc != nullptr, RCV_ERR_CUDA, "narrow_conv: cuTensorMapEncodeTiled not available from the driver");
   CUtensorMap tmap;
-  const cuuint64_t dims[4] = {(cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.CA, (cuuint64_t)p.N};
-  const cuuint64_t strides[3] = {(cuuint64_t)p.Win * 4, (cuuint64_t)p.Win * p.Hin * 4,
-                                 (cuuint64_t)p.Win * p.Hin * p.CA * 4};
-  const cuuint32_t box[4] = {(cuuint32_t)cfg.pitch, (cuuint32_t)cfg.R, (cuuint32_t)cfg.CC, 1u};
-  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.in), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RCV_REQUIRE(r == CUDA_SUCCESS, RCV_ERR_CUDA, "narrow_conv: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  int rc = make_nchw_map(&tmap, p.in, p.N, p.CA, p.Hin, p.Win, cfg.pitch, cfg.R, cfg.CC, "narrow_conv");
+  if (rc) return rc;
   static int ctas_per_sm[2] = {0, 0};  // [smem bucket is irrelevant: keyed per (CBP, KIND)] occupancy at this block size
   static int last_nt = 0;
   static size_t last_smem = 0;

@@ -6,6 +6,8 @@
 // channel assignment keeps the float4 reads bank-conflict free).  The pixel
 // range is split over grid.z; partial tiles are combined with fp32 RED atomics
 // into the zero-initialised gradient.
+#include <stdlib.h>
+
 #include "rcv_common.cuh"
 
 namespace {
@@ -329,9 +331,20 @@ int launch_cfg(RcvWgrad p, cudaStream_t st) {
 
 }  // namespace
 
+// Which engine runs a weight-gradient problem (rcv_engine).  RCV_NARROW_WGRAD=0: A/B runs.
+int rcv_pick_wgrad_engine(const RcvWgrad& p) {
+  static const int use_narrow = getenv("RCV_NARROW_WGRAD") ? atoi(getenv("RCV_NARROW_WGRAD")) : 1;
+  if (p.math == RCV_MATH_TF32X3) return RCV_ENGINE_UMMA;
+  // few channels on the dense side: TMA-staged register-accumulating kernel
+  if (use_narrow && rcv_narrow_wgrad_supported(p)) return RCV_ENGINE_NARROW;
+  if (p.math == RCV_MATH_AUTO && rcv_umma_wgrad_pays(p)) return RCV_ENGINE_UMMA;
+  return RCV_ENGINE_SIMT;
+}
+
 int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st) {
-  if (p.math == RCV_MATH_TF32X3 || (p.math == RCV_MATH_AUTO && rcv_umma_wgrad_pays(p)))
-    return rcv_launch_wgrad_umma(p, st);
+  const int eng = rcv_pick_wgrad_engine(p);
+  if (eng == RCV_ENGINE_NARROW) return rcv_launch_narrow_wgrad(p, st);
+  if (eng == RCV_ENGINE_UMMA) return rcv_launch_wgrad_umma(p, st);
   if (p.CB <= 8 && p.taps.n == 9 && p.CA <= 16) return launch_small<9, 8, 1>(p, st);
   if (p.CB <= 8 && p.taps.n == 1 && p.CA <= 64) return launch_small<1, 8, 8>(p, st);
   if (p.CB > 64) return launch_cfg<128, 128, 8, 8>(p, st);

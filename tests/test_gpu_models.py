@@ -251,13 +251,19 @@ def test_step_async_matches_step():
             got.append(prev.wait())
         prev = h
     got.append(prev.wait())
-    # (fp32 RED atomics in the weight gradient make two runs agree to rounding, not bit for bit; Adam
-    # normalises near-zero gradients, so that noise grows over the 5 steps: 2e-5 observed headroom)
+    # fp32 RED atomics in the weight gradient make two runs agree to rounding, not bit for bit, and Adam
+    # turns that rounding into a discrete event: a weight whose gradient is ~0 moves by +lr or -lr at the
+    # first steps depending on the sign of the noise (tools/step_repeat.py: identical runs split into a few
+    # distinct trajectories, parameters 2*lr apart in a handful of elements, loss 1e-5 apart by step 5).
+    # So: losses to 1e-4, parameters equal to rounding except a few elements at most 2*lr*steps apart.
+    lr, nsteps = 1e-3, len(xs)
     for (l0, c0), (ce, tot, c1) in zip(ref_losses, got):
-        assert abs(l0 - tot) <= 2e-5 * abs(l0) and abs(c0 - c1) <= 8
+        assert abs(l0 - tot) <= 1e-4 * abs(l0) and abs(c0 - c1) <= 16
     for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
         if a.is_floating_point():
-            assert_close(k, a, b, 1e-4)
+            d = (a - b).abs()
+            assert float(d.max()) <= 2.2 * lr * nsteps + 1e-4 * float(a.abs().max()), k
+            assert float((d > 1e-5 * max(1.0, float(a.abs().max()))).float().mean()) <= 0.02, k
         else:
             assert torch.equal(a, b), k
 

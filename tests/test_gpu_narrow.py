@@ -112,3 +112,39 @@ def test_narrow_falls_back_on_odd_widths():
     assert _engine(g, 2, 9, 7) != _lib.ENGINE_NARROW
     assert_close("odd width", ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), math=ops.MATH_AUTO),
                  _ref_conv("k3s1d1", x, wt, b), 2e-6)
+
+
+WGRAD_CASES = [
+    # geom, cin, cout, n, h, w -- the dense ("row") side has <= 16 channels: Cout for a conv, Cin for a transposed conv
+    ("k3s1d1", 3, 8, 2, 12, 20),     # 3 roles, two pixel parts
+    ("k3s1d1", 16, 16, 3, 30, 40),   # 4 channel chunks x 2 row-channel groups
+    ("k3s1d1", 8, 5, 2, 7, 12),      # odd height, 5 row channels
+    ("k3s1d1", 3, 8, 2, 120, 160),
+    ("k3s1d1", 16, 16, 1, 6, 320),   # two column tiles
+    ("k3s1d2", 3, 8, 2, 12, 20),
+    ("k3s1d2", 16, 16, 2, 13, 24),
+    ("k3s2", 8, 16, 2, 24, 40),
+    ("k3s2", 3, 8, 2, 26, 24),
+    ("convT", 16, 8, 2, 12, 20),     # src = dy (8 ch, fine grid), row = x (16 ch, coarse grid)
+    ("convT", 8, 32, 2, 15, 20),     # 8 row channels, 32 src channels
+    ("k1", 8, 5, 2, 12, 20),
+    ("k1", 16, 5, 2, 120, 160),
+]
+
+
+@pytest.mark.parametrize("geom,cin,cout,n,h,w", WGRAD_CASES)
+def test_narrow_wgrad(geom, cin, cout, n, h, w):
+    from robocupvision_b200 import _lib, ops
+    g, x, wt, b = _mk(geom, cin, cout, n, h, w, seed=15)
+    assert _engine(g, n, h, w, 2) == _lib.ENGINE_NARROW
+    wt.requires_grad_(True); b.requires_grad_(True)
+    y = _ref_conv(geom, x, wt, b)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(16))
+    y.backward(dy)
+    dw, db = ops.conv_wgrad(g, x.cuda(), dy.cuda(), want_bias=True, math=ops.MATH_AUTO)
+    assert_close(f"narrow wgrad {geom} {cin}->{cout}", dw, wt.grad, 1e-5)
+    assert_close(f"narrow bgrad {geom}", db, b.grad, 1e-5)
+    # accumulates into a caller-provided gradient
+    dw2 = torch.ones_like(dw)
+    ops.conv_wgrad(g, x.cuda(), dy.cuda(), dw=dw2, math=ops.MATH_AUTO)
+    assert_close("narrow wgrad accumulate", dw2, wt.grad + 1.0, 1e-5)
