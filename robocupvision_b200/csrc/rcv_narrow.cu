@@ -90,11 +90,13 @@ __host__ __device__ constexpr bool win_used(int idx) {  // is register-window sl
   return false;
 }
 
-// Output slots per thread: 2 everywhere except the 16-channel stride-2 kernel, whose 11-wide windows next to
-// 128 accumulator registers spill; one output row per thread there (the two rows would share only one of
-// their five window rows anyway).
+// Output slots per thread.  8-channel kernels: 2 (two output rows share the register window of input rows).
+// 16-channel kernels hold 16 x 4 accumulator pairs per slot: with two slots they need ~200 registers and only
+// 8 warps fit an SM (ncu: issue slots 37% busy, nothing to switch to during LDS / FFMA2 latencies), so they
+// run one output row per thread at ~110 registers and twice the warps; the parity kind keeps both column
+// parities in one thread (8 consecutive output floats per store).
 template <int CBP, int KIND>
-struct Slots { static constexpr int N = (KIND == NK_S2 && CBP > 8) ? 1 : 2; };
+struct Slots { static constexpr int N = (CBP > 8 && KIND != NK_PAR) ? 1 : 2; };
 template <int KIND, int SLOTS>
 __host__ __device__ constexpr int window_rows() {
   return KindTraits<KIND>::PARITY ? KindTraits<KIND>::NR : KindTraits<KIND>::NR - (2 - SLOTS) * KindTraits<KIND>::GS;
@@ -102,6 +104,8 @@ __host__ __device__ constexpr int window_rows() {
 
 struct NarrowCfg {
   int32_t TR, SPR, RS, R, pitch, CC, nchunk, TWg, ctiles, KK, tiles_per_img, total_tiles;
+  int32_t NS;            // pipeline stages (2..4)
+  int32_t NH, cbp;       // channel groups and channels per group (8 or 16): kernel template selectors
   uint32_t stage_bytes;  // stage stride (128-byte multiple)
   uint32_t tx_bytes;     // bytes one box delivers
   uint64_t wmap;         // 4 bits per canonical tap position: index into the 3x3 (or 1x1) weight kernel, 15 = unused
@@ -135,7 +139,7 @@ __device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh)
 }
 
 // The arithmetic of one channel chunk for one thread: fully unrolled over (window row, slot, tap).
-template <int CBP, int KIND, int Z>
+template <int CBP, int KIND, int Z, int CBT>
 __device__ __forceinline__ void chunk_math(unsigned long long (&acc)[Slots<CBP, KIND>::N][PIX][CBP / 2], const float* __restrict__ xs,
                                            uint32_t wrow0, int cn, int plane, int pitch, int wstep) {
   using KT = KindTraits<KIND>;
@@ -186,7 +190,7 @@ __device__ __forceinline__ void chunk_math(unsigned long long (&acc)[Slots<CBP, 
                 float4 w;
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                              : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
-                             : "r"(wrow + (j * CBP + 4 * c4) * 4));
+                             : "r"(wrow + (j * CBT + 4 * c4) * 4));
 #pragma unroll
                 for (int x = 0; x < PIX; ++x) {
                   ffma2(acc[q][x][2 * c4], wv[x * GS + d], w.x, w.y);
@@ -203,34 +207,39 @@ __device__ __forceinline__ void chunk_math(unsigned long long (&acc)[Slots<CBP, 
   }
 }
 
-template <int CBP, int KIND>
-__global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__(CBP <= 8 ? 128 : 224)
+// CBP = output channels one thread accumulates, NH = channel groups the problem is split into (each tile
+// is visited once per group; the weight image and the epilogue constants cover all CBP*NH channels)
+template <int CBP, int KIND, int NH>
+__global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__((CBP <= 8 || KIND != NK_PAR) ? 128 : 224)
     narrow_conv_kernel(const __grid_constant__ CUtensorMap tmap, const RcvIgemm p, const NarrowCfg cfg) {
   using KT = KindTraits<KIND>;
   constexpr int GS = KT::GS;
   constexpr int SLOTS = Slots<CBP, KIND>::N;
+  constexpr int CBT = CBP * NH;
   constexpr bool par = KT::PARITY != 0;
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[2];
-  __shared__ float red[2][NTMAX / 32][CBP];  // per-warp BatchNorm partial sums over this CTA's tiles
+  __shared__ __align__(8) unsigned long long bars[4];
+  __shared__ float red[2][NTMAX / 32][CBT];  // per-warp BatchNorm partial sums over this CTA's tiles
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  float* ws = reinterpret_cast<float*>(sgen + 2 * (size_t)cfg.stage_bytes);  // [CA][KK][CBP]
-  float* cst = ws + (size_t)p.CA * cfg.KK * CBP;                              // [3][CBP]
+  float* ws = reinterpret_cast<float*>(sgen + cfg.NS * (size_t)cfg.stage_bytes);  // [CA][KK][CBT]
+  float* cst = ws + (size_t)p.CA * cfg.KK * CBT;                              // [3][CBT]
   const uint32_t bar0 = smem_u32(&bars[0]);
 
   // Persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ...; a tile = (row parity z, image n, row
   // tile rt, column tile ct).  Work items = (tile, channel chunk), double-buffered through two stages:
-  // the copy of item i+2 is issued when item i's arithmetic is done, so it also runs under the epilogue
+  // the copy of item i+NS is issued when item i's arithmetic is done, so it also runs under the epilogue
   // stores of a tile and across tile boundaries.
   const int nchunk = cfg.nchunk;
   const int ntiles = cfg.total_tiles;
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nitems = my_tiles * nchunk;
-  auto decode = [&](int tile, int& z, int& n, int& i0, int& j0) {
+  auto decode = [&](int tile_h, int& h, int& z, int& n, int& i0, int& j0) {
+    const int tile = tile_h / NH;
+    h = tile_h - tile * NH;  // channel group: fastest, so the groups of a tile read its input back to back
     const int per_z = cfg.tiles_per_img * p.N;
     z = tile / per_z;
     const int r = tile - z * per_z;
@@ -242,38 +251,37 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__(CBP <= 8 ? 1
   };
   auto issue = [&](int item) {  // thread 0 only
     const int t = item / nchunk, k = item - t * nchunk;
-    int z, n, i0, j0;
-    decode((int)blockIdx.x + t * (int)gridDim.x, z, n, i0, j0);
-    const uint32_t bar = bar0 + 8 * (item & 1);
+    int h, z, n, i0, j0;
+    decode((int)blockIdx.x + t * (int)gridDim.x, h, z, n, i0, j0);
+    const int sg = item % cfg.NS;
+    const uint32_t bar = bar0 + 8 * sg;
     mbar_expect_tx(bar, cfg.tx_bytes);
-    tma_load_4d(sbase + (item & 1) * cfg.stage_bytes, &tmap, j0 * GS - 4, i0 * GS + KT::RYMIN, k * cfg.CC, n, bar);
+    tma_load_4d(sbase + sg * cfg.stage_bytes, &tmap, j0 * GS - 4, i0 * GS + KT::RYMIN, k * cfg.CC, n, bar);
   };
 
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    for (int i = 0; i < cfg.NS; ++i) mbar_init(bar0 + 8 * i, 1);
     fence_barrier_init();
     fence_proxy_async_smem();
-    issue(0);
-    if (nitems > 1) issue(1);
+    for (int i = 0; i < cfg.NS && i < nitems; ++i) issue(i);
   }
   // weight image [channel][canonical tap][CBP] and epilogue constants (plain loads; overlaps the first copy)
   {
     const int KK = cfg.KK;
-    const int tot = p.CA * KK * CBP;
+    const int tot = p.CA * KK * CBT;
     for (int e = tid; e < tot; e += blockDim.x) {
-      const int cb = e % CBP, k = e / CBP;
+      const int cb = e % CBT, k = e / CBT;
       const int ca = k / KK, j = k - ca * KK;
       const int wi = (int)((cfg.wmap >> (4 * j)) & 15u);
       ws[e] = (cb < p.CB && wi < 9) ? __ldg(p.w + (size_t)ca * p.wsA + (size_t)cb * p.wsB + wi) : 0.f;
     }
-    if (tid < CBP) {
+    if (tid < CBT) {
       const bool in = tid < p.CB;
       cst[tid] = (in && p.bias) ? __ldg(p.bias + tid) : 0.f;
-      cst[CBP + tid] = (in && p.scale) ? __ldg(p.scale + tid) : 1.f;
-      cst[2 * CBP + tid] = (in && p.shift) ? __ldg(p.shift + tid) : 0.f;
+      cst[CBT + tid] = (in && p.scale) ? __ldg(p.scale + tid) : 1.f;
+      cst[2 * CBT + tid] = (in && p.shift) ? __ldg(p.shift + tid) : 0.f;
     }
-    if (lane < CBP) { red[0][wid][lane] = 0.f; red[1][wid][lane] = 0.f; }
+    if (lane < CBT) { red[0][wid][lane] = 0.f; red[1][wid][lane] = 0.f; }
   }
   __syncthreads();
 
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__(CBP <= 8 ? 1
   const int pitch = cfg.pitch;
   const int plane = cfg.R * pitch;
   const int toff = (ty * cfg.RS * GS) * pitch + 4 + s * PIX * GS;  // thread's window origin in a channel plane
-  const int wstep = cfg.KK * CBP;
+  const int wstep = cfg.KK * CBT;
   const int epi = p.epilogue;
   const bool has_res = p.residual != nullptr;
   const bool do_stats = p.stats != nullptr;
@@ -289,8 +297,8 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__(CBP <= 8 ? 1
 
   int item = 0;
   for (int t = 0; t < my_tiles; ++t) {
-    int z, n, i0, j0;
-    decode((int)blockIdx.x + t * (int)gridDim.x, z, n, i0, j0);
+    int h, z, n, i0, j0;
+    decode((int)blockIdx.x + t * (int)gridDim.x, h, z, n, i0, j0);
     const int gi = i0 + ty * cfg.RS;    // grid row of slot 0
     const int gj = j0 + s * PIX;        // first grid column
     const bool active = ty < cfg.TR && gi < p.Hg && gj < p.Wg;
@@ -304,20 +312,20 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__(CBP <= 8 ? 1
         for (int c = 0; c < CBP / 2; ++c) acc[q][x][c] = 0ull;
 
     for (int k = 0; k < nchunk; ++k, ++item) {
-      const int st = item & 1;
-      mbar_wait(bar0 + 8 * st, (item >> 1) & 1);
+      const int st = item % cfg.NS;
+      mbar_wait(bar0 + 8 * st, (item / cfg.NS) & 1);
       if (active) {
         const float* xs = reinterpret_cast<const float*>(sgen + (size_t)st * cfg.stage_bytes) + toff;
         const int ca0 = k * cfg.CC;
         const int cn = min(cfg.CC, p.CA - ca0);
-        const uint32_t wrow0 = smem_u32(ws) + (uint32_t)(ca0 * wstep) * 4u;
+        const uint32_t wrow0 = smem_u32(ws) + (uint32_t)(ca0 * wstep + h * CBP) * 4u;
         if (par && z == 1)
-          chunk_math<CBP, KIND, 1>(acc, xs, wrow0, cn, plane, pitch, wstep);
+          chunk_math<CBP, KIND, 1, CBT>(acc, xs, wrow0, cn, plane, pitch, wstep);
         else
-          chunk_math<CBP, KIND, 0>(acc, xs, wrow0, cn, plane, pitch, wstep);
+          chunk_math<CBP, KIND, 0, CBT>(acc, xs, wrow0, cn, plane, pitch, wstep);
       }
       __syncthreads();  // every reader is done with this stage
-      if (tid == 0 && item + 2 < nitems) issue(item + 2);
+      if (tid == 0 && item + cfg.NS < nitems) issue(item + cfg.NS);
     }
 
     // ---------------- epilogue of the tile ----------------
@@ -337,17 +345,17 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__(CBP <= 8 ? 1
 #pragma unroll
     for (int c2 = 0; c2 < CBP / 2; ++c2) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int cb = 2 * c2 + h;
+      for (int hl = 0; hl < 2; ++hl) {
+        const int cb = h * CBP + 2 * c2 + hl;  // output channel
         float s1 = 0.f, s2 = 0.f;
         if (cb < p.CB) {
-          const float bi = cst[cb], sc = cst[CBP + cb], sh = cst[2 * CBP + cb];
+          const float bi = cst[cb], sc = cst[CBT + cb], sh = cst[2 * CBT + cb];
           float v[2][PIX];
 #pragma unroll
           for (int q = 0; q < SLOTS; ++q)
 #pragma unroll
             for (int x = 0; x < PIX; ++x)
-              v[q][x] = apply_epi((h ? hi_f(acc[q][x][c2]) : lo_f(acc[q][x][c2])) + bi, epi, sc, sh);
+              v[q][x] = apply_epi((hl ? hi_f(acc[q][x][c2]) : lo_f(acc[q][x][c2])) + bi, epi, sc, sh);
           if constexpr (par) {
             if (vq[0]) {
               float* o = p.out + ob[0] + (size_t)cb * HWo;
@@ -392,8 +400,8 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__(CBP <= 8 ? 1
   }
   if (do_stats) {
     __syncthreads();
-    if (tid < 2 * CBP) {
-      const int which = tid / CBP, c = tid - which * CBP;
+    if (tid < 2 * CBT) {
+      const int which = tid / CBT, c = tid - which * CBT;
       if (c < p.CB) {
         double tsum = 0.0;
         const int nw = (blockDim.x + 31) >> 5;
@@ -488,7 +496,16 @@ bool plan(const RcvIgemm& p, NarrowCfg* out, int* kind_out, int* nthreads, size_
   const int kind = classify(p, wmap);
   if (kind < 0) return false;
   for (int j = 0; j < 9; ++j) c.wmap |= (uint64_t)(wmap[j] < 0 ? 15 : wmap[j]) << (4 * j);
-  const int slots = (kind == NK_S2 && p.CB > 8) ? Slots<16, NK_S2>::N : 2;
+  // > 8 output channels.  Ordinary kinds: one 16-channel pass, one output row per thread (measured faster than
+  // two 8-channel passes: 46 vs 52 us for 16->16 @60x80 x64).  Parity kind: both column parities stay in one
+  // thread, which at 16 channels is ~200 registers and 8 warps per SM; two groups of 8 channels through the
+  // 8-channel kernel run 3-4 CTAs per SM instead (36 vs 44 us for convT 32->16 @30x40 x64).
+  // RCV_NARROW_SPLIT16 = 0 / 1 forces one policy for every kind (A/B runs).
+  static const int split16 = env_int("RCV_NARROW_SPLIT16", -1);
+  const bool split = p.CB > 8 && (split16 < 0 ? kind == NK_PAR : split16 != 0);
+  c.NH = split ? 2 : 1;
+  c.cbp = (p.CB > 8 && !split) ? 16 : 8;
+  const int slots = (c.cbp > 8 && kind != NK_PAR) ? 1 : 2;
   c.RS = par ? 1 : slots;
   c.KK = kind == NK_K1 ? 1 : 9;
   const int NR = kind_nr(kind) - (par ? 0 : (2 - slots) * p.gs);
@@ -500,8 +517,9 @@ bool plan(const RcvIgemm& p, NarrowCfg* out, int* kind_out, int* nthreads, size_
   c.pitch = c.TWg * p.gs + 8;
   if (c.pitch > 256 || c.SPR > NTMAX) return false;
   // tile: rows
-  // 16-channel kernels hold 128 accumulator registers: 128-thread CTAs at <= 224 registers, two per SM
-  int want = p.CB > 8 ? 128 : env_int("RCV_NARROW_THREADS", 160);
+  // 16-channel parity kernels hold 128 accumulator registers: 128-thread CTAs at <= 224 registers, two per SM
+  int want = (c.cbp > 8 && kind == NK_PAR) ? 128 : env_int("RCV_NARROW_THREADS", 160);
+  want = (c.cbp > 8 && want > 128) ? 128 : want;  // launch bounds of the 16-channel kernels
   const int trmax = rcv_cdiv(p.Hg, c.RS);
   int TR = want / c.SPR;
   TR = TR < 1 ? 1 : TR;
@@ -516,16 +534,19 @@ bool plan(const RcvIgemm& p, NarrowCfg* out, int* kind_out, int* nthreads, size_
   const size_t per_ch = (size_t)c.R * c.pitch * 4;
   int CC = p.CA < 8 ? p.CA : 8;
   const size_t budget = (size_t)env_int("RCV_NARROW_SMEM_KB", 56) * 1024;
-  while (CC > 1 && 2 * ((CC * per_ch + 127) & ~(size_t)127) + wbytes > budget) --CC;
+  int NS = env_int("RCV_NARROW_STAGES", 2);
+  NS = NS < 2 ? 2 : NS > 4 ? 4 : NS;
+  c.NS = NS;
+  while (CC > 1 && NS * ((CC * per_ch + 127) & ~(size_t)127) + wbytes > budget) --CC;
   c.nchunk = rcv_cdiv(p.CA, CC);
   CC = rcv_cdiv(p.CA, c.nchunk);
   c.CC = CC;
   c.stage_bytes = (uint32_t)((CC * per_ch + 127) & ~(size_t)127);
   c.tx_bytes = (uint32_t)(CC * per_ch);
-  const size_t total = 2 * (size_t)c.stage_bytes + wbytes + 256;
+  const size_t total = NS * (size_t)c.stage_bytes + wbytes + 256;
   if (total > 200 * 1024) return false;
   c.tiles_per_img = rcv_cdiv(p.Hg, c.TR * c.RS) * c.ctiles;
-  const int64_t tt = (int64_t)c.tiles_per_img * p.N * (par ? 2 : 1);
+  const int64_t tt = (int64_t)c.tiles_per_img * p.N * (par ? 2 : 1) * c.NH;
   if (tt >= (1ll << 31)) return false;
   c.total_tiles = (int)tt;
   *out = c;
@@ -535,7 +556,7 @@ bool plan(const RcvIgemm& p, NarrowCfg* out, int* kind_out, int* nthreads, size_
   return true;
 }
 
-template <int CBP, int KIND>
+template <int CBP, int KIND, int NH>
 int launch(const RcvIgemm& p, const NarrowCfg& cfg, int nthreads, size_t smem, cudaStream_t st) {
   CUtensorMap tmap;
   int rc = make_nchw_map(&tmap, p.in, p.N, p.CA, p.Hin, p.Win, cfg.pitch, cfg.R, cfg.CC, "narrow_conv");
@@ -548,32 +569,32 @@ int launch(const RcvIgemm& p, const NarrowCfg& cfg, int nthreads, size_t smem, c
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(narrow_conv_kernel<CBP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(narrow_conv_kernel<CBP, KIND>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(narrow_conv_kernel<CBP, KIND, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(narrow_conv_kernel<CBP, KIND, NH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
   }
   if (last_nt != nthreads || last_smem != smem) {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, narrow_conv_kernel<CBP, KIND>, nthreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, narrow_conv_kernel<CBP, KIND, NH>, nthreads, smem);
     ctas_per_sm[0] = occ < 1 ? 1 : occ;
     last_nt = nthreads;
     last_smem = smem;
   }
   const int64_t slots = (int64_t)num_sms * ctas_per_sm[0];
   const int grid = (int)(cfg.total_tiles < slots ? cfg.total_tiles : slots);
-  narrow_conv_kernel<CBP, KIND><<<grid, nthreads, smem, st>>>(tmap, p, cfg);
+  narrow_conv_kernel<CBP, KIND, NH><<<grid, nthreads, smem, st>>>(tmap, p, cfg);
   RCV_CHECK_LAUNCH("narrow_conv_kernel");
   return RCV_OK;
 }
 
-template <int CBP>
+template <int CBP, int NH>
 int launch_kind(int kind, const RcvIgemm& p, const NarrowCfg& c, int nt, size_t sm, cudaStream_t st) {
   switch (kind) {
-    case NK_S1D1: return launch<CBP, NK_S1D1>(p, c, nt, sm, st);
-    case NK_S1D2: return launch<CBP, NK_S1D2>(p, c, nt, sm, st);
-    case NK_S2: return launch<CBP, NK_S2>(p, c, nt, sm, st);
-    case NK_PAR: return launch<CBP, NK_PAR>(p, c, nt, sm, st);
-    default: return launch<CBP, NK_K1>(p, c, nt, sm, st);
+    case NK_S1D1: return launch<CBP, NK_S1D1, NH>(p, c, nt, sm, st);
+    case NK_S1D2: return launch<CBP, NK_S1D2, NH>(p, c, nt, sm, st);
+    case NK_S2: return launch<CBP, NK_S2, NH>(p, c, nt, sm, st);
+    case NK_PAR: return launch<CBP, NK_PAR, NH>(p, c, nt, sm, st);
+    default: return launch<CBP, NK_K1, NH>(p, c, nt, sm, st);
   }
 }
 
@@ -591,5 +612,6 @@ int rcv_launch_narrow(const RcvIgemm& p, cudaStream_t st) {
   int nt, kind;
   size_t sm;
   RCV_REQUIRE(plan(p, &c, &kind, &nt, &sm), RCV_ERR_UNSUPPORTED, "narrow_conv: geometry outside the kernel's limits");
-  return p.CB <= 8 ? launch_kind<8>(kind, p, c, nt, sm, st) : launch_kind<16>(kind, p, c, nt, sm, st);
+  if (c.cbp == 16) return launch_kind<16, 1>(kind, p, c, nt, sm, st);
+  return c.NH == 2 ? launch_kind<8, 2>(kind, p, c, nt, sm, st) : launch_kind<8, 1>(kind, p, c, nt, sm, st);
 }

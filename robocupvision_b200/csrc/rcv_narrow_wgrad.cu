@@ -33,6 +33,7 @@ template <> struct WT<WK_K1> { static constexpr int GS = 1, D = 1, KD = 1, MIN =
 struct WgCfg {
   int32_t TR, SPR, R, pitch, CC, G, nroles, nparts, TWg, ctiles, tiles_per_img, total_tiles;
   int32_t rows;          // grid rows per tile = 2*TR
+  int32_t NS;            // pipeline stages (2..4)
   uint32_t src_bytes, row_bytes, stage_bytes, row_off;
   uint64_t wmap;         // 4 bits per canonical tap (ky*KD+kx): index into the 3x3 / 1x1 kernel
 };
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(NTW, 2)
   constexpr int GS = T::GS, D = T::D, KD = T::KD, WC = T::WC, NR = T::NR;
   constexpr int NTAP = KD * KD;
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[2];
+  __shared__ __align__(8) unsigned long long bars[4];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -62,19 +63,18 @@ __global__ void __launch_bounds__(NTW, 2)
     const int r2 = tile - n * cfg.tiles_per_img;
     const int rt = r2 / cfg.ctiles, ct = r2 - rt * cfg.ctiles;
     const int i0 = rt * cfg.rows, j0 = ct * cfg.TWg;
-    const uint32_t bar = bar0 + 8 * (item & 1);
-    const uint32_t dst = sbase + (item & 1) * cfg.stage_bytes;
+    const int sg = item % cfg.NS;
+    const uint32_t bar = bar0 + 8 * sg;
+    const uint32_t dst = sbase + sg * cfg.stage_bytes;
     mbar_expect_tx(bar, cfg.src_bytes + cfg.row_bytes);
     tma_load_4d(dst, &map_src, j0 * GS - 4, i0 * GS + T::MIN, ca0, n, bar);
     tma_load_4d(dst + cfg.row_off, &map_row, j0, i0, 0, n, bar);
   };
   if (tid == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    for (int i = 0; i < cfg.NS; ++i) mbar_init(bar0 + 8 * i, 1);
     fence_barrier_init();
     fence_proxy_async_smem();
-    issue(0);
-    if (my_tiles > 1) issue(1);
+    for (int i = 0; i < cfg.NS && i < my_tiles; ++i) issue(i);
   }
   __syncthreads();
 
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(NTW, 2)
   const int sbeg = part * per, send = min(nstrips, sbeg + per);
 
   for (int item = 0; item < my_tiles; ++item) {
-    const int st = item & 1;
-    mbar_wait(bar0 + 8 * st, (item >> 1) & 1);
+    const int st = item % cfg.NS;
+    mbar_wait(bar0 + 8 * st, (item / cfg.NS) & 1);
     if (has_role) {
       const float* ssrc = reinterpret_cast<const float*>(sgen + (size_t)st * cfg.stage_bytes) + cl * plane;
       const float* srow = reinterpret_cast<const float*>(sgen + (size_t)st * cfg.stage_bytes + cfg.row_off) +
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(NTW, 2)
       }
     }
     __syncthreads();  // every reader is done with this stage
-    if (tid == 0 && item + 2 < my_tiles) issue(item + 2);
+    if (tid == 0 && item + cfg.NS < my_tiles) issue(item + cfg.NS);
   }
 
   // ---------------- reduction ----------------
@@ -271,6 +271,9 @@ bool plan(const RcvWgrad& p, WgCfg* out, int* kind_out, size_t* smem) {
   // rows per tile: the candidate (<= 8 row pairs, two stages within the shared-memory budget) that wastes the
   // fewest lanes: strips per role part against whole warps, image rows against whole tiles
   const size_t budget = (size_t)env_int("RCV_NARROW_WGRAD_SMEM_KB", 100) * 1024;
+  int NS = env_int("RCV_NARROW_WGRAD_STAGES", 2);
+  NS = NS < 2 ? 2 : NS > 4 ? 4 : NS;
+  c.NS = NS;
   const int trmax = rcv_cdiv(p.Hg, 2) < 8 ? rcv_cdiv(p.Hg, 2) : 8;
   double best = -1.0;
   WgCfg bc = c;
@@ -283,7 +286,7 @@ bool plan(const RcvWgrad& p, WgCfg* out, int* kind_out, size_t* smem) {
     t.row_bytes = (uint32_t)((size_t)p.CB * t.rows * t.TWg * 4);
     t.row_off = (t.src_bytes + 127u) & ~127u;
     t.stage_bytes = (t.row_off + t.row_bytes + 127u) & ~127u;
-    if (2 * (size_t)t.stage_bytes > budget && TR > 1) break;
+    if (NS * (size_t)t.stage_bytes > budget && TR > 1) break;
     const int per = rcv_cdiv(TR * t.SPR, t.nparts);
     const double e1 = (double)per / (32.0 * rcv_cdiv(per, 32));
     const double e2 = (double)p.Hg / ((double)rcv_cdiv(p.Hg, t.rows) * t.rows);
@@ -292,15 +295,15 @@ bool plan(const RcvWgrad& p, WgCfg* out, int* kind_out, size_t* smem) {
     if (e >= best) { best = e; bc = t; }
   }
   c = bc;
-  if (c.R > 256 || c.rows > 256 || 2 * (size_t)c.stage_bytes + 256 > 200 * 1024) return false;
-  if ((size_t)(p.CB * c.CC * p.wsA + p.CB) * 4 > 2 * (size_t)c.stage_bytes) return false;  // reduction image reuses the stages
+  if (c.R > 256 || c.rows > 256 || NS * (size_t)c.stage_bytes + 256 > 200 * 1024) return false;
+  if ((size_t)(p.CB * c.CC * p.wsA + p.CB) * 4 > NS * (size_t)c.stage_bytes) return false;  // reduction image reuses the stages
   c.tiles_per_img = rcv_cdiv(p.Hg, c.rows) * c.ctiles;
   const int64_t tt = (int64_t)c.tiles_per_img * p.N;
   if (tt >= (1ll << 31)) return false;
   c.total_tiles = (int)tt;
   *out = c;
   *kind_out = kind;
-  *smem = 2 * (size_t)c.stage_bytes + 256;
+  *smem = NS * (size_t)c.stage_bytes + 256;
   return true;
 }
 
