@@ -321,7 +321,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
-            "roofline": roof, "roofline_whole_step": roof_step}
+            "roofline": roof, "roofline_whole_step": roof_step,
+            "roofline_hbm_layer": narrow_layer_roofline(model, wl, batch, dev, pk)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, ms, threads = cpu_reference(wl, batch, args.cpu_steps, 2)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": ms,
@@ -410,6 +411,43 @@ def dominant_kernel_roofline(model, wl, batch, dev, pk):
         out["tf32_mma_tflops"] = 3.0 * tfl
         out["frac_of_tf32x3_ceiling"] = tfl / (pk["tensor_burst"] / 6.0)
     return out
+
+
+def narrow_layer_roofline(model, wl, batch, dev, pk):
+    """The HBM-shaped end of the net: the first conv node (3 or 8 input channels at full resolution) on the
+    narrow-layer engine (TMA halo staging + FFMA2), timed alone with the L2 flushed, against measured HBM
+    bandwidth.  Algorithmic bytes = input read once + output written once + weights."""
+    from robocupvision_b200 import _lib, ops
+    plan = model._get_plan()
+    nd = next(n for n in plan.nodes if n.kind == "conv")
+    g = nd.geom
+    h, w = wl["h"], wl["w"]
+    x = torch.randn(batch, g.cin, h, w, device=dev)
+    wt = nd.conv.weight.detach()
+    ho, wo = g.out_hw(h, w)
+    y = torch.empty(batch, g.cout, ho, wo, device=dev)
+    eng = ops.conv_engine(g, batch, h, w, ops.PACK_FWD, ops.MATH_AUTO)
+    flush = torch.empty(64 * 1024 * 1024, device=dev)
+    times = []
+    for i in range(13):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv_fwd(g, x, wt, None, epilogue=ops.EPI_RELU, out=y, math=ops.MATH_AUTO)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    bytes_alg = 4.0 * (x.numel() + y.numel() + wt.numel())
+    flops = 2.0 * g.cin * g.cout * g.k ** 2 * ho * wo * batch
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    names = {_lib.ENGINE_SIMT: "igemm (fp32 FFMA)", _lib.ENGINE_DIRECT: "direct_conv (fp32 FFMA)",
+             _lib.ENGINE_UMMA: "umma_igemm (tcgen05 3xTF32)", _lib.ENGINE_NARROW: "narrow_conv (TMA halo staging + FFMA2)"}
+    return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+            "kernel": f"{names.get(eng, str(eng))} conv fwd {g.cin}->{g.cout} k{g.k} s{g.stride} d{g.dil} @{h}x{w} batch {batch}",
+            "us_per_launch": ms * 1e3, "algorithmic_bytes": bytes_alg, "flop_per_byte": flops / bytes_alg,
+            "fp32_tflops": flops / (ms * 1e-3) / 1e12}
 
 
 if __name__ == "__main__":

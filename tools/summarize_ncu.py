@@ -16,7 +16,10 @@ KEYS = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fma", "l1tex__t_bytes",
         "lts__t_bytes.sum", "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "launch__shared_mem_per_block",
-        "smsp__inst_executed.sum", "sm__inst_executed_pipe_uniform", "smsp__warp_issue_stalled")
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_uniform", "smsp__warp_issue_stalled",
+        "smsp__average_warps_issue_stalled", "smsp__issue_active.avg", "sm__pipe_fma_cycles_active.avg",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "launch__waves_per_multiprocessor", "smsp__warps_eligible.avg")
 
 
 def short(name):
