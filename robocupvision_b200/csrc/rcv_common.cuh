@@ -86,7 +86,7 @@ struct RcvPackJob {
   RcvIgemm p;
   unsigned char* packed;
   long long chunk_begin, chunks;  // 16-byte chunks: prefix sum over the table, count of this job
-  int32_t BN, ntiles, kbmax, pad_;
+  int32_t BN, ntiles, kbmax, kb;  // kb = fp32 elements per K block of the layer's configuration
 };
 int rcv_umma_pack_job(const RcvIgemm& p, void* packed, long long chunk_begin, RcvPackJob* job);
 int rcv_launch_umma_pack_multi(const RcvPackJob* dev_jobs, int njobs, long long total_chunks, cudaStream_t st);

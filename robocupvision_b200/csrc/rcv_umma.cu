@@ -89,15 +89,21 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&a)[16], int lane
 }
 
 // Tile configuration per output-channel tile width.
-template <int BN_, int G_>
+// KB_ = fp32 elements per K block = one swizzle row: 32 (128-byte swizzle) or 16 (64-byte swizzle: stages half
+// the size, so the BN = 128 configuration fits two CTAs per SM -- 150 tiles on 148 SMs become one wave, and
+// a second CTA's MMAs fill the barrier-latency bubbles of the first)
+template <int BN_, int G_, int KB_ = 32>
 struct Cfg {
   static constexpr int BN = BN_;
   static constexpr int G = G_;                       // producer groups = ring depth
+  static constexpr int KB = KB_;
+  static constexpr int ROWB = KB_ * 4;               // bytes per operand row
   static constexpr int NPROD = G_ * GTHREADS;
   static constexpr int NT = NPROD + 64;              // + the MMA-issuer warp + the B-loader warp
-  static constexpr int A_BYTES = BM * 128;           // one hi or lo A tile
+  static constexpr int A_BYTES = BM * ROWB;          // one hi or lo A tile
   static constexpr int A_STAGE = 2 * A_BYTES;
-  static constexpr int B_STAGE = BN_ * 256;          // hi rows then lo rows
+  static constexpr int B_STAGE = BN_ * ROWB * 2;     // hi rows then lo rows
+  static constexpr int CTAS = (G_ * (BM + BN_) * KB_ * 8 <= 100 * 1024) ? 2 : 1;  // CTAs per SM the ring is sized for
   static constexpr int STAGE = A_STAGE + B_STAGE;    // one ring stage: A hi, A lo, B hi, B lo
   static constexpr int TILE_BYTES = G_ * STAGE;
   static constexpr int FIXED = TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/ + 3 * BN_ * 4;
@@ -105,16 +111,42 @@ struct Cfg {
   static constexpr int TCOLS = 2 * BN_ < 32 ? 32 : 2 * BN_;  // main + correction accumulators
 };
 
-static int g_bn_cap = 0, g_force_g = 0;  // experiments: RCV_UMMA_BNCAP / RCV_UMMA_G
+// byte offset of 16-byte chunk c of operand row `row` in the K-major swizzled canonical layout
+template <int KB>
+__host__ __device__ __forceinline__ int sw_off(int row, int c) {
+  return KB == 32 ? row * 128 + ((c ^ (row & 7)) << 4)          // Swizzle<3,4,3>: chunk ^= address bits [7,10)
+                  : row * 64 + ((c ^ ((row >> 1) & 3)) << 4);   // Swizzle<2,4,3>: chunk ^= address bits [7,9)
+}
+// shared-memory matrix descriptor of a K-major swizzled tile with rows of KB fp32 (see make_desc in rcv_umma.cuh)
+template <int KB>
+__device__ __forceinline__ uint64_t make_desc_kb(uint32_t saddr) {
+  if (KB == 32) return make_desc(saddr);
+  // SWIZZLE_64B: stride between 8-row groups = 8 x 64 B, layout type 4
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
+static int g_bn_cap = 0, g_force_g = 0, g_kb128 = 0, g_kb64 = 0;  // experiments: RCV_UMMA_BNCAP / RCV_UMMA_G
 __host__ inline int umma_bn(int CB) {
   if (g_bn_cap == 0) {
     const char* e = getenv("RCV_UMMA_BNCAP");
     g_bn_cap = e ? atoi(e) : 128;
     e = getenv("RCV_UMMA_G");
     g_force_g = e ? atoi(e) : -1;
+    e = getenv("RCV_UMMA_KB128");  // K block of the BN = 128 configuration: 16 (default) or 32
+    g_kb128 = e ? atoi(e) : 16;
+    if (g_kb128 != 16 && g_kb128 != 32) g_kb128 = 16;
+    e = getenv("RCV_UMMA_KB64");   // K block of the BN = 64 configuration: 32 (two 48 KB stages) or 16 (four 24 KB stages)
+    g_kb64 = e ? atoi(e) : 32;
+    if (g_kb64 != 16 && g_kb64 != 32) g_kb64 = 32;
   }
   const int bn = CB > 64 ? 128 : CB > 32 ? 64 : CB > 16 ? 32 : 16;
   return bn > g_bn_cap ? g_bn_cap : bn;
+}
+// fp32 elements per K block of a layer's configuration (the packed panel layout depends on it)
+__host__ inline int umma_kb(int CB) {
+  const int bn = umma_bn(CB);
+  return bn == 128 ? g_kb128 : bn == 64 ? g_kb64 : 32;
 }
 __host__ __device__ inline int max_taps(const RcvIgemm& p) {
   int m = 0;
@@ -122,10 +154,11 @@ __host__ __device__ inline int max_taps(const RcvIgemm& p) {
   return m;
 }
 
-template <int BN, int G>
-__global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const RcvIgemm p) {
-  using C = Cfg<BN, G>;
+template <int BN, int G, int KB>
+__global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma_igemm_kernel(const RcvIgemm p) {
+  using C = Cfg<BN, G, KB>;
   constexpr int NPROD = C::NPROD, NT = C::NT;
+  constexpr int BK = KB;  // shadows the file-level default inside the kernel
 
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -217,8 +250,8 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
             RCV_PROF_I(0);
             tc_fence_after();
             const uint32_t abase = tiles + st * C::STAGE, bbase = abase + C::A_STAGE;
-            const uint64_t a_hi = make_desc(abase), a_lo = make_desc(abase + C::A_BYTES);
-            const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + BN * 128);
+            const uint64_t a_hi = make_desc_kb<KB>(abase), a_lo = make_desc_kb<KB>(abase + C::A_BYTES);
+            const uint64_t b_hi = make_desc_kb<KB>(bbase), b_lo = make_desc_kb<KB>(bbase + BN * C::ROWB);
             const int krem = K - kb * BK;
             const int ksteps = krem >= BK ? BK / 8 : (krem + 7) / 8;
             if (!(p.debug & 1)) {
@@ -308,13 +341,13 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
       RCV_PROF_P(2);
       if (!(p.debug & 4))
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < BK / 4; ++c) {
         float4 h, l;
         split_tf32(va[4 * c + 0], h.x, l.x);
         split_tf32(va[4 * c + 1], h.y, l.y);
         split_tf32(va[4 * c + 2], h.z, l.z);
         split_tf32(va[4 * c + 3], h.w, l.w);
-        const int off = row * 128 + ((c ^ (row & 7)) << 4);
+        const int off = sw_off<KB>(row, c);
         *reinterpret_cast<float4*>(a_hi + off) = h;
         *reinterpret_cast<float4*>(a_lo + off) = l;
       }
@@ -399,12 +432,13 @@ __global__ void __launch_bounds__(Cfg<BN, G>::NT, 1) umma_igemm_kernel(const Rcv
 
 // One thread per 16-byte chunk of the packed image: 4 consecutive k of one weight row, split
 // into hi / lo and written at the swizzled position.
-__device__ __forceinline__ void pack_chunk(const RcvIgemm& p, int BN, int ntiles, int kbmax,
+__device__ __forceinline__ void pack_chunk(const RcvIgemm& p, int BN, int ntiles, int kbmax, int KB,
                                            unsigned char* __restrict__ packed, int64_t q) {
-  const int64_t per_block = (int64_t)BN * 8;
+  const int cpr = KB / 4;  // 16-byte chunks per operand row
+  const int64_t per_block = (int64_t)BN * cpr;
   {
     const int row = (int)(q % BN);
-    const int c = (int)((q / BN) % 8);
+    const int c = (int)((q / BN) % cpr);
     int64_t blk = q / per_block;
     const int kb = (int)(blk % kbmax);
     blk /= kbmax;
@@ -412,7 +446,7 @@ __device__ __forceinline__ void pack_chunk(const RcvIgemm& p, int BN, int ntiles
     const int cls = (int)(blk / ntiles);
     const int T = p.taps[cls].n;
     const int co = tile * BN + row;
-    int k = kb * BK + c * 4;
+    int k = kb * KB + c * 4;
     int tap = k / p.CA;
     int ca = k - tap * p.CA;
     float v[4];
@@ -428,19 +462,20 @@ __device__ __forceinline__ void pack_chunk(const RcvIgemm& p, int BN, int ntiles
     split_tf32(v[1], h.y, l.y);
     split_tf32(v[2], h.z, l.z);
     split_tf32(v[3], h.w, l.w);
-    unsigned char* base = packed + ((size_t)(cls * ntiles + tile) * kbmax + kb) * ((size_t)BN * 256);
-    const int off = row * 128 + ((c ^ (row & 7)) << 4);
+    const size_t rowb = (size_t)KB * 4;
+    unsigned char* base = packed + ((size_t)(cls * ntiles + tile) * kbmax + kb) * ((size_t)BN * rowb * 2);
+    const int off = KB == 32 ? sw_off<32>(row, c) : sw_off<16>(row, c);
     *reinterpret_cast<float4*>(base + off) = h;
-    *reinterpret_cast<float4*>(base + (size_t)BN * 128 + off) = l;
+    *reinterpret_cast<float4*>(base + (size_t)BN * rowb + off) = l;
   }
 }
 
-__global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int ntiles, int kbmax,
+__global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int ntiles, int kbmax, int KB,
                                                    unsigned char* __restrict__ packed) {
-  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * 8;
+  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * (KB / 4);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
        q += (int64_t)gridDim.x * blockDim.x)
-    pack_chunk(p, BN, ntiles, kbmax, packed, q);
+    pack_chunk(p, BN, ntiles, kbmax, KB, packed, q);
 }
 
 // All layers' panels in one launch: a device-resident job table (built once on the host, the
@@ -456,19 +491,23 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const RcvPackJob* __res
     int j = 0;
     while (q >= s_begin[j + 1]) ++j;
     const RcvPackJob& jb = jobs[j];
-    pack_chunk(jb.p, jb.BN, jb.ntiles, jb.kbmax, jb.packed, q - s_begin[j]);
+    pack_chunk(jb.p, jb.BN, jb.ntiles, jb.kbmax, jb.kb, jb.packed, q - s_begin[j]);
   }
 }
 
-template <int BN, int G>
+template <int BN, int G, int KB = 32>
 int launch_bn(const RcvIgemm& p, cudaStream_t st) {
-  using C = Cfg<BN, G>;
+  using C = Cfg<BN, G, KB>;
+  constexpr int BK = KB;
   constexpr int MAX_SMEM = C::FIXED + RCV_UMMA_MAX_TABLE_K * 8;
   static_assert(MAX_SMEM <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;  // benign race: idempotent
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(umma_igemm_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_igemm_kernel<BN, G, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          MAX_SMEM);
+    if (C::CTAS > 1)
+      cudaFuncSetAttribute(umma_igemm_kernel<BN, G, KB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       rcv_set_error("umma_igemm: cannot reserve %d B of shared memory: %s", MAX_SMEM, cudaGetErrorString(e));
       return RCV_ERR_CUDA;
@@ -484,7 +523,7 @@ int launch_bn(const RcvIgemm& p, cudaStream_t st) {
               "umma_igemm: problem too large");
   dim3 grid(rcv_cdiv(M, BM), rcv_cdiv(p.CB, BN), p.nclass);
   RCV_REQUIRE(grid.y <= 65535, RCV_ERR_UNSUPPORTED, "umma_igemm: too many output-channel tiles");
-  umma_igemm_kernel<BN, G><<<grid, C::NT, smem, st>>>(p);
+  umma_igemm_kernel<BN, G, KB><<<grid, C::NT, smem, st>>>(p);
   RCV_CHECK_LAUNCH("umma_igemm_kernel");
   return RCV_OK;
 }
@@ -502,27 +541,27 @@ int check_taps(const RcvIgemm& p) {
 }  // namespace
 
 bool rcv_umma_supported(const RcvIgemm& p) {
-  return (p.CA % BK) == 0 || (int64_t)p.CA * max_taps(p) <= RCV_UMMA_MAX_TABLE_K;
+  return (p.CA % umma_kb(p.CB)) == 0 || (int64_t)p.CA * max_taps(p) <= RCV_UMMA_MAX_TABLE_K;
 }
 
 size_t rcv_umma_packed_bytes(const RcvIgemm& p) {
-  const int BN = umma_bn(p.CB);
+  const int BN = umma_bn(p.CB), KB = umma_kb(p.CB);
   const int ntiles = rcv_cdiv(p.CB, BN);
-  const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), BK);
-  return (size_t)p.nclass * ntiles * kbmax * BN * 256;
+  const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), KB);
+  return (size_t)p.nclass * ntiles * kbmax * BN * KB * 8;
 }
 
 int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st) {
   int rc = check_taps(p);
   if (rc) return rc;
   RCV_REQUIRE(((uintptr_t)packed & 127) == 0, RCV_ERR_BAD_ARG, "conv_pack: packed buffer must be 128-byte aligned");
-  const int BN = umma_bn(p.CB);
+  const int BN = umma_bn(p.CB), KB = umma_kb(p.CB);
   const int ntiles = rcv_cdiv(p.CB, BN);
-  const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), BK);
-  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * 8;
+  const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), KB);
+  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * (KB / 4);
   int blocks = rcv_cdiv(total, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_kernel<<<blocks, 256, 0, st>>>(p, BN, ntiles, kbmax, reinterpret_cast<unsigned char*>(packed));
+  pack_kernel<<<blocks, 256, 0, st>>>(p, BN, ntiles, kbmax, KB, reinterpret_cast<unsigned char*>(packed));
   RCV_CHECK_LAUNCH("pack_kernel");
   return RCV_OK;
 }
@@ -534,10 +573,11 @@ int rcv_umma_pack_job(const RcvIgemm& p, void* packed, long long chunk_begin, Rc
   job->p = p;
   job->BN = umma_bn(p.CB);
   job->ntiles = rcv_cdiv(p.CB, job->BN);
-  job->kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), BK);
+  job->kb = umma_kb(p.CB);
+  job->kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), job->kb);
   job->packed = reinterpret_cast<unsigned char*>(packed);
   job->chunk_begin = chunk_begin;
-  job->chunks = (long long)p.nclass * job->ntiles * job->kbmax * job->BN * 8;
+  job->chunks = (long long)p.nclass * job->ntiles * job->kbmax * job->BN * (job->kb / 4);
   return RCV_OK;
 }
 
@@ -571,8 +611,10 @@ int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
   const int bn = umma_bn(p.CB);
   const bool deep = g_force_g > 0 ? g_force_g >= 3 : (int64_t)p.CA * max_taps(p) > 10 * BK;
   switch (bn) {
-    case 128: return launch_bn<128, 3>(p, st);
-    case 64: return deep ? launch_bn<64, 4>(p, st) : launch_bn<64, 2>(p, st);
+    case 128: return umma_kb(p.CB) == 16 ? launch_bn<128, 3, 16>(p, st) : launch_bn<128, 3>(p, st);
+    // BN = 64: two CTAs per SM always (a 150-tile layer is then one wave; measured 38 -> 27 us for 64->64 and
+    // 60 -> 44 us for 128->64 at batch 64, 89 -> 64 / 143 -> 106 us at batch 256)
+    case 64: return umma_kb(p.CB) == 16 ? launch_bn<64, 4, 16>(p, st) : launch_bn<64, 2>(p, st);
     case 32: return deep ? launch_bn<32, 4>(p, st) : launch_bn<32, 2>(p, st);
     default: return deep ? launch_bn<16, 4>(p, st) : launch_bn<16, 2>(p, st);
   }
