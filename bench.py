@@ -231,7 +231,7 @@ def main():
         step = lambda i: ts.step(xs[i % nbatches], ys[i % nbatches])  # noqa: E731
         result = lambda: ts.loss_sums  # noqa: E731
     else:
-        ev = EvalStep(model, cw)
+        ev = EvalStep(model, cw, use_graph=not args.no_graph)
         out = {}
 
         def step(i):
@@ -266,6 +266,8 @@ def main():
     value = batch * world / (ms_step * 1e-3)
     if wl["train"]:
         launches = ts.kernels_per_step * args.steps
+    elif ev.use_graph:
+        launches = ev.kernels_per_call * args.steps
     else:
         launches = ops.launch_count() - k0
 
@@ -314,7 +316,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world,
                        "input": f"{wl['cin']}x{wl['h']}x{wl['w']}", "parallelism": f"dp{world}",
-                       "cuda_graph": bool(wl["train"] and not args.no_graph),
+                       "cuda_graph": bool(not args.no_graph),
                        "l2": "8 rotating input batches; per-step activation working set >> 126 MB L2",
                        "peaks": pk["source"]},
             "clocks": clocks,

@@ -103,7 +103,8 @@ struct Cfg {
   static constexpr int A_BYTES = BM * ROWB;          // one hi or lo A tile
   static constexpr int A_STAGE = 2 * A_BYTES;
   static constexpr int B_STAGE = BN_ * ROWB * 2;     // hi rows then lo rows
-  static constexpr int CTAS = (G_ * (BM + BN_) * KB_ * 8 <= 100 * 1024) ? 2 : 1;  // CTAs per SM the ring is sized for
+  static constexpr int RING = G_ * (BM + BN_) * KB_ * 8;
+  static constexpr int CTAS = RING <= 50 * 1024 ? 3 : RING <= 100 * 1024 ? 2 : 1;  // CTAs per SM the ring is sized for
   static constexpr int STAGE = A_STAGE + B_STAGE;    // one ring stage: A hi, A lo, B hi, B lo
   static constexpr int TILE_BYTES = G_ * STAGE;
   static constexpr int FIXED = TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers etc.*/ + 3 * BN_ * 4;
@@ -614,7 +615,9 @@ int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
     case 128: return umma_kb(p.CB) == 16 ? launch_bn<128, 3, 16>(p, st) : launch_bn<128, 3>(p, st);
     // BN = 64: two CTAs per SM always (a 150-tile layer is then one wave; measured 38 -> 27 us for 64->64 and
     // 60 -> 44 us for 128->64 at batch 64, 89 -> 64 / 143 -> 106 us at batch 256)
-    case 64: return umma_kb(p.CB) == 16 ? launch_bn<64, 4, 16>(p, st) : launch_bn<64, 2>(p, st);
+    case 64:
+      if (umma_kb(p.CB) == 16) return g_force_g == 2 ? launch_bn<64, 2, 16>(p, st) : launch_bn<64, 4, 16>(p, st);
+      return launch_bn<64, 2>(p, st);
     case 32: return deep ? launch_bn<32, 4>(p, st) : launch_bn<32, 2>(p, st);
     default: return deep ? launch_bn<16, 4>(p, st) : launch_bn<16, 2>(p, st);
   }

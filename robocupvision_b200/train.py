@@ -341,12 +341,17 @@ class EvalStep:
     """Validation batch (train.py:114-153): logits, weighted CE, argmax, correct-pixel count,
     per-image confusion and IoU sums -- no host syncs (the reference does 3+25*B `.item()`s)."""
 
-    def __init__(self, model: nn.Module, class_weights=None):
+    def __init__(self, model: nn.Module, class_weights=None, use_graph: bool = False):
+        """use_graph: replay the batch from a CUDA graph (one capture per input shape and per state of
+        the model's parameters / buffers).  The returned tensors are then the graph's static buffers:
+        valid until the next call with the same shapes."""
         self.model = model
         dev = next(model.parameters()).device
         self.class_w = None if class_weights is None else torch.as_tensor(
             class_weights, dtype=torch.float32).to(dev)
         self._pipe = None
+        self.use_graph = use_graph
+        self._graphs = {}
 
     @torch.no_grad()
     def run_async(self, x_host, y_host):
@@ -381,13 +386,50 @@ class EvalStep:
         return float(pipe.out_f[k][0]), int(pipe.out_i[k])
 
     @torch.no_grad()
-    def __call__(self, x, y):
+    def _eager(self, x, y):
         self.model.eval()
         logits = self.model(x)
         sums, am, conf, corr = ops.ce_fwd(logits, y, self.class_w, want_argmax=True, want_conf=True,
                                           want_correct=True)
         return {"logits": logits, "loss": sums[0] / sums[1], "argmax": am, "conf": conf, "correct": corr,
                 "iou_sum": iou_sums(conf)}
+
+    def _state_key(self):
+        """Anything a captured forward bakes in: folded BatchNorm constants and packed weight panels are
+        cached per (tensor, version), so a graph is only valid while no parameter / buffer was written."""
+        ts = list(self.model.parameters()) + list(self.model.buffers())
+        plan = self.model._get_plan() if hasattr(self.model, "_get_plan") else None
+        return (tuple((t.data_ptr(), t._version) for t in ts), plan.epoch if plan is not None else 0)
+
+    @torch.no_grad()
+    def __call__(self, x, y):
+        if not self.use_graph:
+            return self._eager(x, y)
+        key = (tuple(x.shape), tuple(y.shape))
+        ent = self._graphs.get(key)
+        state = self._state_key()
+        if ent is None or ent["state"] != state:
+            sx, sy = torch.empty_like(x), torch.empty_like(y)
+            sx.copy_(x)
+            sy.copy_(y)
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up outside capture: lazy module loading, caches, packs
+                self._eager(sx, sy)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(x.device)
+            g = torch.cuda.CUDAGraph()
+            k0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                out = self._eager(sx, sy)
+            self.kernels_per_call = ops.launch_count() - k0  # rcv_* kernels one replay launches
+            ent = {"graph": g, "sx": sx, "sy": sy, "out": out, "state": self._state_key()}
+            self._graphs[key] = ent
+        ent["sx"].copy_(x, non_blocking=True)
+        ent["sy"].copy_(y, non_blocking=True)
+        ent["graph"].replay()
+        return dict(ent["out"])
 
 
 def iou_sums(conf: torch.Tensor) -> torch.Tensor:

@@ -321,3 +321,26 @@ def test_full_size_properties():
     assert int(full["conf"].sum()) == 64 * 120 * 160
     assert (full["conf"].sum((1, 2)) == 120 * 160).all()
     assert int(full["correct"]) == int(torch.diagonal(full["conf"], dim1=1, dim2=2).sum())
+
+
+def test_eval_step_graph_replay_matches_eager():
+    """EvalStep(use_graph=True) replays the validation batch from a CUDA graph: same logits, label maps,
+    confusion counts and loss as the eager path, and a parameter write invalidates the capture (folded
+    BatchNorm constants and packed weight panels are baked into it)."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import EvalStep
+    torch.manual_seed(12345678)
+    m = ROBO_UNet().cuda().eval()
+    eager, graph = EvalStep(m, synth.CLASS_WEIGHTS), EvalStep(m, synth.CLASS_WEIGHTS, use_graph=True)
+    for rnd in range(2):
+        for s in range(3):
+            x = synth.images(4, 3, 48, 64, seed=300 + s).cuda()
+            y = synth.labels_random(4, 48, 64, seed=400 + s).cuda()
+            a = eager(x, y)
+            b = graph(x, y)
+            assert torch.equal(a["logits"], b["logits"]) and torch.equal(a["argmax"], b["argmax"])
+            assert torch.equal(a["conf"], b["conf"]) and int(a["correct"]) == int(b["correct"])
+            assert float(a["loss"]) == float(b["loss"])
+        with torch.no_grad():  # change the weights: the next graph call must re-capture
+            for p in m.parameters():
+                p.mul_(1.01)
