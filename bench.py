@@ -50,6 +50,8 @@ WORKLOADS = {
     "train_lp":    dict(net="LabelProp", kw={}, cin=8, h=120, w=160, train=True, mflop=357.6, mb=23.040, mb_step=2.58,
                         name="LabelProp two-frame training (16 samples = 8 frame pairs)", batch=16),
 }
+ENGINE_NAMES = {0: "igemm (fp32 FFMA)", 1: "direct_conv (fp32 FFMA)", 2: "umma_igemm (tcgen05 3xTF32)",
+                3: "narrow_conv (TMA halo staging + FFMA2)"}  # rcv_engine
 METRIC = "robo_unet_160x120_train_frames_per_sec"
 UNIT = "frames/s"
 
@@ -370,7 +372,8 @@ def dominant_kernel_roofline(model, wl, batch, dev, pk):
     wt = best.conv.weight.detach()
     ho, wo = g.out_hw(best_in[1], best_in[2])
     y = torch.empty(batch, g.cout, ho, wo, device=dev)
-    on_tc = ops.conv_uses_tensor_cores(g, ops.PACK_FWD, ops.MATH_AUTO)
+    eng = ops.conv_engine(g, batch, best_in[1], best_in[2], ops.PACK_FWD, ops.MATH_AUTO)
+    on_tc = eng == ops.ENGINE_UMMA
     wp = ops.conv_pack(g, wt, ops.PACK_FWD) if on_tc else None
     flush = torch.empty(64 * 1024 * 1024, device=dev)  # 256 MB > L2
     times = []
@@ -396,10 +399,10 @@ def dominant_kernel_roofline(model, wl, batch, dev, pk):
     else:
         achieved, peak, unit, bound = bytes_alg / (ms * 1e-3) / 1e9, pk["hbm"], "GB/s", "hbm"
     out = {"bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak, "traffic": None,
-           "kernel": f"{'umma_igemm (tcgen05 3xTF32)' if on_tc else 'igemm (fp32 FFMA)'} conv fwd {g.cin}->{g.cout} "
+           "kernel": f"{ENGINE_NAMES.get(eng, str(eng))} conv fwd {g.cin}->{g.cout} "
                      f"k{g.k} s{g.stride} d{g.dil} @{best_in[1]}x{best_in[2]} batch {batch}",
            "us_per_launch": ms * 1e3, "flop_per_byte": intensity,
-           "math": "tcgen05 kind::tf32 x3 (fp32-level accuracy), TMEM accumulators" if on_tc else "fp32 FFMA (CUDA cores)",
+           "math": "tcgen05 kind::tf32 x3 (fp32-level accuracy), TMEM accumulators" if on_tc else "fp32 FMA (CUDA cores)",
            "achieved_tflops": tfl, "achieved_gbs": bytes_alg / (ms * 1e-3) / 1e9, "peak_is": "measured bf16 dense (burst)"}
     tfile = ROOT / "profiles" / "r1_traffic.json"
     if tfile.exists():
@@ -444,8 +447,7 @@ def narrow_layer_roofline(model, wl, batch, dev, pk):
     bytes_alg = 4.0 * (x.numel() + y.numel() + wt.numel())
     flops = 2.0 * g.cin * g.cout * g.k ** 2 * ho * wo * batch
     gbs = bytes_alg / (ms * 1e-3) / 1e9
-    names = {_lib.ENGINE_SIMT: "igemm (fp32 FFMA)", _lib.ENGINE_DIRECT: "direct_conv (fp32 FFMA)",
-             _lib.ENGINE_UMMA: "umma_igemm (tcgen05 3xTF32)", _lib.ENGINE_NARROW: "narrow_conv (TMA halo staging + FFMA2)"}
+    names = ENGINE_NAMES
     return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
             "kernel": f"{names.get(eng, str(eng))} conv fwd {g.cin}->{g.cout} k{g.k} s{g.stride} d{g.dil} @{h}x{w} batch {batch}",
             "us_per_launch": ms * 1e3, "algorithmic_bytes": bytes_alg, "flop_per_byte": flops / bytes_alg,

@@ -12,15 +12,15 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO,
-                   MATH_FP32, MATH_TF32X3, PACK_DGRAD, PACK_FWD, ConvDesc)
+from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE,
+                   EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO, MATH_FP32, MATH_TF32X3, PACK_DGRAD, PACK_FWD, ConvDesc)
 
 __all__ = [
     "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
     "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
-    "MATH_FP32", "MATH_TF32X3", "MATH_AUTO",
+    "MATH_FP32", "MATH_TF32X3", "MATH_AUTO", "ENGINE_SIMT", "ENGINE_DIRECT", "ENGINE_UMMA", "ENGINE_NARROW",
 ]
 
 _launches = 0  # kernels enqueued through this module (bench.py's gpu_launches)
