@@ -173,7 +173,26 @@ def cpu_reference(wl, batch, steps, warmup):
     return batch / dt, dt * 1e3, threads
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to file descriptor 1 (NCCL's version
+    # banner at NCCL_DEBUG=VERSION/WARN, library chatter) is sent to stderr for the whole run
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -204,7 +223,7 @@ def main():
                 "config": {"workload": wl["name"], "batch_per_step": batch, "host_threads": threads},
                 "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                 "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     if not torch.cuda.is_available():
@@ -216,8 +235,6 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries the JSON line
         torch.distributed.init_process_group("nccl", device_id=dev)
     model = build_model(wl, dev)
     cw = class_weights(wl)
@@ -333,7 +350,7 @@ def main():
                                 "sample": f"{args.cpu_steps} steps of batch {batch} after 2 warm-up "
                                           f"(oracle port of train.py:43-74 on torch {torch.__version__} CPU)"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # NCCL communicators referenced by captured CUDA graphs can stall destroy_process_group()
         # at interpreter teardown (seen on 2xB200: line printed, ranks never exited).  All ranks

@@ -127,7 +127,7 @@ __device__ __forceinline__ uint64_t make_desc_kb(uint32_t saddr) {
          ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 
-static int g_bn_cap = 0, g_force_g = 0, g_kb128 = 0, g_kb64 = 0;  // experiments: RCV_UMMA_BNCAP / RCV_UMMA_G
+static int g_bn_cap = 0, g_force_g = 0, g_kb128 = 0, g_kb64 = 0, g_kb32 = 0;  // experiments: RCV_UMMA_BNCAP / RCV_UMMA_G
 __host__ inline int umma_bn(int CB) {
   if (g_bn_cap == 0) {
     const char* e = getenv("RCV_UMMA_BNCAP");
@@ -140,6 +140,9 @@ __host__ inline int umma_bn(int CB) {
     e = getenv("RCV_UMMA_KB64");   // K block of the BN = 64 configuration: 32 (two 48 KB stages) or 16 (four 24 KB stages)
     g_kb64 = e ? atoi(e) : 32;
     if (g_kb64 != 16 && g_kb64 != 32) g_kb64 = 32;
+    e = getenv("RCV_UMMA_KB32");   // K block of the BN = 32 short-reduction configuration: 32 (2 CTAs/SM) or 16 (3 CTAs/SM)
+    g_kb32 = e ? atoi(e) : 32;
+    if (g_kb32 != 16 && g_kb32 != 32) g_kb32 = 32;
   }
   const int bn = CB > 64 ? 128 : CB > 32 ? 64 : CB > 16 ? 32 : 16;
   return bn > g_bn_cap ? g_bn_cap : bn;
@@ -147,7 +150,7 @@ __host__ inline int umma_bn(int CB) {
 // fp32 elements per K block of a layer's configuration (the packed panel layout depends on it)
 __host__ inline int umma_kb(int CB) {
   const int bn = umma_bn(CB);
-  return bn == 128 ? g_kb128 : bn == 64 ? g_kb64 : 32;
+  return bn == 128 ? g_kb128 : bn == 64 ? g_kb64 : bn == 32 ? g_kb32 : 32;
 }
 __host__ __device__ inline int max_taps(const RcvIgemm& p) {
   int m = 0;
@@ -618,7 +621,9 @@ int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
     case 64:
       if (umma_kb(p.CB) == 16) return g_force_g == 2 ? launch_bn<64, 2, 16>(p, st) : launch_bn<64, 4, 16>(p, st);
       return launch_bn<64, 2>(p, st);
-    case 32: return deep ? launch_bn<32, 4>(p, st) : launch_bn<32, 2>(p, st);
+    case 32:
+      if (umma_kb(p.CB) == 16) return launch_bn<32, 2, 16>(p, st);
+      return deep ? launch_bn<32, 4>(p, st) : launch_bn<32, 2>(p, st);
     default: return deep ? launch_bn<16, 4>(p, st) : launch_bn<16, 2>(p, st);
   }
 }
