@@ -276,6 +276,28 @@ int rcv_lp_assemble(int64_t P, int32_t C, int64_t HW, const float* ya, const flo
                     const int64_t* la, const int64_t* lb, float* inputs, int64_t* targets,
                     void* stream);
 
+/* Training-split augmentation of SSYUVDataset.__getitem__ (dataset.py:123-131) over a whole batch:
+ * Normalize ((x - mean[c]) / std[c], mean / std: HOST arrays of 3 floats), horizontal flip of image and
+ * label (img.flip(2)), ColorJitter (dataset.py:19-39: y0 = (y0 + b) * c; (u, v) = M (u, v)).  Per-image
+ * parameters in DEVICE memory, params[n] = {flip (0/1), b, c, m00, m01, m10, m11, unused}: the caller draws
+ * them (random.uniform in the reference) -- the kernel is deterministic.  x, y float [N,3,H,W] (not in
+ * place); labels_in / labels_out int64 [N,H,W] or both NULL. */
+int rcv_augment(int32_t N, int32_t H, int32_t W, const float* x, float* y,
+                const int64_t* labels_in, int64_t* labels_out, const float* params,
+                const float* mean, const float* std_, void* stream);
+
+/* ---- DiceLoss (model.py:5-43, the --useDice option), C = 2..8 classes ----- */
+/* sums (double[2*C], caller zeroes): sums[c] += sum_p softmax_c(p)*[y_p==c] (intersection),
+ * sums[C+c] += sum_p (softmax_c(p) + [y_p==c]) (cardinality).
+ * loss = 1 - mean_c(2*w_c*sums[c] / (sums[C+c] + eps)), w = weights/sum(weights)*C (host side). */
+int rcv_dice_fwd(int32_t N, int32_t C, int64_t HW, const float* logits,
+                 const int64_t* target, double* sums, void* stream);
+/* dlogits = gscale * dloss/dlogits through the softmax; weights: the normalised w (device, may be NULL = 1),
+ * gscale: device float or NULL (= 1). */
+int rcv_dice_bwd(int32_t N, int32_t C, int64_t HW, const float* logits,
+                 const int64_t* target, const float* weights, const double* sums,
+                 float eps, const float* gscale, float* dlogits, void* stream);
+
 /* ---- train-step tail: L1 regulariser + pruning mask + Adam --------------- */
 /* One fused pass over a flat parameter range (train.py:23-27 l1reg, 59-65 grad
  * mask, torch.optim.Adam defaults amsgrad=False, weight_decay=0):

@@ -77,6 +77,9 @@ SIGNATURES = {
     "rcv_label_lut": [_i64, _p, _i32, _p, _p],
     "rcv_label_to_pred": [_i64, _i32, _i64, _p, _p, _p],
     "rcv_lp_assemble": [_i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _p],
+    "rcv_augment": [_i32, _i32, _i32, _p, _p, _p, _p, _p, C.POINTER(_f32), C.POINTER(_f32), _p],
+    "rcv_dice_fwd": [_i32, _i32, _i64, _p, _p, _p, _p],
+    "rcv_dice_bwd": [_i32, _i32, _i64, _p, _p, _p, _p, _f32, _p, _p, _p],
     "rcv_adam_l1_step": [_i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _i32, _f32, _f32, _p, _p, _p, _p],
     "rcv_counter_add": [_p, _i32, _p],
     "rcv_sgd_step": [_i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, C.c_int, _p],

@@ -104,8 +104,27 @@ class CrossEntropyLoss2d(nn.Module):
         return _WeightedCE.apply(inputs, targets.long(), w)
 
 
+class _Dice(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, weights, eps):
+        sums = ops.dice_fwd(logits, target)
+        c = logits.shape[1]
+        ctx.save_for_backward(logits, target, weights, sums)
+        ctx.eps = eps
+        dice = (2.0 * weights.double() * sums[:c] / (sums[c:] + eps)).mean()
+        return (1.0 - dice).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        logits, target, weights, sums = ctx.saved_tensors
+        return ops.dice_bwd(logits, target, weights, sums, ctx.eps, gscale=gout), None, None, None
+
+
 class DiceLoss(nn.Module):
-    """Optional `--useDice` loss (model.py:5-43).  Off the hot path: plain tensor ops."""
+    """Optional `--useDice` loss (model.py:5-43): 1 - mean_c(2 w_c I_c / (K_c + eps)) with the soft
+    intersection I and cardinality K of softmax(logits) against the one-hot labels, w normalised to sum to C.
+    CUDA logits, 2..8 classes: one fused kernel forward (rcv_dice_fwd) and one backward (rcv_dice_bwd).
+    The single-logit sigmoid form (model.py:25-32, never used by the drivers) stays plain tensor ops."""
 
     def __init__(self, weights, eps=1e-7):
         super().__init__()
@@ -120,14 +139,16 @@ class DiceLoss(nn.Module):
             pos = torch.sigmoid(logits)
             probas = torch.cat([pos, 1 - pos], dim=1)
             onehot = torch.stack([(lab == 1), (lab == 0)], dim=1).to(logits.dtype)
-        else:
-            probas = torch.softmax(logits, dim=1)
-            onehot = torch.stack([(lab == k) for k in range(c)], dim=1).to(logits.dtype)
-        dims = (0,) + tuple(range(2, logits.dim()))
-        inter = (probas * onehot).sum(dims)
-        card = (probas + onehot).sum(dims)
-        w = self.weights.to(logits.device)
-        return 1 - (2.0 * w * inter / (card + self.eps)).mean()
+            dims = (0,) + tuple(range(2, logits.dim()))
+            inter = (probas * onehot).sum(dims)
+            card = (probas + onehot).sum(dims)
+            w = self.weights.to(logits.device)
+            return 1 - (2.0 * w * inter / (card + self.eps)).mean()
+        if not logits.is_cuda:
+            raise RuntimeError("robocupvision_b200.DiceLoss runs on CUDA only (no CPU fallback)")
+        if self.weights.device != logits.device:
+            self.weights = self.weights.to(logits.device)
+        return _Dice.apply(logits, lab.contiguous(), self.weights, self.eps)
 
 
 # =============================================================================== pruning helpers

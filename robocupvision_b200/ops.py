@@ -18,7 +18,7 @@ from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_A
 __all__ = [
     "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
-    "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
+    "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
     "MATH_FP32", "MATH_TF32X3", "MATH_AUTO", "ENGINE_SIMT", "ENGINE_DIRECT", "ENGINE_UMMA", "ENGINE_NARROW",
 ]
@@ -435,6 +435,60 @@ def lp_assemble(ya, yb, la, lb, num_classes: int = 5):
 
 
 # --------------------------------------------------------------------------- optimiser tail
+def color_jitter_params(flip, b_val, c_val, s_val, h_val, device):
+    """Per-image parameter rows of rcv_augment from the scalars ColorJitter.__call__ draws
+    (dataset.py:27-32): mtx = [[s cos h, -sin h], [sin h, s cos h]], as float32 like torch.FloatTensor."""
+    import math
+    rows = []
+    for f, b, c, s_, h in zip(flip, b_val, c_val, s_val, h_val):
+        rows.append([1.0 if f else 0.0, b, c, s_ * math.cos(h), -math.sin(h), math.sin(h), s_ * math.cos(h), 0.0])
+    return torch.tensor(rows, dtype=torch.float32, device=device)
+
+
+def augment(x, params, labels=None, mean=(0.5, 0.0, 0.0), std=(0.5, 0.5, 0.5)):
+    """Normalize + horizontal flip + ColorJitter over a batch [N,3,H,W] (dataset.py:123-131); params from
+    color_jitter_params.  -> (images, labels or None)."""
+    x = _chk(x, name="images")
+    n, c, h, w = x.shape
+    if c != 3:
+        raise ValueError("augment: 3-channel (YUV) images expected")
+    params = _chk(params, name="params")
+    if tuple(params.shape) != (n, 8):
+        raise ValueError("augment: params must be [N, 8]")
+    y = torch.empty_like(x)
+    lo = None
+    if labels is not None:
+        labels = _chk(labels, torch.int64, "labels")
+        lo = torch.empty_like(labels)
+    m = (_lib._f32 * 3)(*[float(v) for v in mean])
+    sd = (_lib._f32 * 3)(*[float(v) for v in std])
+    _call("rcv_augment", 1, n, h, w, _ptr(x), _ptr(y), _ptr(labels), _ptr(lo), _ptr(params), m, sd, _stream())
+    return y, lo
+
+
+def dice_fwd(logits, target):
+    """-> float64[2C]: per-class soft intersection and cardinality of softmax(logits) vs the labels."""
+    logits = _chk(logits, name="logits")
+    target = _chk(target, torch.int64, "target")
+    n, c = logits.shape[0], logits.shape[1]
+    hw = logits.numel() // (n * c)
+    sums = torch.zeros(2 * c, device=logits.device, dtype=torch.float64)
+    _call("rcv_dice_fwd", 1, n, c, hw, _ptr(logits), _ptr(target), _ptr(sums), _stream())
+    return sums
+
+
+def dice_bwd(logits, target, weights, sums, eps, gscale=None):
+    logits = _chk(logits, name="logits")
+    n, c = logits.shape[0], logits.shape[1]
+    hw = logits.numel() // (n * c)
+    d = torch.empty_like(logits)
+    if gscale is not None:
+        gscale = gscale.to(torch.float32).reshape(1).contiguous()
+    _call("rcv_dice_bwd", 1, n, c, hw, _ptr(logits), _ptr(target), _ptr(weights), _ptr(sums), float(eps),
+          _ptr(gscale), _ptr(d), _stream())
+    return d
+
+
 def adam_l1_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, l1_decay=0.0, grad_scale=1.0,
                  mask=None, l1_sum=None, step_dev=None, lr_dev=None):
     _call("rcv_adam_l1_step", 1, p.numel(), _ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(mask), float(lr),

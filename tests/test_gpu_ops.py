@@ -395,3 +395,56 @@ def test_label_ops():
         tgt[2 * q], tgt[2 * q + 1] = la[q], lb[q]
     gi, gt = ops.lp_assemble(ya.cuda(), yb.cuda(), la.cuda(), lb.cuda(), C)
     assert torch.equal(gi.cpu(), inp) and torch.equal(gt.cpu(), tgt)
+
+
+def test_augment_matches_reference_color_jitter():
+    """rcv_augment (Normalize + flip + ColorJitter in one pass, dataset.py:19-39, 123-131) against the output of
+    the reference's own ColorJitter (golden) and, on a larger seeded batch, against the oracle restatement."""
+    from oracle import ref_transforms as RT
+    from robocupvision_b200 import ops
+    from util import load_golden
+    g = load_golden("augment_dice")
+    sc = g["aug_scalars"]
+    params = ops.color_jitter_params(g["aug_flip"].tolist(), sc[:, 0], sc[:, 1], sc[:, 2], sc[:, 3], "cuda")
+    img, lab = ops.augment(torch.from_numpy(g["aug_in"]).cuda(), params, torch.from_numpy(g["aug_labels"]).cuda())
+    assert_close("augment vs reference ColorJitter", img, torch.from_numpy(g["aug_out"]), 1e-6)
+    assert torch.equal(lab.cpu(), torch.from_numpy(g["aug_labels_out"]))
+    gen = torch.Generator().manual_seed(77)
+    x = torch.rand(5, 3, 120, 160, generator=gen)
+    y = torch.randint(0, 5, (5, 120, 160), generator=gen)
+    flip = [True, False, True, True, False]
+    b, c = [0.1, -0.2, 0.3, 0.0, -0.05], [1.1, 0.8, 1.25, 1.0, 0.7]
+    s, h = [0.9, 1.2, 0.75, 1.0, 1.3], [0.3, -0.4, 0.5, 0.0, -0.1]
+    img, lab = ops.augment(x.cuda(), ops.color_jitter_params(flip, b, c, s, h, "cuda"), y.cuda())
+    for i in range(5):
+        ri, rl = RT.normalize_flip_jitter(x[i], y[i], flip[i], b[i], c[i], s[i], h[i])
+        assert_close(f"augment image {i}", img[i], ri, 1e-6)
+        assert torch.equal(lab[i].cpu(), rl)
+    img2, none = ops.augment(x.cuda(), ops.color_jitter_params(flip, b, c, s, h, "cuda"))
+    assert none is None and torch.equal(img2, img)
+
+
+def test_dice_loss_matches_reference():
+    """DiceLoss (model.py:5-43) on the fused kernels: value and logits gradient against the reference's own
+    (golden), and against the oracle on a second seeded case with non-unit upstream gradient."""
+    from oracle import ref_transforms as RT
+    from robocupvision_b200.model import DiceLoss
+    from util import load_golden
+    g = load_golden("augment_dice")
+    logits = torch.from_numpy(g["dice_logits"]).cuda().requires_grad_(True)
+    loss = DiceLoss(torch.from_numpy(g["dice_weights"]))(logits, torch.from_numpy(g["dice_true"]).cuda())
+    loss.backward()
+    assert abs(float(loss) - float(g["dice_loss"])) <= 1e-6
+    ref_g = torch.from_numpy(g["dice_grad"])
+    assert float((logits.grad.cpu() - ref_g).abs().max()) <= 1e-5 * float(ref_g.abs().max())
+    gen = torch.Generator().manual_seed(5)
+    z = torch.randn(4, 3, 30, 40, generator=gen) * 2
+    t = torch.randint(0, 3, (4, 30, 40), generator=gen)
+    w = torch.tensor([1.0, 4.0, 0.5])
+    zr = z.clone().requires_grad_(True)
+    (RT.dice_loss(zr, t, w) * 2.5).backward()
+    zc = z.cuda().requires_grad_(True)
+    lc = DiceLoss(w)(zc, t.unsqueeze(1).cuda())   # the [B,1,H,W] target form the docstring names
+    (lc * 2.5).backward()
+    assert abs(float(lc) - float(RT.dice_loss(z, t, w))) <= 1e-6
+    assert float((zc.grad.cpu() - zr.grad).abs().max()) <= 1e-5 * float(zr.grad.abs().max())

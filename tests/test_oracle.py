@@ -248,3 +248,22 @@ def test_mask_label_lut_matches_reference_logic():
         return label
     for flags in itertools.product([False, True], repeat=4):
         assert mask_label_lut(*flags) == ref_mask(np.arange(5), *flags).tolist(), flags
+
+
+def test_transform_and_dice_oracle_matches_reference_golden():
+    """oracle/ref_transforms.py (normalize + flip + ColorJitter, DiceLoss) against what the reference's own
+    dataset.ColorJitter and model.DiceLoss produced (tests/golden/augment_dice.npz, oracle/make_golden_aux.py)."""
+    from oracle import ref_transforms as RT
+    from util import load_golden
+    g = load_golden("augment_dice")
+    for i in range(g["aug_in"].shape[0]):
+        b, c, s, h = (float(v) for v in g["aug_scalars"][i])
+        img, lab = RT.normalize_flip_jitter(torch.from_numpy(g["aug_in"][i]), torch.from_numpy(g["aug_labels"][i]),
+                                            bool(g["aug_flip"][i]), b, c, s, h)
+        assert float((img - torch.from_numpy(g["aug_out"][i])).abs().max()) <= 1e-6
+        assert torch.equal(lab, torch.from_numpy(g["aug_labels_out"][i]))
+    logits = torch.from_numpy(g["dice_logits"]).requires_grad_(True)
+    loss = RT.dice_loss(logits, torch.from_numpy(g["dice_true"]), torch.from_numpy(g["dice_weights"]))
+    loss.backward()
+    assert abs(float(loss) - float(g["dice_loss"])) <= 1e-7
+    assert float((logits.grad - torch.from_numpy(g["dice_grad"])).abs().max()) <= 1e-9
