@@ -518,7 +518,7 @@ bool plan(const RcvIgemm& p, NarrowCfg* out, int* kind_out, int* nthreads, size_
   if (c.pitch > 256 || c.SPR > NTMAX) return false;
   // tile: rows
   // 16-channel parity kernels hold 128 accumulator registers: 128-thread CTAs at <= 224 registers, two per SM
-  int want = (c.cbp > 8 && kind == NK_PAR) ? 128 : env_int("RCV_NARROW_THREADS", 160);
+  int want = (c.cbp > 8 && kind == NK_PAR) ? 128 : env_int("RCV_NARROW_THREADS", 128);
   want = (c.cbp > 8 && want > 128) ? 128 : want;  // launch bounds of the 16-channel kernels
   const int trmax = rcv_cdiv(p.Hg, c.RS);
   int TR = want / c.SPR;

@@ -211,6 +211,7 @@ class TrainStep:
             x = x.to(self.dev, non_blocking=True)
             y = y.to(self.dev, non_blocking=True)
             self.loss_sums, self.l1_sum, self.correct = self._step_impl(x, y)
+            self.plan.epoch += 1  # the optimiser wrote the weights after the step's panels were packed
             return self.loss_sums, self.l1_sum, self.correct
         if self.graph is None or self.static_x.shape != x.shape:
             self._capture(x, y)
@@ -218,6 +219,9 @@ class TrainStep:
             self.static_x.copy_(x, non_blocking=True)
             self.static_y.copy_(y, non_blocking=True)
             self.graph.replay()
+        # the optimiser wrote the weights AFTER this step's tensor-core panels were packed: an eval-mode forward
+        # that follows must not reuse them (packed-panel / folded-BN caches are keyed on the plan epoch)
+        self.plan.epoch += 1
         return self.loss_sums, self.l1_sum, self.correct
 
     def step_async(self, x: torch.Tensor, y: torch.Tensor) -> "StepResult":
@@ -251,6 +255,7 @@ class TrainStep:
         pipe.out_f[k][2:3].copy_(self.l1_sum, non_blocking=True)
         pipe.out_i[k].copy_(self.correct, non_blocking=True)
         pipe.done[k].record(cur)
+        self.plan.epoch += 1  # as in step(): the weights changed after the panels were packed
         return StepResult(pipe, k, self.l1_decay)
 
     def _state(self):

@@ -344,3 +344,25 @@ def test_eval_step_graph_replay_matches_eager():
         with torch.no_grad():  # change the weights: the next graph call must re-capture
             for p in m.parameters():
                 p.mul_(1.01)
+
+
+def test_eval_after_train_step_uses_updated_weights():
+    """An eval-mode forward right after TrainStep.step must see the weights the optimiser just wrote: the
+    tensor-core weight panels packed for the training forward are one update behind (regression: the
+    packed-panel cache was keyed on a plan epoch that only advanced before the step)."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import EvalStep, TrainStep
+    for use_graph in (False, True):
+        torch.manual_seed(12345678)
+        m = ROBO_UNet().cuda()
+        ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-2, l1_decay=1e-6, use_graph=use_graph)
+        ev = EvalStep(m, synth.CLASS_WEIGHTS)
+        x = synth.images(2, 3, 24, 32, seed=1)
+        y = synth.labels_learnable(x)
+        for _ in range(2):
+            ts.step(x.cuda(), y.cuda())
+            out = ev(x.cuda(), y.cuda())
+            sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+            with torch.no_grad():
+                ref = R.robo_unet_forward(sd, x, training=False)
+            assert_close(f"eval after train step (graph={use_graph})", out["logits"], ref, LOGIT_TOL)

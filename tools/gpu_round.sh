@@ -4,6 +4,7 @@ set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest_exit=$?"
 tail -2 gpurun_out/pytest_gpu.log
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke_exit=$?"; tail -1 gpurun_out/smoke.log
 python bench.py --impl reference --steps 6 --warmup 2 > gpurun_out/bench_reference.json 2> gpurun_out/bench.err; echo "bench_ref_exit=$?"
 python bench.py --steps 50 --warmup 10 > gpurun_out/bench.json 2>> gpurun_out/bench.err; echo "bench_exit=$?"
 python bench.py --workload infer --steps 30 --warmup 5 --cpu-steps 3 > gpurun_out/bench_infer.json 2>> gpurun_out/bench.err; echo "bench_infer_exit=$?"
