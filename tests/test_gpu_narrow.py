@@ -148,3 +148,41 @@ def test_narrow_wgrad(geom, cin, cout, n, h, w):
     dw2 = torch.ones_like(dw)
     ops.conv_wgrad(g, x.cuda(), dy.cuda(), dw=dw2, math=ops.MATH_AUTO)
     assert_close("narrow wgrad accumulate", dw2, wt.grad + 1.0, 1e-5)
+
+
+FULL_SIZE_LAYERS = [  # ROBO-UNet 160x120 layer table at the bench batch
+    ("k3s1d1", 3, 8, 120, 160), ("k3s2", 8, 16, 120, 160), ("k3s1d1", 16, 16, 60, 80), ("k3s2", 16, 32, 60, 80),
+    ("k3s1d1", 32, 32, 30, 40), ("k3s2", 32, 64, 30, 40), ("k3s1d1", 64, 64, 15, 20), ("k3s1d1", 64, 128, 15, 20),
+    ("k3s1d1", 128, 128, 15, 20), ("k3s1d1", 128, 64, 15, 20), ("convT", 64, 32, 15, 20), ("convT", 32, 16, 30, 40),
+    ("convT", 16, 8, 60, 80), ("k1", 8, 5, 120, 160),
+]
+
+
+@pytest.mark.parametrize("geom,cin,cout,h,w", FULL_SIZE_LAYERS)
+def test_full_size_adjoint_identities(geom, cin, cout, h, w):
+    """Size-independent properties at the BASELINE batch (64 frames), where the CPU oracle is too slow: a
+    convolution is bilinear, so <dy, conv(x; w)> = <dgrad(dy; w), x> = <wgrad(x, dy), w>, and conv(x1 + x2) =
+    conv(x1) + conv(x2).  Each engine (tensor-core, narrow-layer) computes the three sides with different
+    kernels and different tilings of the 1.2 M-pixel grid; inner products are taken in fp64 on the device."""
+    from robocupvision_b200 import ops
+    n = 64
+    k, s, p, d, tr = GEOMS[geom]
+    g = ops.ConvGeom(cin, cout, k, s, p, d, tr)
+    gen = torch.Generator(device="cuda").manual_seed(cin * 1000 + cout)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=gen)
+    x2 = torch.randn(n, cin, h, w, device="cuda", generator=gen)
+    wt = torch.randn((cin, cout, 3, 3) if tr else (cout, cin, k, k), device="cuda", generator=gen) / (cin * k * k) ** 0.5
+    eng = [ops.conv_engine(g, n, h, w, dd, ops.MATH_AUTO) for dd in (0, 1, 2)]
+    wp = {dd: ops.conv_pack(g, wt, dd) for dd in (0, 1) if eng[dd] == ops.ENGINE_UMMA}
+    y = ops.conv_fwd(g, x, wt, None, math=ops.MATH_AUTO, wpacked=wp.get(0))
+    dy = torch.randn(y.shape, device="cuda", generator=gen)
+    dx = ops.conv_dgrad(g, dy, wt, (h, w), math=ops.MATH_AUTO, wpacked=wp.get(1))
+    dw, _ = ops.conv_wgrad(g, x, dy, math=ops.MATH_AUTO)
+    a = float((dy.double() * y.double()).sum())
+    b = float((dx.double() * x.double()).sum())
+    c = float((dw.double() * wt.double()).sum())
+    scale = float(dy.double().norm() * y.double().norm())
+    assert abs(a - b) <= 2e-6 * scale and abs(a - c) <= 2e-6 * scale, (a, b, c, scale, eng)
+    y12 = ops.conv_fwd(g, x + x2, wt, None, math=ops.MATH_AUTO, wpacked=wp.get(0))
+    y2 = ops.conv_fwd(g, x2, wt, None, math=ops.MATH_AUTO, wpacked=wp.get(0))
+    assert_close(f"linearity {geom} {cin}->{cout}", y12, y + y2, 1e-5)
