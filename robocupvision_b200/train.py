@@ -445,3 +445,57 @@ def iou_sums(conf: torch.Tensor) -> torch.Tensor:
     union = confd.sum(2) + confd.sum(1) - inter
     iou = torch.where(union == 0, torch.ones_like(inter), inter / union.clamp(min=1))
     return iou.sum(0)
+
+
+class ValidationMeter:
+    """Epoch sums of a validation pass and the reference's summary (train.py:104-178): every batch adds its
+    per-image confusion counts, IoU sums, correct-pixel count and loss on the device (no host syncs; the reference
+    does 3 + 25*B `.item()` reads per batch), and `summary()` reduces them over the data-parallel group once
+    (one int64 and one float64 all-reduce: validation shards over independent images) and
+    returns pixel accuracy, the column-normalised confusion matrix in percent, mean class accuracy, mean IoU and
+    the model-selection score (meanClassAcc + meanIoU) / 2 exactly as train.py:157-164 computes them."""
+
+    def __init__(self, num_classes: int, device, process_group=None):
+        self.nc = num_classes
+        self.pg = process_group
+        # [conf (nc*nc) | correct | images | pixels | batches]
+        self.ints = torch.zeros(num_classes * num_classes + 4, dtype=torch.int64, device=device)
+        # [iou_sum (nc) | loss sum]
+        self.flts = torch.zeros(num_classes + 1, dtype=torch.float64, device=device)
+
+    @torch.no_grad()
+    def update(self, out: dict, extra_loss=None) -> None:
+        """`out` = EvalStep.__call__ result of one batch; extra_loss (device scalar or float) is added to the
+        batch loss (train.py:121-124 adds the L1 term when not fine-tuning)."""
+        conf = out["conf"]
+        nc2 = self.nc * self.nc
+        self.ints[:nc2] += conf.sum(0).reshape(-1)
+        self.ints[nc2] += out["correct"].reshape(())
+        self.ints[nc2 + 1] += conf.shape[0]
+        self.ints[nc2 + 2] += out["argmax"].numel()
+        self.ints[nc2 + 3] += 1
+        self.flts[:self.nc] += out["iou_sum"]
+        loss = out["loss"].to(torch.float64)
+        if extra_loss is not None:
+            loss = loss + extra_loss
+        self.flts[self.nc] += loss.reshape(())
+
+    def summary(self) -> dict:
+        ints, flts = self.ints.clone(), self.flts.clone()
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            ws = torch.distributed.get_world_size(self.pg)
+            if ws > 1:
+                torch.distributed.all_reduce(ints, group=self.pg)
+                torch.distributed.all_reduce(flts, group=self.pg)
+        nc, nc2 = self.nc, self.nc * self.nc
+        ints_h, flts_h = ints.cpu(), flts.cpu()  # the one host read of the pass
+        conf = ints_h[:nc2].reshape(nc, nc).to(torch.float64)
+        correct, imgs, pixels, batches = (int(v) for v in ints_h[nc2:nc2 + 4])
+        lab_cnts = conf.sum(0)                                   # train.py:143 labCnts (per label = column sums)
+        conf_pct = conf / (lab_cnts.view(1, -1) / 100.0)         # train.py:158-160
+        mean_class_acc = float(torch.diagonal(conf_pct).sum()) / nc   # train.py:163-164
+        mean_iou = float((flts_h[:nc] / max(imgs, 1)).sum()) / nc * 100  # train.py:162
+        return {"pixel_acc": 100.0 * correct / max(pixels, 1),  # train.py:129 running_acc*outSize*100 / imgCnt
+                "conf_pct": conf_pct, "conf": ints_h[:nc2].reshape(nc, nc), "mean_class_acc": mean_class_acc,
+                "mean_iou": mean_iou, "score": (mean_class_acc + mean_iou) / 2, "images": imgs,
+                "loss": float(flts_h[nc]) / max(batches, 1)}   # train.py:172 losstotal / len(valloader)

@@ -167,3 +167,57 @@ def test_data_parallel_gradient_averaging_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def _rank_batches(rank, nb=3, B=2, H=12, W=16, C=5):
+    g = torch.Generator().manual_seed(100 + rank)
+    return [(torch.randint(0, C, (B, H, W), generator=g), torch.randint(0, C, (B, H, W), generator=g),
+             float(torch.rand(1, generator=g))) for _ in range(nb)]
+
+
+def _meter_worker(rank, world, port, out):
+    import numpy as np
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import ref_metrics as RM
+    from robocupvision_b200.train import ValidationMeter, iou_sums
+    C = 5
+    meter = ValidationMeter(C, "cpu")
+    for pred, tgt, loss in _rank_batches(rank):
+        conf = torch.from_numpy(RM.confusion_per_image(pred.numpy(), tgt.numpy(), C))
+        meter.update({"conf": conf, "iou_sum": iou_sums(conf), "correct": (pred == tgt).sum(), "argmax": pred,
+                      "loss": torch.tensor(loss)})
+    got = meter.summary()
+    # the oracle over the union of every rank's batches (train.py:133-164)
+    conf_tot, iou, imgs, correct, pixels, losses = np.zeros((C, C), np.int64), np.zeros(C), 0, 0, 0, []
+    for r in range(world):
+        for pred, tgt, loss in _rank_batches(r):
+            cpi = RM.confusion_per_image(pred.numpy(), tgt.numpy(), C)
+            conf_tot += cpi.sum(0); iou += RM.iou_sums(cpi); imgs += pred.shape[0]
+            correct += int((pred == tgt).sum()); pixels += pred.numel(); losses.append(loss)
+    mca, miou, score = RM.epoch_summary(conf_tot, iou, imgs)
+    ok = (abs(got["mean_class_acc"] - mca) < 1e-9 and abs(got["mean_iou"] - miou) < 1e-9 and
+          abs(got["score"] - score) < 1e-9 and got["images"] == imgs and
+          abs(got["pixel_acc"] - 100.0 * correct / pixels) < 1e-9 and
+          abs(got["loss"] - sum(losses) / len(losses)) < 1e-6 and
+          bool((got["conf"].numpy() == conf_tot).all()))
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_validation_meter_reduces_over_ranks_gloo():
+    """world_size-2 gloo: ValidationMeter's epoch summary (pixel accuracy, column-normalised confusion, mean class
+    accuracy, mean IoU, score) over image-sharded ranks == the oracle's train.py:133-164 over all images."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_meter_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

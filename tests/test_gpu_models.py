@@ -366,3 +366,26 @@ def test_eval_after_train_step_uses_updated_weights():
             with torch.no_grad():
                 ref = R.robo_unet_forward(sd, x, training=False)
             assert_close(f"eval after train step (graph={use_graph})", out["logits"], ref, LOGIT_TOL)
+
+
+def test_validation_meter_matches_reference_loop():
+    """EvalStep + ValidationMeter over three batches on the GPU == the oracle's restatement of the reference's
+    per-image confusion / IoU loop and epoch summary (train.py:133-164)."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import EvalStep, ValidationMeter
+    torch.manual_seed(12345678)
+    m = ROBO_UNet().cuda().eval()
+    ev = EvalStep(m, synth.CLASS_WEIGHTS)
+    meter = ValidationMeter(5, "cuda")
+    conf_tot, iou, imgs = np.zeros((5, 5), np.int64), np.zeros(5), 0
+    for s in range(3):
+        x = synth.images(3, 3, 48, 64, seed=500 + s)
+        y = synth.labels_learnable(x)
+        out = ev(x.cuda(), y.cuda())
+        meter.update(out)
+        cpi = ref_metrics.confusion_per_image(out["argmax"].cpu().numpy(), y.numpy(), 5)
+        conf_tot += cpi.sum(0); iou += ref_metrics.iou_sums(cpi); imgs += 3
+    got = meter.summary()
+    mca, miou, score = ref_metrics.epoch_summary(conf_tot, iou, imgs)
+    assert (got["conf"].numpy() == conf_tot).all() and got["images"] == imgs
+    assert abs(got["mean_class_acc"] - mca) < 1e-9 and abs(got["mean_iou"] - miou) < 1e-9 and abs(got["score"] - score) < 1e-9
