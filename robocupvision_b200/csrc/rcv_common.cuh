@@ -99,6 +99,8 @@ int rcv_launch_narrow(const RcvIgemm& p, cudaStream_t st);      // fp32 FFMA2 di
 bool rcv_narrow_supported(const RcvIgemm& p);
 int rcv_pick_engine(const RcvIgemm& p, bool have_packed);      // rcv_engine that rcv_launch_igemm dispatches to
 int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF32, TMEM accumulators
+bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb);    // stride-1 3x3, halo-staged A operand (rcv_umma_halo.cu)
+int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st);
 bool rcv_umma_pays(const RcvIgemm& p);  // RCV_MATH_AUTO: is the reduction long enough for tensor cores
 bool rcv_umma_supported(const RcvIgemm& p);  // geometry within the tensor-core engine's limits
 size_t rcv_umma_packed_bytes(const RcvIgemm& p);

@@ -614,6 +614,8 @@ int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
   // K blocks per tile): 2 stages so that 2 CTAs share an SM and overlap prologue / epilogue.
   const int bn = umma_bn(p.CB);
   const bool deep = g_force_g > 0 ? g_force_g >= 3 : (int64_t)p.CA * max_taps(p) > 10 * BK;
+  // stride-1 3x3 layers: nine tap-shifted descriptors over one staged patch instead of nine gathers
+  if (rcv_umma_halo_ok(p, bn, umma_kb(p.CB))) return rcv_launch_igemm_umma_halo(p, bn, umma_kb(p.CB), st);
   switch (bn) {
     case 128: return umma_kb(p.CB) == 16 ? launch_bn<128, 3, 16>(p, st) : launch_bn<128, 3>(p, st);
     // BN = 64: two CTAs per SM always (a 150-tile layer is then one wave; measured 38 -> 27 us for 64->64 and

@@ -1,0 +1,371 @@
+// tcgen05 implicit GEMM with a HALO-STAGED A operand: stride-1 3x3 convolutions (dilation 1 or 2) and their
+// input gradients, the belly of every net on the path (model.py:105-116, 126-142, 166-176).
+//
+// The general engine (rcv_umma.cu) re-gathers the im2col operand once per tap: 9 x (128 pixels x 32 channels)
+// global loads, tf32 splits and swizzled stores per channel block, and that gather -- not the tensor pipe -- is
+// what bounds it.  Here the pixels of the whole batch are laid out as ONE padded,
+// flattened image: row r = d + n*(H+d) + i, pitch PW = W + d, so consecutive images share their halo rows and
+// consecutive rows share their halo columns, and every tap is the constant offset dy*PW + dx in that space.
+// A tile is 128 consecutive positions (halo positions are computed and discarded: 11 % at 15x20, 6 % at
+// 30x40).  Per 32-channel block the producers stage the positions the tile and its halo touch ONCE --
+// L = 128 + 2*(d*PW + d) rows of 128 bytes, tf32 hi and lo copies, written with the 128-byte swizzle of their
+// absolute shared-memory address -- and the MMA issuer reads the nine taps through nine matrix descriptors whose
+// start address is shifted by whole rows (tools/umma_shift_probe.cu: the hardware swizzle is a function of the
+// absolute address, so any row shift reads the right data).  6.7x less staging work at 15x20.
+// The B operand is the same pre-packed panel the general engine uses (rcv_conv_pack), streamed by bulk copies
+// through a ring; 3xTF32 with two TMEM accumulators and the fused epilogue are unchanged.
+// Roles: 8 producer / epilogue warps, one MMA-issuer warp, one B-loader warp; two CTAs per SM.
+#include <stdlib.h>
+
+#include "rcv_common.cuh"
+#include "rcv_umma.cuh"
+
+namespace {
+using namespace rcv_umma;
+
+constexpr int BM = 128;
+constexpr int NPROD = 256;
+constexpr int NT = NPROD + 64;
+constexpr int MAXL = 256;  // staged rows per channel block: one per producer thread
+
+struct HaloGeo {
+  int32_t d, PW, HP, S, L, Lpad, nkc, kbmax;
+  int64_t Mh;
+  int8_t dy[9], dx[9];
+};
+
+template <int KBB>
+__device__ __forceinline__ uint64_t make_desc_b(uint32_t saddr) {
+  if (KBB == 32) return make_desc(saddr);
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);  // SWIZZLE_64B rows of 16 fp32
+}
+
+__device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh) {
+  switch (epi) {
+    case RCV_EPI_RELU: return fmaxf(v, 0.f);
+    case RCV_EPI_RELU_AFFINE: return fmaf(sc, fmaxf(v, 0.f), sh);
+    case RCV_EPI_AFFINE_RELU: return fmaxf(fmaf(sc, v, sh), 0.f);
+    case RCV_EPI_AFFINE: return fmaf(sc, v, sh);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void warp_transpose_reduce16(float (&a)[16], int lane) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int half = 8 >> s;
+    const int mask = 16 >> s;
+    const bool up = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? a[i] : a[i + half];
+      const float keep = up ? a[i + half] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+  }
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+
+template <int BN, int KBB>
+struct HCfg {
+  static constexpr int BROWB = KBB * 4;               // bytes per B row
+  static constexpr int B_STAGE = BN * BROWB * 2;      // hi rows then lo rows
+  static constexpr int NBS = BN == 128 ? 4 : (BN == 64 ? 3 : 4);  // B ring depth
+  static constexpr int SUB = 32 / KBB;                // B K-blocks per (tap, 32-channel block)
+  static constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int MISC = 256 + 3 * BN * 4;
+};
+
+// position in the padded flattened space -> pixel; false for halo positions
+__device__ __forceinline__ bool decode_pos(long long q, const HaloGeo& g, int N, int H, int W, int& n, int& i, int& j) {
+  if (q < 0 || q >= g.Mh) return false;
+  const int r = (int)(q / g.PW);
+  j = (int)(q - (long long)r * g.PW);
+  const int rr = r - g.d;
+  if (rr < 0 || j >= W) return false;
+  n = rr / g.HP;
+  i = rr - n * g.HP;
+  return n < N && i < H;
+}
+
+template <int BN, int KBB>
+__global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, const HaloGeo g) {
+  using C = HCfg<BN, KBB>;
+  constexpr int NBS = C::NBS, SUB = C::SUB;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gen = smem_raw + (base - raw);
+  const uint32_t patch_bytes = (uint32_t)g.Lpad * 128u;
+  const uint32_t a_hi_s = base, a_lo_s = base + patch_bytes, b_s = base + 2 * patch_bytes;
+  unsigned char* misc = gen + 2 * patch_bytes + NBS * C::B_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // patch_full, patch_empty, done, bfull[NBS], bempty[NBS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 120);
+  float* s_cst = reinterpret_cast<float*>(misc + 256);
+  const uint32_t bar_pfull = smem_u32(bars), bar_pempty = bar_pfull + 8, bar_done = bar_pfull + 16;
+  const uint32_t bar_bfull = bar_pfull + 24, bar_bempty = bar_bfull + 8 * NBS;
+  static_assert(24 + 16 * NBS <= 120, "barrier area");
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int CA = p.CA, H = p.Hin, W = p.Win, HW = H * W;
+  const long long q0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int nkc = g.nkc;
+
+  for (int c = tid; c < BN; c += NT) {
+    const int co = n0 + c;
+    const bool in = co < p.CB;
+    s_cst[c] = (in && p.bias) ? __ldg(p.bias + co) : 0.f;
+    s_cst[BN + c] = (in && p.scale) ? __ldg(p.scale + co) : 1.f;
+    s_cst[2 * BN + c] = (in && p.shift) ? __ldg(p.shift + co) : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(bar_pfull, NPROD / 32);
+    mbar_init(bar_pempty, 1);
+    mbar_init(bar_done, 1);
+    for (int s = 0; s < NBS; ++s) {
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == NPROD / 32) tmem_alloc(smem_u32(tmem_slot), C::TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == NPROD / 32 + 1) {
+    // ================================ B LOADER ========================================
+    if (lane == 0) {
+      const unsigned char* gB = reinterpret_cast<const unsigned char*>(p.wpacked) +
+                                ((size_t)blockIdx.y * g.kbmax) * C::B_STAGE;
+      const int kper = CA / KBB;  // B K-blocks per tap in the pack (K = tap-major, then channel)
+      int it = 0;
+      for (int cb = 0; cb < nkc; ++cb)
+        for (int t = 0; t < 9; ++t)
+          for (int sub = 0; sub < SUB; ++sub, ++it) {
+            const int st = it % NBS, u = it / NBS;
+            if (u > 0) mbar_wait(bar_bempty + 8 * st, (uint32_t)((u - 1) & 1));
+            mbar_expect_tx(bar_bfull + 8 * st, C::B_STAGE);
+            const int kbp = t * kper + cb * SUB + sub;
+            bulk_g2s(b_s + st * C::B_STAGE, gB + (size_t)kbp * C::B_STAGE, C::B_STAGE, bar_bfull + 8 * st);
+          }
+    }
+  } else if (warp == NPROD / 32) {
+    // ================================ MMA ISSUER ======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
+      int it = 0;
+      for (int cb = 0; cb < nkc; ++cb) {
+        mbar_wait(bar_pfull, (uint32_t)(cb & 1));
+        tc_fence_after();
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t roff = (uint32_t)(g.S + g.dy[t] * g.PW + g.dx[t]) * 128u;
+          const uint64_t a_hi = make_desc(a_hi_s + roff), a_lo = make_desc(a_lo_s + roff);
+#pragma unroll
+          for (int sub = 0; sub < SUB; ++sub, ++it) {
+            const int st = it % NBS;
+            mbar_wait(bar_bfull + 8 * st, (uint32_t)((it / NBS) & 1));
+            tc_fence_after();
+            const uint32_t bb = b_s + st * C::B_STAGE;
+            const uint64_t b_hi = make_desc_b<KBB>(bb), b_lo = make_desc_b<KBB>(bb + BN * C::BROWB);
+#pragma unroll
+            for (int ks = 0; ks < KBB / 8; ++ks) {
+              const int ka = sub * (KBB / 8) + ks;  // K step inside the 32-channel A row
+              const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
+              umma_tf32(d_corr, a_lo + 2 * ka, b_hi + 2 * ks, idesc, first);
+              umma_tf32(d_corr, a_hi + 2 * ka, b_lo + 2 * ks, idesc, 1u);
+              umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc, first);
+            }
+            umma_commit(bar_bempty + 8 * st);
+          }
+        }
+        umma_commit(bar_pempty);  // the patch may be overwritten once these MMAs have read it
+      }
+      umma_commit(bar_done);
+    }
+  } else {
+    // ================================ PRODUCERS =======================================
+    // thread = one staged position (row of the patch); 32 channels of it per channel block
+    const bool has_row = tid < g.L;
+    int pn = 0, pi = 0, pj = 0;
+    const bool pvalid = has_row && decode_pos(q0 - g.S + tid, g, p.N, H, W, pn, pi, pj);
+    const char* inb = reinterpret_cast<const char*>(p.in);
+    const uint32_t boff0 = 4u * (uint32_t)((pn * CA) * HW + pi * W + pj);
+    const uint32_t cstride = 4u * (uint32_t)HW;
+    for (int cb = 0; cb < nkc; ++cb) {
+      float va[32];
+      const uint32_t b = boff0 + (uint32_t)(cb * 32) * cstride;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        va[i] = pvalid ? __ldg(reinterpret_cast<const float*>(inb + (b + (uint32_t)i * cstride))) : 0.f;
+      if (cb > 0) mbar_wait(bar_pempty, (uint32_t)((cb - 1) & 1));
+      if (has_row) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 h, l;
+          split_tf32(va[4 * c + 0], h.x, l.x);
+          split_tf32(va[4 * c + 1], h.y, l.y);
+          split_tf32(va[4 * c + 2], h.z, l.z);
+          split_tf32(va[4 * c + 3], h.w, l.w);
+          const int off = tid * 128 + ((c ^ (tid & 7)) << 4);
+          *reinterpret_cast<float4*>(gen + off) = h;
+          *reinterpret_cast<float4*>(gen + patch_bytes + off) = l;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pfull);
+    }
+
+    // ================================ EPILOGUE ========================================
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int row = tid & (BM - 1);
+    const int grp = tid / BM;  // column half
+    int en = 0, ei = 0, ej = 0;
+    const bool mrow = decode_pos(q0 + row, g, p.N, H, W, en, ei, ej);
+    const int epi = p.epilogue;
+    const int HWo = p.Hout * p.Wout;
+    const size_t obase = mrow ? (size_t)en * p.CB * HWo + (size_t)ei * p.Wout + ej : 0;
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const bool has_res = p.residual != nullptr, has_stats = p.stats != nullptr;
+#pragma unroll 1
+    for (int c0 = grp * 16; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.CB) break;
+      uint32_t rm[16], rc[16];
+      tmem_ld16_nowait(trow + c0, rm);
+      tmem_ld16_nowait(trow + BN + c0, rc);
+      const int nvalid = min(16, p.CB - (n0 + c0));
+      float* optr = p.out + obase + (size_t)(n0 + c0) * HWo;
+      const float* rptr = has_res ? p.residual + obase + (size_t)(n0 + c0) * HWo : nullptr;
+      float res[16];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) res[j] = (mrow && j < nvalid) ? __ldg(rptr + (size_t)j * HWo) : 0.f;
+      }
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float acc = __uint_as_float(rm[j]) + __uint_as_float(rc[j]) + s_cst[c0 + j];
+        float y = apply_epi(acc, epi, s_cst[BN + c0 + j], s_cst[2 * BN + c0 + j]);
+        if (has_res) y += res[j];
+        v[j] = (mrow && j < nvalid) ? y : 0.f;
+      }
+      if (mrow) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) optr[(size_t)j * HWo] = v[j];
+      }
+      if (has_stats) {
+        float s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s2[j] = v[j] * v[j];
+        warp_transpose_reduce16(v, lane);
+        warp_transpose_reduce16(s2, lane);
+        const int co = n0 + c0 + (lane >> 1);
+        if ((lane & 1) == 0 && co < p.CB) {
+          atomicAdd(p.stats + co, (double)v[0]);
+          atomicAdd(p.stats + p.CB + co, (double)s2[0]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NPROD / 32) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, C::TCOLS);
+  }
+}
+
+bool geometry(const RcvIgemm& p, HaloGeo* out) {
+  if (p.nclass != 1 || p.gs != 1 || p.ostep != 1 || p.taps[0].n != 9) return false;
+  if (p.Hout != p.Hin || p.Wout != p.Win || p.Hg != p.Hin || p.Wg != p.Win) return false;
+  if ((p.CA % 32) != 0) return false;
+  HaloGeo g;
+  memset(&g, 0, sizeof(g));
+  int d = 0;
+  for (int t = 0; t < 9; ++t) {
+    const int a = abs((int)p.taps[0].dy[t]), b = abs((int)p.taps[0].dx[t]);
+    d = a > d ? a : d;
+    d = b > d ? b : d;
+  }
+  if (d != 1 && d != 2) return false;
+  bool seen[9] = {false};
+  for (int t = 0; t < 9; ++t) {
+    const int dy = p.taps[0].dy[t], dx = p.taps[0].dx[t];
+    if ((dy != -d && dy != 0 && dy != d) || (dx != -d && dx != 0 && dx != d)) return false;
+    const int k = (dy / d + 1) * 3 + (dx / d + 1);
+    if (seen[k]) return false;
+    seen[k] = true;
+    g.dy[t] = (int8_t)dy;
+    g.dx[t] = (int8_t)dx;
+  }
+  g.d = d;
+  g.PW = p.Win + d;
+  g.HP = p.Hin + d;
+  g.S = d * g.PW + d;
+  g.L = BM + 2 * g.S;
+  g.Lpad = (g.L + 7) & ~7;
+  g.nkc = p.CA / 32;
+  g.Mh = ((int64_t)p.N * g.HP + d) * g.PW;
+  if (g.L > MAXL) return false;
+  if ((int64_t)p.N * p.CA * p.Hin * p.Win >= (1ll << 30) || g.Mh >= (1ll << 31)) return false;
+  *out = g;
+  return true;
+}
+
+template <int BN, int KBB>
+int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
+  using C = HCfg<BN, KBB>;
+  g.kbmax = (p.CA * 9) / KBB;
+  const size_t smem = 1024 + 2 * (size_t)g.Lpad * 128 + (size_t)C::NBS * C::B_STAGE + C::MISC;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(umma_halo_kernel<BN, KBB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         113 * 1024);
+    if (e != cudaSuccess) {
+      rcv_set_error("umma_halo: cannot reserve shared memory: %s", cudaGetErrorString(e));
+      return RCV_ERR_CUDA;
+    }
+    cudaFuncSetAttribute(umma_halo_kernel<BN, KBB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    attr_done = true;
+  }
+  RCV_REQUIRE(smem <= 113 * 1024, RCV_ERR_UNSUPPORTED, "umma_halo: %zu B of shared memory", smem);
+  dim3 grid(rcv_cdiv(g.Mh, BM), rcv_cdiv(p.CB, BN), 1);
+  umma_halo_kernel<BN, KBB><<<grid, NT, smem, st>>>(p, g);
+  RCV_CHECK_LAUNCH("umma_halo_kernel");
+  return RCV_OK;
+}
+
+}  // namespace
+
+// Stride-1 3x3 (dilation 1 or 2) problems whose reduced channel count is a multiple of 32 and whose rows are
+// short enough for a one-row-per-thread patch: bn / kbb are the N tile and B K-block of the layer's packed panel.
+bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb) {
+  static const int on = getenv("RCV_UMMA_HALO") ? atoi(getenv("RCV_UMMA_HALO")) : 1;
+  HaloGeo g;
+  if (!on || !geometry(p, &g)) return false;
+  const int nbs = bn == 128 ? 4 : (bn == 64 ? 3 : 4);
+  const size_t smem = 1024 + 2 * (size_t)g.Lpad * 128 + (size_t)nbs * bn * kbb * 8 + 256 + 3 * bn * 4;
+  return bn >= 32 && smem <= 113 * 1024;
+}
+
+int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st) {
+  HaloGeo g;
+  RCV_REQUIRE(geometry(p, &g), RCV_ERR_UNSUPPORTED, "umma_halo: geometry outside the kernel's limits");
+  if (bn == 128 && kbb == 16) return launch_h<128, 16>(p, g, st);
+  if (bn == 128 && kbb == 32) return launch_h<128, 32>(p, g, st);
+  if (bn == 64 && kbb == 32) return launch_h<64, 32>(p, g, st);
+  if (bn == 64 && kbb == 16) return launch_h<64, 16>(p, g, st);
+  if (bn == 32 && kbb == 32) return launch_h<32, 32>(p, g, st);
+  rcv_set_error("umma_halo: no configuration for BN=%d, K block %d", bn, kbb);
+  return RCV_ERR_UNSUPPORTED;
+}
