@@ -50,7 +50,7 @@ WORKLOADS = {
     "train_lp":    dict(net="LabelProp", kw={}, cin=8, h=120, w=160, train=True, mflop=357.6, mb=23.040, mb_step=2.58,
                         name="LabelProp two-frame training (16 samples = 8 frame pairs)", batch=16),
 }
-ENGINE_NAMES = {0: "igemm (fp32 FFMA)", 1: "direct_conv (fp32 FFMA)", 2: "umma_igemm (tcgen05 3xTF32)",
+ENGINE_NAMES = {0: "igemm (fp32 FFMA)", 1: "direct_conv (fp32 FFMA)", 2: "umma_halo / umma_igemm (tcgen05 3xTF32, halo-staged A operand for stride-1 3x3)",
                 3: "narrow_conv (TMA halo staging + FFMA2)"}  # rcv_engine
 METRIC = "robo_unet_160x120_train_frames_per_sec"
 UNIT = "frames/s"

@@ -11,7 +11,7 @@ python bench.py --workload infer --steps 30 --warmup 5 --cpu-steps 3 > gpurun_ou
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu1.log 2>&1; echo "ncu1=$?"
-for K in umma_igemm_kernel narrow_conv_kernel narrow_wgrad_kernel; do
+for K in umma_halo_kernel umma_igemm_kernel narrow_conv_kernel narrow_wgrad_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:"$K" -s 20 -c 6 -f -o gpurun_out/prof_$K \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/ncu_$K.log 2>&1; echo "ncu_$K=$?"
 done
