@@ -29,7 +29,7 @@ constexpr int NT = NPROD + 64;
 constexpr int MAXL = 256;  // staged rows per channel block: one per producer thread
 
 struct HaloGeo {
-  int32_t d, PW, HP, S, L, Lpad, nkc, kbmax;
+  int32_t d, PW, HP, S, L, Lpad, nkc, kbmax, nbs;  // nbs: B ring depth (2..4), as many stages as fit beside the patch
   int64_t Mh;
   int8_t dy[9], dx[9];
 };
@@ -71,7 +71,7 @@ template <int BN, int KBB>
 struct HCfg {
   static constexpr int BROWB = KBB * 4;               // bytes per B row
   static constexpr int B_STAGE = BN * BROWB * 2;      // hi rows then lo rows
-  static constexpr int NBS = BN == 128 ? 4 : (BN == 64 ? 3 : 4);  // B ring depth
+  static constexpr int MAXBS = 4;                     // deepest B ring
   static constexpr int SUB = 32 / KBB;                // B K-blocks per (tap, 32-channel block)
   static constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int MISC = 256 + 3 * BN * 4;
@@ -92,7 +92,8 @@ __device__ __forceinline__ bool decode_pos(long long q, const HaloGeo& g, int N,
 template <int BN, int KBB>
 __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, const HaloGeo g) {
   using C = HCfg<BN, KBB>;
-  constexpr int NBS = C::NBS, SUB = C::SUB;
+  constexpr int SUB = C::SUB;
+  const int NBS = g.nbs;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 120);
   float* s_cst = reinterpret_cast<float*>(misc + 256);
   const uint32_t bar_pfull = smem_u32(bars), bar_pempty = bar_pfull + 8, bar_done = bar_pfull + 16;
-  const uint32_t bar_bfull = bar_pfull + 24, bar_bempty = bar_bfull + 8 * NBS;
-  static_assert(24 + 16 * NBS <= 120, "barrier area");
+  const uint32_t bar_bfull = bar_pfull + 24, bar_bempty = bar_bfull + 8 * C::MAXBS;
+  static_assert(24 + 16 * C::MAXBS <= 120, "barrier area");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int CA = p.CA, H = p.Hin, W = p.Win, HW = H * W;
@@ -321,11 +322,26 @@ bool geometry(const RcvIgemm& p, HaloGeo* out) {
   return true;
 }
 
+// B ring depth that fits beside the patch in a two-CTAs-per-SM shared-memory budget (0: nothing fits)
+int ring_depth(const HaloGeo& g, int bn, int kbb, size_t* smem) {
+  const size_t budget = 113 * 1024;
+  const size_t fixed = 1024 + 2 * (size_t)g.Lpad * 128 + 256 + 3 * (size_t)bn * 4;
+  const size_t stage = (size_t)bn * kbb * 8;
+  for (int nbs = 4; nbs >= 2; --nbs)
+    if (fixed + nbs * stage <= budget) {
+      if (smem) *smem = fixed + nbs * stage;
+      return nbs;
+    }
+  return 0;
+}
+
 template <int BN, int KBB>
 int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
   using C = HCfg<BN, KBB>;
   g.kbmax = (p.CA * 9) / KBB;
-  const size_t smem = 1024 + 2 * (size_t)g.Lpad * 128 + (size_t)C::NBS * C::B_STAGE + C::MISC;
+  size_t smem = 0;
+  g.nbs = ring_depth(g, BN, KBB, &smem);
+  RCV_REQUIRE(g.nbs >= 2, RCV_ERR_UNSUPPORTED, "umma_halo: the patch leaves no room for the weight ring");
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(umma_halo_kernel<BN, KBB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -338,7 +354,6 @@ int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
                          cudaSharedmemCarveoutMaxShared);
     attr_done = true;
   }
-  RCV_REQUIRE(smem <= 113 * 1024, RCV_ERR_UNSUPPORTED, "umma_halo: %zu B of shared memory", smem);
   dim3 grid(rcv_cdiv(g.Mh, BM), rcv_cdiv(p.CB, BN), 1);
   umma_halo_kernel<BN, KBB><<<grid, NT, smem, st>>>(p, g);
   RCV_CHECK_LAUNCH("umma_halo_kernel");
@@ -353,9 +368,7 @@ bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb) {
   static const int on = getenv("RCV_UMMA_HALO") ? atoi(getenv("RCV_UMMA_HALO")) : 1;
   HaloGeo g;
   if (!on || !geometry(p, &g)) return false;
-  const int nbs = bn == 128 ? 4 : (bn == 64 ? 3 : 4);
-  const size_t smem = 1024 + 2 * (size_t)g.Lpad * 128 + (size_t)nbs * bn * kbb * 8 + 256 + 3 * bn * 4;
-  return bn >= 32 && smem <= 113 * 1024;
+  return bn >= 32 && ring_depth(g, bn, kbb, nullptr) >= 2;
 }
 
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st) {
