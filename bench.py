@@ -465,10 +465,17 @@ def narrow_layer_roofline(model, wl, batch, dev, pk):
     flops = 2.0 * g.cin * g.cout * g.k ** 2 * ho * wo * batch
     gbs = bytes_alg / (ms * 1e-3) / 1e9
     names = ENGINE_NAMES
-    return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-            "kernel": f"{names.get(eng, str(eng))} conv fwd {g.cin}->{g.cout} k{g.k} s{g.stride} d{g.dil} @{h}x{w} batch {batch}",
-            "us_per_launch": ms * 1e3, "algorithmic_bytes": bytes_alg, "flop_per_byte": flops / bytes_alg,
-            "fp32_tflops": flops / (ms * 1e-3) / 1e12}
+    out = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+           "kernel": f"{names.get(eng, str(eng))} conv fwd {g.cin}->{g.cout} k{g.k} s{g.stride} d{g.dil} @{h}x{w} batch {batch}",
+           "us_per_launch": ms * 1e3, "algorithmic_bytes": bytes_alg, "flop_per_byte": flops / bytes_alg,
+           "fp32_tflops": flops / (ms * 1e-3) / 1e12}
+    tfile = ROOT / "profiles" / "r1_traffic.json"
+    if tfile.exists():
+        ent = json.loads(tfile.read_text()).get(
+            f"conv fwd {g.cin}->{g.cout} k{g.k} s{g.stride} d{g.dil} @{h}x{w} batch {batch}")
+        if ent:
+            out["traffic"], out["traffic_source"] = ent["bytes"], ent["source"]
+    return out
 
 
 if __name__ == "__main__":
