@@ -130,17 +130,31 @@ __global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
   const int64_t stride = (int64_t)gridDim.x * NT;
   if (VEC) {
     const int64_t hw4 = HW >> 2, tot4 = total >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < tot4; i += stride) {
-      const int c = (int)((i / hw4) % C);
-      const float sc = s_ss[c], sh = s_ss[C + c];
+    // two quads per trip: both loads (and the two residual loads) are in flight before either is used
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < tot4; i += 2 * stride) {
+      const int64_t i2 = i + stride;
+      const bool two = i2 < tot4;
       float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
-      v.x = fmaf(sc, v.x, sh); v.y = fmaf(sc, v.y, sh); v.z = fmaf(sc, v.z, sh); v.w = fmaf(sc, v.w, sh);
-      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      float4 w = two ? __ldg(reinterpret_cast<const float4*>(z) + i2) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f), q = r;
       if (residual) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(residual) + i);
-        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        r = __ldg(reinterpret_cast<const float4*>(residual) + i);
+        if (two) q = __ldg(reinterpret_cast<const float4*>(residual) + i2);
       }
+      const int c = (int)((i / hw4) % C), c2 = two ? (int)((i2 / hw4) % C) : c;
+      const float sc = s_ss[c], sh = s_ss[C + c], sc2 = s_ss[c2], sh2 = s_ss[C + c2];
+      v.x = fmaf(sc, v.x, sh); v.y = fmaf(sc, v.y, sh); v.z = fmaf(sc, v.z, sh); v.w = fmaf(sc, v.w, sh);
+      w.x = fmaf(sc2, w.x, sh2); w.y = fmaf(sc2, w.y, sh2); w.z = fmaf(sc2, w.z, sh2); w.w = fmaf(sc2, w.w, sh2);
+      if (relu) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+      }
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
       reinterpret_cast<float4*>(y)[i] = v;
+      if (two) {
+        w.x += q.x; w.y += q.y; w.z += q.z; w.w += q.w;
+        reinterpret_cast<float4*>(y)[i2] = w;
+      }
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
@@ -289,6 +303,16 @@ int ew_blocks(int64_t work_items) {
   return (int)b;
 }
 
+// bn_finalize_apply: every block re-derives scale / shift from the fp64 statistics, so fewer, fatter blocks:
+// one resident wave (8 x 256 threads per SM) and at least two quads per thread
+int fa_blocks(int64_t quads) {
+  int64_t b = (quads + 2 * NT - 1) / (2 * NT);
+  const int64_t cap = 148 * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
 int chan_splits(int C, int64_t E) {
   int s = rcv_cdiv(148 * 8, C);
   const int64_t maxs = (E + NT * 16 - 1) / (NT * 16);
@@ -349,7 +373,7 @@ extern "C" int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const dou
   const double count = (double)N * (double)HW;
   const size_t smem = (size_t)2 * C * sizeof(float);
   if ((HW & 3) == 0)
-    bn_finalize_apply_kernel<true><<<ew_blocks(total / 4), NT, smem, (cudaStream_t)stream>>>(
+    bn_finalize_apply_kernel<true><<<fa_blocks(total / 4), NT, smem, (cudaStream_t)stream>>>(
         total, C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, y,
         scale, shift, save_mean, save_invstd);
   else
