@@ -217,15 +217,29 @@ __global__ void __launch_bounds__(NT) bn_bwd_kernel(int N, int C, int64_t HW, in
   if (vec) {
     const int step = NT * 4;
     int iter = 0;
-    for (int64_t e = beg + (int64_t)threadIdx.x * 4; e < end; e += step) {
+    // two quads per trip: all four loads are in flight before the first is used
+    for (int64_t e = beg + (int64_t)threadIdx.x * 4; e < end; e += 2 * step) {
+      const int64_t e2 = e + step;
+      const bool two = e2 < end;
       const int64_t n = e / HW, r = e - n * HW;
       const size_t off = ((size_t)n * C + c) * HW + r;
+      size_t off2 = off;
+      if (two) {
+        const int64_t n2 = e2 / HW, r2 = e2 - n2 * HW;
+        off2 = ((size_t)n2 * C + c) * HW + r2;
+      }
       const float4 g4 = __ldg(reinterpret_cast<const float4*>(dy + off));
       const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + off));
+      const float4 h4 = __ldg(reinterpret_cast<const float4*>(dy + off2));
+      const float4 y4 = __ldg(reinterpret_cast<const float4*>(z + off2));
       float4 o;
       elem(g4.x, z4.x, o.x); elem(g4.y, z4.y, o.y); elem(g4.z, z4.z, o.z); elem(g4.w, z4.w, o.w);
       if (PASS == 1) *reinterpret_cast<float4*>(dconv + off) = o;
-      if ((++iter & 15) == 0) { s1 += fs1; s2 += fs2; fs1 = fs2 = 0.f; }
+      if (two) {
+        elem(h4.x, y4.x, o.x); elem(h4.y, y4.y, o.y); elem(h4.z, y4.z, o.z); elem(h4.w, y4.w, o.w);
+        if (PASS == 1) *reinterpret_cast<float4*>(dconv + off2) = o;
+      }
+      if ((++iter & 7) == 0) { s1 += fs1; s2 += fs2; fs1 = fs2 = 0.f; }
     }
   } else {
     int iter = 0;
