@@ -228,7 +228,14 @@ def test_train_step_matches_reference_steps():
 
 def test_step_async_matches_step():
     """The pipelined host-fed API (H2D on a copy stream, staged D2D, D2H of the scalars) performs
-    exactly the same steps as step() on device-resident inputs."""
+    exactly the same steps as step() on device-resident inputs.
+
+    Two runs of the same steps agree to rounding, not bit for bit (fp32 RED atomics in the weight gradients), and
+    with torch's default eps = 1e-8 Adam turns that rounding into discrete events: a weight whose gradient is ~0
+    (e.g. a conv bias feeding BatchNorm: analytically zero) moves by +lr or -lr according to the sign of the noise
+    (tools/step_repeat.py: identical runs split into a few distinct trajectories 2*lr apart in a handful of
+    elements).  The comparison therefore runs Adam with eps = 1e-3, where an update is proportional to a tiny
+    gradient instead of to its sign, and can then be tight."""
     from robocupvision_b200.model import ROBO_UNet
     from robocupvision_b200.train import TrainStep
     models, steps = [], []
@@ -236,14 +243,14 @@ def test_step_async_matches_step():
         torch.manual_seed(12345678)
         m = ROBO_UNet().cuda()
         models.append(m)
-        steps.append(TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, use_graph=True))
+        steps.append(TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, eps=1e-3, use_graph=True))
     xs = [synth.images(4, 3, 48, 64, seed=200 + s) for s in range(5)]
     ys = [synth.labels_learnable(x) for x in xs]
     ref_losses = []
     for x, y in zip(xs, ys):
         steps[0].step(x.cuda(), y.cuda())
         ref_losses.append((steps[0].loss_value(), int(steps[0].correct)))
-    handles, got = [], []
+    got = []
     prev = None
     for x, y in zip(xs, ys):
         h = steps[1].step_async(x.pin_memory(), y.pin_memory())
@@ -251,19 +258,11 @@ def test_step_async_matches_step():
             got.append(prev.wait())
         prev = h
     got.append(prev.wait())
-    # fp32 RED atomics in the weight gradient make two runs agree to rounding, not bit for bit, and Adam
-    # turns that rounding into a discrete event: a weight whose gradient is ~0 moves by +lr or -lr at the
-    # first steps depending on the sign of the noise (tools/step_repeat.py: identical runs split into a few
-    # distinct trajectories, parameters 2*lr apart in a handful of elements, loss 1e-5 apart by step 5).
-    # So: losses to 1e-4, parameters equal to rounding except a few elements at most 2*lr*steps apart.
-    lr, nsteps = 1e-3, len(xs)
     for (l0, c0), (ce, tot, c1) in zip(ref_losses, got):
-        assert abs(l0 - tot) <= 1e-4 * abs(l0) and abs(c0 - c1) <= 16
+        assert abs(l0 - tot) <= 2e-6 * abs(l0) and abs(c0 - c1) <= 8
     for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
         if a.is_floating_point():
-            d = (a - b).abs()
-            assert float(d.max()) <= 2.2 * lr * nsteps + 1e-4 * float(a.abs().max()), k
-            assert float((d > 1e-5 * max(1.0, float(a.abs().max()))).float().mean()) <= 0.02, k
+            assert_close(k, a, b, 1e-4)  # (observed spread with eps = 1e-3: <= 4.4e-5; a sign flip would be 2e-3)
         else:
             assert torch.equal(a, b), k
 

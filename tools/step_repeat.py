@@ -15,7 +15,8 @@ runs = []
 for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 6):
     torch.manual_seed(12345678)
     m = ROBO_UNet().cuda()
-    st = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, use_graph=(rep % 2 == 0))
+    eps = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-8
+    st = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, eps=eps, use_graph=(rep % 2 == 0))
     losses = []
     for x, y in zip(xs, ys):
         st.step(x.cuda(), y.cuda())
