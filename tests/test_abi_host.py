@@ -221,3 +221,36 @@ def test_validation_meter_reduces_over_ranks_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_engine_dispatch_table_without_gpu():
+    """rcv_conv_engine is pure host logic: the dispatch of every ROBO-UNet layer
+    at the bench batch -- narrow-layer engine where <= 16 channels sit on the narrow side, tensor cores for the
+    rest, and the CUDA-core fallbacks for widths the TMA tensor maps cannot take."""
+    from robocupvision_b200 import _lib, ops
+    N, U, S = _lib.ENGINE_NARROW, _lib.ENGINE_UMMA, _lib.ENGINE_SIMT
+    table = [  # geom, cin, cout, h, w -> (fwd, dgrad, wgrad)
+        (("k3s1d1", 3, 8, 120, 160), (N, N, N)),
+        (("k3s2", 8, 16, 120, 160), (N, N, N)),
+        (("k3s1d1", 16, 16, 60, 80), (N, N, N)),
+        (("k3s2", 16, 32, 60, 80), (U, N, U)),
+        (("k3s1d1", 32, 32, 30, 40), (U, U, U)),
+        (("k3s1d1", 128, 128, 15, 20), (U, U, U)),
+        (("convT", 64, 32, 15, 20), (U, U, U)),
+        (("convT", 32, 16, 30, 40), (N, U, U)),
+        (("convT", 16, 8, 60, 80), (N, N, N)),
+        (("k1", 8, 5, 120, 160), (N, N, N)),
+    ]
+    geoms = {"k3s1d1": (3, 1, 1, 1, False), "k3s2": (3, 2, 1, 1, False), "k1": (1, 1, 0, 1, False),
+             "convT": (3, 2, 1, 1, True)}
+    for (geom, cin, cout, h, w), want in table:
+        k, s, p, d, tr = geoms[geom]
+        g = ops.ConvGeom(cin, cout, k, s, p, d, tr)
+        got = tuple(ops.conv_engine(g, 64, h, w, direction, ops.MATH_AUTO) for direction in (0, 1, 2))
+        assert got == want, (geom, cin, cout, got, want)
+    # a width that is not a multiple of 4 cannot be a TMA row: no narrow engine
+    g = ops.ConvGeom(3, 8, 3, 1, 1, 1, False)
+    assert ops.conv_engine(g, 2, 9, 7, 0, ops.MATH_AUTO) != N
+    # RCV_MATH_FP32 never picks the tensor cores
+    g = ops.ConvGeom(128, 128, 3, 1, 1, 1, False)
+    assert ops.conv_engine(g, 64, 15, 20, 0, ops.MATH_FP32) == S
