@@ -188,9 +188,17 @@ __device__ __forceinline__ void chunk_math(unsigned long long (&acc)[Slots<CBP, 
                 // volatile: one load per use -- no common-subexpression reuse of a tap's weights between
                 // the two slots, which would keep up to 3 taps x CBP registers alive across window rows
                 float4 w;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                             : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
-                             : "r"(wrow + (j * CBT + 4 * c4) * 4));
+                if constexpr (CBP <= 8) {
+                  // 8-channel kernels have the registers to keep a tap's weights for the second slot: a plain
+                  // load lets the compiler share it between the two slots (half the weight LDS traffic)
+                  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                      : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                      : "r"(wrow + (j * CBT + 4 * c4) * 4));
+                } else {
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                               : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                               : "r"(wrow + (j * CBT + 4 * c4) * 4));
+                }
 #pragma unroll
                 for (int x = 0; x < PIX; ++x) {
                   ffma2(acc[q][x][2 * c4], wv[x * GS + d], w.x, w.y);
