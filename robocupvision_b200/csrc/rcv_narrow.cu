@@ -28,7 +28,6 @@ using namespace rcv_narrow;
 
 constexpr int PIX = 4;    // grid points per thread along x
 constexpr int HL = 2;     // window slots left of the first centre column (dx >= -2)
-constexpr int MAXR = 8;   // window rows
 constexpr int NTMAX = 256;
 
 // Tap structure of a problem, fixed at compile time so the whole (row, slot, tap) nest unrolls into
@@ -569,7 +568,7 @@ int launch(const RcvIgemm& p, const NarrowCfg& cfg, int nthreads, size_t smem, c
   CUtensorMap tmap;
   int rc = make_nchw_map(&tmap, p.in, p.N, p.CA, p.Hin, p.Win, cfg.pitch, cfg.R, cfg.CC, "narrow_conv");
   if (rc) return rc;
-  static int ctas_per_sm[2] = {0, 0};  // [smem bucket is irrelevant: keyed per (CBP, KIND)] occupancy at this block size
+  static int ctas_per_sm = 1;  // occupancy of this instantiation at the last (block size, shared memory) it was asked for
   static int last_nt = 0;
   static size_t last_smem = 0;
   static int num_sms = 0;
@@ -584,11 +583,11 @@ int launch(const RcvIgemm& p, const NarrowCfg& cfg, int nthreads, size_t smem, c
   if (last_nt != nthreads || last_smem != smem) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, narrow_conv_kernel<CBP, KIND, NH>, nthreads, smem);
-    ctas_per_sm[0] = occ < 1 ? 1 : occ;
+    ctas_per_sm = occ < 1 ? 1 : occ;
     last_nt = nthreads;
     last_smem = smem;
   }
-  const int64_t slots = (int64_t)num_sms * ctas_per_sm[0];
+  const int64_t slots = (int64_t)num_sms * ctas_per_sm;
   const int grid = (int)(cfg.total_tiles < slots ? cfg.total_tiles : slots);
   narrow_conv_kernel<CBP, KIND, NH><<<grid, nthreads, smem, st>>>(tmap, p, cfg);
   RCV_CHECK_LAUNCH("narrow_conv_kernel");
