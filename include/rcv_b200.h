@@ -147,6 +147,18 @@ int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float* w,
                  const float* shift,
                  const float* residual, float* y, double* stats, void* stream);
 
+/* Normalise-on-load: rcv_conv_fwd on the tensor in_scale[c]*x + in_shift[c] (then ReLU if in_relu), i.e. on the
+ * output of the BatchNorm block that produced x, without that output ever being written: the staging loop of the
+ * halo-staged tensor-core kernel applies it to real pixels and keeps the zero padding zero.  in_scale / in_shift:
+ * float[Cin] (rcv_bn_finalize's scale / shift).  Only layers for which rcv_conv_normalises_on_load(d) returns 1
+ * (stride-1 3x3, Cin a multiple of 32, rows short enough for the kernel's patch) -- RCV_ERR_UNSUPPORTED otherwise.
+ * Takes a training-mode BatchNorm apply pass (model.py:113, 171) off the forward critical path. */
+int rcv_conv_normalises_on_load(const rcv_conv_desc* d);
+int rcv_conv_fwd_nl(const rcv_conv_desc* d, const float* x, const float* in_scale,
+                    const float* in_shift, int in_relu, const float* w, const void* wpacked,
+                    const float* bias, const float* scale, const float* shift,
+                    const float* residual, float* y, double* stats, void* stream);
+
 /* dx = d(conv)/dx applied to dy (shape of y) [+ residual].  residual (may be
  * NULL, may alias dx) has the shape of dx: the gradient arriving at the same
  * tensor from a second consumer (the decoder skip), summed in the epilogue.

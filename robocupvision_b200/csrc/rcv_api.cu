@@ -266,9 +266,37 @@ extern "C" int rcv_conv_pack_table_run(const void* device_table, int32_t njobs, 
                                     (cudaStream_t)stream);
 }
 
+static int conv_fwd_impl(const rcv_conv_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                         int in_relu, const float* w, const void* wpacked, const float* bias, const float* scale,
+                         const float* shift, const float* residual, float* y, double* stats, void* stream);
+
 extern "C" int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float* w, const void* wpacked,
                             const float* bias, const float* scale, const float* shift,
                             const float* residual, float* y, double* stats, void* stream) {
+  return conv_fwd_impl(d, x, nullptr, nullptr, 0, w, wpacked, bias, scale, shift, residual, y, stats, stream);
+}
+
+extern "C" int rcv_conv_normalises_on_load(const rcv_conv_desc* d) {
+  RcvIgemm p;
+  if (pack_problem(d, RCV_PACK_FWD, &p, "rcv_conv_normalises_on_load")) return 0;
+  if (rcv_pick_engine(p, true) != RCV_ENGINE_UMMA) return 0;
+  return rcv_umma_takes_input_transform(p) ? 1 : 0;
+}
+
+extern "C" int rcv_conv_fwd_nl(const rcv_conv_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                               int in_relu, const float* w, const void* wpacked, const float* bias,
+                               const float* scale, const float* shift, const float* residual, float* y,
+                               double* stats, void* stream) {
+  RCV_REQUIRE(in_scale && in_shift, RCV_ERR_BAD_ARG, "rcv_conv_fwd_nl: null input scale / shift");
+  RCV_REQUIRE(rcv_conv_normalises_on_load(d), RCV_ERR_UNSUPPORTED,
+              "rcv_conv_fwd_nl: this layer does not run on the halo-staged tensor-core kernel "
+              "(query rcv_conv_normalises_on_load first)");
+  return conv_fwd_impl(d, x, in_scale, in_shift, in_relu, w, wpacked, bias, scale, shift, residual, y, stats, stream);
+}
+
+static int conv_fwd_impl(const rcv_conv_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                         int in_relu, const float* w, const void* wpacked, const float* bias, const float* scale,
+                         const float* shift, const float* residual, float* y, double* stats, void* stream) {
   int rc = validate(d, "rcv_conv_fwd");
   if (rc) return rc;
   RCV_REQUIRE(x && w && y, RCV_ERR_BAD_ARG, "rcv_conv_fwd: null tensor");
@@ -283,6 +311,7 @@ extern "C" int rcv_conv_fwd(const rcv_conv_desc* d, const float* x, const float*
   RCV_REQUIRE(p.Hout > 0 && p.Wout > 0, RCV_ERR_BAD_ARG, "rcv_conv_fwd: empty output");
   p.in = x; p.w = w; p.wpacked = wpacked; p.out = y; p.bias = bias; p.scale = scale; p.shift = shift;
   p.residual = residual; p.stats = stats;
+  p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
   return rcv_launch_igemm(p, (cudaStream_t)stream);
 }
 

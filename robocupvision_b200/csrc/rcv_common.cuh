@@ -49,6 +49,12 @@ struct RcvIgemm {
   const float* shift;
   const float* residual;
   double* stats;
+  // normalise-on-load (forward, halo-staged tensor-core kernel only): the kernel reads in_scale[c]*x + in_shift[c]
+  // (then ReLU if in_relu) in place of x -- the BatchNorm of the block that produced x, never materialised; the
+  // zero padding applies to the transformed tensor.  NULL: x is read as it is.
+  const float* in_scale;
+  const float* in_shift;
+  int32_t in_relu;
   int32_t N, CA, CB;
   int32_t Hin, Win, Hout, Wout, Hg, Wg;
   int32_t gs, ostep;
@@ -101,6 +107,7 @@ int rcv_pick_engine(const RcvIgemm& p, bool have_packed);      // rcv_engine tha
 int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF32, TMEM accumulators
 bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb);    // stride-1 3x3, halo-staged A operand (rcv_umma_halo.cu)
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st);
+bool rcv_umma_takes_input_transform(const RcvIgemm& p);      // would rcv_launch_igemm_umma run the halo-staged kernel
 bool rcv_umma_pays(const RcvIgemm& p);  // RCV_MATH_AUTO: is the reduction long enough for tensor cores
 bool rcv_umma_supported(const RcvIgemm& p);  // geometry within the tensor-core engine's limits
 size_t rcv_umma_packed_bytes(const RcvIgemm& p);

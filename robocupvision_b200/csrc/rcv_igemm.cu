@@ -312,7 +312,10 @@ int rcv_pick_engine(const RcvIgemm& p, bool have_packed) {
 }
 
 int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st) {
-  switch (rcv_pick_engine(p, p.wpacked != nullptr)) {
+  const int eng = rcv_pick_engine(p, p.wpacked != nullptr);
+  RCV_REQUIRE(p.in_scale == nullptr || eng == RCV_ENGINE_UMMA, RCV_ERR_UNSUPPORTED,
+              "normalise-on-load is a feature of the halo-staged tensor-core kernel only");
+  switch (eng) {
     case RCV_ENGINE_UMMA: return rcv_launch_igemm_umma(p, st);
     case RCV_ENGINE_NARROW: return rcv_launch_narrow(p, st);
     case RCV_ENGINE_DIRECT: return rcv_launch_direct(p, st);

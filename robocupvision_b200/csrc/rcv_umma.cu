@@ -596,6 +596,10 @@ int rcv_launch_umma_pack_multi(const RcvPackJob* dev_jobs, int njobs, long long 
   return RCV_OK;
 }
 
+bool rcv_umma_takes_input_transform(const RcvIgemm& p) {
+  return rcv_umma_halo_ok(p, umma_bn(p.CB), umma_kb(p.CB));
+}
+
 int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
   RcvIgemm p = p_in;
   static int dbg = -1;  // RCV_UMMA_DEBUG: timing experiments only (results are wrong when set)
@@ -616,6 +620,8 @@ int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
   const bool deep = g_force_g > 0 ? g_force_g >= 3 : (int64_t)p.CA * max_taps(p) > 10 * BK;
   // stride-1 3x3 layers: nine tap-shifted descriptors over one staged patch instead of nine gathers
   if (rcv_umma_halo_ok(p, bn, umma_kb(p.CB))) return rcv_launch_igemm_umma_halo(p, bn, umma_kb(p.CB), st);
+  RCV_REQUIRE(p.in_scale == nullptr, RCV_ERR_UNSUPPORTED,
+              "normalise-on-load needs the halo-staged kernel (stride-1 3x3, reduced channels a multiple of 32, short rows)");
   switch (bn) {
     case 128: return umma_kb(p.CB) == 16 ? launch_bn<128, 3, 16>(p, st) : launch_bn<128, 3>(p, st);
     // BN = 64: two CTAs per SM always (a 150-tile layer is then one wave; measured 38 -> 27 us for 64->64 and

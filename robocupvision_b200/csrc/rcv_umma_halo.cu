@@ -74,7 +74,7 @@ struct HCfg {
   static constexpr int MAXBS = 4;                     // deepest B ring
   static constexpr int SUB = 32 / KBB;                // B K-blocks per (tap, 32-channel block)
   static constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
-  static constexpr int MISC = 256 + 3 * BN * 4;
+  static constexpr int MISC = 256 + 3 * BN * 4;       // barriers, epilogue constants (+ 2*CA floats of input scale / shift)
 };
 
 // position in the padded flattened space -> pixel; false for halo positions
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // patch_full, patch_empty, done, bfull[NBS], bempty[NBS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 120);
   float* s_cst = reinterpret_cast<float*>(misc + 256);
+  float* s_in = s_cst + 3 * BN;  // [2][CA] input scale, shift (normalise-on-load)
   const uint32_t bar_pfull = smem_u32(bars), bar_pempty = bar_pfull + 8, bar_done = bar_pfull + 16;
   const uint32_t bar_bfull = bar_pfull + 24, bar_bempty = bar_bfull + 8 * C::MAXBS;
   static_assert(24 + 16 * C::MAXBS <= 120, "barrier area");
@@ -120,6 +121,13 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
     s_cst[c] = (in && p.bias) ? __ldg(p.bias + co) : 0.f;
     s_cst[BN + c] = (in && p.scale) ? __ldg(p.scale + co) : 1.f;
     s_cst[2 * BN + c] = (in && p.shift) ? __ldg(p.shift + co) : 0.f;
+  }
+  const bool nl = p.in_scale != nullptr;
+  if (nl) {
+    for (int c = tid; c < CA; c += NT) {
+      s_in[c] = __ldg(p.in_scale + c);
+      s_in[CA + c] = __ldg(p.in_shift + c);
+    }
   }
   if (tid == 0) {
     mbar_init(bar_pfull, NPROD / 32);
@@ -203,6 +211,14 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         va[i] = pvalid ? __ldg(reinterpret_cast<const float*>(inb + (b + (uint32_t)i * cstride))) : 0.f;
+      if (nl && pvalid) {  // the producer block's BatchNorm, applied to real pixels only: halo positions stay zero
+        const bool rl = p.in_relu != 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float t = fmaf(s_in[cb * 32 + i], va[i], s_in[CA + cb * 32 + i]);
+          va[i] = rl ? fmaxf(t, 0.f) : t;
+        }
+      }
       if (cb > 0) mbar_wait(bar_pempty, (uint32_t)((cb - 1) & 1));
       if (has_row) {
 #pragma unroll
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
 bool geometry(const RcvIgemm& p, HaloGeo* out) {
   if (p.nclass != 1 || p.gs != 1 || p.ostep != 1 || p.taps[0].n != 9) return false;
   if (p.Hout != p.Hin || p.Wout != p.Win || p.Hg != p.Hin || p.Wg != p.Win) return false;
-  if ((p.CA % 32) != 0) return false;
+  if ((p.CA % 32) != 0 || p.CA > 1024) return false;
   HaloGeo g;
   memset(&g, 0, sizeof(g));
   int d = 0;
@@ -323,9 +339,9 @@ bool geometry(const RcvIgemm& p, HaloGeo* out) {
 }
 
 // B ring depth that fits beside the patch in a two-CTAs-per-SM shared-memory budget (0: nothing fits)
-int ring_depth(const HaloGeo& g, int bn, int kbb, size_t* smem) {
+int ring_depth(const HaloGeo& g, int bn, int kbb, int ca, size_t* smem) {
   const size_t budget = 113 * 1024;
-  const size_t fixed = 1024 + 2 * (size_t)g.Lpad * 128 + 256 + 3 * (size_t)bn * 4;
+  const size_t fixed = 1024 + 2 * (size_t)g.Lpad * 128 + 256 + 3 * (size_t)bn * 4 + 2 * (size_t)ca * 4;
   const size_t stage = (size_t)bn * kbb * 8;
   for (int nbs = 4; nbs >= 2; --nbs)
     if (fixed + nbs * stage <= budget) {
@@ -340,7 +356,7 @@ int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
   using C = HCfg<BN, KBB>;
   g.kbmax = (p.CA * 9) / KBB;
   size_t smem = 0;
-  g.nbs = ring_depth(g, BN, KBB, &smem);
+  g.nbs = ring_depth(g, BN, KBB, p.CA, &smem);
   RCV_REQUIRE(g.nbs >= 2, RCV_ERR_UNSUPPORTED, "umma_halo: the patch leaves no room for the weight ring");
   static bool attr_done = false;
   if (!attr_done) {
@@ -368,7 +384,7 @@ bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb) {
   static const int on = getenv("RCV_UMMA_HALO") ? atoi(getenv("RCV_UMMA_HALO")) : 1;
   HaloGeo g;
   if (!on || !geometry(p, &g)) return false;
-  return bn >= 32 && ring_depth(g, bn, kbb, nullptr) >= 2;
+  return bn >= 32 && ring_depth(g, bn, kbb, p.CA, nullptr) >= 2;
 }
 
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st) {

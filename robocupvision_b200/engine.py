@@ -29,6 +29,10 @@ import os as _os
 
 DEFAULT_MATH = {"fp32": MATH_FP32, "auto": MATH_AUTO}[_os.environ.get("RCV_B200_MATH", "auto").lower()]
 WGRAD_SIDE_STREAM = _os.environ.get("RCV_B200_WGRAD_STREAM", "1") != "0"
+# Training forward: where every consumer of a BatchNorm block's output is a conv the halo-staged tensor-core
+# kernel runs, the block's apply pass is skipped and the consumers normalise on load (rcv_conv_fwd_nl); the
+# normalised tensor the consumers' weight gradients read is produced later, on the side stream.
+BN_ON_LOAD = _os.environ.get("RCV_B200_BN_ON_LOAD", "1") != "0"
 
 
 class Node:
@@ -128,6 +132,13 @@ class Plan:
         # bumped whenever parameters / BN buffers may have been written behind torch's back (raw
         # kernels of a training forward or of TrainStep): invalidates folded-BN and packed caches
         self.epoch = 0
+        # consumers of every activation: (node index, "src" | "skip")
+        self._consumers = {}
+        for t, nd in enumerate(self.nodes):
+            self._consumers.setdefault(nd.src, []).append((t, "src"))
+            if nd.skip is not None and nd.skip >= 0:
+                self._consumers.setdefault(nd.skip, []).append((t, "skip"))
+        self._defer_cache = {}
         self.n_stats = 0
         self._sum_off = {}
         for t, nd in enumerate(self.nodes):
@@ -154,6 +165,22 @@ class Plan:
         for nd, d in jobs:
             nd._pack_key[d] = nd.pack_key(self.epoch)
 
+    def _defer_bn_apply(self, t: int, n: int, h: int, w: int) -> bool:
+        """Can node t's BatchNorm apply pass be left to its consumers (normalise-on-load)?  Its output must feed only
+        conv nodes, as their main input, that the halo-staged tensor-core kernel runs at this size; it must not be
+        a plan output and the node must not add a skip tensor after the BatchNorm."""
+        key = (t, n, h, w)
+        hit = self._defer_cache.get(key)
+        if hit is None:
+            nd = self.nodes[t]
+            cons = self._consumers.get(t + 1, [])
+            hit = (BN_ON_LOAD and self.math != MATH_FP32 and nd.skip < 0 and (t + 1) not in self.outputs and
+                   len(cons) > 0 and
+                   all(role == "src" and self.nodes[c].kind == "conv" and
+                       ops.conv_normalises_on_load(self.nodes[c].geom, n, h, w, self.math) for c, role in cons))
+            self._defer_cache[key] = hit
+        return hit
+
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, training: bool, save: bool):
         """-> (outputs, saved).  training selects batch statistics for BatchNorm nodes whose
@@ -163,6 +190,7 @@ class Plan:
             raise ValueError(f"expected NCHW input, got shape {tuple(x.shape)}")
         dev = x.device
         acts: List[torch.Tensor] = [x]
+        lazy: Dict[int, tuple] = {}  # activation index -> (scale, shift, relu): acts[i] holds the tensor BEFORE that affine
         saved: List[Optional[tuple]] = [None] * len(self.nodes)
         stats_arena = None
         soff = 0
@@ -182,8 +210,9 @@ class Plan:
             b = conv.bias.detach() if conv.bias is not None else None
             skip = acts[nd.skip] if (nd.skip >= 0 and nd.skip_mode == "add") else None
             wp = nd._pack[PACK_FWD] if nd.uses_tc(PACK_FWD, self.math) else None
+            ina = lazy.get(nd.src)  # the producer's BatchNorm, applied on load
             if bn is None:
-                y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, math=self.math, wpacked=wp)
+                y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, math=self.math, wpacked=wp, in_affine=ina)
                 saved[t] = (y if nd.order == EPI_RELU else None,)
             elif training and bn.training:
                 if stats_arena is None:
@@ -191,24 +220,31 @@ class Plan:
                 stats = stats_arena[soff:soff + 2 * g.cout]
                 soff += 2 * g.cout
                 z = ops.conv_fwd(g, src, w, b, epilogue=EPI_RELU if nd.order == EPI_RELU_AFFINE else EPI_NONE,
-                                 stats=stats, math=self.math, wpacked=wp)
+                                 stats=stats, math=self.math, wpacked=wp, in_affine=ina)
                 count = z.numel() // g.cout
                 if bn.momentum is None:
                     momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
                 else:
                     momentum = bn.momentum
                 track = bn.track_running_stats and bn.running_mean is not None
-                y, scale, shift, mean, invstd = ops.bn_finalize_apply(
-                    z, stats, bn.weight.detach(), bn.bias.detach(),
-                    bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps,
-                    relu=(nd.order == EPI_AFFINE_RELU), residual=skip)
+                if self._defer_bn_apply(t, z.shape[0], z.shape[2], z.shape[3]):
+                    scale, shift, mean, invstd = ops.bn_finalize(
+                        stats, count, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
+                        bn.running_var if track else None, momentum, bn.eps)
+                    lazy[t + 1] = (scale, shift, nd.order == EPI_AFFINE_RELU)
+                    y = z  # consumers read z through the affine
+                else:
+                    y, scale, shift, mean, invstd = ops.bn_finalize_apply(
+                        z, stats, bn.weight.detach(), bn.bias.detach(),
+                        bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps,
+                        relu=(nd.order == EPI_AFFINE_RELU), residual=skip)
                 saved[t] = (z, scale, shift, mean, invstd)
                 if track and bn.num_batches_tracked is not None:
                     nbt.append(bn.num_batches_tracked)
             else:
                 scale, shift = nd.folded(self.epoch)
                 y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, scale=scale, shift=shift, residual=skip,
-                                 math=self.math, wpacked=wp)
+                                 math=self.math, wpacked=wp, in_affine=ina)
             if nd.skip >= 0 and nd.skip_mode == "partial":
                 y[:, :nd.skip_ch] += acts[nd.skip]
             elif nd.skip >= 0 and nd.skip_mode == "cat":
@@ -217,7 +253,7 @@ class Plan:
         if nbt:
             torch._foreach_add_(nbt, 1)
         outs = [acts[i] for i in self.outputs]
-        return outs, ((acts, saved) if save else None)
+        return outs, ((acts, saved, lazy) if save else None)
 
     # ------------------------------------------------------------------ backward
     def backward(self, saved_all, gouts: Sequence[Optional[torch.Tensor]], x_needs_grad: bool,
@@ -225,7 +261,8 @@ class Plan:
         """-> (dx or None, {id(param): grad}).  grad_views, if given, maps id(param) to zero-filled
         tensors that receive the gradients (the train step's flat arena).  node_done(t) is called
         once node t's parameter gradients are final (nodes are visited last to first)."""
-        acts, saved = saved_all
+        acts, saved, lazy = saved_all
+        self._lazy, self._lazy_done = lazy, {}
         dev = acts[0].device
         if grad_views is None:
             total = sum(p.numel() for p in self.params)
@@ -306,14 +343,30 @@ class Plan:
                 wp = nd._pack[PACK_DGRAD] if nd.uses_tc(PACK_DGRAD, self.math) else None
                 grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
                                                wpacked=wp)
+            la = self._lazy.get(nd.src)
+
+            def wgrad_src():
+                """The tensor the weight gradient reads: for a normalise-on-load input, the producer's BatchNorm output,
+                produced now (once per activation) on the stream the weight gradient runs on."""
+                if la is None:
+                    return src
+                y = self._lazy_done.get(nd.src)
+                if y is None:
+                    y = ops.bn_apply(src, la[0], la[1], la[2])
+                    self._lazy_done[nd.src] = y
+                    if keep is not None:
+                        keep.append(y)
+                return y
+
             if side is None:
-                ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math)
+                ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math)
             else:
                 cur = torch.cuda.current_stream(src.device)
                 side.wait_stream(cur)  # dconv (and every earlier write to the gradient arena) is ordered before
                 keep.append(dconv)
                 with torch.cuda.stream(side):
-                    ops.conv_wgrad(geom, src, dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math)
+                    ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias,
+                                   math=self.math)
 
 
 class _PlanFn(torch.autograd.Function):

@@ -16,7 +16,7 @@ from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_A
                    EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO, MATH_FP32, MATH_TF32X3, PACK_DGRAD, PACK_FWD, ConvDesc)
 
 __all__ = [
-    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
+    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
     "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
@@ -183,8 +183,14 @@ def _packed_for(g, w, wpacked, math, direction):
     return wpacked
 
 
+def conv_normalises_on_load(g: ConvGeom, n: int, h: int, w: int, math: int = MATH_AUTO) -> bool:
+    """Would conv_fwd(..., in_affine=...) be accepted for this layer at this size (halo-staged tensor-core kernel)."""
+    d = g.desc(n, h, w, EPI_NONE, math)
+    return bool(_lib.load().rcv_conv_normalises_on_load(C.byref(d)))
+
+
 def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=None, residual=None,
-             stats=None, math=MATH_FP32, out=None, wpacked=None):
+             stats=None, math=MATH_FP32, out=None, wpacked=None, in_affine=None):
     x = _chk(x, name="x")
     w = _chk(w, name="weight")
     wpacked = _packed_for(g, w, wpacked, math, PACK_FWD)
@@ -203,6 +209,14 @@ def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 2 * g.cout):
         raise ValueError("conv_fwd: stats must be float64[2*Cout]")
     d = g.desc(n, h, wd, epilogue, math)
+    if in_affine is not None:
+        # (in_scale, in_shift, relu): the BatchNorm of the block that produced x, applied on load (rcv_conv_fwd_nl)
+        isc, ish, irelu = in_affine
+        if isc.numel() != g.cin or ish.numel() != g.cin:
+            raise ValueError("conv_fwd: in_affine must have Cin entries")
+        _call("rcv_conv_fwd_nl", 1, C.byref(d), _ptr(x), _ptr(isc), _ptr(ish), 1 if irelu else 0, _ptr(w),
+              _ptr(wpacked), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(residual), _ptr(y), _ptr(stats), _stream())
+        return y
     _call("rcv_conv_fwd", 1, C.byref(d), _ptr(x), _ptr(w), _ptr(wpacked), _ptr(bias), _ptr(scale), _ptr(shift),
           _ptr(residual), _ptr(y), _ptr(stats), _stream())
     return y

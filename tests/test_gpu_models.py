@@ -147,6 +147,43 @@ def test_robo_unet_backward(tag):
                 synth.CLASS_WEIGHTS)
 
 
+def test_bn_normalise_on_load_matches_materialised():
+    """Training forward/backward with the BatchNorm apply passes left to the consuming tensor-core convs
+    (engine.BN_ON_LOAD) == the same step with every BatchNorm output materialised: logits, loss, every gradient,
+    running statistics.  Also checks the schedule really defers blocks at this size."""
+    from robocupvision_b200 import engine
+    from robocupvision_b200.model import ROBO_UNet, CrossEntropyLoss2d
+    x = synth.images(8, 3, 120, 160, seed=21).cuda()
+    y = synth.labels_learnable(x.cpu()).cuda()
+    crit = CrossEntropyLoss2d(torch.tensor(synth.CLASS_WEIGHTS)).cuda()
+    res = {}
+    old = engine.BN_ON_LOAD
+    try:
+        for flag in (False, True):
+            engine.BN_ON_LOAD = flag
+            torch.manual_seed(77)
+            m = ROBO_UNet().cuda().train()
+            pred = m(x)
+            loss = crit(pred, y)
+            loss.backward()
+            plan = m._get_plan()
+            res[flag] = (pred.detach(), float(loss), {k: p.grad.clone() for k, p in m.named_parameters()},
+                         {k: b.clone() for k, b in m.named_buffers()}, sum(plan._defer_cache.values()))
+    finally:
+        engine.BN_ON_LOAD = old
+    assert res[False][4] == 0 and res[True][4] >= 4, f"deferred blocks: {res[True][4]}"
+    assert_close("logits", res[True][0], res[False][0].cpu(), 2e-5)
+    assert abs(res[True][1] - res[False][1]) <= 2e-6 * max(1.0, abs(res[False][1]))
+    gmax = max(float(g.abs().max()) for g in res[False][2].values())
+    for k, g in res[False][2].items():
+        scale = max(float(g.abs().max()), 1e-3 * gmax)
+        err = float((res[True][2][k] - g).abs().max()) / scale
+        assert err <= 1e-4, f"grad {k} rel err {err:.3e}"
+    for k, b in res[False][3].items():
+        if b.is_floating_point():
+            assert_close(f"buffer {k}", res[True][3][k], b.cpu(), 1e-5)
+
+
 def test_pb_fcn_backward():
     from robocupvision_b200.model import PB_FCN, load_legacy_state_dict
     osd, raw = pb_fcn_state("bestModelSeg")

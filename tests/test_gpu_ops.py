@@ -129,6 +129,46 @@ def test_conv_epilogues(epi, geom, cin, cout, engine):
     assert_close("stats sumsq", stats[cout:], (rd * rd).sum((0, 2, 3)), 1e-6 * f, atol=1e-3)
 
 
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("geom,cin,cout,nhw", [("k3s1d1", 32, 64, (4, 30, 40)), ("k3s1d2", 64, 128, (3, 15, 20)),
+                                               ("k3s1d1", 128, 128, (2, 9, 7)), ("k3s1d2", 128, 64, (5, 12, 16)),
+                                               ("k3s1d1", 64, 32, (2, 24, 50))])
+def test_conv_fwd_normalise_on_load(geom, cin, cout, nhw, relu):
+    """rcv_conv_fwd_nl: the producer block's BatchNorm (per-channel scale/shift [+ReLU]) applied to the input while
+    the halo-staged tensor-core kernel stages it == the conv of the normalised tensor; the zero padding stays zero."""
+    from robocupvision_b200 import ops
+    n, h, w_ = nhw
+    g, x, w, b = _mk(geom, cin, cout, n, h, w_, seed=4)
+    if not ops.conv_normalises_on_load(g, n, h, w_, ops.MATH_AUTO):
+        pytest.skip("layer not on the halo-staged tensor-core kernel at this size")
+    gen = torch.Generator().manual_seed(11)
+    sc, sh = torch.randn(cin, generator=gen), torch.randn(cin, generator=gen)
+    xn = sc.view(1, -1, 1, 1) * x + sh.view(1, -1, 1, 1)
+    if relu:
+        xn = F.relu(xn)
+    ref = F.relu(_ref_conv(geom, xn, w, b))
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    wp = ops.conv_pack(g, w.cuda(), ops.PACK_FWD)
+    got = ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda(), epilogue=ops.EPI_RELU, stats=stats, math=ops.MATH_AUTO,
+                       wpacked=wp, in_affine=(sc.cuda(), sh.cuda(), relu))
+    assert_close(f"conv_fwd_nl {geom} {cin}->{cout} relu={relu}", got, ref, 8e-6)
+    same = ops.conv_fwd(g, xn.cuda(), w.cuda(), b.cuda(), epilogue=ops.EPI_RELU, math=ops.MATH_AUTO, wpacked=wp)
+    assert_close("conv_fwd_nl vs conv_fwd of the normalised tensor", got, same.cpu(), 2e-6)
+    assert_close("stats sum", stats[:cout], ref.double().sum((0, 2, 3)), 4e-6, atol=1e-3)
+
+
+def test_conv_fwd_normalise_on_load_refused_elsewhere():
+    """Engines other than the halo-staged tensor-core kernel refuse an input transform (no silent ignore)."""
+    from robocupvision_b200 import ops
+    for geom, cin, cout, math in [("k3s2", 32, 64, ops.MATH_AUTO), ("k3s1d1", 3, 8, ops.MATH_AUTO),
+                                  ("k3s1d1", 32, 64, ops.MATH_FP32), ("convT", 32, 16, ops.MATH_AUTO)]:
+        g, x, w, b = _mk(geom, cin, cout, 2, 12, 16)
+        assert not ops.conv_normalises_on_load(g, 2, 12, 16, math)
+        one = torch.ones(cin, device="cuda")
+        with pytest.raises(RuntimeError):
+            ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda(), math=math, in_affine=(one, one, False))
+
+
 @pytest.mark.parametrize("engine", list(MATHS))
 @pytest.mark.parametrize("geom", list(GEOMS))
 @pytest.mark.parametrize("cin,cout", [(3, 8), (8, 16), (32, 64), (128, 128), (64, 32), (16, 5)])
