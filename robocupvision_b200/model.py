@@ -613,13 +613,45 @@ class LabelProp(_PlanModule):
         return b.conv(x, self.classifier, None, EPI_NONE)
 
 
-class PB_FCN_2(nn.Module):
-    """Older separable-conv experiment (model.py:416-459): no checkpoint, not on the hot path."""
+class PB_FCN_2(_PlanModule):
+    """model.py:416-459: the ROBO_UNet trunk (one conv in Level0, strided LevelDowns, belly, transposed-conv decoder
+    with additive skips) with a fixed option set and an extra image-classification head.  The segmentation branch
+    (classify=False) runs on the plan; the classification branch (global average pool + dropout + 1x1 conv on the
+    belly output, model.py:452-453) is outside the hot path and raises."""
 
-    def __init__(self, *a, **k):
+    def __init__(self, classify, nClass=5, planes=8, depth=4, levels=2, bellySize=5, bellyPlanes=128):
         super().__init__()
-        raise NotImplementedError("PB_FCN_2 is outside the hot path this package accelerates "
-                                  "(SURVEY.md section 2, row 8)")
+        self.classify = classify
+        self.img_shape = (120, 160)
+        maxDepth = planes * pow(2, depth - 1)
+        self.downPart = nn.ModuleList()
+        self.downPart.add_module("Level0", LevelDown(3, planes, 1, False))
+        for i in range(depth - 1):
+            c = planes * pow(2, i)
+            self.downPart.add_module("Level%d" % (i + 1), LevelDown(c, c * 2, levels, True))
+        self.PB = nn.Sequential()
+        self.PB.add_module("PB_1", LevelDown(maxDepth, bellyPlanes, bellySize - 1, False))
+        self.PB.add_module("PB_2", LevelDown(bellyPlanes, maxDepth, 1, False))
+        self.upPart = nn.ModuleList()
+        for i in range(depth - 1):
+            c = planes * pow(2, depth - 1 - i)
+            self.upPart.add_module("Up%d" % i, upSampleTransposeConv(c, c // 2))
+        self.classifier = UltClassifier(maxDepth, nClass, True)
+        self.segmenter = UltClassifier(planes, nClass, False)
+
+    def _emit(self, b, src, **kw):
+        if self.classify:
+            raise NotImplementedError("PB_FCN_2(classify=True) is the image-classification branch "
+                                      "(outside the segmentation hot path this package accelerates)")
+        downs = [src]
+        for level in self.downPart:
+            downs.append(level._emit(b, downs[-1]))
+        for level in self.PB:
+            downs[-1] = level._emit(b, downs[-1])
+        up = downs[-1]
+        for i, layer in enumerate(self.upPart):
+            up = layer._emit(b, up, skip=downs[-(i + 2)])
+        return self.segmenter._emit(b, up)
 
 
 # =============================================================================== checkpoints

@@ -254,3 +254,20 @@ def test_engine_dispatch_table_without_gpu():
     # RCV_MATH_FP32 never picks the tensor cores
     g = ops.ConvGeom(128, 128, 3, 1, 1, 1, False)
     assert ops.conv_engine(g, 64, 15, 20, 0, ops.MATH_FP32) == S
+
+
+def test_pb_fcn_2_is_the_unet_trunk_plus_a_classification_head():
+    """model.py:416-459: PB_FCN_2 registers the ROBO_UNet default trunk under the same names plus `classifier`; its
+    segmentation branch builds a plan with the same 16 conv nodes, the classification branch is refused."""
+    from robocupvision_b200.model import PB_FCN_2, ROBO_UNet
+    torch.manual_seed(3)
+    m2, mu = PB_FCN_2(False), ROBO_UNet()
+    k2, ku = list(m2.state_dict().keys()), list(mu.state_dict().keys())
+    assert [k for k in k2 if not k.startswith("classifier.")] == ku
+    assert [k for k in k2 if k.startswith("classifier.")] == ["classifier.layers.Class.weight",
+                                                              "classifier.layers.Class.bias"]
+    assert all(m2.state_dict()[k].shape == mu.state_dict()[k].shape for k in ku)
+    p2, pu = m2._get_plan(), mu._get_plan()
+    assert [(n.kind, n.src, n.skip, n.order) for n in p2.nodes] == [(n.kind, n.src, n.skip, n.order) for n in pu.nodes]
+    with pytest.raises(NotImplementedError):
+        PB_FCN_2(True)._get_plan()

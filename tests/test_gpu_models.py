@@ -184,6 +184,33 @@ def test_bn_normalise_on_load_matches_materialised():
             assert_close(f"buffer {k}", res[True][3][k], b.cpu(), 1e-5)
 
 
+def test_pb_fcn_2_segmentation_branch_matches_unet():
+    """PB_FCN_2(classify=False) (model.py:416-459) == ROBO_UNet default on the same weights (the oracle-pinned net):
+    eval logits and train-mode gradients, bit for bit (same plan, same kernels)."""
+    from robocupvision_b200.model import PB_FCN_2, ROBO_UNet, CrossEntropyLoss2d
+    torch.manual_seed(5)
+    mu, m2 = ROBO_UNet().cuda(), PB_FCN_2(False).cuda()
+    m2.load_state_dict(mu.state_dict(), strict=False)
+    x = synth.images(4, 3, 120, 160, seed=3).cuda()
+    y = synth.labels_random(4, 120, 160).cuda()
+    mu.eval(), m2.eval()
+    with torch.no_grad():
+        assert torch.equal(m2(x), mu(x))
+    crit = CrossEntropyLoss2d(torch.tensor(synth.CLASS_WEIGHTS)).cuda()
+    mu.train(), m2.train()
+    lu, l2 = crit(mu(x), y), crit(m2(x), y)
+    lu.backward(), l2.backward()
+    assert abs(float(lu.detach()) - float(l2.detach())) <= 1e-6
+    gu = dict(mu.named_parameters())
+    gmax = max(float(p.grad.abs().max()) for p in gu.values())
+    for k, p in m2.named_parameters():
+        if k.startswith("classifier."):
+            assert p.grad is None
+        else:
+            scale = max(float(gu[k].grad.abs().max()), 1e-3 * gmax)
+            assert float((p.grad - gu[k].grad).abs().max()) <= 2e-5 * scale, k  # atomics order only
+
+
 def test_pb_fcn_backward():
     from robocupvision_b200.model import PB_FCN, load_legacy_state_dict
     osd, raw = pb_fcn_state("bestModelSeg")
