@@ -174,6 +174,16 @@ int rcv_conv_dgrad(const rcv_conv_desc* d, const float* dy, const float* w,
 int rcv_conv_wgrad(const rcv_conv_desc* d, const float* x, const float* dy,
                    float* dw, float* dbias, void* stream);
 
+/* Normalise-on-load for the weight gradient: rcv_conv_wgrad with in_scale[c]*x + in_shift[c] (then ReLU if
+ * in_relu) in place of x -- the companion of rcv_conv_fwd_nl, so that the BatchNorm output the forward pass never
+ * wrote does not have to be written for the backward pass either.  Only layers for which
+ * rcv_conv_wgrad_normalises_on_load(d) returns 1 (tensor-core weight gradient with the quad gather: stride-1 3x3,
+ * rows a multiple of 4 pixels wide, not transposed) -- RCV_ERR_UNSUPPORTED otherwise. */
+int rcv_conv_wgrad_normalises_on_load(const rcv_conv_desc* d);
+int rcv_conv_wgrad_nl(const rcv_conv_desc* d, const float* x, const float* in_scale,
+                      const float* in_shift, int in_relu, const float* dy, float* dw,
+                      float* dbias, void* stream);
+
 /* ---- BatchNorm2d, training mode (model.py:113,134,171,188) --------------- */
 
 /* From stats (sum, sum of squares over count = N*H*W elements per channel):

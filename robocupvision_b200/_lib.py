@@ -62,6 +62,8 @@ SIGNATURES = {
     "rcv_conv_fwd_nl": [C.POINTER(ConvDesc), _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_conv_dgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p, _p],
     "rcv_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
+    "rcv_conv_wgrad_normalises_on_load": [C.POINTER(ConvDesc)],
+    "rcv_conv_wgrad_nl": [C.POINTER(ConvDesc), _p, _p, _p, C.c_int, _p, _p, _p, _p],
     "rcv_bn_finalize": [_i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p],
     "rcv_bn_fold": [_i32, _p, _p, _p, _p, _f32, _p, _p, _p],
     "rcv_bn_apply": [_i32, _i32, _i64, _p, _p, _p, C.c_int, _p, _p, _p],

@@ -354,14 +354,39 @@ void wgrad_problem(const rcv_conv_desc* d, RcvWgrad* pp) {
 }
 }  // namespace
 
+extern "C" int rcv_conv_wgrad_normalises_on_load(const rcv_conv_desc* d) {
+  if (validate(d, "rcv_conv_wgrad_normalises_on_load") || d->transposed) return 0;
+  RcvWgrad p;
+  wgrad_problem(d, &p);
+  return (rcv_pick_wgrad_engine(p) == RCV_ENGINE_UMMA && rcv_umma_wgrad_takes_input_transform(p)) ? 1 : 0;
+}
+
+static int conv_wgrad_impl(const rcv_conv_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                           int in_relu, const float* dy, float* dw, float* dbias, void* stream);
+
 extern "C" int rcv_conv_wgrad(const rcv_conv_desc* d, const float* x, const float* dy, float* dw,
                               float* dbias, void* stream) {
+  return conv_wgrad_impl(d, x, nullptr, nullptr, 0, dy, dw, dbias, stream);
+}
+
+extern "C" int rcv_conv_wgrad_nl(const rcv_conv_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                                 int in_relu, const float* dy, float* dw, float* dbias, void* stream) {
+  RCV_REQUIRE(in_scale && in_shift, RCV_ERR_BAD_ARG, "rcv_conv_wgrad_nl: null input scale / shift");
+  RCV_REQUIRE(rcv_conv_wgrad_normalises_on_load(d), RCV_ERR_UNSUPPORTED,
+              "rcv_conv_wgrad_nl: this layer's weight gradient does not run on the tensor-core quad-gather kernel "
+              "(query rcv_conv_wgrad_normalises_on_load first)");
+  return conv_wgrad_impl(d, x, in_scale, in_shift, in_relu, dy, dw, dbias, stream);
+}
+
+static int conv_wgrad_impl(const rcv_conv_desc* d, const float* x, const float* in_scale, const float* in_shift,
+                           int in_relu, const float* dy, float* dw, float* dbias, void* stream) {
   int rc = validate(d, "rcv_conv_wgrad");
   if (rc) return rc;
   RCV_REQUIRE(x && dy && dw, RCV_ERR_BAD_ARG, "rcv_conv_wgrad: null tensor");
   RcvWgrad p;
   wgrad_problem(d, &p);
   p.dw = dw;
+  p.in_scale = in_scale; p.in_shift = in_shift; p.in_relu = in_relu;
   if (!d->transposed) {
     p.src = x; p.row = dy; p.dbias = dbias;
   } else {

@@ -82,6 +82,11 @@ struct RcvWgrad {
   int32_t qunits;    // tensor-core quad gather: (channel, tap-row) units per k tile
   int32_t math;      // rcv_math
   long long* prof;   // see RcvIgemm::prof
+  // normalise-on-load (tensor-core quad gather only): the kernel reads in_scale[ca]*src + in_shift[ca] (then ReLU if
+  // in_relu) in place of src at real pixels -- see RcvIgemm::in_scale; padding positions stay zero.  NULL: off.
+  const float* in_scale;
+  const float* in_shift;
+  int32_t in_relu;
   RcvTapSet taps;
 };
 
@@ -108,6 +113,7 @@ int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF3
 bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb);    // stride-1 3x3, halo-staged A operand (rcv_umma_halo.cu)
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st);
 bool rcv_umma_takes_input_transform(const RcvIgemm& p);      // would rcv_launch_igemm_umma run the halo-staged kernel
+bool rcv_umma_wgrad_takes_input_transform(const RcvWgrad& p);  // tensor-core weight gradient with the quad gather
 bool rcv_umma_pays(const RcvIgemm& p);  // RCV_MATH_AUTO: is the reduction long enough for tensor cores
 bool rcv_umma_supported(const RcvIgemm& p);  // geometry within the tensor-core engine's limits
 size_t rcv_umma_packed_bytes(const RcvIgemm& p);

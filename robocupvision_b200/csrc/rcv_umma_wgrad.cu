@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
       const int qu0 = gt >> 3;   // QUAD: units qu0 + 16*r
       if (QUAD) {
         const int d = p.taps.dx[2];  // dilation: taps are (-d, 0, +d)
+        const bool nl = p.in_scale != nullptr, nl_relu = p.in_relu != 0;  // normalise-on-load (uniform)
         const int m = mc + qq * 4;
         const bool ok = m < M;       // values beyond this CTA's pixel range are still needed as neighbours
         int n = 0, i0 = 0, j0 = 0;
@@ -215,6 +216,22 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
           const bool uok = ok && u < p.qunits && ca < p.CA && (unsigned)iy < (unsigned)p.Hin;
           const float* src = p.src + ((size_t)n * p.CA + ca) * HWin + iy * p.Win + j0;
           qv[r] = uok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // the producer block's BatchNorm, applied to real pixels only (padding stays zero)
+          float isc = 1.f, ish = 0.f;
+          if (nl && uok) {
+            isc = __ldg(p.in_scale + ca);
+            ish = __ldg(p.in_shift + ca);
+            qv[r].x = fmaf(isc, qv[r].x, ish);
+            qv[r].y = fmaf(isc, qv[r].y, ish);
+            qv[r].z = fmaf(isc, qv[r].z, ish);
+            qv[r].w = fmaf(isc, qv[r].w, ish);
+            if (nl_relu) {
+              qv[r].x = fmaxf(qv[r].x, 0.f);
+              qv[r].y = fmaxf(qv[r].y, 0.f);
+              qv[r].z = fmaxf(qv[r].z, 0.f);
+              qv[r].w = fmaxf(qv[r].w, 0.f);
+            }
+          }
           // neighbours from the adjacent lanes (same unit, adjacent quad) ...
           ql[r][0] = __shfl_up_sync(0xffffffffu, qv[r].z, 1);
           ql[r][1] = __shfl_up_sync(0xffffffffu, qv[r].w, 1);
@@ -228,6 +245,18 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
           if (qq == 7) {
             qr[r][0] = (uok && has_r) ? __ldg(src + 4) : 0.f;
             qr[r][1] = (uok && has_r && d == 2) ? __ldg(src + 5) : 0.f;
+          }
+          if (nl && uok && (qq == 0 || qq == 7)) {  // the edge values came from memory: same transform
+            if (qq == 0 && has_l) {
+              ql[r][1] = fmaf(isc, ql[r][1], ish);
+              if (d == 2) ql[r][0] = fmaf(isc, ql[r][0], ish);
+              if (nl_relu) { ql[r][1] = fmaxf(ql[r][1], 0.f); ql[r][0] = fmaxf(ql[r][0], 0.f); }
+            }
+            if (qq == 7 && has_r) {
+              qr[r][0] = fmaf(isc, qr[r][0], ish);
+              if (d == 2) qr[r][1] = fmaf(isc, qr[r][1], ish);
+              if (nl_relu) { qr[r][0] = fmaxf(qr[r][0], 0.f); qr[r][1] = fmaxf(qr[r][1], 0.f); }
+            }
           }
           if (!has_l) { ql[r][0] = 0.f; ql[r][1] = 0.f; }
           if (!has_r) { qr[r][0] = 0.f; qr[r][1] = 0.f; }
@@ -411,13 +440,8 @@ bool rcv_umma_wgrad_pays(const RcvWgrad& p) {
          (int64_t)p.N * p.CA * p.Hin * p.Win < (1ll << 31);
 }
 
-int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st) {
-  const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
-  RCV_REQUIRE(M < (1ll << 31), RCV_ERR_UNSUPPORTED, "wgrad: problem too large");
-  RCV_REQUIRE(p.taps.n >= 1 && p.taps.n <= MAXT, RCV_ERR_UNSUPPORTED, "wgrad: %d taps", p.taps.n);
-  RCV_REQUIRE(((p.Hg * p.Wg) & 3) == 0, RCV_ERR_UNSUPPORTED,
-              "tensor-core wgrad needs a pixel count per image that is a multiple of 4 (got %d)", p.Hg * p.Wg);
-  // QUAD gather: stride-1 3x3 taps (-d,0,+d)^2 in row-major order, rows a multiple of 4 pixels wide
+// QUAD gather: stride-1 3x3 taps (-d,0,+d)^2 in row-major order, rows a multiple of 4 pixels wide
+static bool quad_gather_ok(const RcvWgrad& p) {
   bool quad = p.taps.n == 9 && p.gs == 1 && p.Win == p.Wg && p.Hin == p.Hg && (p.Wg & 3) == 0;
   const int d = p.taps.dx[2];
   quad = quad && (d == 1 || d == 2);
@@ -428,7 +452,23 @@ int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st) {
     const char* e = getenv("RCV_WGRAD_QUAD");
     no_quad = (e && atoi(e) == 0) ? 1 : 0;
   }
-  if (no_quad) quad = false;
+  return quad && !no_quad;
+}
+
+bool rcv_umma_wgrad_takes_input_transform(const RcvWgrad& p) {
+  const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
+  return M < (1ll << 31) && ((p.Hg * p.Wg) & 3) == 0 && quad_gather_ok(p);
+}
+
+int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st) {
+  const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
+  RCV_REQUIRE(M < (1ll << 31), RCV_ERR_UNSUPPORTED, "wgrad: problem too large");
+  RCV_REQUIRE(p.taps.n >= 1 && p.taps.n <= MAXT, RCV_ERR_UNSUPPORTED, "wgrad: %d taps", p.taps.n);
+  RCV_REQUIRE(((p.Hg * p.Wg) & 3) == 0, RCV_ERR_UNSUPPORTED,
+              "tensor-core wgrad needs a pixel count per image that is a multiple of 4 (got %d)", p.Hg * p.Wg);
+  const bool quad = quad_gather_ok(p);
+  RCV_REQUIRE(p.in_scale == nullptr || quad, RCV_ERR_UNSUPPORTED,
+              "wgrad: normalise-on-load needs the quad gather (stride-1 3x3, rows a multiple of 4 pixels wide)");
   if (quad) {
     if (p.CB > 64) return launch_w<128, true>(p, st);
     if (p.CB > 32) return launch_w<64, true>(p, st);

@@ -343,6 +343,8 @@ int rcv_pick_wgrad_engine(const RcvWgrad& p) {
 
 int rcv_launch_wgrad(const RcvWgrad& p, cudaStream_t st) {
   const int eng = rcv_pick_wgrad_engine(p);
+  RCV_REQUIRE(p.in_scale == nullptr || eng == RCV_ENGINE_UMMA, RCV_ERR_UNSUPPORTED,
+              "wgrad: normalise-on-load is a feature of the tensor-core quad-gather kernel only");
   if (eng == RCV_ENGINE_NARROW) return rcv_launch_narrow_wgrad(p, st);
   if (eng == RCV_ENGINE_UMMA) return rcv_launch_wgrad_umma(p, st);
   if (p.CB <= 8 && p.taps.n == 9 && p.CA <= 16) return launch_small<9, 8, 1>(p, st);

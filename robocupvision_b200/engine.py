@@ -33,6 +33,11 @@ WGRAD_SIDE_STREAM = _os.environ.get("RCV_B200_WGRAD_STREAM", "1") != "0"
 # kernel runs, the block's apply pass is skipped and the consumers normalise on load (rcv_conv_fwd_nl); the
 # normalised tensor the consumers' weight gradients read is produced later, on the side stream.
 BN_ON_LOAD = _os.environ.get("RCV_B200_BN_ON_LOAD", "1") != "0"
+# ... and where the consumer's weight gradient runs on the tensor-core quad-gather kernel it can normalise on load
+# too (rcv_conv_wgrad_nl): the BatchNorm output is then never written at all.  Off by default: measured slower
+# (2.206 vs 2.150 ms per step, same box) -- the transform sits on the gather's critical path, while the materialising
+# pass runs on the side stream in the shadow of the input gradients.
+WGRAD_ON_LOAD = _os.environ.get("RCV_B200_WGRAD_ON_LOAD", "0") != "0"
 
 
 class Node:
@@ -344,6 +349,11 @@ class Plan:
                 grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
                                                wpacked=wp)
             la = self._lazy.get(nd.src)
+            if la is not None and WGRAD_ON_LOAD and ops.conv_wgrad_normalises_on_load(
+                    geom, src.shape[0], src.shape[2], src.shape[3], self.math):
+                wg_affine, la = la, None  # the weight-gradient kernel applies the BatchNorm itself
+            else:
+                wg_affine = None
 
             def wgrad_src():
                 """The tensor the weight gradient reads: for a normalise-on-load input, the producer's BatchNorm output,
@@ -359,14 +369,15 @@ class Plan:
                 return y
 
             if side is None:
-                ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math)
+                ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math,
+                               in_affine=wg_affine)
             else:
                 cur = torch.cuda.current_stream(src.device)
                 side.wait_stream(cur)  # dconv (and every earlier write to the gradient arena) is ordered before
                 keep.append(dconv)
                 with torch.cuda.stream(side):
                     ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias,
-                                   math=self.math)
+                                   math=self.math, in_affine=wg_affine)
 
 
 class _PlanFn(torch.autograd.Function):

@@ -243,8 +243,15 @@ def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=M
     return dx
 
 
-def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False, math=MATH_FP32):
-    """Weight (and bias) gradient, accumulated into dw/dbias (zero-filled if not given)."""
+def conv_wgrad_normalises_on_load(g: ConvGeom, n: int, h: int, w: int, math: int = MATH_AUTO) -> bool:
+    """Would conv_wgrad(..., in_affine=...) be accepted for this layer at this size (tensor-core quad gather)."""
+    d = g.desc(n, h, w, EPI_NONE, math)
+    return bool(_lib.load().rcv_conv_wgrad_normalises_on_load(C.byref(d)))
+
+
+def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False, math=MATH_FP32, in_affine=None):
+    """Weight (and bias) gradient, accumulated into dw/dbias (zero-filled if not given).  in_affine = (scale, shift,
+    relu): the gradient with respect to a conv of relu?(scale*x + shift) (rcv_conv_wgrad_nl)."""
     x = _chk(x, name="x")
     dy = _chk(dy, name="dy")
     n, _, h, wd = x.shape
@@ -253,6 +260,13 @@ def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False, math=MA
     if dbias is None and want_bias:
         dbias = torch.zeros(g.cout, device=x.device, dtype=torch.float32)
     d = g.desc(n, h, wd, EPI_NONE, math)
+    if in_affine is not None:
+        isc, ish, irelu = in_affine
+        if isc.numel() != g.cin or ish.numel() != g.cin:
+            raise ValueError("conv_wgrad: in_affine must have Cin entries")
+        _call("rcv_conv_wgrad_nl", 1, C.byref(d), _ptr(x), _ptr(isc), _ptr(ish), 1 if irelu else 0, _ptr(dy),
+              _ptr(dw), _ptr(dbias), _stream())
+        return dw, dbias
     _call("rcv_conv_wgrad", 2 if (g.transposed and dbias is not None) else 1, C.byref(d), _ptr(x),
           _ptr(dy), _ptr(dw), _ptr(dbias), _stream())
     return dw, dbias

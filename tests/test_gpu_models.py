@@ -157,10 +157,12 @@ def test_bn_normalise_on_load_matches_materialised():
     y = synth.labels_learnable(x.cpu()).cuda()
     crit = CrossEntropyLoss2d(torch.tensor(synth.CLASS_WEIGHTS)).cuda()
     res = {}
-    old = engine.BN_ON_LOAD
+    old = engine.BN_ON_LOAD, engine.WGRAD_ON_LOAD
     try:
-        for flag in (False, True):
-            engine.BN_ON_LOAD = flag
+        # False: every BatchNorm output written in the forward pass; "fwd": applied on load by the consuming conv and
+        # written on the side stream for its weight gradient; True: applied on load by the weight gradient as well
+        for flag in (False, "fwd", True):
+            engine.BN_ON_LOAD, engine.WGRAD_ON_LOAD = bool(flag), flag is True
             torch.manual_seed(77)
             m = ROBO_UNet().cuda().train()
             pred = m(x)
@@ -170,18 +172,20 @@ def test_bn_normalise_on_load_matches_materialised():
             res[flag] = (pred.detach(), float(loss), {k: p.grad.clone() for k, p in m.named_parameters()},
                          {k: b.clone() for k, b in m.named_buffers()}, sum(plan._defer_cache.values()))
     finally:
-        engine.BN_ON_LOAD = old
-    assert res[False][4] == 0 and res[True][4] >= 4, f"deferred blocks: {res[True][4]}"
-    assert_close("logits", res[True][0], res[False][0].cpu(), 2e-5)
-    assert abs(res[True][1] - res[False][1]) <= 2e-6 * max(1.0, abs(res[False][1]))
+        engine.BN_ON_LOAD, engine.WGRAD_ON_LOAD = old
+    assert res[False][4] == 0 and res[True][4] >= 4 and res["fwd"][4] == res[True][4], \
+        f"deferred blocks: {res[True][4]}"
     gmax = max(float(g.abs().max()) for g in res[False][2].values())
-    for k, g in res[False][2].items():
-        scale = max(float(g.abs().max()), 1e-3 * gmax)
-        err = float((res[True][2][k] - g).abs().max()) / scale
-        assert err <= 1e-4, f"grad {k} rel err {err:.3e}"
-    for k, b in res[False][3].items():
-        if b.is_floating_point():
-            assert_close(f"buffer {k}", res[True][3][k], b.cpu(), 1e-5)
+    for mode in ("fwd", True):
+        assert_close(f"logits [{mode}]", res[mode][0], res[False][0].cpu(), 2e-5)
+        assert abs(res[mode][1] - res[False][1]) <= 2e-6 * max(1.0, abs(res[False][1]))
+        for k, g in res[False][2].items():
+            scale = max(float(g.abs().max()), 1e-3 * gmax)
+            err = float((res[mode][2][k] - g).abs().max()) / scale
+            assert err <= 1e-4, f"[{mode}] grad {k} rel err {err:.3e}"
+        for k, b in res[False][3].items():
+            if b.is_floating_point():
+                assert_close(f"[{mode}] buffer {k}", res[mode][3][k], b.cpu(), 1e-5)
 
 
 def test_pb_fcn_2_segmentation_branch_matches_unet():

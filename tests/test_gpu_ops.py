@@ -157,6 +157,50 @@ def test_conv_fwd_normalise_on_load(geom, cin, cout, nhw, relu):
     assert_close("stats sum", stats[:cout], ref.double().sum((0, 2, 3)), 4e-6, atol=1e-3)
 
 
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("geom,cin,cout,nhw", [("k3s1d1", 32, 64, (4, 30, 40)), ("k3s1d2", 64, 128, (3, 15, 20)),
+                                               ("k3s1d1", 128, 128, (2, 9, 8)), ("k3s1d2", 128, 64, (5, 12, 16)),
+                                               ("k3s1d1", 24, 40, (2, 18, 24)), ("k3s1d1", 64, 32, (2, 24, 52))])
+def test_conv_wgrad_normalise_on_load(geom, cin, cout, nhw, relu):
+    """rcv_conv_wgrad_nl: weight / bias gradient with the producer block's BatchNorm applied to x on load == the
+    gradient computed from the normalised tensor (CPU autograd and the plain entry point)."""
+    from robocupvision_b200 import ops
+    n, h, w_ = nhw
+    g, x, w, b = _mk(geom, cin, cout, n, h, w_, seed=6)
+    assert ops.conv_wgrad_normalises_on_load(g, n, h, w_, ops.MATH_AUTO)
+    gen = torch.Generator().manual_seed(13)
+    sc, sh = torch.randn(cin, generator=gen), torch.randn(cin, generator=gen)
+    xn = sc.view(1, -1, 1, 1) * x + sh.view(1, -1, 1, 1)
+    if relu:
+        xn = F.relu(xn)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    out = _ref_conv(geom, xn, wr, br)
+    dy = torch.randn(out.shape, generator=gen)
+    out.backward(dy)
+    dw, db = ops.conv_wgrad(g, x.cuda(), dy.cuda(), want_bias=True, math=ops.MATH_AUTO,
+                            in_affine=(sc.cuda(), sh.cuda(), relu))
+    assert_close(f"wgrad_nl {geom} {cin}->{cout} relu={relu}", dw, wr.grad, 8e-6)
+    assert_close("dbias", db, br.grad, 4e-6)
+    dw2, _ = ops.conv_wgrad(g, xn.cuda(), dy.cuda(), want_bias=True, math=ops.MATH_AUTO)
+    assert_close("wgrad_nl vs wgrad of the normalised tensor", dw, dw2.cpu(), 4e-6)
+
+
+def test_conv_wgrad_normalise_on_load_refused_elsewhere():
+    from robocupvision_b200 import ops
+    for geom, cin, cout, math in [("k3s2", 32, 64, ops.MATH_AUTO), ("k3s1d1", 16, 8, ops.MATH_AUTO),
+                                  ("k3s1d1", 32, 64, ops.MATH_FP32), ("convT", 32, 16, ops.MATH_AUTO),
+                                  ("k1", 64, 64, ops.MATH_AUTO)]:
+        g, x, w, b = _mk(geom, cin, cout, 2, 12, 16)
+        assert not ops.conv_wgrad_normalises_on_load(g, 2, 12, 16, math)
+        one = torch.ones(cin, device="cuda")
+        dy = torch.zeros(2, cout, *g.out_hw(12, 16), device="cuda")
+        with pytest.raises(RuntimeError):
+            ops.conv_wgrad(g, x.cuda(), dy, math=math, in_affine=(one, one, False))
+    g, x, w, b = _mk("k3s1d1", 32, 64, 2, 9, 7)   # odd row width: element-wise gather
+    assert not ops.conv_wgrad_normalises_on_load(g, 2, 9, 7, ops.MATH_AUTO)
+
+
 def test_conv_fwd_normalise_on_load_refused_elsewhere():
     """Engines other than the halo-staged tensor-core kernel refuse an input transform (no silent ignore)."""
     from robocupvision_b200 import ops
