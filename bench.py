@@ -79,7 +79,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
@@ -89,7 +89,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self) -> int:
+        """Rows read so far: stop(first=mark()) keeps the samples taken after this point."""
+        return len(self.rows)
+
+    def stop(self, first: int = 0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +103,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[first:]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -262,14 +266,17 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi needs a few hundred ms before its first row: start it ahead of the warm-up, keep the rows that
+    # arrive from the start of the timed region on
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
     k0 = ops.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    row0 = sampler.mark()
     e0.record()
     for i in range(args.steps):
         step(i)
@@ -280,7 +287,25 @@ def main():
         t = torch.tensor([ms_total], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_total = float(t)
-    clocks = sampler.stop()
+    k1 = ops.launch_count()
+    # a timed region shorter than a few sampling periods: keep the same load running (untimed) until three samples
+    # have been taken under it, and say so
+    extra = 0
+    per_round = max(8, int(200.0 / max(ms_total / args.steps, 1e-3)))  # ~0.2 s of steps
+    for _ in range(8):
+        need = 1 if (sampler.proc and sampler.mark() - row0 < 3) else 0
+        if world > 1:  # every rank runs the same number of steps (the step holds a collective)
+            t = torch.tensor([need], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            need = int(t)
+        if not need:
+            break
+        for i in range(per_round):
+            step(i)
+        extra += per_round
+        barrier()
+    clocks = sampler.stop(first=row0)
+    clocks["window"] = "timed region" if extra == 0 else f"timed region + {extra} untimed steps of the same load"
     ms_step = ms_total / args.steps
     value = batch * world / (ms_step * 1e-3)
     if wl["train"]:
@@ -288,7 +313,7 @@ def main():
     elif ev.use_graph:
         launches = ev.kernels_per_call * args.steps
     else:
-        launches = ops.launch_count() - k0
+        launches = k1 - k0
 
     # ---- e2e: pinned host inputs -> H2D -> step -> D2H of the loss, every step ----------------
     # The public pipelined API (TrainStep.step_async / EvalStep.run_async): step i's inputs are
