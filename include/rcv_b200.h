@@ -89,6 +89,14 @@ typedef struct rcv_conv_desc {
 int rcv_version(void);
 const char* rcv_last_error(void);
 
+/* Programmatic dependent launch.  When on, every kernel of the library is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization: the next grid of the stream is set up while the current one
+ * drains (every kernel starts with griddepcontrol.launch_dependents + griddepcontrol.wait, so data dependences stay
+ * those of plain stream order; capture-safe).  Default: the RCV_PDL environment variable, else off.
+ * rcv_set_pdl returns the previous setting. */
+int rcv_set_pdl(int on);
+int rcv_get_pdl(void);
+
 /* Output spatial size of a layer (H_out, W_out). */
 int rcv_conv_out_hw(const rcv_conv_desc* d, int32_t* Ho, int32_t* Wo);
 

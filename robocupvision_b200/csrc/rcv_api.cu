@@ -209,6 +209,25 @@ namespace {
 void wgrad_problem(const rcv_conv_desc* d, RcvWgrad* pp);
 }
 
+// Programmatic dependent launch for every kernel (rcv_common.cuh: rcv_launch / rcv_pdl_enter): RCV_PDL in the
+// environment, else off, until rcv_set_pdl says otherwise.
+static int g_pdl = -1;
+bool rcv_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("RCV_PDL");
+    g_pdl = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_pdl != 0;
+}
+
+extern "C" int rcv_set_pdl(int on) {
+  const int prev = rcv_pdl_enabled() ? 1 : 0;
+  g_pdl = on ? 1 : 0;
+  return prev;
+}
+
+extern "C" int rcv_get_pdl(void) { return rcv_pdl_enabled() ? 1 : 0; }
+
 extern "C" int rcv_conv_engine(const rcv_conv_desc* d, int direction) {
   if (direction == RCV_DIR_WGRAD) {
     int rc = validate(d, "rcv_conv_engine");

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(NT) augment_kernel(int H, int W, const float* 
                                                       long long* __restrict__ lab_out,
                                                       const float* __restrict__ params, float m0, float m1, float m2,
                                                       float s0, float s1, float s2) {
+  rcv_pdl_enter();
   const int n = blockIdx.y;
   const float* pr = params + (size_t)n * 8;
   const bool flip = pr[0] != 0.f;
@@ -64,6 +65,7 @@ __device__ __forceinline__ void softmax_px(const float* __restrict__ lp, int64_t
 template <int C>
 __global__ void __launch_bounds__(NT) dice_fwd_kernel(int64_t HW, const float* __restrict__ logits,
                                                        const long long* __restrict__ target, double* sums) {
+  rcv_pdl_enter();
   __shared__ double red[2 * CMAX][NT / 32];
   const int n = blockIdx.y;
   float inter[CMAX], card[CMAX];
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(NT) dice_bwd_kernel(int64_t HW, const float* _
                                                        const float* __restrict__ weights,
                                                        const double* __restrict__ sums, float eps,
                                                        const float* __restrict__ gscale, float* __restrict__ dlogits) {
+  rcv_pdl_enter();
   const int n = blockIdx.y;
   float a[CMAX], b[CMAX];
   const float gs = gscale ? __ldg(gscale) : 1.f;
@@ -167,9 +170,9 @@ extern "C" int rcv_augment(int32_t N, int32_t H, int32_t W, const float* x, floa
   const int64_t HW = (int64_t)H * W;
   int bx = rcv_cdiv(148 * 8, N);
   dim3 grid(blocks_for(HW, bx < 1 ? 1 : bx), N);
-  augment_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(H, W, x, y, reinterpret_cast<const long long*>(labels_in),
-                                                       reinterpret_cast<long long*>(labels_out), params, mean[0],
-                                                       mean[1], mean[2], std_[0], std_[1], std_[2]);
+  rcv_launch(augment_kernel, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, H, W, x, y,
+             reinterpret_cast<const long long*>(labels_in), reinterpret_cast<long long*>(labels_out), params,
+             mean[0], mean[1], mean[2], std_[0], std_[1], std_[2]);
   RCV_CHECK_LAUNCH("augment");
   return RCV_OK;
 }
@@ -182,8 +185,8 @@ extern "C" int rcv_dice_fwd(int32_t N, int32_t C, int64_t HW, const float* logit
   int bx = rcv_cdiv(148 * 8, N);
   dim3 grid(blocks_for(HW, bx < 1 ? 1 : bx), N);
   cudaStream_t st = (cudaStream_t)stream;
-  RCV_DICE_DISPATCH(C, (dice_fwd_kernel<CC><<<grid, NT, 0, st>>>(HW, logits,
-                                                                 reinterpret_cast<const long long*>(target), sums)));
+  RCV_DICE_DISPATCH(C, (rcv_launch(dice_fwd_kernel<CC>, dim3(grid), dim3(NT), 0, st, HW, logits,
+                                   reinterpret_cast<const long long*>(target), sums)));
   RCV_CHECK_LAUNCH("dice_fwd");
   return RCV_OK;
 }
@@ -197,9 +200,9 @@ extern "C" int rcv_dice_bwd(int32_t N, int32_t C, int64_t HW, const float* logit
   int bx = rcv_cdiv(148 * 8, N);
   dim3 grid(blocks_for(HW, bx < 1 ? 1 : bx), N);
   cudaStream_t st = (cudaStream_t)stream;
-  RCV_DICE_DISPATCH(C, (dice_bwd_kernel<CC><<<grid, NT, 0, st>>>(HW, logits,
-                                                                 reinterpret_cast<const long long*>(target), weights,
-                                                                 sums, eps, gscale, dlogits)));
+  RCV_DICE_DISPATCH(C, (rcv_launch(dice_bwd_kernel<CC>, dim3(grid), dim3(NT), 0, st, HW, logits,
+                                   reinterpret_cast<const long long*>(target), weights, sums, eps, gscale,
+                                   dlogits)));
   RCV_CHECK_LAUNCH("dice_bwd");
   return RCV_OK;
 }

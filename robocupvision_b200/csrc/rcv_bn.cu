@@ -28,6 +28,7 @@ __global__ void bn_finalize_kernel(int C, double count, const double* __restrict
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum, float eps,
                                    float* scale, float* shift, float* save_mean, float* save_invstd) {
+  rcv_pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = stats[c] / count;
@@ -50,6 +51,7 @@ __global__ void bn_finalize_kernel(int C, double count, const double* __restrict
 __global__ void bn_fold_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var,
                                float eps, float* scale, float* shift) {
+  rcv_pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   // same operation order as ATen's eval batch_norm: invstd = 1/sqrt(var+eps)
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(NT) bn_apply_kernel(int64_t total, int C, int6
                                                        const float* __restrict__ shift, int relu,
                                                        const float* __restrict__ residual,
                                                        float* __restrict__ y) {
+  rcv_pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * NT;
   if (VEC) {
     const int64_t hw4 = HW >> 2, tot4 = total >> 2;
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
     const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
     float momentum, float eps, const float* __restrict__ z, int relu, const float* __restrict__ residual,
     float* __restrict__ y, float* scale_out, float* shift_out, float* save_mean, float* save_invstd) {
+  rcv_pdl_enter();
   extern __shared__ float s_ss[];  // [2][C]
   for (int c = threadIdx.x; c < C; c += NT) {
     const double mean = stats[c] / count;
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_kernel(int N, int C, int64_t HW, in
                                                      const float* __restrict__ save_invstd,
                                                      double* sums, float* __restrict__ dconv,
                                                      float* dgamma, float* dbeta, float* dbias) {
+  rcv_pdl_enter();
   __shared__ double sh[NT / 32];
   const int c = blockIdx.x;
   const float sc = scale[c], sft = shift[c], mean = save_mean[c], invstd = save_invstd[c];
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_kernel(int N, int C, int64_t HW, in
 __global__ void __launch_bounds__(NT) relu_bwd_kernel(int64_t n, const float* __restrict__ dy,
                                                        const float* __restrict__ y,
                                                        float* __restrict__ dx) {
+  rcv_pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * NT;
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n4; i += stride) {
@@ -289,6 +295,7 @@ __global__ void __launch_bounds__(NT) relu_bwd_kernel(int64_t n, const float* __
 
 __global__ void __launch_bounds__(NT) channel_sum_kernel(int N, int C, int64_t HW,
                                                           const float* __restrict__ dy, float* dbias) {
+  rcv_pdl_enter();
   __shared__ double sh[NT / 32];
   const int c = blockIdx.x;
   const int64_t E = (int64_t)N * HW;
@@ -343,9 +350,8 @@ extern "C" int rcv_bn_finalize(int32_t C, int64_t count, const double* stats, co
                                float momentum, float eps, float* scale, float* shift,
                                float* save_mean, float* save_invstd, void* stream) {
   RCV_REQUIRE(C > 0 && count > 0 && stats && scale && shift, RCV_ERR_BAD_ARG, "bn_finalize: bad arg");
-  bn_finalize_kernel<<<rcv_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(
-      C, (double)count, stats, gamma, beta, running_mean, running_var, momentum, eps, scale, shift,
-      save_mean, save_invstd);
+  rcv_launch(bn_finalize_kernel, dim3(rcv_cdiv(C, 128)), dim3(128), 0, (cudaStream_t)stream, C, (double)count, stats,
+             gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd);
   RCV_CHECK_LAUNCH("bn_finalize");
   return RCV_OK;
 }
@@ -353,8 +359,8 @@ extern "C" int rcv_bn_finalize(int32_t C, int64_t count, const double* stats, co
 extern "C" int rcv_bn_fold(int32_t C, const float* gamma, const float* beta, const float* mean,
                            const float* var, float eps, float* scale, float* shift, void* stream) {
   RCV_REQUIRE(C > 0 && mean && var && scale && shift, RCV_ERR_BAD_ARG, "bn_fold: bad arg");
-  bn_fold_kernel<<<rcv_cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, mean, var, eps,
-                                                                    scale, shift);
+  rcv_launch(bn_fold_kernel, dim3(rcv_cdiv(C, 128)), dim3(128), 0, (cudaStream_t)stream, C, gamma, beta, mean, var,
+             eps, scale, shift);
   RCV_CHECK_LAUNCH("bn_fold");
   return RCV_OK;
 }
@@ -366,11 +372,11 @@ extern "C" int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z, co
               "bn_apply: bad arg");
   const int64_t total = (int64_t)N * C * HW;
   if ((HW & 3) == 0)
-    bn_apply_kernel<true><<<ew_blocks(total / 4), NT, 0, (cudaStream_t)stream>>>(
-        total, C, HW, z, scale, shift, relu, residual, y);
+    rcv_launch(bn_apply_kernel<true>, dim3(ew_blocks(total / 4)), dim3(NT), 0, (cudaStream_t)stream, total, C, HW, z,
+               scale, shift, relu, residual, y);
   else
-    bn_apply_kernel<false><<<ew_blocks(total), NT, 0, (cudaStream_t)stream>>>(
-        total, C, HW, z, scale, shift, relu, residual, y);
+    rcv_launch(bn_apply_kernel<false>, dim3(ew_blocks(total)), dim3(NT), 0, (cudaStream_t)stream, total, C, HW, z,
+               scale, shift, relu, residual, y);
   RCV_CHECK_LAUNCH("bn_apply");
   return RCV_OK;
 }
@@ -387,13 +393,13 @@ extern "C" int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const dou
   const double count = (double)N * (double)HW;
   const size_t smem = (size_t)2 * C * sizeof(float);
   if ((HW & 3) == 0)
-    bn_finalize_apply_kernel<true><<<fa_blocks(total / 4), NT, smem, (cudaStream_t)stream>>>(
-        total, C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, y,
-        scale, shift, save_mean, save_invstd);
+    rcv_launch(bn_finalize_apply_kernel<true>, dim3(fa_blocks(total / 4)), dim3(NT), smem, (cudaStream_t)stream,
+               total, C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual,
+               y, scale, shift, save_mean, save_invstd);
   else
-    bn_finalize_apply_kernel<false><<<ew_blocks(total), NT, smem, (cudaStream_t)stream>>>(
-        total, C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, y,
-        scale, shift, save_mean, save_invstd);
+    rcv_launch(bn_finalize_apply_kernel<false>, dim3(ew_blocks(total)), dim3(NT), smem, (cudaStream_t)stream, total,
+               C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, y,
+               scale, shift, save_mean, save_invstd);
   RCV_CHECK_LAUNCH("bn_finalize_apply");
   return RCV_OK;
 }
@@ -407,9 +413,8 @@ extern "C" int rcv_bn_bwd_reduce(int32_t N, int32_t C, int64_t HW, int order, co
   RCV_REQUIRE(order == RCV_EPI_RELU_AFFINE || order == RCV_EPI_AFFINE_RELU || order == RCV_EPI_AFFINE,
               RCV_ERR_BAD_ARG, "bn_bwd_reduce: bad order %d", order);
   dim3 grid(C, chan_splits(C, (int64_t)N * HW));
-  bn_bwd_kernel<0><<<grid, NT, 0, (cudaStream_t)stream>>>(N, C, HW, order, dy, z, scale, shift,
-                                                          save_mean, save_invstd, sums, nullptr,
-                                                          nullptr, nullptr, nullptr);
+  rcv_launch(bn_bwd_kernel<0>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, N, C, HW, order, dy, z, scale, shift,
+             save_mean, save_invstd, sums, nullptr, nullptr, nullptr, nullptr);
   RCV_CHECK_LAUNCH("bn_bwd_reduce");
   return RCV_OK;
 }
@@ -425,10 +430,8 @@ extern "C" int rcv_bn_bwd_apply(int32_t N, int32_t C, int64_t HW, int order, con
   RCV_REQUIRE(order == RCV_EPI_RELU_AFFINE || order == RCV_EPI_AFFINE_RELU || order == RCV_EPI_AFFINE,
               RCV_ERR_BAD_ARG, "bn_bwd_apply: bad order %d", order);
   dim3 grid(C, chan_splits(C, (int64_t)N * HW));
-  bn_bwd_kernel<1><<<grid, NT, 0, (cudaStream_t)stream>>>(N, C, HW, order, dy, z, scale, shift,
-                                                          save_mean, save_invstd,
-                                                          const_cast<double*>(sums), dconv, dgamma,
-                                                          dbeta, dbias);
+  rcv_launch(bn_bwd_kernel<1>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, N, C, HW, order, dy, z, scale, shift,
+             save_mean, save_invstd, const_cast<double*>(sums), dconv, dgamma, dbeta, dbias);
   RCV_CHECK_LAUNCH("bn_bwd_apply");
   return RCV_OK;
 }
@@ -437,7 +440,7 @@ extern "C" int rcv_relu_bwd(int64_t n, const float* dy, const float* y, float* d
   RCV_REQUIRE(n > 0 && dy && y && dx, RCV_ERR_BAD_ARG, "relu_bwd: bad arg");
   RCV_REQUIRE((((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) & 15) == 0, RCV_ERR_BAD_ARG,
               "relu_bwd: pointers must be 16-byte aligned");
-  relu_bwd_kernel<<<ew_blocks(n / 4 + 1), NT, 0, (cudaStream_t)stream>>>(n, dy, y, dx);
+  rcv_launch(relu_bwd_kernel, dim3(ew_blocks(n / 4 + 1)), dim3(NT), 0, (cudaStream_t)stream, n, dy, y, dx);
   RCV_CHECK_LAUNCH("relu_bwd");
   return RCV_OK;
 }
@@ -446,7 +449,7 @@ extern "C" int rcv_channel_sum(int32_t N, int32_t C, int64_t HW, const float* dy
                                void* stream) {
   RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && dy && dbias, RCV_ERR_BAD_ARG, "channel_sum: bad arg");
   dim3 grid(C, chan_splits(C, (int64_t)N * HW));
-  channel_sum_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(N, C, HW, dy, dbias);
+  rcv_launch(channel_sum_kernel, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, N, C, HW, dy, dbias);
   RCV_CHECK_LAUNCH("channel_sum");
   return RCV_OK;
 }

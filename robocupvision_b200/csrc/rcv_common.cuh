@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "rcv_b200.h"
 
 void rcv_set_error(const char* fmt, ...);
@@ -26,6 +27,45 @@ void rcv_set_error(const char* fmt, ...);
   } while (0)
 
 static inline int rcv_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch.  A training step is ~100 short kernels back to back on one stream; with
+// RCV_PDL=1 every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so the next grid is
+// rasterised and its CTAs become resident while the current one drains.  Every kernel of the library starts with
+// rcv_pdl_enter(): it releases its dependents immediately (they only pre-stage) and then waits until all
+// prerequisite grids have completed and flushed -- no kernel touches memory before that, so the data dependences
+// are exactly those of plain stream order.  Both instructions are no-ops in a grid launched the ordinary way.
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void rcv_pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
+bool rcv_pdl_enabled();  // RCV_PDL (rcv_api.cu)
+
+// The one way kernels are launched: plain stream order, or programmatic dependent launch when enabled.  Errors
+// are picked up by RCV_CHECK_LAUNCH right after.
+template <typename... KArgs, typename... Args>
+inline void rcv_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  memset(&attr, 0, sizeof(attr));
+  if (rcv_pdl_enabled()) {
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+  }
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------------------
 // Implicit-GEMM problem shared by conv forward, conv dgrad and the

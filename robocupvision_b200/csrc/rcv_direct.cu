@@ -27,6 +27,7 @@ __device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh)
 
 template <int CBP, int PIX>
 __global__ void __launch_bounds__(NT) direct_conv_kernel(const RcvIgemm p) {
+  rcv_pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int cls = blockIdx.z;
   const int T = p.taps[cls].n;
@@ -209,7 +210,7 @@ int launch_direct(const RcvIgemm& p, cudaStream_t st) {
   const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
   RCV_REQUIRE(M < (1ll << 31), RCV_ERR_UNSUPPORTED, "direct_conv: problem too large");
   dim3 grid(rcv_cdiv(M, NT * PIX), 1, p.nclass);
-  direct_conv_kernel<CBP, PIX><<<grid, NT, smem, st>>>(p);
+  rcv_launch(direct_conv_kernel<CBP, PIX>, dim3(grid), dim3(NT), smem, st, p);
   RCV_CHECK_LAUNCH("direct_conv_kernel");
   return RCV_OK;
 }

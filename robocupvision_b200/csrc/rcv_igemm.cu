@@ -49,6 +49,7 @@ __device__ __forceinline__ float apply_epi(float v, int epi, float sc, float sh)
 
 template <int BM, int BN, int TN, int KC>
 __global__ void __launch_bounds__(NT) igemm_kernel(const RcvIgemm p) {
+  rcv_pdl_enter();
   using C = Cfg<BM, BN, TN, KC>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* As = reinterpret_cast<float*>(smem_raw);   // [2][KC][BM]
@@ -277,7 +278,7 @@ int launch_cfg(const RcvIgemm& p, cudaStream_t st) {
   RCV_REQUIRE(M < (1ll << 31) && (int64_t)p.N * p.CB * p.Hout * p.Wout < (1ll << 40), RCV_ERR_UNSUPPORTED,
               "igemm: problem too large");
   dim3 grid(rcv_cdiv(M, BM), rcv_cdiv(p.CB, BN), p.nclass);
-  igemm_kernel<BM, BN, TN, KC><<<grid, NT, smem, st>>>(p);
+  rcv_launch(igemm_kernel<BM, BN, TN, KC>, dim3(grid), dim3(NT), smem, st, p);
   RCV_CHECK_LAUNCH("igemm_kernel");
   return RCV_OK;
 }

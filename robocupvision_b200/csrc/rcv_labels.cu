@@ -11,6 +11,7 @@ constexpr int NT = 256;
 
 __global__ void __launch_bounds__(NT) label_lut_kernel(int64_t n, long long* __restrict__ lab, int nlut,
                                                         const long long* __restrict__ lut) {
+  rcv_pdl_enter();
   __shared__ long long s[64];
   if (threadIdx.x < nlut) s[threadIdx.x] = lut[threadIdx.x];
   __syncthreads();
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(NT) label_lut_kernel(int64_t n, long long* __r
 __global__ void __launch_bounds__(NT) label_to_pred_kernel(int64_t B, int C, int64_t HW,
                                                             const long long* __restrict__ lab,
                                                             float* __restrict__ out) {
+  rcv_pdl_enter();
   const int64_t total = B * HW;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
     const int64_t b = i / HW, p = i - b * HW;
@@ -39,6 +41,7 @@ __global__ void __launch_bounds__(NT) lp_assemble_kernel(int64_t P, int C, int64
                                                           const long long* __restrict__ lb,
                                                           float* __restrict__ inputs,
                                                           long long* __restrict__ targets) {
+  rcv_pdl_enter();
   const int64_t total = P * HW;
   const int CH = 3 + C;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += (int64_t)gridDim.x * NT) {
@@ -69,16 +72,16 @@ int blocks_for(int64_t items) {
 
 extern "C" int rcv_label_lut(int64_t n, int64_t* labels, int32_t nlut, const int64_t* lut, void* stream) {
   RCV_REQUIRE(n > 0 && labels && lut && nlut >= 1 && nlut <= 64, RCV_ERR_BAD_ARG, "label_lut: bad arg");
-  label_lut_kernel<<<blocks_for(n), NT, 0, (cudaStream_t)stream>>>(n, reinterpret_cast<long long*>(labels), nlut,
-                                                                  reinterpret_cast<const long long*>(lut));
+  rcv_launch(label_lut_kernel, dim3(blocks_for(n)), dim3(NT), 0, (cudaStream_t)stream, n,
+             reinterpret_cast<long long*>(labels), nlut, reinterpret_cast<const long long*>(lut));
   RCV_CHECK_LAUNCH("label_lut");
   return RCV_OK;
 }
 
 extern "C" int rcv_label_to_pred(int64_t B, int32_t C, int64_t HW, const int64_t* labels, float* out, void* stream) {
   RCV_REQUIRE(B > 0 && C >= 1 && C <= 64 && HW > 0 && labels && out, RCV_ERR_BAD_ARG, "label_to_pred: bad arg");
-  label_to_pred_kernel<<<blocks_for(B * HW), NT, 0, (cudaStream_t)stream>>>(
-      B, C, HW, reinterpret_cast<const long long*>(labels), out);
+  rcv_launch(label_to_pred_kernel, dim3(blocks_for(B * HW)), dim3(NT), 0, (cudaStream_t)stream, B, C, HW,
+             reinterpret_cast<const long long*>(labels), out);
   RCV_CHECK_LAUNCH("label_to_pred");
   return RCV_OK;
 }
@@ -88,9 +91,9 @@ extern "C" int rcv_lp_assemble(int64_t P, int32_t C, int64_t HW, const float* ya
                                void* stream) {
   RCV_REQUIRE(P > 0 && C >= 1 && C <= 64 && HW > 0 && ya && yb && la && lb && inputs && targets, RCV_ERR_BAD_ARG,
               "lp_assemble: bad arg");
-  lp_assemble_kernel<<<blocks_for(P * HW), NT, 0, (cudaStream_t)stream>>>(
-      P, C, HW, ya, yb, reinterpret_cast<const long long*>(la), reinterpret_cast<const long long*>(lb), inputs,
-      reinterpret_cast<long long*>(targets));
+  rcv_launch(lp_assemble_kernel, dim3(blocks_for(P * HW)), dim3(NT), 0, (cudaStream_t)stream, P, C, HW, ya, yb,
+             reinterpret_cast<const long long*>(la), reinterpret_cast<const long long*>(lb), inputs,
+             reinterpret_cast<long long*>(targets));
   RCV_CHECK_LAUNCH("lp_assemble");
   return RCV_OK;
 }

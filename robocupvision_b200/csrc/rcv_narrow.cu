@@ -219,6 +219,7 @@ __device__ __forceinline__ void chunk_math(unsigned long long (&acc)[Slots<CBP, 
 template <int CBP, int KIND, int NH>
 __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__((CBP <= 8 || KIND != NK_PAR) ? 128 : 224)
     narrow_conv_kernel(const __grid_constant__ CUtensorMap tmap, const RcvIgemm p, const NarrowCfg cfg) {
+  rcv_pdl_enter();
   using KT = KindTraits<KIND>;
   constexpr int GS = KT::GS;
   constexpr int SLOTS = Slots<CBP, KIND>::N;
@@ -589,7 +590,7 @@ int launch(const RcvIgemm& p, const NarrowCfg& cfg, int nthreads, size_t smem, c
   }
   const int64_t slots = (int64_t)num_sms * ctas_per_sm;
   const int grid = (int)(cfg.total_tiles < slots ? cfg.total_tiles : slots);
-  narrow_conv_kernel<CBP, KIND, NH><<<grid, nthreads, smem, st>>>(tmap, p, cfg);
+  rcv_launch(narrow_conv_kernel<CBP, KIND, NH>, dim3(grid), dim3(nthreads), smem, st, tmap, p, cfg);
   RCV_CHECK_LAUNCH("narrow_conv_kernel");
   return RCV_OK;
 }

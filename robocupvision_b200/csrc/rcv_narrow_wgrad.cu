@@ -42,6 +42,7 @@ template <int KIND, bool BIAS>
 __global__ void __launch_bounds__(NTW, 2)
     narrow_wgrad_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_row,
                         const RcvWgrad p, const WgCfg cfg) {
+  rcv_pdl_enter();
   using T = WT<KIND>;
   constexpr int GS = T::GS, D = T::D, KD = T::KD, WC = T::WC, NR = T::NR;
   constexpr int NTAP = KD * KD;
@@ -336,7 +337,7 @@ int launch(const RcvWgrad& p, const WgCfg& cfg, size_t smem, cudaStream_t st) {
   walkers = walkers < 1 ? 1 : walkers;
   walkers = walkers > cfg.total_tiles ? cfg.total_tiles : walkers;
   dim3 grid(walkers, nchunks, 1);
-  narrow_wgrad_kernel<KIND, BIAS><<<grid, NTW, smem, st>>>(ms, mr, p, cfg);
+  rcv_launch(narrow_wgrad_kernel<KIND, BIAS>, dim3(grid), dim3(NTW), smem, st, ms, mr, p, cfg);
   RCV_CHECK_LAUNCH("narrow_wgrad_kernel");
   return RCV_OK;
 }

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(NT) adam_l1_kernel(int64_t n, float* __restric
                                                       double* l1_sum,
                                                       const int32_t* __restrict__ step_dev,
                                                       const float* __restrict__ lr_dev) {
+  rcv_pdl_enter();
   __shared__ double sh[NT / 32];
   const int64_t stride = (int64_t)gridDim.x * NT;
   if (step_dev) {  // graph-replayable form: step count and lr live in device memory
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(NT) sgd_kernel(int64_t n, float* __restrict__ 
                                                   const uint8_t* __restrict__ mask, float lr,
                                                   float momentum, float wd, float grad_scale,
                                                   int first_step) {
+  rcv_pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * NT;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += stride) {
     const float pv = p[i];
@@ -93,18 +95,17 @@ extern "C" int rcv_adam_l1_step(int64_t n, float* p, const float* g, float* m, f
   if (step < 1) step = 1;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_l1_kernel<<<blocks_for(n), NT, 0, (cudaStream_t)stream>>>(
-      n, p, g, m, v, mask, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), l1_decay, grad_scale,
-      l1_sum, step_dev, lr_dev);
+  rcv_launch(adam_l1_kernel, dim3(blocks_for(n)), dim3(NT), 0, (cudaStream_t)stream, n, p, g, m, v, mask, lr, beta1,
+             beta2, eps, (float)bc1, (float)sqrt(bc2), l1_decay, grad_scale, l1_sum, step_dev, lr_dev);
   RCV_CHECK_LAUNCH("adam_l1_step");
   return RCV_OK;
 }
 
-__global__ void counter_add_kernel(int32_t* c, int32_t inc) { *c += inc; }
+__global__ void counter_add_kernel(int32_t* c, int32_t inc) { rcv_pdl_enter(); *c += inc; }
 
 extern "C" int rcv_counter_add(int32_t* counter, int32_t inc, void* stream) {
   RCV_REQUIRE(counter, RCV_ERR_BAD_ARG, "counter_add: bad arg");
-  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, inc);
+  rcv_launch(counter_add_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, counter, inc);
   RCV_CHECK_LAUNCH("counter_add");
   return RCV_OK;
 }
@@ -113,8 +114,8 @@ extern "C" int rcv_sgd_step(int64_t n, float* p, const float* g, float* buf, con
                             float lr, float momentum, float weight_decay, float grad_scale,
                             int first_step, void* stream) {
   RCV_REQUIRE(n > 0 && p && g && (momentum == 0.f || buf), RCV_ERR_BAD_ARG, "sgd_step: bad arg");
-  sgd_kernel<<<blocks_for(n), NT, 0, (cudaStream_t)stream>>>(n, p, g, buf, mask, lr, momentum,
-                                                             weight_decay, grad_scale, first_step);
+  rcv_launch(sgd_kernel, dim3(blocks_for(n)), dim3(NT), 0, (cudaStream_t)stream, n, p, g, buf, mask, lr, momentum,
+             weight_decay, grad_scale, first_step);
   RCV_CHECK_LAUNCH("sgd_step");
   return RCV_OK;
 }

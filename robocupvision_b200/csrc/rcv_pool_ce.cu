@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(NT) maxpool_fwd_kernel(int64_t total, int H, i
                                                           const float* __restrict__ x,
                                                           float* __restrict__ y, int64_t* idx,
                                                           uint8_t* code) {
+  rcv_pdl_enter();
   const int Ho = H >> 1, Wo = W >> 1;
   const int64_t stride = (int64_t)gridDim.x * NT;
   for (int64_t o = (int64_t)blockIdx.x * NT + threadIdx.x; o < total; o += stride) {
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(NT) maxpool_bwd_kernel(int64_t total, int H, i
                                                           const float* __restrict__ dy,
                                                           const uint8_t* __restrict__ code,
                                                           float* __restrict__ dx) {
+  rcv_pdl_enter();
   const int Ho = H >> 1, Wo = W >> 1;
   const int64_t stride = (int64_t)gridDim.x * NT;
   for (int64_t o = (int64_t)blockIdx.x * NT + threadIdx.x; o < total; o += stride) {
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(NT) ce_fwd_kernel(int64_t HW, const float* __r
                                                      double* loss_sums, int64_t* argmax_out,
                                                      unsigned long long* conf,
                                                      unsigned long long* correct) {
+  rcv_pdl_enter();
   __shared__ int hist[CMAX * CMAX];
   __shared__ double red[2][NT / 32];
   __shared__ int ncorrect;
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(NT) ce_bwd_kernel(int64_t HW, const float* __r
                                                      const double* __restrict__ loss_sums,
                                                      const float* __restrict__ gscale,
                                                      float* __restrict__ dlogits) {
+  rcv_pdl_enter();
   const int n = blockIdx.y;
   float w[CMAX];
 #pragma unroll
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(NT) confusion_kernel(int C, int64_t HW,
                                                         const int64_t* __restrict__ pred,
                                                         const int64_t* __restrict__ target,
                                                         unsigned long long* conf) {
+  rcv_pdl_enter();
   __shared__ int hist[CMAX * CMAX];
   const int n = blockIdx.y;
   if (threadIdx.x < CMAX * CMAX) hist[threadIdx.x] = 0;
@@ -212,8 +217,8 @@ extern "C" int rcv_maxpool2x2_fwd(int32_t N, int32_t C, int32_t H, int32_t W, co
   RCV_REQUIRE((H & 1) == 0 && (W & 1) == 0, RCV_ERR_UNSUPPORTED,
               "maxpool_fwd: H and W must be even (got %dx%d)", H, W);
   const int64_t total = (int64_t)N * C * (H / 2) * (W / 2);
-  maxpool_fwd_kernel<<<blocks_for(total, 148 * 16), NT, 0, (cudaStream_t)stream>>>(total, H, W, x, y,
-                                                                                   idx, code);
+  rcv_launch(maxpool_fwd_kernel, dim3(blocks_for(total, 148 * 16)), dim3(NT), 0, (cudaStream_t)stream, total, H, W,
+             x, y, idx, code);
   RCV_CHECK_LAUNCH("maxpool_fwd");
   return RCV_OK;
 }
@@ -224,8 +229,8 @@ extern "C" int rcv_maxpool2x2_bwd(int32_t N, int32_t C, int32_t H, int32_t W, co
               "maxpool_bwd: bad arg");
   RCV_REQUIRE((H & 1) == 0 && (W & 1) == 0, RCV_ERR_UNSUPPORTED, "maxpool_bwd: H, W must be even");
   const int64_t total = (int64_t)N * C * (H / 2) * (W / 2);
-  maxpool_bwd_kernel<<<blocks_for(total, 148 * 16), NT, 0, (cudaStream_t)stream>>>(total, H, W, dy,
-                                                                                   code, dx);
+  rcv_launch(maxpool_bwd_kernel, dim3(blocks_for(total, 148 * 16)), dim3(NT), 0, (cudaStream_t)stream, total, H, W,
+             dy, code, dx);
   RCV_CHECK_LAUNCH("maxpool_bwd");
   return RCV_OK;
 }
@@ -251,10 +256,9 @@ extern "C" int rcv_ce_fwd(int32_t N, int32_t C, int64_t HW, const float* logits,
   RCV_REQUIRE(N <= 65535, RCV_ERR_UNSUPPORTED, "ce_fwd: N=%d > 65535", N);
   dim3 grid(blocks_for(HW, rcv_cdiv(148 * 8, N) < 1 ? 1 : rcv_cdiv(148 * 8, N)), N);
   cudaStream_t st = (cudaStream_t)stream;
-  RCV_CE_DISPATCH(C, (ce_fwd_kernel<CC><<<grid, NT, 0, st>>>(
-                         HW, logits, target, class_w, loss_sums, argmax,
-                         reinterpret_cast<unsigned long long*>(conf),
-                         reinterpret_cast<unsigned long long*>(correct))));
+  RCV_CE_DISPATCH(C, (rcv_launch(ce_fwd_kernel<CC>, dim3(grid), dim3(NT), 0, st, HW, logits, target, class_w,
+                                 loss_sums, argmax, reinterpret_cast<unsigned long long*>(conf),
+                                 reinterpret_cast<unsigned long long*>(correct))));
   RCV_CHECK_LAUNCH("ce_fwd");
   return RCV_OK;
 }
@@ -268,8 +272,8 @@ extern "C" int rcv_ce_bwd(int32_t N, int32_t C, int64_t HW, const float* logits,
   RCV_REQUIRE(N <= 65535, RCV_ERR_UNSUPPORTED, "ce_bwd: N=%d > 65535", N);
   dim3 grid(blocks_for(HW, rcv_cdiv(148 * 8, N) < 1 ? 1 : rcv_cdiv(148 * 8, N)), N);
   cudaStream_t st = (cudaStream_t)stream;
-  RCV_CE_DISPATCH(C, (ce_bwd_kernel<CC><<<grid, NT, 0, st>>>(HW, logits, target, class_w, loss_sums,
-                                                             gscale, dlogits)));
+  RCV_CE_DISPATCH(C, (rcv_launch(ce_bwd_kernel<CC>, dim3(grid), dim3(NT), 0, st, HW, logits, target, class_w,
+                                 loss_sums, gscale, dlogits)));
   RCV_CHECK_LAUNCH("ce_bwd");
   return RCV_OK;
 }
@@ -280,8 +284,8 @@ extern "C" int rcv_confusion(int32_t N, int32_t C, int64_t HW, const int64_t* pr
   RCV_REQUIRE(C >= 1 && C <= CMAX, RCV_ERR_UNSUPPORTED, "confusion: C=%d (supported 1..8)", C);
   RCV_REQUIRE(N <= 65535, RCV_ERR_UNSUPPORTED, "confusion: N=%d > 65535", N);
   dim3 grid(blocks_for(HW, rcv_cdiv(148 * 8, N) < 1 ? 1 : rcv_cdiv(148 * 8, N)), N);
-  confusion_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(
-      C, HW, pred, target, reinterpret_cast<unsigned long long*>(conf));
+  rcv_launch(confusion_kernel, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, C, HW, pred, target,
+             reinterpret_cast<unsigned long long*>(conf));
   RCV_CHECK_LAUNCH("confusion");
   return RCV_OK;
 }

@@ -160,6 +160,7 @@ __host__ __device__ inline int max_taps(const RcvIgemm& p) {
 
 template <int BN, int G, int KB>
 __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma_igemm_kernel(const RcvIgemm p) {
+  rcv_pdl_enter();
   using C = Cfg<BN, G, KB>;
   constexpr int NPROD = C::NPROD, NT = C::NT;
   constexpr int BK = KB;  // shadows the file-level default inside the kernel
@@ -476,6 +477,7 @@ __device__ __forceinline__ void pack_chunk(const RcvIgemm& p, int BN, int ntiles
 
 __global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int ntiles, int kbmax, int KB,
                                                    unsigned char* __restrict__ packed) {
+  rcv_pdl_enter();
   const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * (KB / 4);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
        q += (int64_t)gridDim.x * blockDim.x)
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int
 // All layers' panels in one launch: a device-resident job table (built once on the host, the
 // weight and panel pointers are stable) with the prefix sum of 16-byte chunks per job.
 __global__ void __launch_bounds__(256) pack_multi_kernel(const RcvPackJob* __restrict__ jobs, int njobs) {
+  rcv_pdl_enter();
   __shared__ long long s_begin[RCV_PACK_MAX_JOBS + 1];
   for (int j = threadIdx.x; j <= njobs; j += blockDim.x)
     s_begin[j] = j < njobs ? jobs[j].chunk_begin : jobs[njobs - 1].chunk_begin + jobs[njobs - 1].chunks;
@@ -527,7 +530,7 @@ int launch_bn(const RcvIgemm& p, cudaStream_t st) {
               "umma_igemm: problem too large");
   dim3 grid(rcv_cdiv(M, BM), rcv_cdiv(p.CB, BN), p.nclass);
   RCV_REQUIRE(grid.y <= 65535, RCV_ERR_UNSUPPORTED, "umma_igemm: too many output-channel tiles");
-  umma_igemm_kernel<BN, G, KB><<<grid, C::NT, smem, st>>>(p);
+  rcv_launch(umma_igemm_kernel<BN, G, KB>, dim3(grid), dim3(C::NT), smem, st, p);
   RCV_CHECK_LAUNCH("umma_igemm_kernel");
   return RCV_OK;
 }
@@ -565,7 +568,8 @@ int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st) {
   const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * (KB / 4);
   int blocks = rcv_cdiv(total, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_kernel<<<blocks, 256, 0, st>>>(p, BN, ntiles, kbmax, KB, reinterpret_cast<unsigned char*>(packed));
+  rcv_launch(pack_kernel, dim3(blocks), dim3(256), 0, st, p, BN, ntiles, kbmax, KB,
+             reinterpret_cast<unsigned char*>(packed));
   RCV_CHECK_LAUNCH("pack_kernel");
   return RCV_OK;
 }
@@ -591,7 +595,7 @@ int rcv_launch_umma_pack_multi(const RcvPackJob* dev_jobs, int njobs, long long 
   long long blocks = (total_chunks + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  pack_multi_kernel<<<(int)blocks, 256, 0, st>>>(dev_jobs, njobs);
+  rcv_launch(pack_multi_kernel, dim3((int)blocks), dim3(256), 0, st, dev_jobs, njobs);
   RCV_CHECK_LAUNCH("pack_multi_kernel");
   return RCV_OK;
 }

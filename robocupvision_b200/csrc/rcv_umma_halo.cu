@@ -91,6 +91,7 @@ __device__ __forceinline__ bool decode_pos(long long q, const HaloGeo& g, int N,
 
 template <int BN, int KBB>
 __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, const HaloGeo g) {
+  rcv_pdl_enter();
   using C = HCfg<BN, KBB>;
   constexpr int SUB = C::SUB;
   const int NBS = g.nbs;
@@ -371,7 +372,7 @@ int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
     attr_done = true;
   }
   dim3 grid(rcv_cdiv(g.Mh, BM), rcv_cdiv(p.CB, BN), 1);
-  umma_halo_kernel<BN, KBB><<<grid, NT, smem, st>>>(p, g);
+  rcv_launch(umma_halo_kernel<BN, KBB>, dim3(grid), dim3(NT), smem, st, p, g);
   RCV_CHECK_LAUNCH("umma_halo_kernel");
   return RCV_OK;
 }

@@ -52,6 +52,7 @@ constexpr int QUNITS = 42;  // most (channel, tap-row) units per k tile in QUAD 
 
 template <int BN, bool QUAD>
 __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWgrad p) {
+  rcv_pdl_enter();
   using C = WCfg<BN>;
   constexpr int G = C::G, NPROD = C::NPROD, NT = C::NT;
   extern __shared__ unsigned char smem_raw[];
@@ -427,7 +428,7 @@ int launch_w(RcvWgrad p, cudaStream_t st) {
   splits = rcv_cdiv(M, slab);
   p.slab = slab;
   dim3 grid(ktiles, rcv_cdiv(p.CB, BN), splits);
-  umma_wgrad_kernel<BN, QUAD><<<grid, C::NT, C::SMEM, st>>>(p);
+  rcv_launch(umma_wgrad_kernel<BN, QUAD>, dim3(grid), dim3(C::NT), C::SMEM, st, p);
   RCV_CHECK_LAUNCH("umma_wgrad_kernel");
   return RCV_OK;
 }

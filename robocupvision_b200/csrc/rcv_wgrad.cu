@@ -18,6 +18,7 @@ constexpr int MCP = 20;  // smem pitch (floats)
 
 template <int BMW, int BNW, int TMW, int TNW>
 __global__ void __launch_bounds__(NT) wgrad_kernel(const RcvWgrad p) {
+  rcv_pdl_enter();
   constexpr int TXN = BMW / TMW, TYN = BNW / TNW;
   static_assert(TXN * TYN == NT, "thread grid");
   constexpr int DQ = (BMW * 4 + NT - 1) / NT;  // row-tensor quads per thread
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(const RcvWgrad p) {
 // weight per CTA.  blockIdx.y walks the gathered channels in groups of CAG.
 template <int T, int CBP, int CAG>
 __global__ void __launch_bounds__(NT) small_wgrad_kernel(const RcvWgrad p) {
+  rcv_pdl_enter();
   constexpr int NACC = CAG * T * CBP;
   __shared__ float red[NT / 32][NACC + CBP];
   const int tid = threadIdx.x;
@@ -304,7 +306,7 @@ int launch_small(const RcvWgrad& p, cudaStream_t st) {
   if (xblocks > maxx) xblocks = maxx;
   if (xblocks < 1) xblocks = 1;
   dim3 grid(xblocks, ygroups);
-  small_wgrad_kernel<T, CBP, CAG><<<grid, NT, 0, st>>>(p);
+  rcv_launch(small_wgrad_kernel<T, CBP, CAG>, dim3(grid), dim3(NT), 0, st, p);
   RCV_CHECK_LAUNCH("small_wgrad_kernel");
   return RCV_OK;
 }
@@ -324,7 +326,7 @@ int launch_cfg(RcvWgrad p, cudaStream_t st) {
   splits = rcv_cdiv(M, slab);
   p.slab = slab;
   dim3 grid(rcv_cdiv(K, BNW), rcv_cdiv(p.CB, BMW), splits);
-  wgrad_kernel<BMW, BNW, TMW, TNW><<<grid, NT, 0, st>>>(p);
+  rcv_launch(wgrad_kernel<BMW, BNW, TMW, TNW>, dim3(grid), dim3(NT), 0, st, p);
   RCV_CHECK_LAUNCH("wgrad_kernel");
   return RCV_OK;
 }

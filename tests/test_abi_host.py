@@ -271,3 +271,21 @@ def test_pb_fcn_2_is_the_unet_trunk_plus_a_classification_head():
     assert [(n.kind, n.src, n.skip, n.order) for n in p2.nodes] == [(n.kind, n.src, n.skip, n.order) for n in pu.nodes]
     with pytest.raises(NotImplementedError):
         PB_FCN_2(True)._get_plan()
+
+
+def test_pdl_switch_policy(monkeypatch):
+    """rcv_set_pdl / rcv_get_pdl round trip, and the loader's policy: programmatic dependent launch on for
+    single-process runs, off under a multi-process launcher, RCV_PDL overrides."""
+    import subprocess, sys
+    from robocupvision_b200 import _lib
+    lib = _lib.load()
+    prev = lib.rcv_set_pdl(0)
+    assert lib.rcv_get_pdl() == 0 and lib.rcv_set_pdl(1) == 0 and lib.rcv_get_pdl() == 1
+    lib.rcv_set_pdl(prev)
+    code = "from robocupvision_b200 import _lib; print(_lib.load().rcv_get_pdl())"
+    for env, want in [({}, "1"), ({"WORLD_SIZE": "2"}, "0"), ({"WORLD_SIZE": "2", "RCV_PDL": "1"}, "1"),
+                      ({"RCV_PDL": "0"}, "0")]:
+        e = {k: v for k, v in os.environ.items() if k not in ("WORLD_SIZE", "RCV_PDL")}
+        e.update(env)
+        out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, cwd=str(ROOT))
+        assert out.stdout.strip().splitlines()[-1] == want, (env, out.stdout, out.stderr)
