@@ -289,10 +289,12 @@ class Plan:
         # wgrad CTAs fill the SMs a dgrad's partial last wave leaves idle (150 tiles on 148 SMs at
         # 15x20) and overlap the next node's BatchNorm backward.  Tensors the side stream reads are
         # kept alive until the streams join, so the caching allocator cannot hand them out early.
-        cur = torch.cuda.current_stream(dev)
-        if self._wgrad_stream is None or self._wgrad_stream.device != dev:
-            self._wgrad_stream = torch.cuda.Stream(device=dev)
-        side = self._wgrad_stream if WGRAD_SIDE_STREAM else None
+        side = None
+        if WGRAD_SIDE_STREAM:
+            cur = torch.cuda.current_stream(dev)
+            if self._wgrad_stream is None or self._wgrad_stream.device != dev:
+                self._wgrad_stream = torch.cuda.Stream(device=dev)
+            side = self._wgrad_stream
         keep: List[torch.Tensor] = []
         for t in range(len(self.nodes) - 1, -1, -1):
             self._backward_node(t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side, keep)

@@ -1,0 +1,218 @@
+"""Host logic of the drop-in modules without a GPU: the execution plan each model family builds (node list, epilogue
+orders, skip wiring, outputs), interpreted with ATen CPU ops (tests/plan_interp.py), against the CPU oracle on seeded
+inputs -- eval mode and train mode (batch statistics + running-statistic updates)."""
+import copy
+
+import pytest
+import torch
+
+import synth
+from oracle import ref_model as R
+from plan_interp import run_plan_cpu
+
+
+def _warm(sd, fwd_train, cin=3):
+    with torch.no_grad():
+        for s in range(2):
+            fwd_train(sd, synth.images(3, cin, 48, 64, seed=70 + s))
+    return sd
+
+
+def _cases():
+    from robocupvision_b200 import model as M
+    u = lambda **okw: (lambda sd, x, training=False: R.robo_unet_forward(sd, x, training=training, **okw))  # noqa: E731
+    return {
+        "robo_default": (lambda: M.ROBO_UNet(), u(), 3),
+        "robo_unet_pool": (lambda: M.ROBO_UNet(pool=True, levels=3, bellySize=0), u(pool=True, levels=3, belly_size=0), 3),
+        "robo_noscale": (lambda: M.ROBO_UNet(noScale=True), u(no_scale=True), 3),
+        "robo_v2": (lambda: M.ROBO_UNet(v2=True, classSize=3), u(v2=True, class_size=3), 3),
+        "robo_v2_shallow": (lambda: M.ROBO_UNet(v2=True, levels=1, bellySize=9, classSize=3, bellyPlanes=64, depth=3),
+                            u(v2=True, levels=1, belly_size=9, class_size=3, depth=3), 3),
+        "pb_fcn_2": (lambda: M.PB_FCN_2(False), u(), 3),
+        "pb_fcn": (lambda: M.PB_FCN(32, 5, 1, False, 0),
+                   lambda sd, x, training=False: R.pb_fcn_forward(sd, x, False, training), 3),
+        "pb_fcn_vga": (lambda: M.PB_FCN(32, 5, 1, True, 0),
+                       lambda sd, x, training=False: R.pb_fcn_forward(sd, x, True, training), 3),
+        "fcn": (lambda: M.FCN(), lambda sd, x, training=False: R.fcn_forward(sd, x, training), 3),
+        "labelprop": (lambda: M.LabelProp(5, 32, 0), lambda sd, x, training=False: R.labelprop_forward(sd, x, training), 8),
+    }
+
+
+@pytest.mark.parametrize("tag", list(_cases()))
+def test_plan_wiring_matches_oracle(tag):
+    make, oracle, cin = _cases()[tag]
+    torch.manual_seed(12345678)
+    m = make()
+    sd = _warm({k: v.clone() for k, v in m.state_dict().items()}, lambda s, x: oracle(s, x, training=True), cin)
+    m.load_state_dict(sd)
+    plan = m._get_plan()
+    x = synth.images(2, cin, 48, 64, seed=9)
+    with torch.no_grad():
+        m.eval()
+        got = run_plan_cpu(plan, x, training=False)[0]
+        ref = oracle(sd, x)
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max())), tag
+        # train mode: batch statistics in the same places, running statistics updated identically
+        m.train()
+        sd_t = {k: v.clone() for k, v in sd.items()}
+        got_t = run_plan_cpu(plan, x, training=True)[0]
+        ref_t = oracle(sd_t, x, training=True)
+        assert float((got_t - ref_t).abs().max()) <= 1e-5 * max(1.0, float(ref_t.abs().max())), tag
+        for k, v in m.state_dict().items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                assert torch.allclose(v, sd_t[k], rtol=1e-6, atol=1e-7), (tag, k)
+
+
+def test_downsampler_plan_has_the_five_feature_maps():
+    """DownSampler.forward returns (x4|None, x3, x2, x1, x0) (model.py:218-226): the plan's outputs in that order."""
+    from robocupvision_b200 import model as M
+    for no_scale in (False, True):
+        torch.manual_seed(4)
+        m = M.DownSampler(32, no_scale).eval()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        x = synth.images(2, 3, 48, 64, seed=3)
+        with torch.no_grad():
+            outs = run_plan_cpu(m._get_plan(), x)
+            ref = [t for t in R.downsampler_forward(sd, x, no_scale, pfx="") if t is not None]
+        assert len(outs) == len(ref)
+        for a, b in zip(outs, ref):
+            assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max()))
+
+
+def test_deferred_batchnorm_schedule_is_conservative():
+    """engine.Plan._defer_bn_apply (normalise-on-load): only blocks whose output feeds tensor-core stride-1 3x3 convs as
+    their main input, is not a skip source and not a plan output."""
+    from robocupvision_b200 import model as M, ops
+    m = M.ROBO_UNet()
+    plan = m._get_plan()
+    shapes = {0: (64, 3, 120, 160)}
+    deferred = []
+    for t, nd in enumerate(plan.nodes):
+        n, c, h, w = shapes[nd.src]
+        if nd.kind == "pool":
+            shapes[t + 1] = (n, c, h // 2, w // 2)
+            continue
+        ho, wo = nd.geom.out_hw(h, w)
+        shapes[t + 1] = (n, nd.geom.cout, ho, wo)
+        if nd.bn is not None and plan._defer_bn_apply(t, n, ho, wo):
+            deferred.append(t)
+    assert len(deferred) == 7
+    skip_sources = {nd.skip for nd in plan.nodes if nd.kind == "conv" and nd.skip >= 0}
+    for t in deferred:
+        assert (t + 1) not in plan.outputs and (t + 1) not in skip_sources
+        cons = [nd for nd in plan.nodes if nd.src == t + 1]
+        assert cons and all(nd.kind == "conv" and nd.geom.k == 3 and nd.geom.stride == 1 and not nd.geom.transposed
+                            and nd.geom.cin % 32 == 0 for nd in cons)
+        n, c, h, w = shapes[t + 1]
+        assert all(ops.conv_normalises_on_load(nd.geom, n, h, w, ops.MATH_AUTO) for nd in cons)
+
+
+# ------------------------------------------------------------------ the real engine on CPU stand-ins for the kernels
+@pytest.fixture
+def cpu_engine(monkeypatch):
+    """engine.Plan with its kernels replaced by ATen-CPU stand-ins (tests/fake_ops.py); single stream."""
+    import fake_ops
+    from robocupvision_b200 import engine
+    monkeypatch.setattr(engine, "ops", fake_ops)
+    monkeypatch.setattr(engine, "WGRAD_SIDE_STREAM", False)
+    fake_ops.calls.clear()
+    return engine, fake_ops
+
+
+@pytest.mark.parametrize("wgrad_on_load", [False, True])
+@pytest.mark.parametrize("tag", list(_cases()))
+def test_engine_schedule_forward_backward_on_cpu(tag, wgrad_on_load, cpu_engine, monkeypatch):
+    """Plan.forward(training) + Plan.backward -- the code the GPU runs, including the normalise-on-load schedule --
+    against autograd over the oracle: logits, every parameter gradient, input gradient, running statistics."""
+    engine, fake = cpu_engine
+    monkeypatch.setattr(engine, "WGRAD_ON_LOAD", wgrad_on_load)
+    make, oracle, cin = _cases()[tag]
+    torch.manual_seed(12345678)
+    m = make().train()
+    sd = _warm({k: v.clone() for k, v in m.state_dict().items()}, lambda s, x: oracle(s, x, training=True), cin)
+    m.load_state_dict(sd)
+    # batch / size at which the tensor-core layers are eligible for normalise-on-load (host logic of the library)
+    # (the five-level nets need H, W divisible by 32)
+    h, w = (96, 128) if tag in ("robo_noscale", "pb_fcn_vga") else (120, 160)
+    x = synth.images(8, cin, h, w, seed=11)
+    y = synth.labels_learnable(x)
+
+    def oracle_grads(dtype):
+        """Autograd over the oracle in `dtype` -> (logits, d loss / d logits, state with .grad, d loss / d x)."""
+        osd = R.leaf_state_dict({k: (v.clone().to(dtype) if v.is_floating_point() else v.clone()) for k, v in sd.items()})
+        xr = x.detach().clone().to(dtype).requires_grad_(True)
+        ref = oracle(osd, xr, training=True)
+        # the gradient the training step feeds in: weighted cross entropy (train.py:52-56)
+        lg = ref.detach().requires_grad_(True)
+        R.cross_entropy_2d(lg, y, torch.tensor(synth.CLASS_WEIGHTS, dtype=dtype)).backward()
+        ref.backward(lg.grad)
+        return ref.detach(), lg.grad, osd, xr.grad
+
+    ref, gout, osd, dx_ref = oracle_grads(torch.float32)
+    _, _, osd64, dx64 = oracle_grads(torch.float64)
+
+    plan = m._get_plan()
+    with torch.no_grad():
+        outs, saved = plan.forward(x, training=True, save=True)
+        dx, gv = plan.backward(saved, [gout], x_needs_grad=True)
+    assert float((outs[0] - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    # Gate.  This test is about wiring (which tensor feeds which kernel, which gradient goes where): an error there is
+    # O(1) on whole tensors.  Element-wise fp32 agreement is the GPU tests' business and is not attainable here at
+    # full size: a ReLU that follows a BatchNorm flips on values within an ulp of zero (about one pixel per run at
+    # 8 x 128 x 15 x 20 x 10 layers), which moves one output channel's gradient by a few per cent and everything
+    # below it by ~1e-3 -- the fp32 oracle shows the same against the fp64 oracle.  So: relative L2 error per tensor
+    # <= 1e-2 against the fp64 oracle, or within 4x the fp32 oracle's own deviation, whichever is larger.
+    gmax = max(float(v.grad.abs().max()) for v in osd64.values() if v.grad is not None)
+    # a conv bias feeding a train-mode BatchNorm directly (upSampleTransposeConv, model.py:191-193) has an exactly
+    # zero true gradient: both sides hold rounding noise there
+    from robocupvision_b200.model import upSampleTransposeConv
+    noise = {f"{n}.conv.bias" for n, mod in m.named_modules() if isinstance(mod, upSampleTransposeConv)}
+
+    def rel_l2(a, b):
+        den = max(float(b.norm()), 1e-3 * gmax * b.numel() ** 0.5)
+        return float((a.double() - b).norm()) / den
+
+    for k, p in m.named_parameters():
+        if osd64[k].grad is None or k in noise:
+            continue
+        g64 = osd64[k].grad
+        err, floor = rel_l2(gv[id(p)], g64), rel_l2(osd[k].grad, g64)
+        assert err <= max(1e-2, 4 * floor), f"{tag}: grad {k} rel L2 err {err:.3e} (fp32 oracle {floor:.3e})"
+    assert rel_l2(dx, dx64) <= max(1e-2, 4 * rel_l2(dx_ref, dx64))
+    for k, b in m.named_buffers():
+        if b.is_floating_point():
+            assert torch.allclose(b, osd[k], rtol=1e-5, atol=1e-6), (tag, k)
+        else:
+            assert int(b) == int(osd[k]), (tag, k)
+    # the schedule: every deferred block is consumed on load, and materialised for a weight gradient only when that
+    # gradient cannot normalise on load itself
+    n_def = sum(plan._defer_cache.values())
+    on_load = sum(1 for c in fake.calls if c == ("conv_fwd", True))
+    assert (n_def > 0) == (on_load > 0)
+    if tag == "robo_default":
+        assert n_def == 7
+    if wgrad_on_load:
+        assert sum(1 for c in fake.calls if c == ("conv_wgrad", True)) == on_load
+        assert sum(1 for c in fake.calls if c[0] == "bn_apply") == 0
+    else:
+        assert sum(1 for c in fake.calls if c == ("conv_wgrad", True)) == 0
+        assert sum(1 for c in fake.calls if c[0] == "bn_apply") == n_def
+
+
+def test_engine_eval_forward_on_cpu(cpu_engine):
+    """Eval-mode plan (folded BatchNorm in the conv epilogue, no deferral) on the stand-ins == oracle."""
+    engine, fake = cpu_engine
+    for tag in ("robo_default", "robo_v2", "fcn", "pb_fcn_vga", "labelprop"):
+        make, oracle, cin = _cases()[tag]
+        torch.manual_seed(12345678)
+        m = make()
+        sd = _warm({k: v.clone() for k, v in m.state_dict().items()}, lambda s, x: oracle(s, x, training=True), cin)
+        m.load_state_dict(sd)
+        m.eval()
+        x = synth.images(2, cin, 48, 64, seed=12)
+        with torch.no_grad():
+            outs, saved = m._get_plan().forward(x, training=False, save=False)
+            ref = oracle(sd, x)
+        assert saved is None and not any(c == ("conv_fwd", True) for c in fake.calls)
+        assert float((outs[0] - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), tag
