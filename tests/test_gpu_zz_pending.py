@@ -1,0 +1,61 @@
+"""GPU parity tests whose first run is still pending (they sort after every other GPU test file on purpose: a fault in
+an unproven path cannot disturb the verified suite).  Same gates as tests/test_gpu_models.py."""
+import pytest
+import torch
+
+import synth
+from oracle import ref_model as R
+from test_gpu_models import LOGIT_TOL, _grad_check
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+# The two model families below are SURVEY.md section 8(f) N4 rows ("FCN / --v2 variants: cat-skip, 3x3 head").  The
+# tests were written after this round's GPU budget was spent: their first run is the driver's, hence non-strict
+# xfail (a pass shows as XPASS, a failure does not hide the verified suite).  Drop the marker once seen green.
+_first_run = pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU budget)")
+
+
+def _seeded_state(model, oracle_fwd_train, cin=3):
+    """Seeded init + three oracle training forwards (running statistics away from the identity)."""
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        for s in range(3):
+            oracle_fwd_train(sd, synth.images(4, cin, 48, 64, seed=77 + s))
+    return sd
+
+
+@_first_run
+def test_robo_unet_v2_cat_skips_eval_and_backward():
+    """`--v2` (model.py:462-511 with v2=True): decoder concatenates the skip tensors, 3x3 head on 16 channels."""
+    from robocupvision_b200.model import ROBO_UNet
+    kw = dict(v2=True, classSize=3)
+    okw = dict(v2=True, class_size=3)
+    torch.manual_seed(12345678)
+    m = ROBO_UNet(**kw)
+    sd = _seeded_state(m, lambda s, xx: R.robo_unet_forward(s, xx, training=True, **okw))
+    m.load_state_dict(sd)
+    m.cuda().eval()
+    x = synth.images(3, 3, 120, 160, seed=31)
+    with torch.no_grad():
+        assert_close("v2 eval logits", m(x.cuda()), R.robo_unet_forward(sd, x, **okw), LOGIT_TOL)
+    xb = synth.images(4, 3, 48, 64, seed=5)
+    _grad_check("robo_v2", m, lambda s, xx: R.robo_unet_forward(s, xx, training=True, **okw), sd, xb,
+                synth.labels_learnable(xb), synth.CLASS_WEIGHTS)
+
+
+@_first_run
+def test_fcn_eval_and_backward():
+    """`FCN` (model.py:311-331): DownSamplerThick encoder (ConvPoolDouble blocks), three up blocks, 1x1 head."""
+    from robocupvision_b200.model import FCN
+    torch.manual_seed(12345678)
+    m = FCN()
+    sd = _seeded_state(m, lambda s, xx: R.fcn_forward(s, xx, training=True))
+    m.load_state_dict(sd)
+    m.cuda().eval()
+    x = synth.images(3, 3, 120, 160, seed=32)
+    with torch.no_grad():
+        assert_close("FCN eval logits", m(x.cuda()), R.fcn_forward(sd, x), LOGIT_TOL)
+    xb = synth.images(4, 3, 48, 64, seed=6)
+    _grad_check("fcn", m, lambda s, xx: R.fcn_forward(s, xx, training=True), sd, xb, synth.labels_learnable(xb),
+                synth.CLASS_WEIGHTS)
