@@ -7,6 +7,8 @@
   robo_train.npz         3 reference training steps (train.py:43-74 restated with the reference's
                          own ROBO_UNet / CrossEntropyLoss2d / torch.optim.Adam): losses, grad norms
   weightsLP_head.npz     first/last values + sha256 of weightsLP/weights.dat (paramSave.py format)
+  bestModelSegFinetunedPruned_bu*   the channel-pruned legacy PB_FCN (reference blocks + PB_FCN forward; `... bu` alone
+                         regenerates just this one)
 Everything is produced by importing /root/reference/model.py unmodified (plus the LabelProp
 constructor shim of SURVEY.md section 8c, since the shipped constructor raises TypeError).
 """
@@ -166,5 +168,56 @@ def main():
     print("losses", losses)
 
 
+class RefChannelPBFCN(torch.nn.Module):
+    """The legacy 16-plane PB_FCN that pth/bestModelSegFinetunedPruned_bu.pth belongs to, assembled from the
+    REFERENCE's own blocks (model.py:126-199, 256-267) with PB_FCN's forward (model.py:291-309, noScale=False).  No
+    class of the current model.py has these widths; the checkpoint strict-loads into this one (SURVEY 8c vi)."""
+
+    def __init__(self, enc, ups, num_classes):
+        super().__init__()
+        f = torch.nn.Module()
+        f.conv0 = REFM.ConvPoolSimple(3, enc[0], 3, 1, 2, 2, False)
+        f.conv1 = REFM.ConvPoolSimple(enc[0], enc[1], 3, 2, 1, 1, False)
+        f.conv2 = REFM.ConvPool(enc[1], enc[2])
+        f.conv3 = REFM.ConvPool(enc[2], enc[3])
+        for i in range(4, 9):
+            setattr(f, "conv%d" % i, REFM.ConvPoolSimple(enc[i - 1], enc[i], 3, 1, 2, 2, False))
+        self.FCN = f
+        self.up1 = REFM.upSampleTransposeConv(enc[8], ups[0])
+        self.up2 = REFM.upSampleTransposeConv(ups[0], ups[1])
+        self.up3 = REFM.upSampleTransposeConv(ups[1], ups[2])
+        self.classifier = REFM.Classifier(ups[2], num_classes)
+
+    def forward(self, x):
+        f = self.FCN
+        x0 = f.conv0(x)
+        x1 = f.conv1(x0)
+        x2 = f.conv2(x1)
+        x3 = f.conv8(f.conv7(f.conv6(f.conv5(f.conv4(f.conv3(x2))))))
+        x = self.up1(x3) + x2
+        x = self.up2(x) + x1
+        x = self.up3(x) + x0
+        return self.classifier(x)
+
+
+def channel_pruned():
+    """`python -m oracle.make_golden bu`: the irregular-channel checkpoint (BASELINE configs[2])."""
+    torch.set_num_threads(1)
+    name = "bestModelSegFinetunedPruned_bu"
+    sd = load_pth(name + ".pth")
+    save_ckpt(name, sd)
+    enc = [sd[f"FCN.conv{i}.{'pool' if i in (2, 3) else 'conv'}.weight"].shape[0] for i in range(9)]
+    ups = [sd[f"up{i}.conv.weight"].shape[1] for i in (1, 2, 3)]
+    m = RefChannelPBFCN(enc, ups, sd["classifier.classifier.weight"].shape[0])
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.endswith("num_batches_tracked") for k in res.missing_keys), res
+    eval_golden(name, m, lambda mm, x: mm(x), [(2, 3, 24, 32), (4, 3, 120, 160)])
+    print(name, "enc", enc, "ups", ups)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "bu":
+        channel_pruned()
+    else:
+        main()
+        channel_pruned()

@@ -335,20 +335,27 @@ class upSampleTransposeConv(_PlanModule):
 class DownSampler(_PlanModule):
     """PB-FCN encoder (model.py:201-232); forward returns (x4, x3, x2, x1, x0)."""
 
-    def __init__(self, planes, noScale):
+    def __init__(self, planes, noScale, channels=None):
+        """channels (extension, default None = the reference's planes-derived widths): output channels of
+        conv0..conv8 given explicitly -- the layout of channel-pruned checkpoints (PB_FCN_Channels)."""
         super().__init__()
         self.noScale = noScale
-        q = planes // 4
-        self.conv0 = ConvPoolSimple(3, q, 3, 1, 2, 2, False)
-        self.conv1 = ConvPoolSimple(q, planes // 2, 3, 2, 1, 1, False)
-        self.conv2 = ConvPool(planes // 2, planes)
-        self.conv_ext = ConvPool(planes, planes) if noScale else None
-        self.conv3 = ConvPool(planes, planes * 2)
-        self.conv4 = ConvPoolSimple(planes * 2, planes * 4, 3, 1, 2, 2, False)
-        self.conv5 = ConvPoolSimple(planes * 4, planes * 4, 3, 1, 2, 2, False)
-        self.conv6 = ConvPoolSimple(planes * 4, planes * 4, 3, 1, 2, 2, False)
-        self.conv7 = ConvPoolSimple(planes * 4, planes * 4, 3, 1, 2, 2, False)
-        self.conv8 = ConvPoolSimple(planes * 4, planes * 2, 3, 1, 2, 2, False)
+        p = planes
+        c = [p // 4, p // 2, p, p * 2, p * 4, p * 4, p * 4, p * 4, p * 2] if channels is None else [int(v) for v in channels]
+        if len(c) != 9:
+            raise ValueError("DownSampler: channels must list the outputs of conv0..conv8")
+        if channels is not None and noScale:
+            raise ValueError("DownSampler: an explicit channel list describes the 160x120 encoder (noScale=False)")
+        self.conv0 = ConvPoolSimple(3, c[0], 3, 1, 2, 2, False)
+        self.conv1 = ConvPoolSimple(c[0], c[1], 3, 2, 1, 1, False)
+        self.conv2 = ConvPool(c[1], c[2])
+        self.conv_ext = ConvPool(c[2], c[2]) if noScale else None
+        self.conv3 = ConvPool(c[2], c[3])
+        self.conv4 = ConvPoolSimple(c[3], c[4], 3, 1, 2, 2, False)
+        self.conv5 = ConvPoolSimple(c[4], c[5], 3, 1, 2, 2, False)
+        self.conv6 = ConvPoolSimple(c[5], c[6], 3, 1, 2, 2, False)
+        self.conv7 = ConvPoolSimple(c[6], c[7], 3, 1, 2, 2, False)
+        self.conv8 = ConvPoolSimple(c[7], c[8], 3, 1, 2, 2, False)
 
     def _emit_all(self, b, src):
         x0 = self.conv0._emit(b, src)
@@ -457,6 +464,42 @@ class PB_FCN(_PlanModule):
             x = self.up2._emit(b, x, skip=f1)
             x = self.up3._emit(b, x, skip=f0)
         return self.segmenter._emit(b, x)
+
+
+class PB_FCN_Channels(PB_FCN):
+    """PB_FCN at 160x120 (model.py:269-309) with every layer's width given explicitly: the layout of channel-pruned
+    checkpoints, e.g. pth/bestModelSegFinetunedPruned_bu.pth (encoder 16-16-16-32-64-64-128-64-32, decoder 16-16-16,
+    head 5x16), which no class of the reference's model.py can load.  Same blocks, same forward, same state_dict key
+    names as PB_FCN(planes, C, k, False, 0) (the segmentation head is `segmenter`; legacy files call it `classifier`:
+    load_legacy_state_dict); the unused patch-classification head is not built."""
+
+    def __init__(self, enc, ups, num_classes=5, kernelSize=1):
+        _PlanModule.__init__(self)
+        enc, ups = [int(v) for v in enc], [int(v) for v in ups]
+        if len(enc) != 9 or len(ups) != 3:
+            raise ValueError("PB_FCN_Channels: enc lists conv0..conv8, ups lists up1..up3")
+        if (ups[0], ups[1], ups[2]) != (enc[2], enc[1], enc[0]):
+            raise ValueError(f"PB_FCN_Channels: decoder widths {ups} must equal the skip widths "
+                             f"{[enc[2], enc[1], enc[0]]} (up_k(x) + f_k, model.py:303-305)")
+        self.noScale, self.classify, self.img_shape = False, 0, (120, 160)
+        self.enc, self.ups = tuple(enc), tuple(ups)
+        self.FCN = DownSampler(0, False, channels=enc)
+        self.up1 = upSampleTransposeConv(enc[8], ups[0])
+        self.up2 = upSampleTransposeConv(ups[0], ups[1])
+        self.up3 = upSampleTransposeConv(ups[1], ups[2])
+        self.up4 = None
+        self.segmenter = Classifier(ups[2], num_classes, kernelSize=kernelSize)
+
+    @classmethod
+    def from_state_dict(cls, state_dict):
+        """Build the net a PB_FCN-family checkpoint describes (widths read off the weight shapes) and load it."""
+        sd = state_dict
+        enc = [sd[f"FCN.conv{i}.{'pool' if i in (2, 3) else 'conv'}.weight"].shape[0] for i in range(9)]
+        ups = [sd[f"up{i}.conv.weight"].shape[1] for i in (1, 2, 3)]
+        head = "segmenter.classifier.weight" if "segmenter.classifier.weight" in sd else "classifier.classifier.weight"
+        m = cls(enc, ups, num_classes=sd[head].shape[0], kernelSize=sd[head].shape[2])
+        load_legacy_state_dict(m, sd)
+        return m
 
 
 class FCN(_PlanModule):

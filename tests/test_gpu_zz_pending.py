@@ -5,7 +5,9 @@ import torch
 
 import synth
 from oracle import ref_model as R
-from test_gpu_models import LOGIT_TOL, _grad_check
+from nets import pb_fcn_state
+from test_gpu_models import LOGIT_TOL, _check_eval, _grad_check
+from util import load_golden
 from util import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -59,3 +61,16 @@ def test_fcn_eval_and_backward():
     xb = synth.images(4, 3, 48, 64, seed=6)
     _grad_check("fcn", m, lambda s, xx: R.fcn_forward(s, xx, training=True), sd, xb, synth.labels_learnable(xb),
                 synth.CLASS_WEIGHTS)
+
+
+@_first_run
+def test_pb_fcn_channel_pruned_checkpoint():
+    """BASELINE configs[2] "irregular channel counts": pth/bestModelSegFinetunedPruned_bu.pth (encoder
+    16-16-16-32-64-64-128-64-32, decoder 16-16-16; 70.8 % zero weights) through PB_FCN_Channels, against the golden
+    outputs of the reference's own blocks (oracle/make_golden.py bu) and the oracle."""
+    from robocupvision_b200.model import PB_FCN_Channels
+    name = "bestModelSegFinetunedPruned_bu"
+    osd, raw = pb_fcn_state(name)
+    m = PB_FCN_Channels.from_state_dict(raw)
+    m.cuda().eval()
+    _check_eval(name, m, lambda x: R.pb_fcn_forward(osd, x, False), load_golden(name + "_eval"))

@@ -53,7 +53,8 @@ def _check_golden(fwd, golden, num_classes=5, weights=synth.CLASS_WEIGHTS, only_
 
 
 @pytest.mark.parametrize("name,no_scale", [("bestModelSeg", False), ("bestModelSegFinetunedPruned", False),
-                                           ("bestModelSegVGA", True)])
+                                           ("bestModelSegVGA", True),
+                                           ("bestModelSegFinetunedPruned_bu", False)])  # channel-pruned widths
 def test_oracle_pb_fcn_vs_golden(name, no_scale):
     osd, _ = pb_fcn_state(name)
     _check_golden(lambda x: R.pb_fcn_forward(osd, x, no_scale), load_golden(name + "_eval"), only_small=no_scale)

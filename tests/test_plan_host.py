@@ -33,6 +33,8 @@ def _cases():
                    lambda sd, x, training=False: R.pb_fcn_forward(sd, x, False, training), 3),
         "pb_fcn_vga": (lambda: M.PB_FCN(32, 5, 1, True, 0),
                        lambda sd, x, training=False: R.pb_fcn_forward(sd, x, True, training), 3),
+        "pb_fcn_channels": (lambda: M.PB_FCN_Channels((16, 16, 16, 32, 64, 64, 128, 64, 32), (16, 16, 16)),
+                            lambda sd, x, training=False: R.pb_fcn_forward(sd, x, False, training), 3),
         "fcn": (lambda: M.FCN(), lambda sd, x, training=False: R.fcn_forward(sd, x, training), 3),
         "labelprop": (lambda: M.LabelProp(5, 32, 0), lambda sd, x, training=False: R.labelprop_forward(sd, x, training), 8),
     }
@@ -216,3 +218,39 @@ def test_engine_eval_forward_on_cpu(cpu_engine):
             ref = oracle(sd, x)
         assert saved is None and not any(c == ("conv_fwd", True) for c in fake.calls)
         assert float((outs[0] - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), tag
+
+
+@pytest.mark.parametrize("name", ["bestModelSeg", "bestModelSegFinetunedPruned", "bestModelSegFinetunedPruned_bu"])
+def test_released_checkpoint_through_the_plan_matches_reference_golden(name):
+    """Released PB_FCN-family checkpoints (incl. the channel-pruned `_bu` file no reference class loads) built with
+    PB_FCN_Channels.from_state_dict: widths read off the shapes, legacy head name, no num_batches_tracked.  The
+    module's plan, interpreted on the CPU, reproduces the REFERENCE's golden logits / label maps / confusion."""
+    import numpy as np
+    from robocupvision_b200 import model as M
+    from util import load_ckpt, load_golden
+    raw = load_ckpt(name)
+    m = M.PB_FCN_Channels.from_state_dict(raw).eval()
+    if name.endswith("_bu"):
+        assert m.enc == (16, 16, 16, 32, 64, 64, 128, 64, 32) and m.ups == (16, 16, 16)
+        assert sum(p.numel() for p in m.parameters()) == 252661
+    else:  # the regular checkpoints describe PB_FCN(32, 5, 1, False, 0)
+        ref = M.PB_FCN(32, 5, 1, False, 0)
+        assert [tuple(p.shape) for p in m.parameters()] == \
+               [tuple(p.shape) for n, p in ref.named_parameters() if not n.startswith("classifier.")]
+    g = load_golden(name + "_eval")
+    i = 0
+    while f"shape{i}" in g:
+        n, c, h, w = (int(v) for v in g[f"shape{i}"])
+        x = synth.images(n, c, h, w, seed=1234 + i)
+        with torch.no_grad():
+            logits = run_plan_cpu(m._get_plan(), x)[0]
+        lf = logits.reshape(-1)
+        sub = lf[::13] if lf.numel() > 50000 else lf
+        gs = torch.from_numpy(g[f"logits_sub{i}"])
+        assert float((sub - gs).abs().max()) <= 1e-4 * float(g[f"logits_absmax{i}"])
+        am = logits.argmax(1)
+        am_ref = torch.from_numpy(g[f"argmax{i}"].astype(np.int64))
+        top2 = logits.topk(2, dim=1).values
+        assert not bool(((am != am_ref) & ((top2[:, 0] - top2[:, 1]) >= 1e-4)).any())
+        i += 1
+    assert i == 2
