@@ -254,3 +254,52 @@ def test_released_checkpoint_through_the_plan_matches_reference_golden(name):
         assert not bool(((am != am_ref) & ((top2[:, 0] - top2[:, 1]) >= 1e-4)).any())
         i += 1
     assert i == 2
+
+
+def test_every_released_checkpoint_layout_loads():
+    """tests/golden/pth_manifest.json (oracle/make_pth_manifest.py: keys, shapes, dtypes of all 18 pth/*.pth of the
+    reference): each file of the segmentation / label-propagation path loads strictly -- same keys in the same
+    order, same shapes -- into the class it belongs to; the three files of the
+    patch-classification baselines are out of scope."""
+    import json
+    from robocupvision_b200 import model as M
+    from util import GOLDEN
+    man = json.loads((GOLDEN / "pth_manifest.json").read_text())
+    assert len(man) == 18
+
+    def owner(name):
+        if name in ("bestClass", "bestModelHessL", "bestModelHessMC"):
+            return None
+        if name.endswith("_bu"):
+            return "channels"
+        if name.startswith("bestModelSegVGA"):
+            return M.PB_FCN(32, 5, 1, True, 0)
+        if name.startswith("bestModelSeg1"):
+            return M.FCN()
+        if name.startswith("bestModelSeg"):
+            return M.PB_FCN(32, 5, 1, False, 0)
+        if name.startswith("bestModelLP"):
+            return M.LabelProp(5, 32, 0)
+        return M.DownSampler(32, name == "bestModelVGA")
+
+    loaded = 0
+    for name, info in man.items():
+        sd = {k: torch.full(shape, 0.5, dtype=getattr(torch, dt)) for k, shape, dt in info["entries"]}
+        m = owner(name)
+        if m is None:
+            continue
+        if m == "channels":
+            m = M.PB_FCN_Channels.from_state_dict(sd)
+        else:
+            missing, unexpected = M.load_legacy_state_dict(m, sd)   # strict: raises on any mismatch
+            assert missing == [] and unexpected == []
+        # the same parameter set as the file (the legacy files list keys in their own order; load is by name)
+        file_params = [k for k, _, _ in info["entries"] if not k.endswith(("running_mean", "running_var"))]
+        file_params = [("segmenter." + k[len("classifier."):]) if k.startswith("classifier.classifier.") and
+                       not isinstance(m, M.FCN) else k for k in file_params]
+        own = [n for n, _ in m.named_parameters() if not (isinstance(m, M.PB_FCN) and n.startswith("classifier."))]
+        assert sorted(own) == sorted(file_params), name
+        assert all(float(p.detach().reshape(-1)[0]) == 0.5 for n, p in m.named_parameters()
+                   if not (isinstance(m, M.PB_FCN) and n.startswith("classifier."))), name
+        loaded += 1
+    assert loaded == 15
