@@ -303,3 +303,44 @@ def test_every_released_checkpoint_layout_loads():
                    if not (isinstance(m, M.PB_FCN) and n.startswith("classifier."))), name
         loaded += 1
     assert loaded == 15
+
+
+def test_net_cfg_emitted_from_the_plan_matches_the_reference_files():
+    """export.net_cfg (paramSave.py's companion file: the layer list an external engine reads next to weights.dat)
+    emitted from the module's own plan == the reference's hand-written weights/net.cfg (PB_FCN 160x120),
+    weightsVGA/net.cfg (PB_FCN 640x480) and weightsLP/net.cfg (LabelProp): same sections, keys, values, order, and the
+    same text up to trailing blank lines (tests/golden/netcfg_manifest.json, oracle/make_pth_manifest.py)."""
+    import hashlib
+    import json
+    from robocupvision_b200 import export as E, model as M
+    from util import GOLDEN
+    man = json.loads((GOLDEN / "netcfg_manifest.json").read_text())
+    cases = {"weights": (M.PB_FCN(32, 5, 1, False, 0), {}),
+             "weightsVGA": (M.PB_FCN(32, 5, 1, True, 0), dict(height=480, width=640)),
+             "weightsLP": (M.LabelProp(5, 32, 0), {})}
+    for name, (m, kw) in cases.items():
+        text = E.net_cfg(m, **kw)
+        got = [[sec, [[k, str(v)] for k, v in kvs]] for sec, kvs in E.net_cfg_sections(m, **kw)]
+        assert got == man[name]["sections"], name
+        assert [[s, [list(kv) for kv in kvs]] for s, kvs in E.parse_net_cfg(text)] == man[name]["sections"]
+        assert hashlib.sha256(text.rstrip().encode()).hexdigest() == man[name]["sha256_rstrip"], name
+    # the pair (net.cfg, weights.dat) is consistent: the values the layer list implies == the flatten's length
+    lp = cases["weightsLP"][0]
+    cin, n = 8, 0
+    for sec, kvs in E.net_cfg_sections(lp):
+        kv = dict(kvs)
+        if sec in ("convolutional", "transposedconv"):
+            bias = sec == "transposedconv" or "hasBias" not in kv
+            n += kv["filters"] * cin * kv["size"] ** 2 + (kv["filters"] if bias else 0)
+            cin = kv["filters"]
+        elif sec == "batchnorm":
+            n += 4 * cin
+    assert n == int(json.loads((GOLDEN / "pth_manifest.json").read_text())["bestModelLPFinetunedPruned"]["params"])
+    # nets the reference ships no cfg for: --UNet pools, --v2 routes, ROBO_UNet's conv -> ReLU -> BatchNorm order
+    secs = [s for s, _ in E.net_cfg_sections(M.ROBO_UNet(pool=True, levels=3, bellySize=0))]
+    assert secs.count("maxpool") == 3 and secs[-1] == "softmax"
+    secs = E.net_cfg_sections(M.ROBO_UNet(v2=True, classSize=3))
+    assert [s for s, _ in secs].count("route") == 3 and [s for s, _ in secs].count("shortcut") == 0
+    d = E.net_cfg_sections(M.ROBO_UNet())
+    assert d[1] == ("convolutional", [("filters", 8), ("size", 3), ("stride", 1), ("pad", 1), ("activation", "relu")])
+    assert d[2] == ("batchnorm", [("activation", "linear")])
