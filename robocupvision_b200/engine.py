@@ -267,7 +267,7 @@ class Plan:
         tensors that receive the gradients (the train step's flat arena).  node_done(t) is called
         once node t's parameter gradients are final (nodes are visited last to first)."""
         acts, saved, lazy = saved_all
-        self._lazy, self._lazy_done = lazy, {}
+        lazy_done: Dict[int, torch.Tensor] = {}  # BatchNorm outputs materialised for a weight gradient, per activation
         dev = acts[0].device
         if grad_views is None:
             total = sum(p.numel() for p in self.params)
@@ -297,7 +297,8 @@ class Plan:
             side = self._wgrad_stream
         keep: List[torch.Tensor] = []
         for t in range(len(self.nodes) - 1, -1, -1):
-            self._backward_node(t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side, keep)
+            self._backward_node(t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side, keep,
+                                lazy, lazy_done)
             if node_done is not None:
                 node_done(t)
         if side is not None:
@@ -306,7 +307,7 @@ class Plan:
         return grads[0], grad_views
 
     def _backward_node(self, t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side=None,
-                       keep=None):
+                       keep=None, lazy=None, lazy_done=None):
         if True:
             nd = self.nodes[t]
             g = grads[t + 1]
@@ -350,7 +351,7 @@ class Plan:
                 wp = nd._pack[PACK_DGRAD] if nd.uses_tc(PACK_DGRAD, self.math) else None
                 grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
                                                wpacked=wp)
-            la = self._lazy.get(nd.src)
+            la = lazy.get(nd.src) if lazy else None
             if la is not None and WGRAD_ON_LOAD and ops.conv_wgrad_normalises_on_load(
                     geom, src.shape[0], src.shape[2], src.shape[3], self.math):
                 wg_affine, la = la, None  # the weight-gradient kernel applies the BatchNorm itself
@@ -362,10 +363,10 @@ class Plan:
                 produced now (once per activation) on the stream the weight gradient runs on."""
                 if la is None:
                     return src
-                y = self._lazy_done.get(nd.src)
+                y = lazy_done.get(nd.src)
                 if y is None:
                     y = ops.bn_apply(src, la[0], la[1], la[2])
-                    self._lazy_done[nd.src] = y
+                    lazy_done[nd.src] = y
                     if keep is not None:
                         keep.append(y)
                 return y
