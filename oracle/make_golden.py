@@ -215,9 +215,24 @@ def channel_pruned():
     print(name, "enc", enc, "ups", ups)
 
 
+def fcn_checkpoint():
+    """`python -m oracle.make_golden fcn`: the released FCN checkpoint (model.py:311-331, pth/bestModelSeg1.pth)."""
+    torch.set_num_threads(1)
+    name = "bestModelSeg1"
+    sd = load_pth(name + ".pth")
+    save_ckpt(name, sd)
+    m = REFM.FCN()
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.endswith("num_batches_tracked") for k in res.missing_keys), res
+    eval_golden(name, m, lambda mm, x: mm(x), [(2, 3, 24, 32), (2, 3, 120, 160)])
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "bu":
         channel_pruned()
+    elif len(sys.argv) > 1 and sys.argv[1] == "fcn":
+        fcn_checkpoint()
     else:
         main()
         channel_pruned()
+        fcn_checkpoint()

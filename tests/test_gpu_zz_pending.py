@@ -7,7 +7,7 @@ import synth
 from oracle import ref_model as R
 from nets import pb_fcn_state
 from test_gpu_models import LOGIT_TOL, _check_eval, _grad_check
-from util import load_golden
+from util import load_ckpt, load_golden, with_nbt
 from util import assert_close
 
 pytestmark = pytest.mark.gpu
@@ -74,3 +74,15 @@ def test_pb_fcn_channel_pruned_checkpoint():
     m = PB_FCN_Channels.from_state_dict(raw)
     m.cuda().eval()
     _check_eval(name, m, lambda x: R.pb_fcn_forward(osd, x, False), load_golden(name + "_eval"))
+
+
+@_first_run
+def test_fcn_released_checkpoint():
+    """pth/bestModelSeg1.pth through the drop-in FCN on the GPU, against the reference's golden outputs."""
+    from robocupvision_b200.model import FCN, load_legacy_state_dict
+    raw = load_ckpt("bestModelSeg1")
+    osd = with_nbt(raw)
+    m = FCN()
+    load_legacy_state_dict(m, raw)
+    m.cuda().eval()
+    _check_eval("bestModelSeg1", m, lambda x: R.fcn_forward(osd, x), load_golden("bestModelSeg1_eval"))

@@ -60,6 +60,12 @@ def test_oracle_pb_fcn_vs_golden(name, no_scale):
     _check_golden(lambda x: R.pb_fcn_forward(osd, x, no_scale), load_golden(name + "_eval"), only_small=no_scale)
 
 
+def test_oracle_fcn_vs_golden():
+    """pth/bestModelSeg1.pth: the oracle's FCN forward against the reference's golden outputs."""
+    osd = with_nbt(load_ckpt("bestModelSeg1"))
+    _check_golden(lambda x: R.fcn_forward(osd, x), load_golden("bestModelSeg1_eval"))
+
+
 def test_oracle_labelprop_vs_golden():
     osd = with_nbt(load_ckpt("bestModelLPFinetunedPruned"))
     _check_golden(lambda x: R.labelprop_forward(osd, x), load_golden("bestModelLPFinetunedPruned_eval"),

@@ -220,6 +220,40 @@ def test_engine_eval_forward_on_cpu(cpu_engine):
         assert float((outs[0] - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), tag
 
 
+def _golden_eval_on_cpu(m, g, cin=3):
+    """The module's plan, interpreted on the CPU, against the reference's golden logits / label maps."""
+    import numpy as np
+    i = 0
+    while f"shape{i}" in g:
+        n, c, h, w = (int(v) for v in g[f"shape{i}"])
+        x = synth.images(n, c, h, w, seed=1234 + i)
+        with torch.no_grad():
+            logits = run_plan_cpu(m._get_plan(), x)[0]
+        lf = logits.reshape(-1)
+        sub = lf[::13] if lf.numel() > 50000 else lf
+        gs = torch.from_numpy(g[f"logits_sub{i}"])
+        assert float((sub - gs).abs().max()) <= 1e-4 * float(g[f"logits_absmax{i}"])
+        am = logits.argmax(1)
+        am_ref = torch.from_numpy(g[f"argmax{i}"].astype(np.int64))
+        top2 = logits.topk(2, dim=1).values
+        assert not bool(((am != am_ref) & ((top2[:, 0] - top2[:, 1]) >= 1e-4)).any())
+        i += 1
+    return i
+
+
+def test_released_fcn_and_labelprop_checkpoints_through_the_plan():
+    """pth/bestModelSeg1.pth (FCN, model.py:311-331) and pth/bestModelLPFinetunedPruned.pth (LabelProp) loaded into
+    the drop-in classes: the plan reproduces the reference's golden outputs on the CPU."""
+    from robocupvision_b200 import model as M
+    from util import load_ckpt, load_golden
+    m = M.FCN()
+    M.load_legacy_state_dict(m, load_ckpt("bestModelSeg1"))
+    assert _golden_eval_on_cpu(m.eval(), load_golden("bestModelSeg1_eval")) == 2
+    lp = M.LabelProp(5, 32, 0)
+    M.load_legacy_state_dict(lp, load_ckpt("bestModelLPFinetunedPruned"))
+    assert _golden_eval_on_cpu(lp.eval(), load_golden("bestModelLPFinetunedPruned_eval")) == 2
+
+
 @pytest.mark.parametrize("name", ["bestModelSeg", "bestModelSegFinetunedPruned", "bestModelSegFinetunedPruned_bu"])
 def test_released_checkpoint_through_the_plan_matches_reference_golden(name):
     """Released PB_FCN-family checkpoints (incl. the channel-pruned `_bu` file no reference class loads) built with
@@ -237,23 +271,7 @@ def test_released_checkpoint_through_the_plan_matches_reference_golden(name):
         ref = M.PB_FCN(32, 5, 1, False, 0)
         assert [tuple(p.shape) for p in m.parameters()] == \
                [tuple(p.shape) for n, p in ref.named_parameters() if not n.startswith("classifier.")]
-    g = load_golden(name + "_eval")
-    i = 0
-    while f"shape{i}" in g:
-        n, c, h, w = (int(v) for v in g[f"shape{i}"])
-        x = synth.images(n, c, h, w, seed=1234 + i)
-        with torch.no_grad():
-            logits = run_plan_cpu(m._get_plan(), x)[0]
-        lf = logits.reshape(-1)
-        sub = lf[::13] if lf.numel() > 50000 else lf
-        gs = torch.from_numpy(g[f"logits_sub{i}"])
-        assert float((sub - gs).abs().max()) <= 1e-4 * float(g[f"logits_absmax{i}"])
-        am = logits.argmax(1)
-        am_ref = torch.from_numpy(g[f"argmax{i}"].astype(np.int64))
-        top2 = logits.topk(2, dim=1).values
-        assert not bool(((am != am_ref) & ((top2[:, 0] - top2[:, 1]) >= 1e-4)).any())
-        i += 1
-    assert i == 2
+    assert _golden_eval_on_cpu(m, load_golden(name + "_eval")) == 2
 
 
 def test_every_released_checkpoint_layout_loads():
