@@ -86,3 +86,31 @@ def test_fcn_released_checkpoint():
     load_legacy_state_dict(m, raw)
     m.cuda().eval()
     _check_eval("bestModelSeg1", m, lambda x: R.fcn_forward(osd, x), load_golden("bestModelSeg1_eval"))
+
+
+# Per-kernel parity for the channel combinations the three families above add to the verified matrix (same checks as
+# tests/test_gpu_ops.py::test_conv_fwd / test_conv_dgrad_wgrad, automatic engine choice).
+@_first_run
+@pytest.mark.parametrize("geom,cin,cout", [("k3s1d2", 3, 16), ("k3s1d2", 16, 32), ("k3s2", 16, 16), ("k3s2", 32, 32),
+                                           ("convT", 64, 16), ("convT", 32, 8), ("convT", 32, 16), ("k3s1d1", 16, 5),
+                                           ("k3s1d2", 64, 32), ("k3s1d2", 32, 64)])
+def test_conv_kernels_for_the_new_families(geom, cin, cout):
+    import torch.nn.functional as F  # noqa: F401
+    from robocupvision_b200 import ops
+    from test_gpu_ops import _mk, _ref_conv
+    g, x, w, b = _mk(geom, cin, cout, 3, 12, 20, seed=5)
+    x.requires_grad_(True); w.requires_grad_(True); b.requires_grad_(True)
+    y = _ref_conv(geom, x, w, b)
+    dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(6))
+    y.backward(dy)
+    wc = w.detach().cuda()
+    tc_f, tc_d = (ops.conv_uses_tensor_cores(g, d, ops.MATH_AUTO) for d in (ops.PACK_FWD, ops.PACK_DGRAD))
+    got = ops.conv_fwd(g, x.detach().cuda(), wc, b.detach().cuda(), math=ops.MATH_AUTO,
+                       wpacked=ops.conv_pack(g, wc, ops.PACK_FWD) if tc_f else None)
+    assert_close(f"fwd {geom} {cin}->{cout}", got, y.detach(), 8e-6)
+    dx = ops.conv_dgrad(g, dy.cuda(), wc, (12, 20), math=ops.MATH_AUTO,
+                        wpacked=ops.conv_pack(g, wc, ops.PACK_DGRAD) if tc_d else None)
+    assert_close(f"dgrad {geom} {cin}->{cout}", dx, x.grad, 1.2e-5)
+    dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True, math=ops.MATH_AUTO)
+    assert_close(f"wgrad {geom} {cin}->{cout}", dw, w.grad, 1e-5)
+    assert_close(f"bgrad {geom}", db, b.grad, 1e-5)
