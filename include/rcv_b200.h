@@ -248,6 +248,16 @@ int rcv_bn_bwd_apply(int32_t N, int32_t C, int64_t HW, int order,
                      float* dconv, float* dgamma, float* dbeta, float* dbias,
                      void* stream);
 
+/* EXPERIMENTAL: both passes in one cooperative launch for tensors that fit in the register files of one co-resident
+ * grid (about 3 M elements on a B200; HW % 4 == 0): dy and z are read once.  Same arguments and results as
+ * rcv_bn_bwd_reduce followed by rcv_bn_bwd_apply (sums: zeroed double[2C]).  RCV_ERR_UNSUPPORTED when the tensor
+ * does not fit: query rcv_bn_bwd_fused_supported first. */
+int rcv_bn_bwd_fused_supported(int32_t N, int32_t C, int64_t HW);
+int rcv_bn_bwd_fused(int32_t N, int32_t C, int64_t HW, int order, const float* dy, const float* z,
+                     const float* scale, const float* shift, const float* save_mean,
+                     const float* save_invstd, double* sums, float* dconv, float* dgamma,
+                     float* dbeta, float* dbias, void* stream);
+
 /* dx = dy * [y > 0] (threshold_backward for a stored ReLU output y). */
 int rcv_relu_bwd(int64_t n, const float* dy, const float* y, float* dx,
                  void* stream);

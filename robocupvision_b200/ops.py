@@ -7,6 +7,7 @@ stream; every function below enqueues exactly the named librcv_b200 kernels on
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -304,6 +305,11 @@ def bn_apply(z, scale, shift, relu: bool, residual=None, out=None):
     return y
 
 
+# EXPERIMENTAL (default off): one cooperative launch for both BatchNorm-backward passes where the tensors fit in the
+# register files of one co-resident grid (csrc/rcv_bn_fused.cu)
+BN_BWD_FUSED = os.environ.get("RCV_B200_BN_BWD_FUSED", "0") != "0"
+
+
 def bn_bwd(order: int, dy, z, scale, shift, mean, invstd, dgamma=None, dbeta=None, dbias=None,
            want_dbias: bool = False, sums=None):
     """-> (dconv, dgamma, dbeta, dbias|None).  Two passes: reduce, apply.  dgamma/dbeta/dbias are
@@ -322,6 +328,10 @@ def bn_bwd(order: int, dy, z, scale, shift, mean, invstd, dgamma=None, dbeta=Non
             dbias = small[2]
     dconv = torch.empty_like(z)
     st = _stream()
+    if BN_BWD_FUSED and _lib.load().rcv_bn_bwd_fused_supported(n, c, hw):
+        _call("rcv_bn_bwd_fused", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
+              _ptr(invstd), _ptr(sums), _ptr(dconv), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), st)
+        return dconv, dgamma, dbeta, dbias
     _call("rcv_bn_bwd_reduce", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
           _ptr(invstd), _ptr(sums), st)
     _call("rcv_bn_bwd_apply", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),

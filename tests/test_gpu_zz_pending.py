@@ -114,3 +114,44 @@ def test_conv_kernels_for_the_new_families(geom, cin, cout):
     dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True, math=ops.MATH_AUTO)
     assert_close(f"wgrad {geom} {cin}->{cout}", dw, w.grad, 1e-5)
     assert_close(f"bgrad {geom}", db, b.grad, 1e-5)
+
+
+# Cooperative single-launch BatchNorm backward (csrc/rcv_bn_fused.cu): never run on a GPU yet, and a grid-wide barrier
+# is the kind of code whose first run belongs in an interactive session, not in an unattended suite -- opt in with
+# RCV_TEST_EXPERIMENTAL=1 (tools/ab_queue.sh does).
+import os  # noqa: E402
+
+_experimental = pytest.mark.skipif(os.environ.get("RCV_TEST_EXPERIMENTAL", "0") == "0",
+                                   reason="experimental kernel: set RCV_TEST_EXPERIMENTAL=1")
+
+
+@_experimental
+@pytest.mark.parametrize("order", ["relu_affine", "affine_relu"])
+@pytest.mark.parametrize("shape", [(64, 128, 15, 20), (64, 64, 15, 20), (64, 32, 30, 40), (4, 8, 12, 20), (3, 128, 5, 4)])
+def test_bn_bwd_fused_matches_two_pass(order, shape):
+    from robocupvision_b200 import _lib, ops
+    n, c, h, w = shape
+    if not _lib.load().rcv_bn_bwd_fused_supported(n, c, h * w):
+        pytest.skip("tensor does not fit one co-resident grid")
+    gen = torch.Generator().manual_seed(3)
+    z = torch.randn(shape, generator=gen).cuda()
+    if order == "relu_affine":
+        z = torch.relu(z)
+    dy = torch.randn(shape, generator=gen).cuda()
+    gamma, beta = torch.randn(c, generator=gen).cuda(), torch.randn(c, generator=gen).cuda()
+    stats = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+    d = z.double()
+    stats[:c], stats[c:] = d.sum((0, 2, 3)), (d * d).sum((0, 2, 3))
+    scale, shift, mean, invstd = ops.bn_finalize(stats, n * h * w, gamma, beta, None, None, 0.1, 1e-5)
+    code = ops.EPI_RELU_AFFINE if order == "relu_affine" else ops.EPI_AFFINE_RELU
+    old = ops.BN_BWD_FUSED
+    try:
+        ops.BN_BWD_FUSED = False
+        ref = ops.bn_bwd(code, dy, z, scale, shift, mean, invstd, want_dbias=True)
+        ops.BN_BWD_FUSED = True
+        got = ops.bn_bwd(code, dy, z, scale, shift, mean, invstd, want_dbias=True)
+    finally:
+        ops.BN_BWD_FUSED = old
+    torch.cuda.synchronize()
+    for name, a, b in zip(("dconv", "dgamma", "dbeta", "dbias"), got, ref):
+        assert_close(f"bn_bwd_fused {name} {order} {shape}", a, b.cpu(), 2e-6, atol=1e-6)

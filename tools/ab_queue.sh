@@ -12,7 +12,10 @@ run() {  # label, env assignments...
 }
 # the pending GPU tests first (first run of --v2 / FCN / channel-pruned checkpoint): XPASS expected
 timeout 120 python -m pytest tests/test_gpu_zz_pending.py -q -rxX 2>&1 | tail -25
+# experimental kernels: parity first (a hang here must not take the A/B lines with it: bounded)
+RCV_TEST_EXPERIMENTAL=1 timeout 60 python -m pytest tests/test_gpu_zz_pending.py -q -k bn_bwd_fused 2>&1 | tail -5
 run base        RCV_NOOP=1
+run bn_fused    RCV_B200_BN_BWD_FUSED=1
 run pdl_off     RCV_PDL=0
 run bncap64     RCV_UMMA_BNCAP=64
 run wgrad_nl    RCV_B200_WGRAD_ON_LOAD=1
