@@ -361,6 +361,7 @@ def main():
             "config": {"workload": wl["name"], "batch_per_gpu": batch, "global_batch": batch * world,
                        "input": f"{wl['cin']}x{wl['h']}x{wl['w']}", "parallelism": f"dp{world}",
                        "cuda_graph": bool(not args.no_graph),
+                       "programmatic_dependent_launch": bool(_lib.load().rcv_get_pdl()),
                        "l2": "8 rotating input batches; per-step activation working set >> 126 MB L2",
                        "peaks": pk["source"]},
             "clocks": clocks,
