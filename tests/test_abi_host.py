@@ -289,3 +289,52 @@ def test_pdl_switch_policy(monkeypatch):
         e.update(env)
         out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, cwd=str(ROOT))
         assert out.stdout.strip().splitlines()[-1] == want, (env, out.stdout, out.stderr)
+
+
+def test_host_side_dispatch_is_total_over_random_geometries():
+    """The host-side queries of the ABI (engine choice per direction, tensor-core eligibility, packed-panel size,
+    normalise-on-load eligibility) answer for ANY geometry the descriptor can express -- no crash, no out-of-range
+    code -- and agree with each other: a layer that normalises on load runs on the tensor-core engine; a direction
+    that uses tensor cores has a non-empty packed panel."""
+    import random
+    from robocupvision_b200 import ops
+    from robocupvision_b200._lib import RcvError
+    rnd = random.Random(1234)
+    seen, refused = set(), 0
+    for _ in range(3000):
+        tr = rnd.random() < 0.2
+        k = 3 if tr else rnd.choice([1, 3, 3, 3])
+        s = 2 if tr else (1 if k == 1 else rnd.choice([1, 1, 2]))
+        d = 1 if (tr or k == 1) else rnd.choice([1, 1, 2])
+        p = 1 if tr else (0 if k == 1 else d)
+        cin, cout = rnd.choice([1, 3, 5, 8, 16, 24, 32, 40, 64, 96, 128, 256]), rnd.choice([1, 5, 8, 16, 32, 64, 128, 256])
+        g = ops.ConvGeom(cin, cout, k, s, p, d, tr)
+        n, h, w = rnd.choice([1, 2, 8, 64, 256]), rnd.choice([1, 2, 5, 15, 30, 60, 120, 480]), rnd.choice([1, 3, 8, 20, 40, 80, 160, 640])
+        for math in (ops.MATH_FP32, ops.MATH_AUTO):
+            try:
+                engines = [ops.conv_engine(g, n, h, w, direction, math) for direction in (ops.PACK_FWD, ops.PACK_DGRAD, 2)]
+            except RcvError as e:  # e.g. a stride-2 layer on an odd-sized image: refused with a status and a message
+                assert "-2" in str(e) and len(str(e)) > 40, str(e)
+                refused += 1
+                continue
+            assert all(e in (ops.ENGINE_SIMT, ops.ENGINE_DIRECT, ops.ENGINE_UMMA, ops.ENGINE_NARROW) for e in engines)
+            seen.update(engines)
+            if math == ops.MATH_FP32:
+                assert ops.ENGINE_UMMA not in engines
+                assert not ops.conv_normalises_on_load(g, n, h, w, math)
+                assert not ops.conv_wgrad_normalises_on_load(g, n, h, w, math)
+                continue
+            if ops.conv_normalises_on_load(g, n, h, w, math):
+                assert engines[0] == ops.ENGINE_UMMA and k == 3 and s == 1 and not tr and cin % 32 == 0
+            if ops.conv_wgrad_normalises_on_load(g, n, h, w, math):
+                assert engines[2] == ops.ENGINE_UMMA and k == 3 and s == 1 and not tr and w % 4 == 0
+            for direction in (ops.PACK_FWD, ops.PACK_DGRAD):
+                if ops.conv_uses_tensor_cores(g, direction, math):
+                    assert ops.conv_packed_bytes(g, direction) > 0
+    # geometries outside the path are refused with a status and a message, never guessed at
+    assert refused < 2 * 3000 * 0.5
+    for bad in (ops.ConvGeom(8, 8, 1, 2, 0, 1), ops.ConvGeom(8, 8, 5, 1, 2, 1), ops.ConvGeom(8, 8, 3, 3, 1, 1)):
+        with pytest.raises(RcvError):
+            ops.conv_engine(bad, 2, 12, 16, ops.PACK_FWD, ops.MATH_AUTO)
+    assert seen == {ops.ENGINE_SIMT, ops.ENGINE_DIRECT, ops.ENGINE_UMMA, ops.ENGINE_NARROW} or \
+        seen == {ops.ENGINE_SIMT, ops.ENGINE_UMMA, ops.ENGINE_NARROW}
