@@ -362,3 +362,45 @@ def test_net_cfg_emitted_from_the_plan_matches_the_reference_files():
     d = E.net_cfg_sections(M.ROBO_UNet())
     assert d[1] == ("convolutional", [("filters", 8), ("size", 3), ("stride", 1), ("pad", 1), ("activation", "relu")])
     assert d[2] == ("batchnorm", [("activation", "linear")])
+
+
+def test_engine_backward_side_stream_code_path_on_cpu(cpu_engine, monkeypatch):
+    """The weight-gradient side-stream branch of Plan.backward (the default on the GPU) with torch.cuda's stream
+    objects replaced by inert stand-ins: same gradients as the single-stream branch, every tensor the side stream
+    reads is kept alive until the join, and the streams are joined exactly once."""
+    import contextlib
+    engine, fake = cpu_engine
+    log = []
+
+    class Stream:
+        def __init__(self, device=None):
+            self.device = device
+
+        def wait_stream(self, other):
+            log.append(("wait", self is main, other is main))
+
+    main = Stream(torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: main)
+    monkeypatch.setattr(torch.cuda, "Stream", Stream)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    make, oracle, cin = _cases()["robo_default"]
+    res = {}
+    for side in (False, True):
+        monkeypatch.setattr(engine, "WGRAD_SIDE_STREAM", side)
+        torch.manual_seed(12345678)
+        m = make().train()
+        x = synth.images(8, cin, 120, 160, seed=11)
+        gout = torch.randn(8, 5, 120, 160, generator=torch.Generator().manual_seed(4)) * 1e-3
+        plan = m._get_plan()
+        log.clear()
+        with torch.no_grad():
+            outs, saved = plan.forward(x, training=True, save=True)
+            dx, gv = plan.backward(saved, [gout], x_needs_grad=True)
+        res[side] = (dx, [gv[id(p)].clone() for p in m.parameters()], list(log))
+    assert torch.equal(res[True][0], res[False][0])
+    assert all(torch.equal(a, b) for a, b in zip(res[True][1], res[False][1]))
+    assert res[False][2] == []
+    waits = res[True][2]
+    n_conv = sum(1 for nd in plan.nodes if nd.kind == "conv")
+    assert waits.count(("wait", False, True)) == n_conv      # side waits for main before every weight gradient
+    assert waits.count(("wait", True, False)) == 1 and waits[-1] == ("wait", True, False)   # one join, at the end
