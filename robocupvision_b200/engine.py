@@ -308,79 +308,78 @@ class Plan:
 
     def _backward_node(self, t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side=None,
                        keep=None, lazy=None, lazy_done=None):
-        if True:
-            nd = self.nodes[t]
-            g = grads[t + 1]
-            grads[t + 1] = None
-            if nd.bn is not None:
-                soff = self._sum_off[t]
-                sums = sums_arena[soff:soff + 2 * nd.geom.cout]
-            if g is None:
-                return
-            g = ops._chk(g, name="grad")
-            src = acts[nd.src]
-            in_hw = (src.shape[2], src.shape[3])
-            if nd.kind == "pool":
-                add_to(nd.src, ops.maxpool2x2_bwd(g, saved[t][0], in_hw))
-                return
-            geom, conv, bn = nd.geom, nd.conv, nd.bn
-            if nd.skip >= 0:
-                if nd.skip_mode == "add":
-                    add_to(nd.skip, g)
-                elif nd.skip_mode == "partial":
-                    add_to(nd.skip, g[:, :nd.skip_ch].contiguous())
-                else:  # cat
-                    add_to(nd.skip, g[:, geom.cout:].contiguous())
-                    g = g[:, :geom.cout].contiguous()
-            w = conv.weight.detach()
-            has_bias = conv.bias is not None
-            if bn is not None:
-                if saved[t] is None or len(saved[t]) != 5:
-                    raise NotImplementedError(
-                        "backward through an eval-mode BatchNorm block is not on the hot path "
-                        "(call model.train() before the forward pass you differentiate)")
-                z, scale, shift, mean, invstd = saved[t]
-                dconv, _, _, _ = ops.bn_bwd(nd.order, g, z, scale, shift, mean, invstd,
-                                            dgamma=grad_views[id(bn.weight)], dbeta=grad_views[id(bn.bias)],
-                                            dbias=grad_views[id(conv.bias)] if has_bias else None, sums=sums)
-                wg_bias = None
-            else:
-                dconv = ops.relu_bwd(g, saved[t][0]) if nd.order == EPI_RELU else g
-                wg_bias = grad_views[id(conv.bias)] if has_bias else None
-            if nd.src != 0 or x_needs_grad:
-                wp = nd._pack[PACK_DGRAD] if nd.uses_tc(PACK_DGRAD, self.math) else None
-                grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
-                                               wpacked=wp)
-            la = lazy.get(nd.src) if lazy else None
-            if la is not None and WGRAD_ON_LOAD and ops.conv_wgrad_normalises_on_load(
-                    geom, src.shape[0], src.shape[2], src.shape[3], self.math):
-                wg_affine, la = la, None  # the weight-gradient kernel applies the BatchNorm itself
-            else:
-                wg_affine = None
+        nd = self.nodes[t]
+        g = grads[t + 1]
+        grads[t + 1] = None
+        if nd.bn is not None:
+            soff = self._sum_off[t]
+            sums = sums_arena[soff:soff + 2 * nd.geom.cout]
+        if g is None:
+            return
+        g = ops._chk(g, name="grad")
+        src = acts[nd.src]
+        in_hw = (src.shape[2], src.shape[3])
+        if nd.kind == "pool":
+            add_to(nd.src, ops.maxpool2x2_bwd(g, saved[t][0], in_hw))
+            return
+        geom, conv, bn = nd.geom, nd.conv, nd.bn
+        if nd.skip >= 0:
+            if nd.skip_mode == "add":
+                add_to(nd.skip, g)
+            elif nd.skip_mode == "partial":
+                add_to(nd.skip, g[:, :nd.skip_ch].contiguous())
+            else:  # cat
+                add_to(nd.skip, g[:, geom.cout:].contiguous())
+                g = g[:, :geom.cout].contiguous()
+        w = conv.weight.detach()
+        has_bias = conv.bias is not None
+        if bn is not None:
+            if saved[t] is None or len(saved[t]) != 5:
+                raise NotImplementedError(
+                    "backward through an eval-mode BatchNorm block is not on the hot path "
+                    "(call model.train() before the forward pass you differentiate)")
+            z, scale, shift, mean, invstd = saved[t]
+            dconv, _, _, _ = ops.bn_bwd(nd.order, g, z, scale, shift, mean, invstd,
+                                        dgamma=grad_views[id(bn.weight)], dbeta=grad_views[id(bn.bias)],
+                                        dbias=grad_views[id(conv.bias)] if has_bias else None, sums=sums)
+            wg_bias = None
+        else:
+            dconv = ops.relu_bwd(g, saved[t][0]) if nd.order == EPI_RELU else g
+            wg_bias = grad_views[id(conv.bias)] if has_bias else None
+        if nd.src != 0 or x_needs_grad:
+            wp = nd._pack[PACK_DGRAD] if nd.uses_tc(PACK_DGRAD, self.math) else None
+            grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
+                                           wpacked=wp)
+        la = lazy.get(nd.src) if lazy else None
+        if la is not None and WGRAD_ON_LOAD and ops.conv_wgrad_normalises_on_load(
+                geom, src.shape[0], src.shape[2], src.shape[3], self.math):
+            wg_affine, la = la, None  # the weight-gradient kernel applies the BatchNorm itself
+        else:
+            wg_affine = None
 
-            def wgrad_src():
-                """The tensor the weight gradient reads: for a normalise-on-load input, the producer's BatchNorm output,
-                produced now (once per activation) on the stream the weight gradient runs on."""
-                if la is None:
-                    return src
-                y = lazy_done.get(nd.src)
-                if y is None:
-                    y = ops.bn_apply(src, la[0], la[1], la[2])
-                    lazy_done[nd.src] = y
-                    if keep is not None:
-                        keep.append(y)
-                return y
+        def wgrad_src():
+            """The tensor the weight gradient reads: for a normalise-on-load input, the producer's BatchNorm output,
+            produced now (once per activation) on the stream the weight gradient runs on."""
+            if la is None:
+                return src
+            y = lazy_done.get(nd.src)
+            if y is None:
+                y = ops.bn_apply(src, la[0], la[1], la[2])
+                lazy_done[nd.src] = y
+                if keep is not None:
+                    keep.append(y)
+            return y
 
-            if side is None:
-                ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math,
-                               in_affine=wg_affine)
-            else:
-                cur = torch.cuda.current_stream(src.device)
-                side.wait_stream(cur)  # dconv (and every earlier write to the gradient arena) is ordered before
-                keep.append(dconv)
-                with torch.cuda.stream(side):
-                    ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias,
-                                   math=self.math, in_affine=wg_affine)
+        if side is None:
+            ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias, math=self.math,
+                           in_affine=wg_affine)
+        else:
+            cur = torch.cuda.current_stream(src.device)
+            side.wait_stream(cur)  # dconv (and every earlier write to the gradient arena) is ordered before
+            keep.append(dconv)
+            with torch.cuda.stream(side):
+                ops.conv_wgrad(geom, wgrad_src(), dconv, dw=grad_views[id(conv.weight)], dbias=wg_bias,
+                               math=self.math, in_affine=wg_affine)
 
 
 class _PlanFn(torch.autograd.Function):
