@@ -22,3 +22,6 @@ run wgrad_nl    RCV_B200_WGRAD_ON_LOAD=1
 run bn_onload0  RCV_B200_BN_ON_LOAD=0
 run kb128_32    RCV_UMMA_KB128=32
 run base2       RCV_NOOP=1
+# descriptor probe for 16-channel (64-byte-row) halo staging, experiment 6
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -I robocupvision_b200/csrc -I include -o /tmp/umma_shift_probe64 \
+     tools/umma_shift_probe64.cu && timeout 60 /tmp/umma_shift_probe64 | tee gpurun_out/umma_shift_probe64.log
