@@ -79,7 +79,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
@@ -269,7 +269,8 @@ def main():
     # nvidia-smi needs a few hundred ms before its first row: start it ahead of the warm-up, keep the rows that
     # arrive from the start of the timed region on
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:  # one poller per job (rank 0's GPU): NVML queries are not free
+        sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
