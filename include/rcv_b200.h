@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RCV_ABI_VERSION 2
+#define RCV_ABI_VERSION 3
 
 typedef enum rcv_status {
   RCV_OK = 0,
@@ -198,12 +198,13 @@ int rcv_conv_wgrad_nl(const rcv_conv_desc* d, const float* x, const float* in_sc
  * mean, biased var -> scale = gamma/sqrt(var+eps), shift = beta-mean*scale;
  * running_mean = (1-m)*running_mean + m*mean, running_var likewise with the
  * unbiased variance (either may be NULL); save_mean / save_invstd for the
- * backward pass.  One tiny launch. */
+ * backward pass; *num_batches_tracked += 1 (BatchNorm2d's int64 buffer; may be
+ * NULL).  One tiny launch. */
 int rcv_bn_finalize(int32_t C, int64_t count, const double* stats,
                     const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float momentum, float eps, float* scale,
                     float* shift, float* save_mean, float* save_invstd,
-                    void* stream);
+                    int64_t* num_batches_tracked, void* stream);
 
 /* Eval-mode fold (model.eval(), running statistics):
  * scale = gamma/sqrt(var+eps), shift = beta - mean*scale. */
@@ -219,12 +220,14 @@ int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z,
 
 /* rcv_bn_finalize + rcv_bn_apply in one launch (the train-mode forward of a BatchNorm node):
  * every block derives scale/shift from stats; block 0 also writes scale, shift, save_mean,
- * save_invstd (for the backward pass) and updates the running statistics. */
+ * save_invstd (for the backward pass), updates the running statistics and bumps
+ * *num_batches_tracked (may be NULL). */
 int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const double* stats,
                           const float* gamma, const float* beta, float* running_mean,
                           float* running_var, float momentum, float eps, const float* z,
                           int relu, const float* residual, float* y, float* scale,
-                          float* shift, float* save_mean, float* save_invstd, void* stream);
+                          float* shift, float* save_mean, float* save_invstd,
+                          int64_t* num_batches_tracked, void* stream);
 
 /* Backward of y = act(scale*z+shift) composed with the producer's own ReLU.
  * order = RCV_EPI_RELU_AFFINE: z = relu(conv), y = bn(z)      (model.py:116)
@@ -247,16 +250,6 @@ int rcv_bn_bwd_apply(int32_t N, int32_t C, int64_t HW, int order,
                      const float* save_invstd, const double* sums,
                      float* dconv, float* dgamma, float* dbeta, float* dbias,
                      void* stream);
-
-/* EXPERIMENTAL: both passes in one cooperative launch for tensors that fit in the register files of one co-resident
- * grid (about 3 M elements on a B200; HW % 4 == 0): dy and z are read once.  Same arguments and results as
- * rcv_bn_bwd_reduce followed by rcv_bn_bwd_apply (sums: zeroed double[2C]).  RCV_ERR_UNSUPPORTED when the tensor
- * does not fit: query rcv_bn_bwd_fused_supported first. */
-int rcv_bn_bwd_fused_supported(int32_t N, int32_t C, int64_t HW);
-int rcv_bn_bwd_fused(int32_t N, int32_t C, int64_t HW, int order, const float* dy, const float* z,
-                     const float* scale, const float* shift, const float* save_mean,
-                     const float* save_invstd, double* sums, float* dconv, float* dgamma,
-                     float* dbeta, float* dbias, void* stream);
 
 /* dx = dy * [y > 0] (threshold_backward for a stored ReLU output y). */
 int rcv_relu_bwd(int64_t n, const float* dy, const float* y, float* dx,
@@ -354,13 +347,24 @@ int rcv_adam_l1_step(int64_t n, float* p, const float* g, float* m, float* v,
  * the train step is replayed from a CUDA graph: step_dev / lr_dev above, when
  * non-NULL, override the host `step` / `lr`). */
 int rcv_counter_add(int32_t* counter, int32_t inc, void* stream);
-/* SGD with momentum/dampening=0/weight decay (trainer.py:182-184):
- *   g = grad_scale*g + wd*p; masked -> 0; buf = mom*buf + g (buf = g at
- *   first_step); p -= lr*buf. */
+/* SGD with momentum/dampening=0/weight decay (trainer.py:182-184), with the same
+ * optional L1 sub-gradient, pruning mask and device-resident learning rate as
+ * rcv_adam_l1_step:
+ *   g = grad_scale*g + l1_decay*sign(p); masked -> 0; g += wd*p;
+ *   buf = mom*buf + g (buf = g at first_step; a zero-filled buf gives the same
+ *   first step, so graph replays pass first_step = 0); p -= lr*buf.
+ * l1_sum (double[1], may be NULL) += sum |p| before the update; lr_dev (device
+ * float, may be NULL) overrides lr. */
 int rcv_sgd_step(int64_t n, float* p, const float* g, float* buf,
                  const uint8_t* mask, float lr, float momentum,
                  float weight_decay, float grad_scale, int first_step,
+                 float l1_decay, double* l1_sum, const float* lr_dev,
                  void* stream);
+
+/* Stream-ordered zero fill of `bytes` bytes (cudaMemsetAsync: a memset node, not a
+ * kernel, inside a captured graph): the accumulators a step sums into -- gradient
+ * arena (optimizer.zero_grad(), train.py:45), BatchNorm statistics, loss sums. */
+int rcv_zero(void* ptr, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

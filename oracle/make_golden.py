@@ -7,6 +7,7 @@
   robo_train.npz         3 reference training steps (train.py:43-74 restated with the reference's
                          own ROBO_UNet / CrossEntropyLoss2d / torch.optim.Adam): losses, grad norms
   weightsLP_head.npz     first/last values + sha256 of weightsLP/weights.dat (paramSave.py format)
+  robo_curve200.npz      200 reference training steps at two sizes (`... curve` alone regenerates it)
   bestModelSegFinetunedPruned_bu*   the channel-pruned legacy PB_FCN (reference blocks + PB_FCN forward; `... bu` alone
                          regenerates just this one)
 Everything is produced by importing /root/reference/model.py unmodified (plus the LabelProp
@@ -227,12 +228,46 @@ def fcn_checkpoint():
     eval_golden(name, m, lambda mm, x: mm(x), [(2, 3, 24, 32), (2, 3, 120, 160)])
 
 
+def loss_curves():
+    """`python -m oracle.make_golden curve`: 200 REFERENCE training steps (train.py:43-74: zero_grad -> model ->
+    CrossEntropyLoss2d -> + decay * l1reg -> backward -> Adam.step) of the reference's own ROBO_UNet, seed 12345678
+    (train.py:332), Adam 1e-3, L1 1e-6, class weights train.py:309, a fresh synthetic batch with learnable labels
+    every step.  Two sizes: 8x3x48x64 (also re-run by the CPU oracle test) and 8x3x120x160 (the real frame size)."""
+    torch.set_num_threads(1)
+    out = {}
+    for tag, (b, h, w) in (("small", (8, 48, 64)), ("full", (8, 120, 160))):
+        torch.manual_seed(12345678)
+        m = REFM.ROBO_UNet()
+        crit = REFM.CrossEntropyLoss2d(torch.tensor(synth.CLASS_WEIGHTS))
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        m.train()
+        losses, corrects = [], []
+        for s in range(200):
+            x = synth.images(b, 3, h, w, seed=5000 + s)
+            y = synth.labels_learnable(x)
+            opt.zero_grad()
+            pred = m(x)
+            loss = crit(pred, y) + 1e-6 * sum(p.abs().sum() for p in m.parameters())
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+            corrects.append(int((pred.argmax(1) == y).sum()))
+        out[f"losses_{tag}"] = np.array(losses)
+        out[f"corrects_{tag}"] = np.array(corrects)
+        out[f"shape_{tag}"] = np.array([b, 3, h, w])
+        print(tag, "first", losses[:3], "last", losses[-3:])
+    np.savez_compressed(OUT / "robo_curve200.npz", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "bu":
         channel_pruned()
+    elif len(sys.argv) > 1 and sys.argv[1] == "curve":
+        loss_curves()
     elif len(sys.argv) > 1 and sys.argv[1] == "fcn":
         fcn_checkpoint()
     else:
         main()
         channel_pruned()
         fcn_checkpoint()
+        loss_curves()

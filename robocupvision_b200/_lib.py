@@ -66,15 +66,13 @@ SIGNATURES = {
     "rcv_conv_wgrad": [C.POINTER(ConvDesc), _p, _p, _p, _p, _p],
     "rcv_conv_wgrad_normalises_on_load": [C.POINTER(ConvDesc)],
     "rcv_conv_wgrad_nl": [C.POINTER(ConvDesc), _p, _p, _p, C.c_int, _p, _p, _p, _p],
-    "rcv_bn_finalize": [_i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p],
+    "rcv_bn_finalize": [_i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p, _p],
     "rcv_bn_fold": [_i32, _p, _p, _p, _p, _f32, _p, _p, _p],
     "rcv_bn_apply": [_i32, _i32, _i64, _p, _p, _p, C.c_int, _p, _p, _p],
     "rcv_bn_finalize_apply": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, C.c_int, _p, _p, _p, _p, _p,
-                              _p, _p],
+                              _p, _p, _p],
     "rcv_bn_bwd_reduce": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_bn_bwd_apply": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
-    "rcv_bn_bwd_fused_supported": [_i32, _i32, _i64],
-    "rcv_bn_bwd_fused": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_relu_bwd": [_i64, _p, _p, _p, _p],
     "rcv_channel_sum": [_i32, _i32, _i64, _p, _p, _p],
     "rcv_maxpool2x2_fwd": [_i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
@@ -90,12 +88,13 @@ SIGNATURES = {
     "rcv_dice_bwd": [_i32, _i32, _i64, _p, _p, _p, _p, _f32, _p, _p, _p],
     "rcv_adam_l1_step": [_i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _i32, _f32, _f32, _p, _p, _p, _p],
     "rcv_counter_add": [_p, _i32, _p],
-    "rcv_sgd_step": [_i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, C.c_int, _p],
+    "rcv_sgd_step": [_i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, C.c_int, _f32, _p, _p, _p],
+    "rcv_zero": [_p, C.c_size_t, _p],
 }
 _RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t,
              "rcv_conv_pack_table_bytes": C.c_size_t}
 PACK_FWD, PACK_DGRAD = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 

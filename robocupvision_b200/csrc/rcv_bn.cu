@@ -27,10 +27,12 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 __global__ void bn_finalize_kernel(int C, double count, const double* __restrict__ stats,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum, float eps,
-                                   float* scale, float* shift, float* save_mean, float* save_invstd) {
+                                   float* scale, float* shift, float* save_mean, float* save_invstd,
+                                   long long* nbt) {
   rcv_pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (c == 0 && nbt) *nbt += 1;  // BatchNorm2d.num_batches_tracked
   const double mean = stats[c] / count;
   double var = stats[C + c] / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -105,9 +107,11 @@ __global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
     int64_t total, int C, int64_t HW, double count, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
     float momentum, float eps, const float* __restrict__ z, int relu, const float* __restrict__ residual,
-    float* __restrict__ y, float* scale_out, float* shift_out, float* save_mean, float* save_invstd) {
+    float* __restrict__ y, float* scale_out, float* shift_out, float* save_mean, float* save_invstd,
+    long long* nbt) {
   rcv_pdl_enter();
   extern __shared__ float s_ss[];  // [2][C]
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;  // BatchNorm2d.num_batches_tracked
   for (int c = threadIdx.x; c < C; c += NT) {
     const double mean = stats[c] / count;
     double var = stats[C + c] / count - mean * mean;
@@ -348,10 +352,12 @@ int chan_splits(int C, int64_t E) {
 extern "C" int rcv_bn_finalize(int32_t C, int64_t count, const double* stats, const float* gamma,
                                const float* beta, float* running_mean, float* running_var,
                                float momentum, float eps, float* scale, float* shift,
-                               float* save_mean, float* save_invstd, void* stream) {
+                               float* save_mean, float* save_invstd, int64_t* num_batches_tracked,
+                               void* stream) {
   RCV_REQUIRE(C > 0 && count > 0 && stats && scale && shift, RCV_ERR_BAD_ARG, "bn_finalize: bad arg");
   rcv_launch(bn_finalize_kernel, dim3(rcv_cdiv(C, 128)), dim3(128), 0, (cudaStream_t)stream, C, (double)count, stats,
-             gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd);
+             gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean, save_invstd,
+             reinterpret_cast<long long*>(num_batches_tracked));
   RCV_CHECK_LAUNCH("bn_finalize");
   return RCV_OK;
 }
@@ -385,7 +391,7 @@ extern "C" int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const dou
                                      const float* beta, float* running_mean, float* running_var, float momentum,
                                      float eps, const float* z, int relu, const float* residual, float* y,
                                      float* scale, float* shift, float* save_mean, float* save_invstd,
-                                     void* stream) {
+                                     int64_t* num_batches_tracked, void* stream) {
   RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && stats && z && y && scale && shift, RCV_ERR_BAD_ARG,
               "bn_finalize_apply: bad arg");
   RCV_REQUIRE(C <= 4096, RCV_ERR_UNSUPPORTED, "bn_finalize_apply: C=%d > 4096", C);
@@ -395,11 +401,11 @@ extern "C" int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const dou
   if ((HW & 3) == 0)
     rcv_launch(bn_finalize_apply_kernel<true>, dim3(fa_blocks(total / 4)), dim3(NT), smem, (cudaStream_t)stream,
                total, C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual,
-               y, scale, shift, save_mean, save_invstd);
+               y, scale, shift, save_mean, save_invstd, reinterpret_cast<long long*>(num_batches_tracked));
   else
     rcv_launch(bn_finalize_apply_kernel<false>, dim3(ew_blocks(total)), dim3(NT), smem, (cudaStream_t)stream, total,
                C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, y,
-               scale, shift, save_mean, save_invstd);
+               scale, shift, save_mean, save_invstd, reinterpret_cast<long long*>(num_batches_tracked));
   RCV_CHECK_LAUNCH("bn_finalize_apply");
   return RCV_OK;
 }

@@ -60,12 +60,18 @@ __global__ void __launch_bounds__(NT) sgd_kernel(int64_t n, float* __restrict__ 
                                                   const float* __restrict__ g, float* __restrict__ buf,
                                                   const uint8_t* __restrict__ mask, float lr,
                                                   float momentum, float wd, float grad_scale,
-                                                  int first_step) {
+                                                  int first_step, float l1_decay, double* l1_sum,
+                                                  const float* __restrict__ lr_dev) {
   rcv_pdl_enter();
+  __shared__ double sh[NT / 32];
   const int64_t stride = (int64_t)gridDim.x * NT;
+  if (lr_dev) lr = __ldg(lr_dev);
+  float l1 = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += stride) {
     const float pv = p[i];
+    l1 += fabsf(pv);
     float gv = grad_scale * g[i];
+    if (l1_decay != 0.f) gv += l1_decay * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f));
     if (mask && mask[i]) gv = 0.f;
     if (wd != 0.f) gv += wd * pv;
     if (momentum != 0.f) {
@@ -74,6 +80,18 @@ __global__ void __launch_bounds__(NT) sgd_kernel(int64_t n, float* __restrict__ 
       gv = b;
     }
     p[i] = pv - lr * gv;
+  }
+  if (l1_sum) {
+    double s = (double)l1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int i = 0; i < NT / 32; ++i) t += sh[i];
+      atomicAdd(l1_sum, t);
+    }
   }
 }
 
@@ -112,10 +130,24 @@ extern "C" int rcv_counter_add(int32_t* counter, int32_t inc, void* stream) {
 
 extern "C" int rcv_sgd_step(int64_t n, float* p, const float* g, float* buf, const uint8_t* mask,
                             float lr, float momentum, float weight_decay, float grad_scale,
-                            int first_step, void* stream) {
+                            int first_step, float l1_decay, double* l1_sum, const float* lr_dev,
+                            void* stream) {
   RCV_REQUIRE(n > 0 && p && g && (momentum == 0.f || buf), RCV_ERR_BAD_ARG, "sgd_step: bad arg");
   rcv_launch(sgd_kernel, dim3(blocks_for(n)), dim3(NT), 0, (cudaStream_t)stream, n, p, g, buf, mask, lr, momentum,
-             weight_decay, grad_scale, first_step);
+             weight_decay, grad_scale, first_step, l1_decay, l1_sum, lr_dev);
   RCV_CHECK_LAUNCH("sgd_step");
+  return RCV_OK;
+}
+
+// Stream-ordered memset (a memset node when captured into a CUDA graph: no kernel): the zero fill of the
+// accumulators a step sums into (gradient arena, BatchNorm statistics, loss sums).
+extern "C" int rcv_zero(void* ptr, size_t bytes, void* stream) {
+  RCV_REQUIRE(ptr || bytes == 0, RCV_ERR_BAD_ARG, "zero: NULL pointer");
+  if (bytes == 0) return RCV_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    rcv_set_error("zero: %s", cudaGetErrorString(e));
+    return RCV_ERR_CUDA;
+  }
   return RCV_OK;
 }

@@ -187,9 +187,10 @@ class Plan:
         return hit
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, training: bool, save: bool):
+    def forward(self, x: torch.Tensor, training: bool, save: bool, stats_arena: Optional[torch.Tensor] = None):
         """-> (outputs, saved).  training selects batch statistics for BatchNorm nodes whose
-        module is in training mode; save keeps what backward needs."""
+        module is in training mode; save keeps what backward needs.  stats_arena: caller-zeroed float64[n_stats]
+        for the batch statistics (TrainStep zeroes all of a step's accumulators with one memset)."""
         x = ops._chk(x, name="input")
         if x.dim() != 4:
             raise ValueError(f"expected NCHW input, got shape {tuple(x.shape)}")
@@ -197,9 +198,7 @@ class Plan:
         acts: List[torch.Tensor] = [x]
         lazy: Dict[int, tuple] = {}  # activation index -> (scale, shift, relu): acts[i] holds the tensor BEFORE that affine
         saved: List[Optional[tuple]] = [None] * len(self.nodes)
-        stats_arena = None
         soff = 0
-        nbt = []
         if training:
             self.epoch += 1
         self._ensure_packed((PACK_FWD, PACK_DGRAD) if save else (PACK_FWD,), training, x.requires_grad)
@@ -221,7 +220,7 @@ class Plan:
                 saved[t] = (y if nd.order == EPI_RELU else None,)
             elif training and bn.training:
                 if stats_arena is None:
-                    stats_arena = torch.zeros(self.n_stats, device=dev, dtype=torch.float64)
+                    stats_arena = ops.zeros(self.n_stats, torch.float64, dev)
                 stats = stats_arena[soff:soff + 2 * g.cout]
                 soff += 2 * g.cout
                 z = ops.conv_fwd(g, src, w, b, epilogue=EPI_RELU if nd.order == EPI_RELU_AFFINE else EPI_NONE,
@@ -232,20 +231,19 @@ class Plan:
                 else:
                     momentum = bn.momentum
                 track = bn.track_running_stats and bn.running_mean is not None
+                nbt = bn.num_batches_tracked if (track and bn.num_batches_tracked is not None) else None
                 if self._defer_bn_apply(t, z.shape[0], z.shape[2], z.shape[3]):
                     scale, shift, mean, invstd = ops.bn_finalize(
                         stats, count, bn.weight.detach(), bn.bias.detach(), bn.running_mean if track else None,
-                        bn.running_var if track else None, momentum, bn.eps)
+                        bn.running_var if track else None, momentum, bn.eps, num_batches_tracked=nbt)
                     lazy[t + 1] = (scale, shift, nd.order == EPI_AFFINE_RELU)
                     y = z  # consumers read z through the affine
                 else:
                     y, scale, shift, mean, invstd = ops.bn_finalize_apply(
                         z, stats, bn.weight.detach(), bn.bias.detach(),
                         bn.running_mean if track else None, bn.running_var if track else None, momentum, bn.eps,
-                        relu=(nd.order == EPI_AFFINE_RELU), residual=skip)
+                        relu=(nd.order == EPI_AFFINE_RELU), residual=skip, num_batches_tracked=nbt)
                 saved[t] = (z, scale, shift, mean, invstd)
-                if track and bn.num_batches_tracked is not None:
-                    nbt.append(bn.num_batches_tracked)
             else:
                 scale, shift = nd.folded(self.epoch)
                 y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, scale=scale, shift=shift, residual=skip,
@@ -255,23 +253,23 @@ class Plan:
             elif nd.skip >= 0 and nd.skip_mode == "cat":
                 y = torch.cat([y, acts[nd.skip]], 1)
             acts.append(y)
-        if nbt:
-            torch._foreach_add_(nbt, 1)
         outs = [acts[i] for i in self.outputs]
         return outs, ((acts, saved, lazy) if save else None)
 
     # ------------------------------------------------------------------ backward
     def backward(self, saved_all, gouts: Sequence[Optional[torch.Tensor]], x_needs_grad: bool,
-                 grad_views: Optional[Dict[int, torch.Tensor]] = None, node_done=None):
+                 grad_views: Optional[Dict[int, torch.Tensor]] = None, node_done=None,
+                 sums_arena: Optional[torch.Tensor] = None):
         """-> (dx or None, {id(param): grad}).  grad_views, if given, maps id(param) to zero-filled
         tensors that receive the gradients (the train step's flat arena).  node_done(t) is called
-        once node t's parameter gradients are final (nodes are visited last to first)."""
+        once node t's parameter gradients are final (nodes are visited last to first).  sums_arena: caller-zeroed
+        float64[n_stats] for the BatchNorm-backward sums."""
         acts, saved, lazy = saved_all
         lazy_done: Dict[int, torch.Tensor] = {}  # BatchNorm outputs materialised for a weight gradient, per activation
         dev = acts[0].device
         if grad_views is None:
             total = sum(p.numel() for p in self.params)
-            flat = torch.zeros(total, device=dev, dtype=torch.float32)
+            flat = ops.zeros(total, torch.float32, dev)
             grad_views, o = {}, 0
             for p in self.params:
                 grad_views[id(p)] = flat[o:o + p.numel()].view(p.shape)
@@ -284,7 +282,8 @@ class Plan:
         for oi, g in zip(self.outputs, gouts):
             if g is not None:
                 add_to(oi, g)
-        sums_arena = torch.zeros(max(self.n_stats, 1), device=dev, dtype=torch.float64)
+        if sums_arena is None:
+            sums_arena = ops.zeros(max(self.n_stats, 1), torch.float64, dev)
         # Weight gradients run on a side stream: dgrad(t) and wgrad(t) only share their input, so the
         # wgrad CTAs fill the SMs a dgrad's partial last wave leaves idle (150 tiles on 148 SMs at
         # 15x20) and overlap the next node's BatchNorm backward.  Tensors the side stream reads are

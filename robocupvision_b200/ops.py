@@ -19,7 +19,7 @@ from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_A
 __all__ = [
     "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
-    "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "counter_add", "launch_count", "reset_launch_count",
+    "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "zero_", "zeros", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
     "MATH_FP32", "MATH_TF32X3", "MATH_AUTO", "ENGINE_SIMT", "ENGINE_DIRECT", "ENGINE_UMMA", "ENGINE_NARROW",
 ]
@@ -163,7 +163,8 @@ class PackTable:
         _call("rcv_conv_pack_table_run", 1, _ptr(self.table), self.n, self.total, _stream())
 
 
-def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum, eps, relu, residual=None):
+def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum, eps, relu, residual=None,
+                      num_batches_tracked=None):
     """Train-mode BatchNorm forward in one launch -> (y, scale, shift, mean, invstd)."""
     z = _chk(z, name="z")
     n, c = z.shape[0], z.shape[1]
@@ -174,7 +175,7 @@ def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum
         residual = _chk(residual, name="residual")
     _call("rcv_bn_finalize_apply", 1, n, c, hw, _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean),
           _ptr(running_var), float(momentum), float(eps), _ptr(z), 1 if relu else 0, _ptr(residual), _ptr(y),
-          _ptr(buf[0]), _ptr(buf[1]), _ptr(buf[2]), _ptr(buf[3]), _stream())
+          _ptr(buf[0]), _ptr(buf[1]), _ptr(buf[2]), _ptr(buf[3]), _ptr(num_batches_tracked), _stream())
     return y, buf[0], buf[1], buf[2], buf[3]
 
 
@@ -257,9 +258,9 @@ def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False, math=MA
     dy = _chk(dy, name="dy")
     n, _, h, wd = x.shape
     if dw is None:
-        dw = torch.zeros(g.weight_shape(), device=x.device, dtype=torch.float32)
+        dw = zeros(g.weight_shape(), torch.float32, x.device)
     if dbias is None and want_bias:
-        dbias = torch.zeros(g.cout, device=x.device, dtype=torch.float32)
+        dbias = zeros(g.cout, torch.float32, x.device)
     d = g.desc(n, h, wd, EPI_NONE, math)
     if in_affine is not None:
         isc, ish, irelu = in_affine
@@ -274,14 +275,14 @@ def conv_wgrad(g: ConvGeom, x, dy, dw=None, dbias=None, want_bias=False, math=MA
 
 
 # --------------------------------------------------------------------------- batch norm
-def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps):
+def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps, num_batches_tracked=None):
     c = stats.numel() // 2
     dev = stats.device
     buf = torch.empty((4, c), device=dev, dtype=torch.float32)
     scale, shift, mean, invstd = buf[0], buf[1], buf[2], buf[3]
     _call("rcv_bn_finalize", 1, c, int(count), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean),
           _ptr(running_var), float(momentum), float(eps), _ptr(scale), _ptr(shift), _ptr(mean),
-          _ptr(invstd), _stream())
+          _ptr(invstd), _ptr(num_batches_tracked), _stream())
     return scale, shift, mean, invstd
 
 
@@ -305,11 +306,6 @@ def bn_apply(z, scale, shift, relu: bool, residual=None, out=None):
     return y
 
 
-# EXPERIMENTAL (default off): one cooperative launch for both BatchNorm-backward passes where the tensors fit in the
-# register files of one co-resident grid (csrc/rcv_bn_fused.cu)
-BN_BWD_FUSED = os.environ.get("RCV_B200_BN_BWD_FUSED", "0") != "0"
-
-
 def bn_bwd(order: int, dy, z, scale, shift, mean, invstd, dgamma=None, dbeta=None, dbias=None,
            want_dbias: bool = False, sums=None):
     """-> (dconv, dgamma, dbeta, dbias|None).  Two passes: reduce, apply.  dgamma/dbeta/dbias are
@@ -319,19 +315,15 @@ def bn_bwd(order: int, dy, z, scale, shift, mean, invstd, dgamma=None, dbeta=Non
     n, c = z.shape[0], z.shape[1]
     hw = z.numel() // (n * c)
     if sums is None:
-        sums = torch.zeros(2 * c, device=z.device, dtype=torch.float64)
+        sums = zeros(2 * c, torch.float64, z.device)
     if dgamma is None or dbeta is None or (want_dbias and dbias is None):
-        small = torch.zeros((3, c), device=z.device, dtype=torch.float32)
+        small = zeros((3, c), torch.float32, z.device)
         dgamma = small[0] if dgamma is None else dgamma
         dbeta = small[1] if dbeta is None else dbeta
         if want_dbias and dbias is None:
             dbias = small[2]
     dconv = torch.empty_like(z)
     st = _stream()
-    if BN_BWD_FUSED and _lib.load().rcv_bn_bwd_fused_supported(n, c, hw):
-        _call("rcv_bn_bwd_fused", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
-              _ptr(invstd), _ptr(sums), _ptr(dconv), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), st)
-        return dconv, dgamma, dbeta, dbias
     _call("rcv_bn_bwd_reduce", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
           _ptr(invstd), _ptr(sums), st)
     _call("rcv_bn_bwd_apply", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
@@ -352,7 +344,7 @@ def channel_sum(dy, out=None):
     n, c = dy.shape[0], dy.shape[1]
     hw = dy.numel() // (n * c)
     if out is None:
-        out = torch.zeros(c, device=dy.device, dtype=torch.float32)
+        out = zeros(c, torch.float32, dy.device)
     _call("rcv_channel_sum", 1, n, c, hw, _ptr(dy), _ptr(out), _stream())
     return out
 
@@ -378,8 +370,10 @@ def maxpool2x2_bwd(dy, code, in_hw):
 
 
 # --------------------------------------------------------------------------- loss / metrics
-def ce_fwd(logits, target, class_w=None, want_argmax=False, want_conf=False, want_correct=False):
-    """-> (loss_sums float64[2], argmax|None, conf int64[N,C,C]|None, correct int64[1]|None)."""
+def ce_fwd(logits, target, class_w=None, want_argmax=False, want_conf=False, want_correct=False, sums=None,
+           corr=None):
+    """-> (loss_sums float64[2], argmax|None, conf int64[N,C,C]|None, correct int64[1]|None).  sums / corr:
+    caller-zeroed accumulators to use instead of fresh ones."""
     logits = _chk(logits, name="logits")
     target = _chk(target, torch.int64, "target")
     n, c = logits.shape[0], logits.shape[1]
@@ -387,10 +381,12 @@ def ce_fwd(logits, target, class_w=None, want_argmax=False, want_conf=False, wan
     if target.numel() != n * hw:
         raise ValueError(f"ce_fwd: target {tuple(target.shape)} does not match logits {tuple(logits.shape)}")
     dev = logits.device
-    sums = torch.zeros(2, device=dev, dtype=torch.float64)
+    if sums is None:
+        sums = zeros(2, torch.float64, dev)
     am = torch.empty((n, *logits.shape[2:]), device=dev, dtype=torch.int64) if want_argmax else None
-    conf = torch.zeros((n, c, c), device=dev, dtype=torch.int64) if want_conf else None
-    corr = torch.zeros(1, device=dev, dtype=torch.int64) if want_correct else None
+    conf = zeros((n, c, c), torch.int64, dev) if want_conf else None
+    if corr is None and want_correct:
+        corr = zeros(1, torch.int64, dev)
     if class_w is not None:
         class_w = _chk(class_w, name="class_w")
         if class_w.numel() != c:
@@ -418,7 +414,7 @@ def confusion(pred, target, num_classes: int):
     target = _chk(target, torch.int64, "target")
     n = pred.shape[0]
     hw = pred.numel() // n
-    conf = torch.zeros((n, num_classes, num_classes), device=pred.device, dtype=torch.int64)
+    conf = zeros((n, num_classes, num_classes), torch.int64, pred.device)
     _call("rcv_confusion", 1, n, num_classes, hw, _ptr(pred), _ptr(target), _ptr(conf), _stream())
     return conf
 
@@ -443,7 +439,11 @@ def mask_label_lut(nb: bool, nr: bool, ng: bool, nl: bool, num_classes: int = 5)
 
 
 def mask_label_(label, nb, nr, ng, nl, num_classes: int = 5):
-    """In-place maskLabel on a CUDA int64 label tensor (one launch)."""
+    """In-place maskLabel on a CUDA int64 label tensor (one launch).  The tensor must be contiguous and 16-byte
+    aligned: a strided or offset view would be relabelled in a temporary copy, not in place, so it is refused."""
+    if label.is_cuda and (not label.is_contiguous() or label.data_ptr() % 16):
+        raise ValueError("mask_label_: in-place relabel needs a contiguous, 16-byte aligned label tensor "
+                         "(call .contiguous() first and use the returned tensor)")
     label = _chk(label, torch.int64, "label")
     lut = torch.tensor(mask_label_lut(nb, nr, ng, nl, num_classes), dtype=torch.int64, device=label.device)
     _call("rcv_label_lut", 1, label.numel(), _ptr(label), lut.numel(), _ptr(lut), _stream())
@@ -510,7 +510,7 @@ def dice_fwd(logits, target):
     target = _chk(target, torch.int64, "target")
     n, c = logits.shape[0], logits.shape[1]
     hw = logits.numel() // (n * c)
-    sums = torch.zeros(2 * c, device=logits.device, dtype=torch.float64)
+    sums = zeros(2 * c, torch.float64, logits.device)
     _call("rcv_dice_fwd", 1, n, c, hw, _ptr(logits), _ptr(target), _ptr(sums), _stream())
     return sums
 
@@ -534,9 +534,23 @@ def adam_l1_step(p, g, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-8, step=1, l1_de
           _ptr(l1_sum), _ptr(step_dev), _ptr(lr_dev), _stream())
 
 
-def sgd_step(p, g, buf, lr, momentum=0.0, weight_decay=0.0, grad_scale=1.0, mask=None, first_step=False):
+def sgd_step(p, g, buf, lr, momentum=0.0, weight_decay=0.0, grad_scale=1.0, mask=None, first_step=False,
+             l1_decay=0.0, l1_sum=None, lr_dev=None):
     _call("rcv_sgd_step", 1, p.numel(), _ptr(p), _ptr(g), _ptr(buf), _ptr(mask), float(lr), float(momentum),
-          float(weight_decay), float(grad_scale), 1 if first_step else 0, _stream())
+          float(weight_decay), float(grad_scale), 1 if first_step else 0, float(l1_decay), _ptr(l1_sum),
+          _ptr(lr_dev), _stream())
+
+
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    """Stream-ordered zero fill without a kernel (a memset node under graph capture)."""
+    if not t.is_cuda or not t.is_contiguous():
+        raise RuntimeError("robocupvision_b200: zero_ needs a contiguous CUDA tensor")
+    _lib.call("rcv_zero", _ptr(t), C.c_size_t(t.numel() * t.element_size()), _stream())
+    return t
+
+
+def zeros(shape, dtype, device) -> torch.Tensor:
+    return zero_(torch.empty(shape, dtype=dtype, device=device))
 
 
 def counter_add(counter, inc=1):

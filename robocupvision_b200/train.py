@@ -19,27 +19,51 @@ from typing import List, Optional, Sequence
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import dp, ops
 from .engine import Plan
+
+
+ARENA_ALIGN = 4  # floats: every parameter's slice starts on a 16-byte boundary (vector loads, TMA, no clones in ops._chk)
 
 
 def flatten_parameters(model: nn.Module):
     """Move every parameter into one flat fp32 arena (order = model.parameters()); returns
-    (arena, [(param, offset, numel)])."""
+    (arena, [(param, offset, numel)]).  Offsets are padded to multiples of ARENA_ALIGN floats; the padding stays
+    zero under every optimiser of this module (zero gradient, sign(0) = 0, zero moments)."""
     params = list(model.parameters())
     dev = params[0].device
-    total = sum(p.numel() for p in params)
-    # 16-byte aligned slices are not required by the kernels; keep the arena dense so that
-    # range all-reduces and the Adam pass see exactly `total` elements.
-    arena = torch.empty(total, device=dev, dtype=torch.float32)
-    table, o = [], 0
+    offs, o = [], 0
     for p in params:
+        offs.append(o)
+        o += -(-p.numel() // ARENA_ALIGN) * ARENA_ALIGN
+    arena = torch.zeros(o, device=dev, dtype=torch.float32)
+    table = []
+    for p, o in zip(params, offs):
         n = p.numel()
         arena[o:o + n].copy_(p.data.reshape(-1))
         p.data = arena[o:o + n].view(p.shape)
         table.append((p, o, n))
-        o += n
     return arena, table
+
+
+def sync_bn_buffers(model: nn.Module, src: int = 0, group=None, average: bool = False) -> None:
+    """Data-parallel training keeps BatchNorm running statistics rank-local (the reference has no SyncBN), so after
+    training steps on different shards every rank holds slightly different eval-mode models.  Call this before a
+    sharded validation pass and before writing a checkpoint: floating-point buffers are broadcast from rank `src`
+    (or averaged over the group), integer buffers (num_batches_tracked) are broadcast.  No-op without a group."""
+    dist = torch.distributed
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    ws = dist.get_world_size(group)
+    for b in model.buffers():
+        if average and b.is_floating_point():
+            dist.all_reduce(b, group=group)
+            b.div_(ws)
+        else:
+            dist.broadcast(b, src, group=group)
+    plan = model.__dict__.get("_rcv_plan")
+    if plan is not None:
+        plan.epoch += 1  # folded-BatchNorm constants are cached per plan epoch
 
 
 class TrainStep:
@@ -47,11 +71,21 @@ class TrainStep:
                  l1_decay: float = 1e-6, betas=(0.9, 0.999), eps: float = 1e-8,
                  masks: Optional[List[torch.Tensor]] = None, optimizer: str = "adam", momentum: float = 0.0,
                  weight_decay: float = 0.0, lr_mults: Optional[Sequence] = None,
-                 process_group=None, use_graph: bool = True, overlap_comm: bool = True):
+                 process_group=None, use_graph: bool = True, overlap_comm: bool = True, n_buckets: int = 3,
+                 force_comm_path: bool = False):
         """masks: pruneModelNew-style list of bool tensors for the >1-D parameters, in parameter
         order (train.py:59-65); with masks the L1 term is dropped (train.py:53).
-        lr_mults: [(module_or_param_list, multiplier)] for the reference's 10x group
-        (train.py:357-363)."""
+        optimizer: "adam" (train.py:357-363; torch defaults, no weight decay) or "sgd" (trainer.py:182-184:
+        momentum, weight_decay, dampening 0; pass l1_decay=0 for the reference's SGD loop, which has no L1 term).
+        lr_mults: [(module_or_param_list, multiplier)] for the reference's 10x group (train.py:357-363).
+        n_buckets: data-parallel gradient buckets (cut at plan-node boundaries, dp.plan_buckets); each is
+        all-reduced and its optimiser pass run on a side stream as soon as backward has passed its first node.
+        force_comm_path: run the bucketed side-stream schedule even with one rank (tests)."""
+        if optimizer not in ("adam", "sgd"):
+            raise ValueError(f"TrainStep: optimizer must be 'adam' or 'sgd', got {optimizer!r}")
+        if optimizer == "adam" and (weight_decay != 0.0 or momentum != 0.0):
+            raise ValueError("TrainStep: optimizer='adam' is torch.optim.Adam with its defaults (train.py:357-363): "
+                             "weight_decay and momentum must be 0 (they belong to optimizer='sgd')")
         self.model = model
         self.plan: Plan = model._get_plan()
         dev = next(model.parameters()).device
@@ -61,13 +95,13 @@ class TrainStep:
         self.arena, self.table = flatten_parameters(model)
         n = self.arena.numel()
         self.grads = torch.zeros(n, device=dev)
-        self.m = torch.zeros(n, device=dev)
-        self.v = torch.zeros(n, device=dev)
+        self.m = torch.zeros(n, device=dev)          # Adam exp_avg / SGD momentum buffer
+        self.v = torch.zeros(n, device=dev) if optimizer == "adam" else None
         self.grad_views = {id(p): self.grads[o:o + k].view(p.shape) for p, o, k in self.table}
         self.offsets = {id(p): (o, k) for p, o, k in self.table}
         self.optimizer = optimizer
         self.betas, self.eps = betas, eps
-        self.momentum, self.weight_decay = momentum, weight_decay
+        self.momentum, self.weight_decay = float(momentum), float(weight_decay)
         self.l1_decay = 0.0 if masks is not None else float(l1_decay)
         self.mask = None
         if masks is not None:
@@ -79,7 +113,7 @@ class TrainStep:
                     i += 1
         self.class_w = None if class_weights is None else torch.as_tensor(
             class_weights, dtype=torch.float32).to(dev)
-        # lr groups: contiguous arena ranges with a multiplier
+        # lr groups: contiguous arena ranges (padding included) with a multiplier
         mult = torch.ones(len(self.table))
         if lr_mults:
             for group, mu in lr_mults:
@@ -89,22 +123,33 @@ class TrainStep:
                     if id(p) in ids:
                         mult[i] = mu
         self.ranges = []  # (start, end, mult)
-        for (p, o, k), mu in zip(self.table, mult.tolist()):
-            if self.ranges and self.ranges[-1][2] == mu and self.ranges[-1][1] == o:
-                self.ranges[-1] = (self.ranges[-1][0], o + k, mu)
+        ends = [o for _, o, _ in self.table[1:]] + [n]
+        for (p, o, k), e, mu in zip(self.table, ends, mult.tolist()):
+            if self.ranges and self.ranges[-1][2] == mu:
+                self.ranges[-1] = (self.ranges[-1][0], e, mu)
             else:
-                self.ranges.append((o, o + k, mu))
-        self.lr_dev = torch.tensor([lr * r[2] for r in self.ranges], device=dev, dtype=torch.float32)
+                self.ranges.append((o, e, mu))
         self.base_lr = lr
+        self._lr_host = torch.tensor([lr * r[2] for r in self.ranges], dtype=torch.float32).pin_memory()
+        self.lr_dev = self._lr_host.to(dev)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        # every small accumulator of a step in ONE buffer (one memset per step):
+        # [l1 sum | CE loss sums (2) | correct pixels (int64 view) | BN batch statistics | BN backward sums]
+        ns = self.plan.n_stats
+        self._accum = torch.zeros(4 + 2 * ns, device=dev, dtype=torch.float64)
+        self._acc_l1, self._acc_ce = self._accum[0:1], self._accum[1:3]
+        self._acc_corr = self._accum[3:4].view(torch.int64)
+        self._acc_stats, self._acc_sums = self._accum[4:4 + ns], self._accum[4 + ns:4 + 2 * ns]
         # distributed
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
-        self.overlap = overlap_comm and self.world > 1
-        self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
-        self.split_node, self.split_off = self._pick_split()
+        self.comm_path = (overlap_comm and self.world > 1) or force_comm_path
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.comm_path else None
+        # (first plan node, arena start, arena end), in the order backward completes them (arena tail first)
+        self.buckets = dp.plan_buckets([[self.offsets[id(p)] for p in nd.params()] for nd in self.plan.nodes],
+                                       [(o, k) for _, o, k in self.table], n, n_buckets) if self.comm_path else []
         # outputs (device scalars)
         self.loss_sums = None
         self.l1_sum = None
@@ -119,70 +164,38 @@ class TrainStep:
 
     # ------------------------------------------------------------------ helpers
     def set_lr(self, lr: float):
-        """Scheduler hook (CosineAnnealingLR steps once per epoch, train.py:91-92)."""
+        """Every group to lr * its multiplier (ReduceLROnPlateau-style schedulers, trainer.py:193)."""
         self.base_lr = lr
-        self.lr_dev.copy_(torch.tensor([lr * r[2] for r in self.ranges], dtype=torch.float32))
+        self.set_group_lrs([lr * r[2] for r in self.ranges])
 
-    def _pick_split(self):
-        """Node index t such that the parameters of nodes >= t hold at least half of the arena:
-        their gradients are final once backward has passed node t, so that slice is all-reduced
-        while the remaining (encoder) backward runs."""
-        if not self.overlap:
-            return -1, 0
-        total = self.arena.numel()
-        acc, best = 0, (-1, 0)
-        for t in range(len(self.plan.nodes) - 1, -1, -1):
-            ps = self.plan.nodes[t].params()
-            if not ps:
-                continue
-            acc += sum(p.numel() for p in ps)
-            off = min(self.offsets[id(p)][0] for p in ps)
-            if acc >= total // 2:
-                # every parameter at or after `off` in the arena must belong to nodes >= t
-                later = {id(p) for nd in self.plan.nodes[t:] for p in nd.params()}
-                ok = all((id(p) in later) or not self._in_plan(p) for p, o, k in self.table if o >= off)
-                if ok:
-                    best = (t, off)
-                break
-        return best
+    def set_group_lrs(self, lrs: Sequence[float]):
+        """One learning rate per arena range of `self.ranges` (= the reference's param groups, train.py:357-363),
+        staged through pinned memory: the next replay of the step's graph reads them from the device."""
+        if len(lrs) != len(self.ranges):
+            raise ValueError(f"set_group_lrs: {len(self.ranges)} groups, got {len(lrs)} values")
+        self._lr_host.copy_(torch.as_tensor(list(lrs), dtype=torch.float32))
+        self.lr_dev.copy_(self._lr_host, non_blocking=True)
 
-    def _in_plan(self, p):
-        return any(p is q for q in self.plan.params)
+    def set_cosine_lr(self, epoch: int, t_max: int, eta_min: float = 0.0):
+        """CosineAnnealingLR as train.py:364-365 / lr_scheduler.py apply it, stepped once per epoch: each group
+        anneals from ITS OWN base rate (base_lr * multiplier) to the one shared eta_min:
+        eta_min + (base_i - eta_min) * (1 + cos(pi * epoch / t_max)) / 2."""
+        import math
+        f = (1.0 + math.cos(math.pi * epoch / t_max)) / 2.0
+        self.set_group_lrs([eta_min + (self.base_lr * r[2] - eta_min) * f for r in self.ranges])
 
     def _allreduce(self, t: torch.Tensor):
-        torch.distributed.all_reduce(t, group=self.pg)
+        if self.world > 1 or self.pg is not None:
+            torch.distributed.all_reduce(t, group=self.pg)
 
-    # ------------------------------------------------------------------ the step
-    def _step_impl(self, x, y):
-        k0 = ops.launch_count()
-        self.grads.zero_()
-        outs, saved = self.plan.forward(x, training=True, save=True)
-        logits = outs[0]
-        sums, _, _, corr = ops.ce_fwd(logits, y, self.class_w, want_correct=True)
-        dl = ops.ce_bwd(logits, y, self.class_w, sums)
-        if self.world > 1 and self.overlap and self.split_node >= 0:
-            cur = torch.cuda.current_stream()
-
-            def hook(t):
-                if t == self.split_node:
-                    self.comm_stream.wait_stream(cur)
-                    if self.plan._wgrad_stream is not None:  # weight gradients are produced on the side stream
-                        self.comm_stream.wait_stream(self.plan._wgrad_stream)
-                    with torch.cuda.stream(self.comm_stream):
-                        self._allreduce(self.grads[self.split_off:])
-            self._backward(saved, dl, hook)
-            if self.split_off > 0:
-                self._allreduce(self.grads[:self.split_off])
-            cur.wait_stream(self.comm_stream)
-        else:
-            self._backward(saved, dl, None)
-            if self.world > 1:
-                self._allreduce(self.grads)
-        ops.counter_add(self.step_dev, 1)
-        l1 = torch.zeros(1, device=self.dev, dtype=torch.float64)
+    def _optim_range(self, a: int, b: int, l1):
+        """Optimiser pass over arena[a:b), split at the lr-group boundaries."""
         gscale = 1.0 / self.world
-        for i, (a, b, _) in enumerate(self.ranges):
-            sl = slice(a, b)
+        for i, (ra, rb, _) in enumerate(self.ranges):
+            lo, hi = max(a, ra), min(b, rb)
+            if lo >= hi:
+                continue
+            sl = slice(lo, hi)
             mk = None if self.mask is None else self.mask[sl]
             if self.optimizer == "adam":
                 ops.adam_l1_step(self.arena[sl], self.grads[sl], self.m[sl], self.v[sl], lr=self.base_lr,
@@ -190,15 +203,50 @@ class TrainStep:
                                  l1_decay=self.l1_decay, grad_scale=gscale, mask=mk, l1_sum=l1,
                                  step_dev=self.step_dev, lr_dev=self.lr_dev[i:i + 1])
             else:
-                raise NotImplementedError("graph-replayed SGD: use optimizer='adam' or torch.optim.SGD")
+                # zero-initialised momentum buffer: mom*0 + g == torch's first-step `buf = g`, so no first-step flag
+                ops.sgd_step(self.arena[sl], self.grads[sl], self.m[sl], lr=self.base_lr, momentum=self.momentum,
+                             weight_decay=self.weight_decay, grad_scale=gscale, mask=mk, l1_decay=self.l1_decay,
+                             l1_sum=l1, lr_dev=self.lr_dev[i:i + 1])
+
+    # ------------------------------------------------------------------ the step
+    def _step_impl(self, x, y):
+        k0 = ops.launch_count()
+        # two memsets (no kernels) for everything the step accumulates into: optimizer.zero_grad() (train.py:45)
+        # and the scalar / per-channel sums
+        ops.zero_(self.grads)
+        ops.zero_(self._accum)
+        l1 = self._acc_l1
+        ops.counter_add(self.step_dev, 1)
+        outs, saved = self.plan.forward(x, training=True, save=True, stats_arena=self._acc_stats)
+        logits = outs[0]
+        sums, _, _, corr = ops.ce_fwd(logits, y, self.class_w, want_correct=True, sums=self._acc_ce,
+                                      corr=self._acc_corr)
+        dl = ops.ce_bwd(logits, y, self.class_w, sums)
+        if self.comm_path:
+            cur = torch.cuda.current_stream()
+            pending = list(self.buckets)
+
+            def flush(upto):
+                """All-reduce + optimiser pass, on the comm stream, of every bucket whose gradients are final once
+                backward has passed node `upto` (their weights are read by no later backward kernel)."""
+                while pending and pending[0][0] >= upto:
+                    _, a, b = pending.pop(0)
+                    self.comm_stream.wait_stream(cur)
+                    if self.plan._wgrad_stream is not None:  # weight gradients are produced on the side stream
+                        self.comm_stream.wait_stream(self.plan._wgrad_stream)
+                    with torch.cuda.stream(self.comm_stream):
+                        self._allreduce(self.grads[a:b])
+                        self._optim_range(a, b, l1)
+            self.plan.backward(saved, [dl], False, self.grad_views, node_done=flush, sums_arena=self._acc_sums)
+            flush(-1)
+            cur.wait_stream(self.comm_stream)
+        else:
+            self.plan.backward(saved, [dl], False, self.grad_views, sums_arena=self._acc_sums)
+            if self.world > 1:
+                self._allreduce(self.grads)
+            self._optim_range(0, self.arena.numel(), l1)
         self.kernels_per_step = ops.launch_count() - k0
         return sums, l1, corr
-
-    def _backward(self, saved, dl, hook):
-        if hook is None:
-            self.plan.backward(saved, [dl], False, self.grad_views)
-        else:
-            self.plan.backward(saved, [dl], False, self.grad_views, node_done=hook)
 
     def step(self, x: torch.Tensor, y: torch.Tensor):
         """One training step on x [B,Cin,H,W] fp32, y [B,H,W] int64 (device tensors, or pinned
@@ -259,7 +307,7 @@ class TrainStep:
         return StepResult(pipe, k, self.l1_decay)
 
     def _state(self):
-        return [self.arena, self.m, self.v, self.step_dev] + list(self.model.buffers())
+        return [t for t in (self.arena, self.m, self.v, self.step_dev) if t is not None] + list(self.model.buffers())
 
     def _capture(self, x, y):
         """First call for a shape: one eager warm-up step on a side stream (lazy CUDA module
@@ -392,8 +440,12 @@ class EvalStep:
 
     @torch.no_grad()
     def _eager(self, x, y):
+        was_training = self.model.training
         self.model.eval()
-        logits = self.model(x)
+        try:
+            logits = self.model(x)
+        finally:
+            self.model.train(was_training)
         sums, am, conf, corr = ops.ce_fwd(logits, y, self.class_w, want_argmax=True, want_conf=True,
                                           want_correct=True)
         return {"logits": logits, "loss": sums[0] / sums[1], "argmax": am, "conf": conf, "correct": corr,

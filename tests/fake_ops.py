@@ -95,8 +95,18 @@ def conv_wgrad(g, x, dy, dw=None, dbias=None, want_bias=False, math=real.MATH_FP
     return dw, dbias
 
 
-def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps):
+def zeros(shape, dtype, device):
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
+def zero_(t):
+    return t.zero_()
+
+
+def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps, num_batches_tracked=None):
     calls.append(("bn_finalize", None))
+    if num_batches_tracked is not None:
+        num_batches_tracked += 1
     c = stats.numel() // 2
     mean = stats[:c] / count
     var = (stats[c:] / count - mean * mean).clamp_min(0)
@@ -117,10 +127,12 @@ def bn_apply(z, scale, shift, relu, residual=None, out=None):
     return y if residual is None else y + residual
 
 
-def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum, eps, relu, residual=None):
+def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum, eps, relu, residual=None,
+                      num_batches_tracked=None):
     calls.append(("bn_finalize_apply", None))
     count = z.numel() // z.shape[1]
-    scale, shift, mean, invstd = bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps)
+    scale, shift, mean, invstd = bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps,
+                                             num_batches_tracked)
     calls.pop()
     y = bn_apply(z, scale, shift, relu, residual)
     calls.pop()

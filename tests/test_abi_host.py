@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in rcv_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.rcv_version() == 2
+    assert lib.rcv_version() == 3
 
 
 def test_validation_without_gpu():
@@ -126,8 +126,9 @@ def _dp_worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import synth
     from oracle import ref_model as R
+    from robocupvision_b200 import dp
     from robocupvision_b200.model import ROBO_UNet
-    from robocupvision_b200.dp import bucket_ranges, allreduce_buckets
+    from robocupvision_b200.train import flatten_parameters, sync_bn_buffers
     torch.manual_seed(12345678)
     m = ROBO_UNet()
     sd = R.leaf_state_dict({k: v.clone() for k, v in m.state_dict().items()})
@@ -137,25 +138,72 @@ def _dp_worker(rank, world, port, out):
     y = synth.labels_learnable(synth.images(B * world, 3, 24, 32, seed=5))[rank * B:(rank + 1) * B]
     loss = R.cross_entropy_2d(R.robo_unet_forward(sd, x, training=True), y, torch.tensor(synth.CLASS_WEIGHTS))
     loss.backward()
-    keys = R.param_keys(sd)
-    sizes = [sd[k].numel() for k in keys]
-    flat = torch.cat([sd[k].grad.reshape(-1) for k in keys])
+    # the PRODUCT's arena layout and bucket plan (the exact host logic TrainStep runs), fed the oracle's gradients
+    arena, table = flatten_parameters(m)
+    plan = m._get_plan()
+    offsets = {id(p): (o, k) for p, o, k in table}
+    buckets = dp.plan_buckets([[offsets[id(p)] for p in nd.params()] for nd in plan.nodes],
+                              [(o, k) for _, o, k in table], arena.numel(), 3)
+    flat = torch.zeros_like(arena)
+    for (name, p), (_, o, k) in zip(m.named_parameters(), table):
+        flat[o:o + k] = sd[name].grad.reshape(-1)
     local = flat.clone()
-    ranges = bucket_ranges(sizes, n_buckets=2)
-    allreduce_buckets(flat, ranges)
+    dp.allreduce_buckets(flat, buckets)
     flat /= world
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     expect = sum(gathered) / world
-    ok = torch.allclose(flat, expect, rtol=0, atol=1e-7) and ranges[0][0] == 0 and ranges[-1][1] == flat.numel()
+    ok = torch.allclose(flat, expect, rtol=0, atol=1e-7)
+    # BatchNorm buffers: rank-local after training on different shards; sync_bn_buffers makes the eval models equal
+    osd = {k: v.detach().clone() for k, v in sd.items()}  # running stats were updated by this rank's shard
+    m.load_state_dict(osd)
+    before = [torch.zeros(8) for _ in range(world)]
+    dist.all_gather(before, m.state_dict()["downPart.Level0.layers.Conv0.bn.running_mean"].clone())
+    differ = not torch.equal(before[0], before[1])
+    sync_bn_buffers(m)
+    xe = synth.images(1, 3, 24, 32, seed=9)
+    with torch.no_grad():
+        logits = R.robo_unet_forward({k: v.clone() for k, v in m.state_dict().items()}, xe, training=False)
+    lg = [torch.zeros_like(logits) for _ in range(world)]
+    dist.all_gather(lg, logits.contiguous())
+    same = all(torch.equal(lg[0], t) for t in lg[1:])
     if rank == 0:
-        out.put(bool(ok))
+        out.put(bool(ok and differ and same))
     dist.destroy_process_group()
 
 
+def test_plan_buckets_partition_and_order():
+    """dp.plan_buckets on every model family's real plan: the buckets partition the arena, come in completion order,
+    and every parameter of a node >= first_node lies inside [start, total) (so the bucket's gradients are final once
+    backward has passed first_node)."""
+    from robocupvision_b200 import dp
+    from robocupvision_b200.model import FCN, PB_FCN, LabelProp, ROBO_UNet
+    from robocupvision_b200.train import ARENA_ALIGN
+    nets = [ROBO_UNet(), ROBO_UNet(noScale=True), ROBO_UNet(pool=True, levels=3, bellySize=0), ROBO_UNet(v2=True),
+            PB_FCN(32, 5, 1, False, 0), PB_FCN(32, 5, 1, True, 0), LabelProp(5, 32, 0), FCN()]
+    for m in nets:
+        plan = m._get_plan()
+        offs, table, o = {}, [], 0
+        for p in m.parameters():
+            offs[id(p)] = (o, p.numel()); table.append((o, p.numel()))
+            o += -(-p.numel() // ARENA_ALIGN) * ARENA_ALIGN
+        node_params = [[offs[id(p)] for p in nd.params()] for nd in plan.nodes]
+        for nb in (1, 2, 3, 5):
+            b = dp.plan_buckets(node_params, table, o, nb)
+            assert 1 <= len(b) <= nb and b[0][2] == o and b[-1][0] == 0 and b[-1][1] == 0
+            for (t0, s0, e0), (t1, s1, e1) in zip(b[:-1], b[1:]):
+                assert s0 == e1 and t0 > t1 and s0 < e0
+            for t, start, end in b:
+                for tt in range(t, len(plan.nodes)):
+                    assert all(off >= start for off, _ in node_params[tt]), (type(m).__name__, nb, t, tt)
+        if len(plan.nodes) > 8:
+            assert len(dp.plan_buckets(node_params, table, o, 3)) == 3
+
+
 def test_data_parallel_gradient_averaging_gloo():
-    """world_size-2 gloo: bucketed all-reduce of the flat gradient arena == mean of the per-rank
-    gradients (the N>1 exchange of TrainStep, on CPU)."""
+    """world_size-2 gloo: the product's arena layout + bucket plan (train.flatten_parameters, dp.plan_buckets:
+    exactly what TrainStep runs), all-reduced bucket by bucket == mean of the per-rank oracle gradients; and
+    train.sync_bn_buffers makes the rank-local BatchNorm buffers (hence the eval logits) identical."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -1,5 +1,5 @@
-"""GPU parity tests whose first run is still pending (they sort after every other GPU test file on purpose: a fault in
-an unproven path cannot disturb the verified suite).  Same gates as tests/test_gpu_models.py."""
+"""GPU parity of the remaining model families (`--v2` cat skips + 3x3 head, FCN, the channel-pruned PB_FCN checkpoint)
+and of the conv geometries only they use.  Same gates as tests/test_gpu_models.py."""
 import pytest
 import torch
 
@@ -12,10 +12,8 @@ from util import assert_close
 
 pytestmark = pytest.mark.gpu
 
-# The two model families below are SURVEY.md section 8(f) N4 rows ("FCN / --v2 variants: cat-skip, 3x3 head").  The
-# tests were written after this round's GPU budget was spent: their first run is the driver's, hence non-strict
-# xfail (a pass shows as XPASS, a failure does not hide the verified suite).  Drop the marker once seen green.
-_first_run = pytest.mark.xfail(strict=False, reason="first GPU run pending (added after the round's GPU budget)")
+# SURVEY.md section 8(f) N4 rows ("FCN / --v2 variants: cat-skip, 3x3 head") and BASELINE configs[2]
+# "irregular channel counts"; first seen green on a B200 in round 2 (gpurun_out/ab_queue.log).
 
 
 def _seeded_state(model, oracle_fwd_train, cin=3):
@@ -27,7 +25,6 @@ def _seeded_state(model, oracle_fwd_train, cin=3):
     return sd
 
 
-@_first_run
 def test_robo_unet_v2_cat_skips_eval_and_backward():
     """`--v2` (model.py:462-511 with v2=True): decoder concatenates the skip tensors, 3x3 head on 16 channels."""
     from robocupvision_b200.model import ROBO_UNet
@@ -46,7 +43,6 @@ def test_robo_unet_v2_cat_skips_eval_and_backward():
                 synth.labels_learnable(xb), synth.CLASS_WEIGHTS)
 
 
-@_first_run
 def test_fcn_eval_and_backward():
     """`FCN` (model.py:311-331): DownSamplerThick encoder (ConvPoolDouble blocks), three up blocks, 1x1 head."""
     from robocupvision_b200.model import FCN
@@ -63,7 +59,6 @@ def test_fcn_eval_and_backward():
                 synth.CLASS_WEIGHTS)
 
 
-@_first_run
 def test_pb_fcn_channel_pruned_checkpoint():
     """BASELINE configs[2] "irregular channel counts": pth/bestModelSegFinetunedPruned_bu.pth (encoder
     16-16-16-32-64-64-128-64-32, decoder 16-16-16; 70.8 % zero weights) through PB_FCN_Channels, against the golden
@@ -76,7 +71,6 @@ def test_pb_fcn_channel_pruned_checkpoint():
     _check_eval(name, m, lambda x: R.pb_fcn_forward(osd, x, False), load_golden(name + "_eval"))
 
 
-@_first_run
 def test_fcn_released_checkpoint():
     """pth/bestModelSeg1.pth through the drop-in FCN on the GPU, against the reference's golden outputs."""
     from robocupvision_b200.model import FCN, load_legacy_state_dict
@@ -90,7 +84,6 @@ def test_fcn_released_checkpoint():
 
 # Per-kernel parity for the channel combinations the three families above add to the verified matrix (same checks as
 # tests/test_gpu_ops.py::test_conv_fwd / test_conv_dgrad_wgrad, automatic engine choice).
-@_first_run
 @pytest.mark.parametrize("geom,cin,cout", [("k3s1d2", 3, 16), ("k3s1d2", 16, 32), ("k3s2", 16, 16), ("k3s2", 32, 32),
                                            ("convT", 64, 16), ("convT", 32, 8), ("convT", 32, 16), ("k3s1d1", 16, 5),
                                            ("k3s1d2", 64, 32), ("k3s1d2", 32, 64)])
@@ -114,44 +107,3 @@ def test_conv_kernels_for_the_new_families(geom, cin, cout):
     dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True, math=ops.MATH_AUTO)
     assert_close(f"wgrad {geom} {cin}->{cout}", dw, w.grad, 1e-5)
     assert_close(f"bgrad {geom}", db, b.grad, 1e-5)
-
-
-# Cooperative single-launch BatchNorm backward (csrc/rcv_bn_fused.cu): never run on a GPU yet, and a grid-wide barrier
-# is the kind of code whose first run belongs in an interactive session, not in an unattended suite -- opt in with
-# RCV_TEST_EXPERIMENTAL=1 (tools/ab_queue.sh does).
-import os  # noqa: E402
-
-_experimental = pytest.mark.skipif(os.environ.get("RCV_TEST_EXPERIMENTAL", "0") == "0",
-                                   reason="experimental kernel: set RCV_TEST_EXPERIMENTAL=1")
-
-
-@_experimental
-@pytest.mark.parametrize("order", ["relu_affine", "affine_relu"])
-@pytest.mark.parametrize("shape", [(64, 128, 15, 20), (64, 64, 15, 20), (64, 32, 30, 40), (4, 8, 12, 20), (3, 128, 5, 4)])
-def test_bn_bwd_fused_matches_two_pass(order, shape):
-    from robocupvision_b200 import _lib, ops
-    n, c, h, w = shape
-    if not _lib.load().rcv_bn_bwd_fused_supported(n, c, h * w):
-        pytest.skip("tensor does not fit one co-resident grid")
-    gen = torch.Generator().manual_seed(3)
-    z = torch.randn(shape, generator=gen).cuda()
-    if order == "relu_affine":
-        z = torch.relu(z)
-    dy = torch.randn(shape, generator=gen).cuda()
-    gamma, beta = torch.randn(c, generator=gen).cuda(), torch.randn(c, generator=gen).cuda()
-    stats = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
-    d = z.double()
-    stats[:c], stats[c:] = d.sum((0, 2, 3)), (d * d).sum((0, 2, 3))
-    scale, shift, mean, invstd = ops.bn_finalize(stats, n * h * w, gamma, beta, None, None, 0.1, 1e-5)
-    code = ops.EPI_RELU_AFFINE if order == "relu_affine" else ops.EPI_AFFINE_RELU
-    old = ops.BN_BWD_FUSED
-    try:
-        ops.BN_BWD_FUSED = False
-        ref = ops.bn_bwd(code, dy, z, scale, shift, mean, invstd, want_dbias=True)
-        ops.BN_BWD_FUSED = True
-        got = ops.bn_bwd(code, dy, z, scale, shift, mean, invstd, want_dbias=True)
-    finally:
-        ops.BN_BWD_FUSED = old
-    torch.cuda.synchronize()
-    for name, a, b in zip(("dconv", "dgamma", "dbeta", "dbias"), got, ref):
-        assert_close(f"bn_bwd_fused {name} {order} {shape}", a, b.cpu(), 2e-6, atol=1e-6)

@@ -1,0 +1,257 @@
+"""Training-path parity on the B200 beyond single steps: the 200-step loss curve against the REFERENCE's own curve
+(tests/golden/robo_curve200.npz, oracle/make_golden.py curve), SGD (trainer.py:182-184) through the fused step, the
+640x480 PB_FCN training step, the 5-level --noScale net's backward, learning-rate groups, and the data-parallel
+schedule (bucketed all-reduce + optimiser on the comm stream) against serial gradient accumulation."""
+import math
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from nets import pb_fcn_state, robo_state
+from oracle import ref_model as R
+from oracle.ref_train import OracleTrainer
+from util import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_loss_curve_200_steps(tag):
+    """north_star / SURVEY 8c: 200 synthetic training steps (ROBO_UNet, seed 12345678, Adam 1e-3, L1 1e-6, learnable
+    labels, a fresh batch every step) through the graph-captured TrainStep against the curve the reference's own
+    model.py + torch.optim.Adam produced.  Gates: step 1 <= 1e-5 relative, every step <= 2e-2, final loss (mean of the
+    last 10 steps) within 2 %.  (The reference drifts from itself by up to 3.9e-3 between accumulation orders.)"""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import TrainStep
+    gold = load_golden("robo_curve200")
+    ref = gold[f"losses_{tag}"]
+    b, c, h, w = (int(v) for v in gold[f"shape_{tag}"])
+    torch.manual_seed(12345678)
+    m = ROBO_UNet().cuda()
+    ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, use_graph=True)
+    got, prev = [], None
+    for s in range(200):
+        x = synth.images(b, c, h, w, seed=5000 + s)
+        y = synth.labels_learnable(x)
+        hnd = ts.step_async(x.pin_memory(), y.pin_memory())
+        if prev is not None:
+            got.append(prev.wait()[1])
+        prev = hnd
+    got.append(prev.wait()[1])
+    got = np.array(got)
+    rel = np.abs(got - ref) / np.abs(ref)
+    print(f"curve[{tag}]: step-1 rel {rel[0]:.2e}, max rel {rel.max():.2e} at step {int(rel.argmax())}, "
+          f"final {got[-10:].mean():.5f} vs reference {ref[-10:].mean():.5f}")
+    assert rel[0] <= 1e-5, f"step 1: {got[0]} vs {ref[0]}"
+    assert rel.max() <= 2e-2, f"step {int(rel.argmax())}: {got[rel.argmax()]} vs {ref[rel.argmax()]}"
+    assert abs(got[-10:].mean() - ref[-10:].mean()) <= 2e-2 * ref[-10:].mean()
+    assert got[-1] < 0.5 * got[0], "the net must actually learn the rule"
+    assert int(m.state_dict()["PB.PB_1.layers.Conv1.bn.num_batches_tracked"]) == 200
+
+
+def test_train_step_sgd_matches_oracle():
+    """TrainStep(optimizer='sgd') = trainer.py:182-184 (torch.optim.SGD lr 1e-1, momentum 0.5, weight decay 1e-3, no
+    L1 term), graph-captured: losses and weights over 4 steps against the oracle trainer driving torch.optim.SGD.
+    SGD is linear in the gradient, so the weights can be compared tightly."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import TrainStep
+    torch.manual_seed(12345678)
+    m = ROBO_UNet()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    oracle = OracleTrainer(sd0, lambda s, xx, training: R.robo_unet_forward(s, xx, training=training),
+                           synth.CLASS_WEIGHTS, lr=1e-2, l1_decay=0.0, optimizer="sgd", momentum=0.5, weight_decay=1e-3)
+    m.cuda()
+    ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-2, l1_decay=0.0, optimizer="sgd", momentum=0.5, weight_decay=1e-3,
+                   use_graph=True)
+    for s in range(4):
+        x = synth.images(8, 3, 48, 64, seed=100 + s)
+        y = synth.labels_learnable(x)
+        ts.step(x.cuda(), y.cuda())
+        o_loss = oracle.step(x, y)[0]
+        assert abs(ts.loss_value() - o_loss) <= (1e-5 if s == 0 else 1e-3) * abs(o_loss), (s, ts.loss_value(), o_loss)
+    for k, p in m.named_parameters():
+        ref = oracle.sd[k].detach()
+        err = float((p.detach().cpu() - ref).norm()) / max(float(ref.norm()), 1e-6)
+        assert err <= 2e-4, f"{k}: relative L2 {err:.2e} after 4 SGD steps"
+
+
+def test_train_step_rejects_unsupported_options():
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import TrainStep
+    m = ROBO_UNet().cuda()
+    p0 = next(m.parameters()).data_ptr()
+    with pytest.raises(ValueError):
+        TrainStep(m, optimizer="rmsprop")
+    with pytest.raises(ValueError):
+        TrainStep(m, optimizer="adam", weight_decay=1e-3)
+    with pytest.raises(ValueError):
+        TrainStep(m, optimizer="adam", momentum=0.5)
+    assert next(m.parameters()).data_ptr() == p0, "a rejected constructor must not have re-homed the parameters"
+
+
+def test_lr_groups_and_cosine_schedule():
+    """train.py:357-365: the 10x `downPart[0:transfer]` group anneals from ITS base rate to the one shared eta_min."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import ARENA_ALIGN, TrainStep
+    m = ROBO_UNet().cuda()
+    ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, lr_mults=[(m.downPart[0:2], 10.0)], use_graph=False)
+    assert len(ts.ranges) == 2 and ts.ranges[0][2] == 10.0 and ts.ranges[0][0] == 0
+    assert all(o % ARENA_ALIGN == 0 for _, o, _ in ts.table)
+    assert all(p.data_ptr() % 16 == 0 for p in m.parameters())
+    ref_params = [torch.nn.Parameter(torch.zeros(1)) for _ in range(2)]
+    opt = torch.optim.SGD([{"params": [ref_params[0]], "lr": 1e-2}, {"params": [ref_params[1]]}], lr=1e-3)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=50, eta_min=1e-5)
+    for epoch in range(1, 6):
+        opt.step()
+        sched.step()
+        ts.set_cosine_lr(epoch, 50, eta_min=1e-5)
+        torch.cuda.synchronize()
+        want = [g["lr"] for g in opt.param_groups]
+        assert np.allclose(ts.lr_dev.cpu().numpy(), want, rtol=1e-6), (epoch, ts.lr_dev.cpu(), want)
+    ts.set_lr(5e-4)
+    torch.cuda.synchronize()
+    assert np.allclose(ts.lr_dev.cpu().numpy(), [5e-3, 5e-4], rtol=1e-6)
+
+
+def _rel_l2_grad_check(tag, model, oracle_fwd, sd, x, y, weights, tol):
+    """Full-size gradient gate: relative L2 per tensor, train-mode logits and loss exact to the
+    usual tolerances.  Element-wise gates at full size trip over ReLU-after-BatchNorm flips within an ulp of zero."""
+    from robocupvision_b200.model import CrossEntropyLoss2d
+    osd = R.leaf_state_dict(sd)
+    pred_ref = oracle_fwd(osd, x)
+    loss_ref = R.cross_entropy_2d(pred_ref, y, torch.tensor(weights))
+    loss_ref.backward()
+    model.cuda().train()
+    pred = model(x.cuda())
+    loss = CrossEntropyLoss2d(torch.tensor(weights)).cuda()(pred, y.cuda())
+    loss.backward()
+    assert_close(f"{tag} train logits", pred, pred_ref, 1e-4)
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    gmax = max(float(v.grad.norm()) for v in osd.values() if v.grad is not None)
+    worst = 0.0
+    for k, p in model.named_parameters():
+        gref = osd[k].grad
+        if gref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        err = float((p.grad.cpu() - gref).norm()) / max(float(gref.norm()), 1e-3 * gmax)
+        worst = max(worst, err)
+        assert err <= tol, f"{tag}: grad {k} relative L2 {err:.3e}"
+    print(f"{tag}: worst gradient relative L2 {worst:.2e}")
+
+
+def test_robo_noscale_backward():
+    """ROBO_UNet(noScale=True): the 5-level net (Level4 64->128 s2, 128->128 belly, Up0 128->64) against CPU autograd
+    over the oracle -- element-wise at 4x3x48x64, relative L2 at its real 2x3x240x320."""
+    from robocupvision_b200.model import ROBO_UNet
+    from test_gpu_models import _grad_check
+    sd, kw, okw = robo_state("robo_noscale")
+    fwd = lambda s, xx: R.robo_unet_forward(s, xx, training=True, **okw)  # noqa: E731
+    m = ROBO_UNet(**kw)
+    m.load_state_dict(sd)
+    x = synth.images(4, 3, 48, 64, seed=5)
+    _grad_check("robo_noscale", m, fwd, sd, x, synth.labels_learnable(x), synth.CLASS_WEIGHTS)
+    m2 = ROBO_UNet(**kw)
+    m2.load_state_dict(sd)
+    x = synth.images(2, 3, 240, 320, seed=6)
+    _rel_l2_grad_check("robo_noscale 240x320", m2, fwd, sd, x, synth.labels_learnable(x), synth.CLASS_WEIGHTS, 2e-4)
+
+
+def test_pb_fcn_vga_training_step():
+    """BASELINE configs[3] training: PB_FCN(32,5,1,noScale=True) from pth/bestModelSegVGA.pth at 2x3x480x640 --
+    forward/backward against CPU autograd over the oracle (relative L2 per tensor), then two fused SGD steps
+    (trainer.py:113,182-184: batch 8, lr 1e-1, momentum 0.5, weight decay 1e-3; batch 2 here so the CPU side
+    finishes in seconds) against the oracle trainer."""
+    from robocupvision_b200.model import PB_FCN, load_legacy_state_dict
+    from robocupvision_b200.train import TrainStep
+    osd, raw = pb_fcn_state("bestModelSegVGA")
+    fwd = lambda s, xx: R.pb_fcn_forward(s, xx, True, training=True)  # noqa: E731
+    m = PB_FCN(32, 5, 1, True, 0)
+    load_legacy_state_dict(m, raw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = synth.images(2, 3, 480, 640, seed=11)
+    y = synth.labels_random(2, 480, 640, seed=12)
+    _rel_l2_grad_check("pb_fcn_vga", m, fwd, sd, x, y, synth.CLASS_WEIGHTS, 5e-4)
+
+    m = PB_FCN(32, 5, 1, True, 0)
+    load_legacy_state_dict(m, raw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    oracle = OracleTrainer(sd, lambda s, xx, training: R.pb_fcn_forward(s, xx, True, training=training),
+                           synth.CLASS_WEIGHTS, lr=1e-2, l1_decay=0.0, optimizer="sgd", momentum=0.5, weight_decay=1e-3)
+    m.cuda()
+    ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-2, l1_decay=0.0, optimizer="sgd", momentum=0.5, weight_decay=1e-3,
+                   use_graph=True)
+    for s in range(2):
+        x = synth.images(2, 3, 480, 640, seed=20 + s)
+        y = synth.labels_random(2, 480, 640, seed=30 + s)
+        ts.step(x.cuda(), y.cuda())
+        o_loss = oracle.step(x, y)[0]
+        assert abs(ts.loss_value() - o_loss) <= (1e-5 if s == 0 else 2e-3) * abs(o_loss), (s, ts.loss_value(), o_loss)
+    for k, p in m.named_parameters():
+        if k.startswith("classifier."):
+            continue
+        ref = oracle.sd[k].detach()
+        err = float((p.detach().cpu() - ref).norm()) / max(float(ref.norm()), 1e-6)
+        assert err <= 5e-4, f"{k}: relative L2 {err:.2e} after 2 SGD steps"
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_comm_path_schedule_matches_plain_step(use_graph):
+    """The data-parallel schedule (gradient buckets flushed to the comm stream while backward runs: all-reduce +
+    optimiser pass per bucket) on ONE rank must perform exactly the plain step: same losses, same weights.  Catches
+    stream-ordering bugs between the weight-gradient side stream, the comm stream and the main stream."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import TrainStep
+    models, steps = [], []
+    for comm in (False, True):
+        torch.manual_seed(12345678)
+        m = ROBO_UNet().cuda()
+        models.append(m)
+        steps.append(TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, eps=1e-3, use_graph=use_graph,
+                               force_comm_path=comm))
+    assert len(steps[1].buckets) == 3 and not steps[0].buckets
+    for s in range(5):
+        x = synth.images(8, 3, 120, 160, seed=200 + s).cuda()
+        y = synth.labels_learnable(x.cpu()).cuda()
+        losses = []
+        for ts in steps:
+            ts.step(x, y)
+            losses.append(ts.loss_value())
+        assert abs(losses[0] - losses[1]) <= 2e-6 * abs(losses[0]), (s, losses)
+    for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
+        if a.is_floating_point():
+            assert_close(k, a, b, 1e-4)
+        else:
+            assert torch.equal(a, b), k
+
+
+def test_dp_self_check_single_rank_nccl():
+    """dp.self_check in a fresh process with a one-rank NCCL group: the captured step contains real ncclAllReduce
+    kernels on the comm stream; its result must equal serial gradient accumulation.  (N > 1 runs of the same check
+    are part of bench.py --gpus N: `dp_check` in the JSON line.)"""
+    code = (
+        "import os, sys, json, torch\n"
+        f"sys.path.insert(0, {str(ROOT)!r}); sys.path.insert(0, {str(ROOT / 'tests')!r})\n"
+        "import torch.distributed as dist\n"
+        "os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29671')\n"
+        "torch.cuda.set_device(0)\n"
+        "dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', 0))\n"
+        "from robocupvision_b200 import dp\n"
+        "from robocupvision_b200.model import ROBO_UNet\n"
+        "import synth\n"
+        "r = dp.self_check(ROBO_UNet, synth.CLASS_WEIGHTS, 4, 3, 48, 64, steps=3)\n"
+        "print('DPCHECK ' + json.dumps(r)); sys.stdout.flush(); torch.cuda.synchronize(); os._exit(0)\n")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    line = [l for l in res.stdout.splitlines() if l.startswith("DPCHECK ")]
+    assert line, res.stdout[-2000:] + res.stderr[-2000:]
+    import json
+    r = json.loads(line[0][8:])
+    print(r)
+    assert r["ok"], r

@@ -96,6 +96,25 @@ def test_oracle_trainer_vs_golden_steps():
         assert np.allclose(gn, gold["gnorms"][s], rtol=1e-2 if s == 0 else 0.2, atol=1e-5)
 
 
+def test_oracle_trainer_vs_reference_loss_curve():
+    """The first 40 of the 200 reference training steps in tests/golden/robo_curve200.npz (oracle/make_golden.py curve:
+    the reference's own model.py + torch.optim.Adam, one thread) re-run by the oracle trainer: the gate the GPU test
+    applies to the product (step 1 <= 1e-5, every step <= 2e-2) must hold for the checker itself."""
+    from robocupvision_b200.model import ROBO_UNet
+    gold = load_golden("robo_curve200")
+    ref = gold["losses_small"]
+    b, c, h, w = (int(v) for v in gold["shape_small"])
+    torch.manual_seed(12345678)
+    sd0 = {k: v.clone() for k, v in ROBO_UNet().state_dict().items()}
+    tr = OracleTrainer(sd0, lambda s, x, training: R.robo_unet_forward(s, x, training=training),
+                       synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6)
+    for s in range(40):
+        x = synth.images(b, c, h, w, seed=5000 + s)
+        loss = tr.step(x, synth.labels_learnable(x))[0]
+        assert abs(loss - ref[s]) <= (1e-5 if s == 0 else 2e-2) * abs(ref[s]), (s, loss, ref[s])
+    assert len(ref) == 200 and ref[-1] < 0.5 * ref[0]
+
+
 def test_weights_dat_wire_format():
     """paramSave.py:5-17: float64 flatten of the state dict in key order; weightsLP/weights.dat is
     that flatten of bestModelLPFinetunedPruned.pth (golden head/tail/size recorded from the file)."""
