@@ -60,8 +60,20 @@ typedef enum rcv_math {
   RCV_MATH_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-term error-compensated split,  *
                           * TMEM accumulators: fp32-level accuracy (~1e-6 of the *
                           * output range); needs packed weights (rcv_conv_pack)  */
-  RCV_MATH_AUTO = 2      /* TF32X3 where packed weights are given and the        *
-                          * reduction is long enough to pay, else FP32           */
+  RCV_MATH_AUTO = 2,     /* the PARITY mode of the nets: TF32X3 where packed     *
+                          * weights are given and the reduction is long enough   *
+                          * to pay, else FP32 -- logits within 1e-4 of fp32      */
+  /* Fast modes, reported separately from the parity mode (north_star: "bf16      *
+   * variant stated separately"); engine choice as RCV_MATH_AUTO, the CUDA-core   *
+   * layers (<= 16 output channels) stay exact fp32:                             */
+  RCV_MATH_TF32 = 3,     /* one kind::tf32 MMA per product (operands rounded to  *
+                          * 10 mantissa bits, fp32 accumulate): ~1e-3 per layer  */
+  RCV_MATH_BF16 = 4      /* kind::f16 with bf16 operands (8 mantissa bits, fp32  *
+                          * accumulate, activations stay fp32 in HBM) in the     *
+                          * halo-staged stride-1 3x3 kernel where the reduced    *
+                          * channel count is a multiple of 64; RCV_MATH_TF32 in  *
+                          * the other tensor-core kernels.  The packed panel of  *
+                          * a layer depends on the mode it was packed for.       */
 } rcv_math;
 
 /* Which operand a packed weight panel serves. */

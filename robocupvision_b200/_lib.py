@@ -31,7 +31,7 @@ RCV_OK, RCV_ERR_BAD_ARG, RCV_ERR_UNSUPPORTED, RCV_ERR_CUDA, RCV_ERR_WORKSPACE = 
 # rcv_epilogue
 EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, EPI_AFFINE_RELU, EPI_AFFINE = 0, 1, 2, 3, 4
 # rcv_math
-MATH_FP32, MATH_TF32X3, MATH_AUTO = 0, 1, 2
+MATH_FP32, MATH_TF32X3, MATH_AUTO, MATH_TF32, MATH_BF16 = 0, 1, 2, 3, 4
 # rcv_engine
 ENGINE_SIMT, ENGINE_DIRECT, ENGINE_UMMA, ENGINE_NARROW = 0, 1, 2, 3
 

@@ -45,8 +45,8 @@ int validate(const rcv_conv_desc* d, const char* who) {
     RCV_REQUIRE(ok, RCV_ERR_UNSUPPORTED, "%s: 3x3 geometry s%d p%d d%d outside the hot path", who,
                 d->stride, d->pad, d->dil);
   }
-  RCV_REQUIRE(d->math == RCV_MATH_FP32 || d->math == RCV_MATH_TF32X3 || d->math == RCV_MATH_AUTO,
-              RCV_ERR_BAD_ARG, "%s: bad math mode %d", who, d->math);
+  RCV_REQUIRE(d->math >= RCV_MATH_FP32 && d->math <= RCV_MATH_BF16, RCV_ERR_BAD_ARG, "%s: bad math mode %d", who,
+              d->math);
   return RCV_OK;
 }
 

@@ -27,6 +27,9 @@ void rcv_set_error(const char* fmt, ...);
   } while (0)
 
 static inline int rcv_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// math modes that pick the engine per layer (tensor cores where the reduction pays): the fp32-parity mode and the
+// two fast modes; RCV_MATH_FP32 / RCV_MATH_TF32X3 force one engine
+static inline bool rcv_math_auto(int m) { return m == RCV_MATH_AUTO || m == RCV_MATH_TF32 || m == RCV_MATH_BF16; }
 
 // ---------------------------------------------------------------------------
 // Programmatic dependent launch.  A training step is ~100 short kernels back to back on one stream; with
@@ -152,6 +155,7 @@ int rcv_pick_engine(const RcvIgemm& p, bool have_packed);      // rcv_engine tha
 int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF32, TMEM accumulators
 bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb);    // stride-1 3x3, halo-staged A operand (rcv_umma_halo.cu)
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st);
+bool rcv_umma_halo_bf16_ok(const RcvIgemm& p, int bn);        // RCV_MATH_BF16: would that kernel take bf16 operands (bf16 panel layout)
 bool rcv_umma_takes_input_transform(const RcvIgemm& p);      // would rcv_launch_igemm_umma run the halo-staged kernel
 bool rcv_umma_wgrad_takes_input_transform(const RcvWgrad& p);  // tensor-core weight gradient with the quad gather
 bool rcv_umma_pays(const RcvIgemm& p);  // RCV_MATH_AUTO: is the reduction long enough for tensor cores

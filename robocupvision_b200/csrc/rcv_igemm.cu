@@ -307,7 +307,7 @@ int rcv_pick_engine(const RcvIgemm& p, bool have_packed) {
   if (p.math == RCV_MATH_TF32X3) return RCV_ENGINE_UMMA;
   // <= 16 output channels: TMA-staged FFMA2 direct convolution (exact fp32), whatever the reduction length
   if (use_narrow && rcv_narrow_supported(p)) return RCV_ENGINE_NARROW;
-  if (p.math == RCV_MATH_AUTO && have_packed && rcv_umma_pays(p)) return RCV_ENGINE_UMMA;
+  if (rcv_math_auto(p.math) && have_packed && rcv_umma_pays(p)) return RCV_ENGINE_UMMA;
   if (use_direct && rcv_direct_supported(p)) return RCV_ENGINE_DIRECT;
   return RCV_ENGINE_SIMT;
 }

@@ -30,6 +30,7 @@
 //     bias / ReLU / folded-BN affine / residual, coalesced NCHW stores (lanes = pixels), and the
 //     train-mode BatchNorm per-channel sum / sum-of-squares via a shuffle transpose-reduce and
 //     one double atomic per channel per warp.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "rcv_common.cuh"
@@ -190,6 +191,9 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int nkb = (K + BK - 1) / BK;
+  // fast modes (RCV_MATH_TF32 / RCV_MATH_BF16 on a layer this kernel runs): one TF32 MMA per product -- the lo
+  // halves are neither staged, copied nor multiplied, and the correction accumulator is never read
+  const bool fast = p.math >= RCV_MATH_TF32;
 
   if (tid < MAXT) {
     const int t = tid < T ? tid : 0;
@@ -233,9 +237,9 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb % G, u = kb / G;
         if (u > 0) mbar_wait(bar_empty + 8 * st, (uint32_t)((u - 1) & 1));
-        mbar_expect_tx(bar_full + 8 * st, C::B_STAGE);
-        bulk_g2s(tiles + st * C::STAGE + C::A_STAGE, gB + (size_t)kb * C::B_STAGE, C::B_STAGE,
-                 bar_full + 8 * st);
+        const uint32_t bbytes = fast ? C::B_STAGE / 2 : C::B_STAGE;  // hi rows come first in a packed block
+        mbar_expect_tx(bar_full + 8 * st, bbytes);
+        bulk_g2s(tiles + st * C::STAGE + C::A_STAGE, gB + (size_t)kb * C::B_STAGE, bbytes, bar_full + 8 * st);
       }
     } else if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) mbar_arrive(bar_full + 8 * (kb % G));  // timing experiments only
@@ -261,14 +265,18 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
             const int ksteps = krem >= BK ? BK / 8 : (krem + 7) / 8;
             if (!(p.debug & 1)) {
               // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzled row per step
-              umma_tf32(d_corr, a_lo, b_hi, idesc, kb != 0);
-              umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+              if (!fast) {
+                umma_tf32(d_corr, a_lo, b_hi, idesc, kb != 0);
+                umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+              }
               umma_tf32(d_main, a_hi, b_hi, idesc, kb != 0);
 #pragma unroll
               for (int ks = 1; ks < BK / 8; ++ks) {
                 if (ks < ksteps) {
-                  umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
-                  umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+                  if (!fast) {
+                    umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+                    umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+                  }
                   umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
                 }
               }
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
         split_tf32(va[4 * c + 3], h.w, l.w);
         const int off = sw_off<KB>(row, c);
         *reinterpret_cast<float4*>(a_hi + off) = h;
-        *reinterpret_cast<float4*>(a_lo + off) = l;
+        if (!fast) *reinterpret_cast<float4*>(a_lo + off) = l;
       }
       RCV_PROF_P(3);
       fence_proxy_async_smem();
@@ -385,7 +393,12 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
       if (n0 + c0 >= p.CB || (p.debug & 32)) break;  // warp-uniform
       uint32_t rm[16], rc[16];
       tmem_ld16_nowait(trow + c0, rm);
-      tmem_ld16_nowait(trow + BN + c0, rc);
+      if (!fast) {
+        tmem_ld16_nowait(trow + BN + c0, rc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rc[j] = 0u;
+      }
       const int nvalid = min(16, p.CB - (n0 + c0));  // channels of this chunk that exist
       float* optr = p.out + obase + (size_t)(n0 + c0) * HWo;
       const float* rptr = has_res ? p.residual + obase + (size_t)(n0 + c0) * HWo : nullptr;
@@ -475,13 +488,43 @@ __device__ __forceinline__ void pack_chunk(const RcvIgemm& p, int BN, int ntiles
   }
 }
 
+// bf16 panel (RCV_MATH_BF16, halo-staged kernel): K blocks of 64 channels = rows of 128 bytes, 128-byte swizzle,
+// one copy.  One thread per 16-byte chunk = 8 consecutive channels of one weight row.  KB == 64 marks the layout.
+__device__ __forceinline__ void pack_chunk_bf16(const RcvIgemm& p, int BN, int ntiles, int kbmax,
+                                                unsigned char* __restrict__ packed, int64_t q) {
+  const int row = (int)(q % BN);
+  const int c = (int)((q / BN) % 8);
+  int64_t blk = q / ((int64_t)BN * 8);
+  const int kb = (int)(blk % kbmax);
+  const int tile = (int)(blk / kbmax);
+  const int co = tile * BN + row;
+  const int k = kb * 64 + c * 8;
+  const int tap = k / p.CA, ca = k - tap * p.CA;  // CA % 64 == 0: a chunk never straddles two taps
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float v0 = 0.f, v1 = 0.f;
+    if (tap < p.taps[0].n && co < p.CB) {
+      const float* src = p.w + (size_t)co * p.wsB + p.taps[0].wi[tap];
+      v0 = __ldg(src + (size_t)(ca + 2 * e) * p.wsA);
+      v1 = __ldg(src + (size_t)(ca + 2 * e + 1) * p.wsA);
+    }
+    const __nv_bfloat162 b = __floats2bfloat162_rn(v0, v1);
+    w[e] = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  unsigned char* base = packed + ((size_t)tile * kbmax + kb) * ((size_t)BN * 128);
+  *reinterpret_cast<uint4*>(base + sw_off<32>(row, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __global__ void __launch_bounds__(256) pack_kernel(const RcvIgemm p, int BN, int ntiles, int kbmax, int KB,
                                                    unsigned char* __restrict__ packed) {
   rcv_pdl_enter();
-  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * (KB / 4);
+  const int64_t total = KB == 64 ? (int64_t)ntiles * kbmax * BN * 8 : (int64_t)p.nclass * ntiles * kbmax * BN * (KB / 4);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
-       q += (int64_t)gridDim.x * blockDim.x)
-    pack_chunk(p, BN, ntiles, kbmax, KB, packed, q);
+       q += (int64_t)gridDim.x * blockDim.x) {
+    if (KB == 64) pack_chunk_bf16(p, BN, ntiles, kbmax, packed, q);
+    else pack_chunk(p, BN, ntiles, kbmax, KB, packed, q);
+  }
 }
 
 // All layers' panels in one launch: a device-resident job table (built once on the host, the
@@ -498,7 +541,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const RcvPackJob* __res
     int j = 0;
     while (q >= s_begin[j + 1]) ++j;
     const RcvPackJob& jb = jobs[j];
-    pack_chunk(jb.p, jb.BN, jb.ntiles, jb.kbmax, jb.kb, jb.packed, q - s_begin[j]);
+    if (jb.kb == 64) pack_chunk_bf16(jb.p, jb.BN, jb.ntiles, jb.kbmax, jb.packed, q - s_begin[j]);
+    else pack_chunk(jb.p, jb.BN, jb.ntiles, jb.kbmax, jb.kb, jb.packed, q - s_begin[j]);
   }
 }
 
@@ -551,7 +595,14 @@ bool rcv_umma_supported(const RcvIgemm& p) {
   return (p.CA % umma_kb(p.CB)) == 0 || (int64_t)p.CA * max_taps(p) <= RCV_UMMA_MAX_TABLE_K;
 }
 
+// panel layout of a layer: K-block width in elements (64 = the bf16 layout of RCV_MATH_BF16 halo layers)
+static int panel_kb(const RcvIgemm& p) { return rcv_umma_halo_bf16_ok(p, umma_bn(p.CB)) ? 64 : umma_kb(p.CB); }
+
 size_t rcv_umma_packed_bytes(const RcvIgemm& p) {
+  if (panel_kb(p) == 64) {
+    const int BN = umma_bn(p.CB);
+    return (size_t)rcv_cdiv(p.CB, BN) * (p.CA * 9 / 64) * BN * 128;
+  }
   const int BN = umma_bn(p.CB), KB = umma_kb(p.CB);
   const int ntiles = rcv_cdiv(p.CB, BN);
   const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), KB);
@@ -562,10 +613,10 @@ int rcv_launch_umma_pack(const RcvIgemm& p, void* packed, cudaStream_t st) {
   int rc = check_taps(p);
   if (rc) return rc;
   RCV_REQUIRE(((uintptr_t)packed & 127) == 0, RCV_ERR_BAD_ARG, "conv_pack: packed buffer must be 128-byte aligned");
-  const int BN = umma_bn(p.CB), KB = umma_kb(p.CB);
+  const int BN = umma_bn(p.CB), KB = panel_kb(p);
   const int ntiles = rcv_cdiv(p.CB, BN);
   const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), KB);
-  const int64_t total = (int64_t)p.nclass * ntiles * kbmax * BN * (KB / 4);
+  const int64_t total = KB == 64 ? (int64_t)ntiles * kbmax * BN * 8 : (int64_t)p.nclass * ntiles * kbmax * BN * (KB / 4);
   int blocks = rcv_cdiv(total, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   rcv_launch(pack_kernel, dim3(blocks), dim3(256), 0, st, p, BN, ntiles, kbmax, KB,
@@ -581,11 +632,12 @@ int rcv_umma_pack_job(const RcvIgemm& p, void* packed, long long chunk_begin, Rc
   job->p = p;
   job->BN = umma_bn(p.CB);
   job->ntiles = rcv_cdiv(p.CB, job->BN);
-  job->kb = umma_kb(p.CB);
+  job->kb = panel_kb(p);
   job->kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), job->kb);
   job->packed = reinterpret_cast<unsigned char*>(packed);
   job->chunk_begin = chunk_begin;
-  job->chunks = (long long)p.nclass * job->ntiles * job->kbmax * job->BN * (job->kb / 4);
+  job->chunks = job->kb == 64 ? (long long)job->ntiles * job->kbmax * job->BN * 8
+                              : (long long)p.nclass * job->ntiles * job->kbmax * job->BN * (job->kb / 4);
   return RCV_OK;
 }
 
@@ -601,7 +653,7 @@ int rcv_launch_umma_pack_multi(const RcvPackJob* dev_jobs, int njobs, long long 
 }
 
 bool rcv_umma_takes_input_transform(const RcvIgemm& p) {
-  return rcv_umma_halo_ok(p, umma_bn(p.CB), umma_kb(p.CB));
+  return rcv_umma_halo_ok(p, umma_bn(p.CB), umma_kb(p.CB)) || rcv_umma_halo_bf16_ok(p, umma_bn(p.CB));
 }
 
 int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
@@ -623,7 +675,8 @@ int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
   const int bn = umma_bn(p.CB);
   const bool deep = g_force_g > 0 ? g_force_g >= 3 : (int64_t)p.CA * max_taps(p) > 10 * BK;
   // stride-1 3x3 layers: nine tap-shifted descriptors over one staged patch instead of nine gathers
-  if (rcv_umma_halo_ok(p, bn, umma_kb(p.CB))) return rcv_launch_igemm_umma_halo(p, bn, umma_kb(p.CB), st);
+  if (rcv_umma_halo_ok(p, bn, umma_kb(p.CB)) || rcv_umma_halo_bf16_ok(p, bn))
+    return rcv_launch_igemm_umma_halo(p, bn, umma_kb(p.CB), st);
   RCV_REQUIRE(p.in_scale == nullptr, RCV_ERR_UNSUPPORTED,
               "normalise-on-load needs the halo-staged kernel (stride-1 3x3, reduced channels a multiple of 32, short rows)");
   switch (bn) {

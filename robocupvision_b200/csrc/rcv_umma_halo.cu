@@ -15,6 +15,7 @@
 // The B operand is the same pre-packed panel the general engine uses (rcv_conv_pack), streamed by bulk copies
 // through a ring; 3xTF32 with two TMEM accumulators and the fused epilogue are unchanged.
 // Roles: 8 producer / epilogue warps, one MMA-issuer warp, one B-loader warp; two CTAs per SM.
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "rcv_common.cuh"
@@ -67,15 +68,42 @@ __device__ __forceinline__ void warp_transpose_reduce16(float (&a)[16], int lane
   a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
-template <int BN, int KBB>
+// BF = false: fp32 operands as tf32 hi (+ lo) parts, channel blocks of 32 (one 128-byte row of fp32);
+// BF = true (RCV_MATH_BF16): bf16 operands, channel blocks of 64 (one 128-byte row of bf16), kind::f16 MMAs with
+// K = 16 per instruction, one accumulator; KBB is ignored (the B rows are 128 bytes as well).
+template <int BN, int KBB, bool BF = false>
 struct HCfg {
-  static constexpr int BROWB = KBB * 4;               // bytes per B row
-  static constexpr int B_STAGE = BN * BROWB * 2;      // hi rows then lo rows
+  static constexpr int CBLK = BF ? 64 : 32;           // channels per staged block
+  static constexpr int BROWB = BF ? 128 : KBB * 4;    // bytes per B row
+  static constexpr int B_STAGE = BF ? BN * 128 : BN * BROWB * 2;  // fp32: hi rows then lo rows
   static constexpr int MAXBS = 4;                     // deepest B ring
-  static constexpr int SUB = 32 / KBB;                // B K-blocks per (tap, 32-channel block)
-  static constexpr int TCOLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SUB = BF ? 1 : 32 / KBB;       // B K-blocks per (tap, channel block)
+  static constexpr int KSTEPS = BF ? 4 : KBB / 8;     // MMAs (32 bytes of K each) per B K-block
+  static constexpr int TCOLS = BF ? (BN < 32 ? 32 : BN) : (2 * BN < 32 ? 32 : 2 * BN);
   static constexpr int MISC = 256 + 3 * BN * 4;       // barriers, epilogue constants (+ 2*CA floats of input scale / shift)
 };
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// cute::UMMA::InstrDescriptor for kind::f16: fp32 accumulate (c_format 1 at [4,6)), a_format / b_format = BF16 (1) at
+// [7,10) / [10,13), both operands K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x (low half-word, lower address) = lo
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 
 // position in the padded flattened space -> pixel; false for halo positions
 __device__ __forceinline__ bool decode_pos(long long q, const HaloGeo& g, int N, int H, int W, int& n, int& i, int& j) {
@@ -89,19 +117,21 @@ __device__ __forceinline__ bool decode_pos(long long q, const HaloGeo& g, int N,
   return n < N && i < H;
 }
 
-template <int BN, int KBB>
+template <int BN, int KBB, bool BF>
 __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, const HaloGeo g) {
   rcv_pdl_enter();
-  using C = HCfg<BN, KBB>;
+  using C = HCfg<BN, KBB, BF>;
   constexpr int SUB = C::SUB;
+  constexpr int CBLK = C::CBLK;
   const int NBS = g.nbs;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gen = smem_raw + (base - raw);
   const uint32_t patch_bytes = (uint32_t)g.Lpad * 128u;
-  const uint32_t a_hi_s = base, a_lo_s = base + patch_bytes, b_s = base + 2 * patch_bytes;
-  unsigned char* misc = gen + 2 * patch_bytes + NBS * C::B_STAGE;
+  constexpr uint32_t NPATCH = BF ? 1u : 2u;  // bf16: one copy of the patch; fp32: tf32 hi and lo copies
+  const uint32_t a_hi_s = base, a_lo_s = base + patch_bytes, b_s = base + NPATCH * patch_bytes;
+  unsigned char* misc = gen + NPATCH * patch_bytes + NBS * C::B_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // patch_full, patch_empty, done, bfull[NBS], bempty[NBS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 120);
   float* s_cst = reinterpret_cast<float*>(misc + 256);
@@ -115,6 +145,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
   const long long q0 = (long long)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int nkc = g.nkc;
+  const bool fast = BF || p.math >= RCV_MATH_TF32;  // one MMA per product: no lo halves, no correction accumulator
 
   for (int c = tid; c < BN; c += NT) {
     const int co = n0 + c;
@@ -151,22 +182,23 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
     if (lane == 0) {
       const unsigned char* gB = reinterpret_cast<const unsigned char*>(p.wpacked) +
                                 ((size_t)blockIdx.y * g.kbmax) * C::B_STAGE;
-      const int kper = CA / KBB;  // B K-blocks per tap in the pack (K = tap-major, then channel)
+      const int kper = BF ? CA / 64 : CA / KBB;  // B K-blocks per tap in the pack (K = tap-major, then channel)
       int it = 0;
       for (int cb = 0; cb < nkc; ++cb)
         for (int t = 0; t < 9; ++t)
           for (int sub = 0; sub < SUB; ++sub, ++it) {
             const int st = it % NBS, u = it / NBS;
             if (u > 0) mbar_wait(bar_bempty + 8 * st, (uint32_t)((u - 1) & 1));
-            mbar_expect_tx(bar_bfull + 8 * st, C::B_STAGE);
+            const uint32_t bbytes = (fast && !BF) ? C::B_STAGE / 2 : C::B_STAGE;  // fp32 panels: hi rows come first
+            mbar_expect_tx(bar_bfull + 8 * st, bbytes);
             const int kbp = t * kper + cb * SUB + sub;
-            bulk_g2s(b_s + st * C::B_STAGE, gB + (size_t)kbp * C::B_STAGE, C::B_STAGE, bar_bfull + 8 * st);
+            bulk_g2s(b_s + st * C::B_STAGE, gB + (size_t)kbp * C::B_STAGE, bbytes, bar_bfull + 8 * st);
           }
     }
   } else if (warp == NPROD / 32) {
     // ================================ MMA ISSUER ======================================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc(BM, BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       int it = 0;
       for (int cb = 0; cb < nkc; ++cb) {
@@ -181,13 +213,19 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
             mbar_wait(bar_bfull + 8 * st, (uint32_t)((it / NBS) & 1));
             tc_fence_after();
             const uint32_t bb = b_s + st * C::B_STAGE;
-            const uint64_t b_hi = make_desc_b<KBB>(bb), b_lo = make_desc_b<KBB>(bb + BN * C::BROWB);
+            const uint64_t b_hi = BF ? make_desc(bb) : make_desc_b<KBB>(bb), b_lo = make_desc_b<KBB>(bb + BN * C::BROWB);
 #pragma unroll
-            for (int ks = 0; ks < KBB / 8; ++ks) {
-              const int ka = sub * (KBB / 8) + ks;  // K step inside the 32-channel A row
+            for (int ks = 0; ks < C::KSTEPS; ++ks) {
+              const int ka = sub * C::KSTEPS + ks;  // K step (32 bytes) inside the 128-byte A row
               const uint32_t first = (it == 0 && ks == 0) ? 0u : 1u;
-              umma_tf32(d_corr, a_lo + 2 * ka, b_hi + 2 * ks, idesc, first);
-              umma_tf32(d_corr, a_hi + 2 * ka, b_lo + 2 * ks, idesc, 1u);
+              if (BF) {
+                umma_bf16(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc, first);
+                continue;
+              }
+              if (!fast) {
+                umma_tf32(d_corr, a_lo + 2 * ka, b_hi + 2 * ks, idesc, first);
+                umma_tf32(d_corr, a_hi + 2 * ka, b_lo + 2 * ks, idesc, 1u);
+              }
               umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc, first);
             }
             umma_commit(bar_bempty + 8 * st);
@@ -207,6 +245,36 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
     const uint32_t boff0 = 4u * (uint32_t)((pn * CA) * HW + pi * W + pj);
     const uint32_t cstride = 4u * (uint32_t)HW;
     for (int cb = 0; cb < nkc; ++cb) {
+      if (BF) {
+        // 64 channels of this position as bf16: two half blocks of 32 loads each, four 16-byte chunks per half
+        uint32_t pk[32];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float va[32];
+          const uint32_t b = boff0 + (uint32_t)(cb * 64 + hf * 32) * cstride;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            va[i] = pvalid ? __ldg(reinterpret_cast<const float*>(inb + (b + (uint32_t)i * cstride))) : 0.f;
+          if (nl && pvalid) {
+            const bool rl = p.in_relu != 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float t = fmaf(s_in[cb * 64 + hf * 32 + i], va[i], s_in[CA + cb * 64 + hf * 32 + i]);
+              va[i] = rl ? fmaxf(t, 0.f) : t;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[hf * 16 + i] = pack_bf16x2(va[2 * i], va[2 * i + 1]);
+        }
+        if (cb > 0) mbar_wait(bar_pempty, (uint32_t)((cb - 1) & 1));
+        if (has_row) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int off = tid * 128 + ((c ^ (tid & 7)) << 4);
+            *reinterpret_cast<uint4*>(gen + off) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          }
+        }
+      } else {
       float va[32];
       const uint32_t b = boff0 + (uint32_t)(cb * 32) * cstride;
 #pragma unroll
@@ -231,8 +299,9 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
           split_tf32(va[4 * c + 3], h.w, l.w);
           const int off = tid * 128 + ((c ^ (tid & 7)) << 4);
           *reinterpret_cast<float4*>(gen + off) = h;
-          *reinterpret_cast<float4*>(gen + patch_bytes + off) = l;
+          if (!fast) *reinterpret_cast<float4*>(gen + patch_bytes + off) = l;
         }
+      }
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -256,7 +325,12 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
       if (n0 + c0 >= p.CB) break;
       uint32_t rm[16], rc[16];
       tmem_ld16_nowait(trow + c0, rm);
-      tmem_ld16_nowait(trow + BN + c0, rc);
+      if (!fast) {
+        tmem_ld16_nowait(trow + BN + c0, rc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rc[j] = 0u;
+      }
       const int nvalid = min(16, p.CB - (n0 + c0));
       float* optr = p.out + obase + (size_t)(n0 + c0) * HWo;
       const float* rptr = has_res ? p.residual + obase + (size_t)(n0 + c0) * HWo : nullptr;
@@ -340,10 +414,10 @@ bool geometry(const RcvIgemm& p, HaloGeo* out) {
 }
 
 // B ring depth that fits beside the patch in a two-CTAs-per-SM shared-memory budget (0: nothing fits)
-int ring_depth(const HaloGeo& g, int bn, int kbb, int ca, size_t* smem) {
+int ring_depth(const HaloGeo& g, int bn, int kbb, int ca, bool bf, size_t* smem) {
   const size_t budget = 113 * 1024;
-  const size_t fixed = 1024 + 2 * (size_t)g.Lpad * 128 + 256 + 3 * (size_t)bn * 4 + 2 * (size_t)ca * 4;
-  const size_t stage = (size_t)bn * kbb * 8;
+  const size_t fixed = 1024 + (bf ? 1 : 2) * (size_t)g.Lpad * 128 + 256 + 3 * (size_t)bn * 4 + 2 * (size_t)ca * 4;
+  const size_t stage = bf ? (size_t)bn * 128 : (size_t)bn * kbb * 8;
   for (int nbs = 4; nbs >= 2; --nbs)
     if (fixed + nbs * stage <= budget) {
       if (smem) *smem = fixed + nbs * stage;
@@ -352,27 +426,31 @@ int ring_depth(const HaloGeo& g, int bn, int kbb, int ca, size_t* smem) {
   return 0;
 }
 
-template <int BN, int KBB>
+template <int BN, int KBB, bool BF = false>
 int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
-  using C = HCfg<BN, KBB>;
-  g.kbmax = (p.CA * 9) / KBB;
+  if (BF) {
+    g.nkc = p.CA / 64;
+    g.kbmax = (p.CA * 9) / 64;
+  } else {
+    g.kbmax = (p.CA * 9) / KBB;
+  }
   size_t smem = 0;
-  g.nbs = ring_depth(g, BN, KBB, p.CA, &smem);
+  g.nbs = ring_depth(g, BN, KBB, p.CA, BF, &smem);
   RCV_REQUIRE(g.nbs >= 2, RCV_ERR_UNSUPPORTED, "umma_halo: the patch leaves no room for the weight ring");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(umma_halo_kernel<BN, KBB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(umma_halo_kernel<BN, KBB, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          113 * 1024);
     if (e != cudaSuccess) {
       rcv_set_error("umma_halo: cannot reserve shared memory: %s", cudaGetErrorString(e));
       return RCV_ERR_CUDA;
     }
-    cudaFuncSetAttribute(umma_halo_kernel<BN, KBB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(umma_halo_kernel<BN, KBB, BF>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     attr_done = true;
   }
   dim3 grid(rcv_cdiv(g.Mh, BM), rcv_cdiv(p.CB, BN), 1);
-  rcv_launch(umma_halo_kernel<BN, KBB>, dim3(grid), dim3(NT), smem, st, p, g);
+  rcv_launch(umma_halo_kernel<BN, KBB, BF>, dim3(grid), dim3(NT), smem, st, p, g);
   RCV_CHECK_LAUNCH("umma_halo_kernel");
   return RCV_OK;
 }
@@ -385,12 +463,27 @@ bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb) {
   static const int on = getenv("RCV_UMMA_HALO") ? atoi(getenv("RCV_UMMA_HALO")) : 1;
   HaloGeo g;
   if (!on || !geometry(p, &g)) return false;
-  return bn >= 32 && ring_depth(g, bn, kbb, p.CA, nullptr) >= 2;
+  return bn >= 32 && ring_depth(g, bn, kbb, p.CA, false, nullptr) >= 2;
+}
+
+// RCV_MATH_BF16: the same layers with a reduced channel count that is a multiple of 64 run with bf16 operands
+// (their packed panel then has the bf16 layout: rcv_umma_packed_bytes / pack follow this predicate)
+bool rcv_umma_halo_bf16_ok(const RcvIgemm& p, int bn) {
+  static const int on = getenv("RCV_UMMA_BF16") ? atoi(getenv("RCV_UMMA_BF16")) : 1;
+  static const int halo_on = getenv("RCV_UMMA_HALO") ? atoi(getenv("RCV_UMMA_HALO")) : 1;
+  HaloGeo g;
+  if (!on || !halo_on || p.math != RCV_MATH_BF16 || (p.CA % 64) != 0 || bn < 32 || !geometry(p, &g)) return false;
+  return ring_depth(g, bn, 32, p.CA, true, nullptr) >= 2;
 }
 
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st) {
   HaloGeo g;
   RCV_REQUIRE(geometry(p, &g), RCV_ERR_UNSUPPORTED, "umma_halo: geometry outside the kernel's limits");
+  if (rcv_umma_halo_bf16_ok(p, bn)) {
+    if (bn == 128) return launch_h<128, 32, true>(p, g, st);
+    if (bn == 64) return launch_h<64, 32, true>(p, g, st);
+    if (bn == 32) return launch_h<32, 32, true>(p, g, st);
+  }
   if (bn == 128 && kbb == 16) return launch_h<128, 16>(p, g, st);
   if (bn == 128 && kbb == 32) return launch_h<128, 32>(p, g, st);
   if (bn == 64 && kbb == 32) return launch_h<64, 32>(p, g, st);

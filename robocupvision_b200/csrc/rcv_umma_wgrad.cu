@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
   const int mbeg = blockIdx.z * p.slab;
   const int mend = min(M, mbeg + p.slab);
   const int nchunks = (mend - mbeg + BK - 1) / BK;
+  const bool fast = p.math >= RCV_MATH_TF32;  // one TF32 MMA per product: no lo halves, no correction accumulator
 
   for (int kl = tid; kl < BM; kl += NT) {
     const int k = k0 + kl;
@@ -140,13 +141,17 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
             const uint32_t base = tiles + st * C::STAGE;
             const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + C::A_TILE);
             const uint64_t b_hi = make_desc(base + 2 * C::A_TILE), b_lo = make_desc(base + 2 * C::A_TILE + C::B_TILE);
-            umma_tf32(d_corr, a_lo, b_hi, idesc, c != 0);
-            umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+            if (!fast) {
+              umma_tf32(d_corr, a_lo, b_hi, idesc, c != 0);
+              umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+            }
             umma_tf32(d_main, a_hi, b_hi, idesc, c != 0);
 #pragma unroll
             for (int ks = 1; ks < BK / 8; ++ks) {
-              umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
-              umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+              if (!fast) {
+                umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+                umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+              }
               umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
             }
             if (c + 1 < nchunks) mbar_wait(bar_full + 8 * ((st + 1) % G), st + 1 == G ? par ^ 1u : par);
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
           split_tf32(rb[i].w, h.w, l.w);
           const int off = rowc * 128 + ((bc ^ (rowc & 7)) << 4);
           *reinterpret_cast<float4*>(sb + off) = h;
-          *reinterpret_cast<float4*>(sb + C::B_TILE + off) = l;
+          if (!fast) *reinterpret_cast<float4*>(sb + C::B_TILE + off) = l;
           bsum[i] += (rb[i].x + rb[i].y) + (rb[i].z + rb[i].w);
         }
       }
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
               split_tf32(row[tx].w, h.w, l.w);
               const int off = rowk * 128 + ((qq ^ (rowk & 7)) << 4);
               *reinterpret_cast<float4*>(st + off) = h;
-              *reinterpret_cast<float4*>(st + C::A_TILE + off) = l;
+              if (!fast) *reinterpret_cast<float4*>(st + C::A_TILE + off) = l;
             }
           }
         }
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
         split_tf32(ra[i], h, l);
         const int off = rowk * 128 + (((lane >> 2) ^ (rowk & 7)) << 4) + (lane & 3) * 4;
         *reinterpret_cast<float*>(st + off) = h;
-        *reinterpret_cast<float*>(st + C::A_TILE + off) = l;
+        if (!fast) *reinterpret_cast<float*>(st + C::A_TILE + off) = l;
       }
       }
       fence_proxy_async_smem();
@@ -377,7 +382,12 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
         if (cb0 + c0 >= p.CB) break;  // warp-uniform
         uint32_t rm[16], rc[16];
         tmem_ld16_nowait(trow + c0, rm);
-        tmem_ld16_nowait(trow + BN + c0, rc);
+        if (!fast) {
+          tmem_ld16_nowait(trow + BN + c0, rc);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rc[j] = 0u;
+        }
         tmem_ld_wait();
         if (wo >= 0) {
           float* dst = p.dw + (size_t)(cb0 + c0) * p.wsB + wo;

@@ -339,7 +339,7 @@ int rcv_pick_wgrad_engine(const RcvWgrad& p) {
   if (p.math == RCV_MATH_TF32X3) return RCV_ENGINE_UMMA;
   // few channels on the dense side: TMA-staged register-accumulating kernel
   if (use_narrow && rcv_narrow_wgrad_supported(p)) return RCV_ENGINE_NARROW;
-  if (p.math == RCV_MATH_AUTO && rcv_umma_wgrad_pays(p)) return RCV_ENGINE_UMMA;
+  if (rcv_math_auto(p.math) && rcv_umma_wgrad_pays(p)) return RCV_ENGINE_UMMA;
   return RCV_ENGINE_SIMT;
 }
 

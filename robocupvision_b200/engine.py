@@ -19,15 +19,25 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import (EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO, MATH_FP32, PACK_DGRAD,
-                  PACK_FWD, ConvGeom)
+from .ops import (EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO, MATH_BF16, MATH_FP32, MATH_TF32,
+                  PACK_DGRAD, PACK_FWD, ConvGeom)
 
-# Math mode of the conv engine for every plan: RCV_MATH_AUTO = tcgen05 3xTF32 tensor-core tiles
-# wherever the reduction is long enough, CUDA cores elsewhere.  RCV_B200_MATH=fp32 forces the
-# CUDA-core engine everywhere (A/B comparisons, bisecting a numerical difference).
+# Math mode of the conv engine for every plan (rcv_math):
+#   parity (default, = auto)  tcgen05 3xTF32 tensor-core tiles wherever the reduction is long enough, CUDA cores
+#                             elsewhere: logits within 1e-4 of the fp32 reference (the mode every parity test runs)
+#   tf32 / bf16               the FAST modes, reported separately: one kind::tf32 MMA per product / bf16 operands
+#                             in the halo-staged kernel; their own tolerance tests (tests/test_gpu_fast_math.py)
+#   fp32                      the CUDA-core engine everywhere (A/B comparisons, bisecting a numerical difference)
+# RCV_B200_MATH sets the default; `model.set_math("bf16")` switches one model.
 import os as _os
 
-DEFAULT_MATH = {"fp32": MATH_FP32, "auto": MATH_AUTO}[_os.environ.get("RCV_B200_MATH", "auto").lower()]
+MATH_KEYS = {MATH_FP32: "fp32", MATH_AUTO: "parity", MATH_TF32: "tf32", MATH_BF16: "bf16"}
+MATH_BY_NAME = {"fp32": MATH_FP32, "auto": MATH_AUTO, "parity": MATH_AUTO, "tf32": MATH_TF32, "bf16": MATH_BF16}
+MATH_NAMES = {MATH_FP32: "fp32 FMA (CUDA cores)",
+              MATH_AUTO: "tcgen05 kind::tf32 x3 (fp32-level accuracy), TMEM accumulators",
+              MATH_TF32: "tcgen05 kind::tf32, one MMA per product (fast mode)",
+              MATH_BF16: "tcgen05 kind::f16 with bf16 operands, fp32 accumulate (fast mode)"}
+DEFAULT_MATH = MATH_BY_NAME[_os.environ.get("RCV_B200_MATH", "parity").lower()]
 WGRAD_SIDE_STREAM = _os.environ.get("RCV_B200_WGRAD_STREAM", "1") != "0"
 # Training forward: where every consumer of a BatchNorm block's output is a conv the halo-staged tensor-core
 # kernel runs, the block's apply pass is skipped and the consumers normalise on load (rcv_conv_fwd_nl); the
@@ -53,7 +63,7 @@ class Node:
         self.skip_ch = 0
         self._pack = [None, None]      # persistent packed-weight buffers (fwd, dgrad)
         self._pack_key = [None, None]
-        self._tc = [None, None]        # does this direction run on tensor cores
+        self._tc = {}                  # (direction, math) -> does this direction run on tensor cores
 
     def params(self) -> List[nn.Parameter]:
         out = []
@@ -69,23 +79,25 @@ class Node:
         """Does this layer / direction run on the tensor-core engine (and so need a packed panel)."""
         if math == MATH_FP32 or self.kind != "conv":
             return False
-        if self._tc[direction] is None:
-            self._tc[direction] = ops.conv_uses_tensor_cores(self.geom, direction, math)
-        return self._tc[direction]
+        hit = self._tc.get((direction, math))
+        if hit is None:
+            hit = self._tc[(direction, math)] = ops.conv_uses_tensor_cores(self.geom, direction, math)
+        return hit
 
-    def pack_buffer(self, direction: int) -> torch.Tensor:
-        """Persistent panel buffer (allocated once per device: CUDA-graph safe)."""
+    def pack_buffer(self, direction: int, math: int) -> torch.Tensor:
+        """Persistent panel buffer (allocated once per device and math mode: CUDA-graph safe)."""
         w = self.conv.weight
         buf = self._pack[direction]
-        if buf is None or buf.device != w.device:
-            buf = torch.empty(ops.conv_packed_bytes(self.geom, direction), device=w.device, dtype=torch.uint8)
+        nbytes = ops.conv_packed_bytes(self.geom, direction, math)
+        if buf is None or buf.device != w.device or buf.numel() != nbytes:
+            buf = torch.empty(nbytes, device=w.device, dtype=torch.uint8)
             self._pack[direction] = buf
             self._pack_key[direction] = None
         return buf
 
-    def pack_key(self, epoch: int):
+    def pack_key(self, epoch: int, math: int):
         w = self.conv.weight
-        return (w.data_ptr(), w._version, epoch)
+        return (w.data_ptr(), w._version, epoch, math)
 
     def folded(self, epoch: int = 0):
         bn = self.bn
@@ -158,17 +170,18 @@ class Plan:
                 if nd.uses_tc(d, self.math) and not (d == PACK_DGRAD and nd.src == 0 and not x_requires_grad)]
         if not jobs:
             return
-        bufs = [nd.pack_buffer(d) for nd, d in jobs]
-        if not fresh and all(nd._pack_key[d] == nd.pack_key(self.epoch) for nd, d in jobs):
+        bufs = [nd.pack_buffer(d, self.math) for nd, d in jobs]
+        if not fresh and all(nd._pack_key[d] == nd.pack_key(self.epoch, self.math) for nd, d in jobs):
             return
         tkey = tuple((nd.conv.weight.data_ptr(), b.data_ptr()) for (nd, _), b in zip(jobs, bufs))
-        tbl = self._pack_tables.get(tuple(directions))
+        tbl = self._pack_tables.get((tuple(directions), self.math))
         if tbl is None or tbl.key != tkey:
-            tbl = ops.PackTable([(nd.geom, d, nd.conv.weight.detach(), b) for (nd, d), b in zip(jobs, bufs)])
-            self._pack_tables[tuple(directions)] = tbl
+            tbl = ops.PackTable([(nd.geom, d, nd.conv.weight.detach(), b) for (nd, d), b in zip(jobs, bufs)],
+                                math=self.math)
+            self._pack_tables[(tuple(directions), self.math)] = tbl
         tbl.run()
         for nd, d in jobs:
-            nd._pack_key[d] = nd.pack_key(self.epoch)
+            nd._pack_key[d] = nd.pack_key(self.epoch, self.math)
 
     def _defer_bn_apply(self, t: int, n: int, h: int, w: int) -> bool:
         """Can node t's BatchNorm apply pass be left to its consumers (normalise-on-load)?  Its output must feed only

@@ -57,6 +57,16 @@ class _PlanModule(nn.Module):
     def invalidate_plan(self):
         self.__dict__.pop("_rcv_plan", None)
 
+    def set_math(self, mode: str):
+        """Math mode of this model's tensor-core layers: "parity" (default: 3xTF32, logits within 1e-4 of fp32), the
+        fast modes "tf32" / "bf16" (reported separately; see include/rcv_b200.h rcv_math), or "fp32" (CUDA cores)."""
+        from .engine import MATH_BY_NAME
+        plan = self._get_plan()
+        plan.math = MATH_BY_NAME[mode.lower()]
+        plan.epoch += 1
+        plan._defer_cache.clear()
+        return self
+
     def __deepcopy__(self, memo):
         import copy
         cls = self.__class__

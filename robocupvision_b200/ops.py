@@ -14,14 +14,15 @@ import torch
 
 from . import _lib
 from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE,
-                   EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO, MATH_FP32, MATH_TF32X3, PACK_DGRAD, PACK_FWD, ConvDesc)
+                   EPI_RELU, EPI_RELU_AFFINE, MATH_AUTO, MATH_BF16, MATH_FP32, MATH_TF32, MATH_TF32X3, PACK_DGRAD,
+                   PACK_FWD, ConvDesc)
 
 __all__ = [
     "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
     "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "zero_", "zeros", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
-    "MATH_FP32", "MATH_TF32X3", "MATH_AUTO", "ENGINE_SIMT", "ENGINE_DIRECT", "ENGINE_UMMA", "ENGINE_NARROW",
+    "MATH_FP32", "MATH_TF32X3", "MATH_AUTO", "MATH_TF32", "MATH_BF16", "ENGINE_SIMT", "ENGINE_DIRECT", "ENGINE_UMMA", "ENGINE_NARROW",
 ]
 
 _launches = 0  # kernels enqueued through this module (bench.py's gpu_launches)
@@ -105,8 +106,11 @@ class ConvGeom:
 
 
 # --------------------------------------------------------------------------- conv family
-def conv_packed_bytes(g: ConvGeom, direction: int) -> int:
-    d = g.desc(1, 2, 2)
+def conv_packed_bytes(g: ConvGeom, direction: int, math: int = MATH_AUTO) -> int:
+    """Bytes of the layer's weight panel.  The panel layout depends on the math mode (RCV_MATH_BF16 panels of the
+    halo-staged layers are bf16), and -- for that mode -- on whether the layer runs on the halo-staged kernel, which
+    the geometry decides for any plausible image size: probed at a nominal 16x16 image."""
+    d = g.desc(1, 16, 16, EPI_NONE, math)
     n = _lib.load().rcv_conv_packed_bytes(C.byref(d), int(direction))
     if n == 0:
         raise _lib.RcvError("rcv_conv_packed_bytes", -1, _lib.load().rcv_last_error().decode())
@@ -127,14 +131,14 @@ def conv_engine(g: ConvGeom, n: int, h: int, w: int, direction: int = PACK_FWD, 
     return int(e)
 
 
-def conv_pack(g: ConvGeom, w, direction: int, out=None):
-    """Weight panel of the tensor-core engine for `w` (one launch); `out` is reused when given."""
+def conv_pack(g: ConvGeom, w, direction: int, out=None, math: int = MATH_AUTO):
+    """Weight panel of the tensor-core engine for `w` in math mode `math` (one launch); `out` is reused when given."""
     w = _chk(w, name="weight")
     if tuple(w.shape) != g.weight_shape():
         raise ValueError(f"conv_pack: w {tuple(w.shape)} does not match geometry")
     if out is None:
-        out = torch.empty(conv_packed_bytes(g, direction), device=w.device, dtype=torch.uint8)
-    d = g.desc(1, 2, 2)
+        out = torch.empty(conv_packed_bytes(g, direction, math), device=w.device, dtype=torch.uint8)
+    d = g.desc(1, 16, 16, EPI_NONE, math)
     _call("rcv_conv_pack", 1, C.byref(d), int(direction), _ptr(w), _ptr(out), _stream())
     return out
 
@@ -143,11 +147,11 @@ class PackTable:
     """Device-resident job table that re-packs the weight panels of many layers in one launch
     (rcv_conv_pack_table_*).  Valid while every weight / panel pointer it was built from is."""
 
-    def __init__(self, jobs):
+    def __init__(self, jobs, math: int = MATH_AUTO):
         """jobs: list of (ConvGeom, direction, weight tensor, packed uint8 tensor)."""
         n = len(jobs)
         lib = _lib.load()
-        descs = (ConvDesc * n)(*[g.desc(1, 2, 2) for g, _, _, _ in jobs])
+        descs = (ConvDesc * n)(*[g.desc(1, 16, 16, EPI_NONE, math) for g, _, _, _ in jobs])
         dirs = (C.c_int32 * n)(*[int(d) for _, d, _, _ in jobs])
         ws = (C.c_void_p * n)(*[w.data_ptr() for _, _, w, _ in jobs])
         ps = (C.c_void_p * n)(*[pk.data_ptr() for _, _, _, pk in jobs])
@@ -181,7 +185,7 @@ def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum
 
 def _packed_for(g, w, wpacked, math, direction):
     if wpacked is None and math == MATH_TF32X3:
-        wpacked = conv_pack(g, w, direction)
+        wpacked = conv_pack(g, w, direction, math=math)
     return wpacked
 
 

@@ -122,13 +122,22 @@ class TrainStep:
                 for i, (p, _, _) in enumerate(self.table):
                     if id(p) in ids:
                         mult[i] = mu
+        # Parameters no plan node owns (PB_FCN's unused patch-classification head) never receive a gradient: torch
+        # leaves their .grad None and every optimiser skips them -- unless the L1 term (which sums over ALL
+        # parameters, train.py:23-27) gives them one.  Without L1 they are left out of the optimiser ranges, so
+        # SGD's weight decay does not touch them either.
+        in_plan = {id(q) for q in self.plan.params}
         self.ranges = []  # (start, end, mult)
         ends = [o for _, o, _ in self.table[1:]] + [n]
+        prev_end = None
         for (p, o, k), e, mu in zip(self.table, ends, mult.tolist()):
-            if self.ranges and self.ranges[-1][2] == mu:
+            if id(p) not in in_plan and self.l1_decay == 0.0:
+                continue
+            if self.ranges and self.ranges[-1][2] == mu and prev_end == o:
                 self.ranges[-1] = (self.ranges[-1][0], e, mu)
             else:
                 self.ranges.append((o, e, mu))
+            prev_end = e
         self.base_lr = lr
         self._lr_host = torch.tensor([lr * r[2] for r in self.ranges], dtype=torch.float32).pin_memory()
         self.lr_dev = self._lr_host.to(dev)
