@@ -646,7 +646,7 @@ def dominant_kernel_roofline(model, wl, batch, dev, pk):
     y = torch.empty(batch, g.cout, ho, wo, device=dev)
     eng = ops.conv_engine(g, batch, best_in[1], best_in[2], ops.PACK_FWD, math)
     on_tc = eng == ops.ENGINE_UMMA
-    wp = ops.conv_pack(g, wt, ops.PACK_FWD, math=math) if on_tc else None
+    wp = ops.conv_pack(g, wt, ops.PACK_FWD, math=math, nhw=(batch, best_in[1], best_in[2])) if on_tc else None
     ms = _time_alone(lambda: ops.conv_fwd(g, x, wt, None, epilogue=ops.EPI_RELU, out=y, math=math, wpacked=wp), dev)
     flops = best_fl * batch
     bytes_alg = 4.0 * (x.numel() + y.numel() + wt.numel())

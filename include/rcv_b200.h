@@ -284,6 +284,32 @@ int rcv_maxpool2x2_bwd(int32_t N, int32_t C, int32_t H, int32_t W,
                        const float* dy, const uint8_t* code, float* dx,
                        void* stream);
 
+/* ---- decoder-side resampling extras (north_star: "a fused pool-index/unpool
+ * pair", "transposed-conv/bilinear upsampling").  The reference has neither an
+ * unpool nor a bilinear layer (model.py:178-194 is its only upsampler; "bilinear"
+ * occurs only as a PIL resize, transform.py:8-19), so these replace the
+ * torch.nn.functional calls a decoder variant would make and are pinned
+ * against them. ------------------------------------------------------------- */
+/* out[N,C,H,W] = F.max_unpool2d(y[N,C,H/2,W/2], idx, 2, 2) (+ skip[N,C,H,W] if
+ * not NULL): positions from idx (int64 plane index, as rcv_maxpool2x2_fwd
+ * writes) or, when idx is NULL, from the uint8 window codes.  Every element of
+ * out is written. */
+int rcv_maxunpool2x2_fwd(int32_t N, int32_t C, int32_t H, int32_t W,
+                         const float* y, const int64_t* idx, const uint8_t* code,
+                         const float* skip, float* out, void* stream);
+/* dy[N,C,H/2,W/2] = dout[N,C,H,W] gathered at the stored positions. */
+int rcv_maxunpool2x2_bwd(int32_t N, int32_t C, int32_t H, int32_t W,
+                         const float* dout, const int64_t* idx,
+                         const uint8_t* code, float* dy, void* stream);
+/* out[N,C,2H,2W] = F.interpolate(x[N,C,H,W], scale_factor=2, mode="bilinear",
+ * align_corners=False) (+ skip[N,C,2H,2W] if not NULL). */
+int rcv_upsample_bilinear2x_fwd(int32_t N, int32_t C, int32_t H, int32_t W,
+                                const float* x, const float* skip, float* out,
+                                void* stream);
+/* dx[N,C,H,W] = the adjoint applied to dout[N,C,2H,2W]. */
+int rcv_upsample_bilinear2x_bwd(int32_t N, int32_t C, int32_t H, int32_t W,
+                                const float* dout, float* dx, void* stream);
+
 /* ---- weighted softmax cross-entropy + argmax + confusion ----------------- */
 /* CrossEntropyLoss2d (model.py:76-82), torch.max(pred,1) (train.py:70,128) and
  * the per-image confusion loop (train.py:133-153) in one pass over the logits.

@@ -52,7 +52,7 @@ WGRAD_ON_LOAD = _os.environ.get("RCV_B200_WGRAD_ON_LOAD", "0") != "0"
 
 class Node:
     __slots__ = ("kind", "src", "conv", "bn", "order", "skip", "skip_mode", "geom", "_fold_key",
-                 "_fold_val", "skip_ch", "_pack", "_pack_key", "_tc")
+                 "_fold_val", "skip_ch", "_pack", "_pack_key", "_tc", "_pack_bytes")
 
     def __init__(self, kind, src, conv=None, bn=None, order=EPI_NONE, skip=-1, skip_mode="add"):
         self.kind, self.src, self.conv, self.bn = kind, src, conv, bn
@@ -64,6 +64,7 @@ class Node:
         self._pack = [None, None]      # persistent packed-weight buffers (fwd, dgrad)
         self._pack_key = [None, None]
         self._tc = {}                  # (direction, math) -> does this direction run on tensor cores
+        self._pack_bytes = {}          # (direction, math, nhw) -> panel bytes
 
     def params(self) -> List[nn.Parameter]:
         out = []
@@ -84,20 +85,22 @@ class Node:
             hit = self._tc[(direction, math)] = ops.conv_uses_tensor_cores(self.geom, direction, math)
         return hit
 
-    def pack_buffer(self, direction: int, math: int) -> torch.Tensor:
-        """Persistent panel buffer (allocated once per device and math mode: CUDA-graph safe)."""
+    def pack_buffer(self, direction: int, math: int, nhw) -> torch.Tensor:
+        """Persistent panel buffer (allocated once per device, math mode and panel size: CUDA-graph safe)."""
         w = self.conv.weight
         buf = self._pack[direction]
-        nbytes = ops.conv_packed_bytes(self.geom, direction, math)
+        nbytes = self._pack_bytes.get((direction, math, nhw))
+        if nbytes is None:
+            nbytes = self._pack_bytes[(direction, math, nhw)] = ops.conv_packed_bytes(self.geom, direction, math, nhw)
         if buf is None or buf.device != w.device or buf.numel() != nbytes:
             buf = torch.empty(nbytes, device=w.device, dtype=torch.uint8)
             self._pack[direction] = buf
             self._pack_key[direction] = None
         return buf
 
-    def pack_key(self, epoch: int, math: int):
+    def pack_key(self, epoch: int, math: int, nhw):
         w = self.conv.weight
-        return (w.data_ptr(), w._version, epoch, math)
+        return (w.data_ptr(), w._version, epoch, math, nhw)
 
     def folded(self, epoch: int = 0):
         bn = self.bn
@@ -156,6 +159,7 @@ class Plan:
             if nd.skip is not None and nd.skip >= 0:
                 self._consumers.setdefault(nd.skip, []).append((t, "skip"))
         self._defer_cache = {}
+        self._size_cache = {}
         self.n_stats = 0
         self._sum_off = {}
         for t, nd in enumerate(self.nodes):
@@ -163,25 +167,40 @@ class Plan:
                 self._sum_off[t] = self.n_stats
                 self.n_stats += 2 * nd.geom.cout
 
-    def _ensure_packed(self, directions, fresh: bool, x_requires_grad: bool):
+    def _in_sizes(self, n: int, h: int, w: int):
+        """(N, H, W) of every node's main input for a plan input of that size."""
+        key = (n, h, w)
+        hit = self._size_cache.get(key)
+        if hit is None:
+            hw = [(h, w)]
+            for nd in self.nodes:
+                ih, iw = hw[nd.src]
+                hw.append((ih // 2, iw // 2) if nd.kind == "pool" else nd.geom.out_hw(ih, iw))
+            hit = self._size_cache[key] = [(n, *hw[nd.src]) for nd in self.nodes]
+        return hit
+
+    def _ensure_packed(self, directions, fresh: bool, x_requires_grad: bool, nhw):
         """Weight panels of every tensor-core layer, re-packed in ONE launch when `fresh` (training:
-        the weights change every step) or when any weight tensor / the plan epoch changed."""
-        jobs = [(nd, d) for nd in self.nodes if nd.kind == "conv" for d in directions
+        the weights change every step) or when any weight tensor / the plan epoch changed.  nhw: the plan input's
+        (N, H, W) -- the bf16 fast mode's panel layout follows the kernel each layer runs on at its input size."""
+        sizes = self._in_sizes(*nhw) if self.math == MATH_BF16 else [ops.NOMINAL_NHW] * len(self.nodes)
+        jobs = [(nd, d, sz) for nd, sz in zip(self.nodes, sizes) if nd.kind == "conv" for d in directions
                 if nd.uses_tc(d, self.math) and not (d == PACK_DGRAD and nd.src == 0 and not x_requires_grad)]
         if not jobs:
             return
-        bufs = [nd.pack_buffer(d, self.math) for nd, d in jobs]
-        if not fresh and all(nd._pack_key[d] == nd.pack_key(self.epoch, self.math) for nd, d in jobs):
+        bufs = [nd.pack_buffer(d, self.math, sz) for nd, d, sz in jobs]
+        if not fresh and all(nd._pack_key[d] == nd.pack_key(self.epoch, self.math, sz) for nd, d, sz in jobs):
             return
-        tkey = tuple((nd.conv.weight.data_ptr(), b.data_ptr()) for (nd, _), b in zip(jobs, bufs))
+        tkey = tuple((nd.conv.weight.data_ptr(), b.data_ptr(), sz) for (nd, _, sz), b in zip(jobs, bufs))
         tbl = self._pack_tables.get((tuple(directions), self.math))
         if tbl is None or tbl.key != tkey:
-            tbl = ops.PackTable([(nd.geom, d, nd.conv.weight.detach(), b) for (nd, d), b in zip(jobs, bufs)],
-                                math=self.math)
+            tbl = ops.PackTable([(nd.geom, d, nd.conv.weight.detach(), b) for (nd, d, _), b in zip(jobs, bufs)],
+                                math=self.math, sizes=[sz for _, _, sz in jobs])
+            tbl.key = tkey
             self._pack_tables[(tuple(directions), self.math)] = tbl
         tbl.run()
-        for nd, d in jobs:
-            nd._pack_key[d] = nd.pack_key(self.epoch, self.math)
+        for nd, d, sz in jobs:
+            nd._pack_key[d] = nd.pack_key(self.epoch, self.math, sz)
 
     def _defer_bn_apply(self, t: int, n: int, h: int, w: int) -> bool:
         """Can node t's BatchNorm apply pass be left to its consumers (normalise-on-load)?  Its output must feed only
@@ -214,7 +233,8 @@ class Plan:
         soff = 0
         if training:
             self.epoch += 1
-        self._ensure_packed((PACK_FWD, PACK_DGRAD) if save else (PACK_FWD,), training, x.requires_grad)
+        self._ensure_packed((PACK_FWD, PACK_DGRAD) if save else (PACK_FWD,), training, x.requires_grad,
+                            (x.shape[0], x.shape[2], x.shape[3]))
         for t, nd in enumerate(self.nodes):
             src = acts[nd.src]
             if nd.kind == "pool":

@@ -28,7 +28,7 @@ from .ops import EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE
 
 __all__ = [
     "DiceLoss", "CrossEntropyLoss2d", "pruneModelNew", "pruneModel", "pruneModel2", "count_zero_weights",
-    "getParamSize", "Pool", "Conv", "ConvPool", "ConvPoolDouble", "ConvPoolSimple",
+    "getParamSize", "Pool", "PoolWithIndices", "MaxUnpool2x2", "UpsampleBilinear2x", "Conv", "ConvPool", "ConvPoolDouble", "ConvPoolSimple",
     "upSampleTransposeConv", "DownSampler", "DownSamplerThick", "Classifier", "PB_FCN", "FCN",
     "LevelDown", "UltClassifier", "ROBO_UNet", "LabelProp", "PB_FCN_2", "load_legacy_state_dict",
     "remap_legacy_keys", "torch", "nn",
@@ -255,6 +255,68 @@ class Pool(_PlanModule):
 
     def getComp(self, W, H, pruned):
         return W * H * self.ch, W // self.stride, H // self.stride
+
+
+class _PoolIdx(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y, idx, code = ops.maxpool2x2_fwd(x, want_idx=True, want_code=True)
+        ctx.save_for_backward(code)
+        ctx.in_hw = tuple(x.shape[2:])
+        ctx.mark_non_differentiable(idx)
+        return y, idx
+
+    @staticmethod
+    def backward(ctx, dy, _didx):
+        return ops.maxpool2x2_bwd(dy.contiguous(), ctx.saved_tensors[0], ctx.in_hw)
+
+
+class _Unpool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, idx, skip):
+        ctx.save_for_backward(idx)
+        ctx.has_skip = skip is not None
+        return ops.maxunpool2x2(y, idx=idx, skip=skip)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        return ops.maxunpool2x2_bwd(dout, idx=ctx.saved_tensors[0]), None, (dout if ctx.has_skip else None)
+
+
+class _Bilinear2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, skip):
+        ctx.has_skip = skip is not None
+        return ops.upsample_bilinear2x(x, skip=skip)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        return ops.upsample_bilinear2x_bwd(dout), (dout if ctx.has_skip else None)
+
+
+class PoolWithIndices(nn.Module):
+    """nn.MaxPool2d(2, 2, return_indices=True): the pool half of the pool-index / unpool pair north_star names (the
+    reference's own Pool, model.py:92-100, keeps the indices implicit).  -> (y, int64 indices)."""
+
+    def forward(self, x):
+        return _PoolIdx.apply(x)
+
+
+class MaxUnpool2x2(nn.Module):
+    """nn.MaxUnpool2d(2, 2) with an optional fused skip add (`up = unpool(x, idx) + skip`, the decoder pattern of
+    model.py:505-509 with the transposed convolution swapped for an unpool)."""
+
+    def forward(self, y, indices, skip=None):
+        return _Unpool.apply(y, indices, skip)
+
+
+class UpsampleBilinear2x(nn.Module):
+    """F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) with an optional fused skip add."""
+
+    def forward(self, x, skip=None):
+        return _Bilinear2x.apply(x, skip)
 
 
 def _nnz_ratio(w, pruned):

@@ -19,7 +19,7 @@ from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_A
 
 __all__ = [
     "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
-    "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "ce_fwd", "ce_bwd",
+    "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "maxunpool2x2", "maxunpool2x2_bwd", "upsample_bilinear2x", "upsample_bilinear2x_bwd", "ce_fwd", "ce_bwd",
     "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "zero_", "zeros", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
     "MATH_FP32", "MATH_TF32X3", "MATH_AUTO", "MATH_TF32", "MATH_BF16", "ENGINE_SIMT", "ENGINE_DIRECT", "ENGINE_UMMA", "ENGINE_NARROW",
@@ -106,11 +106,15 @@ class ConvGeom:
 
 
 # --------------------------------------------------------------------------- conv family
-def conv_packed_bytes(g: ConvGeom, direction: int, math: int = MATH_AUTO) -> int:
-    """Bytes of the layer's weight panel.  The panel layout depends on the math mode (RCV_MATH_BF16 panels of the
-    halo-staged layers are bf16), and -- for that mode -- on whether the layer runs on the halo-staged kernel, which
-    the geometry decides for any plausible image size: probed at a nominal 16x16 image."""
-    d = g.desc(1, 16, 16, EPI_NONE, math)
+NOMINAL_NHW = (1, 16, 16)
+
+
+def conv_packed_bytes(g: ConvGeom, direction: int, math: int = MATH_AUTO, nhw=NOMINAL_NHW) -> int:
+    """Bytes of the layer's weight panel.  The panel layout depends on the math mode: RCV_MATH_BF16 panels are bf16
+    for the layers the halo-staged kernel runs AT THE INPUT SIZE `nhw` = (N, H, W) (long rows or deep dilation fall
+    to the single-pass tf32 kernels and their fp32 panels), so that mode must be given the real size; the other
+    modes' panels do not depend on it."""
+    d = g.desc(*nhw, EPI_NONE, math)
     n = _lib.load().rcv_conv_packed_bytes(C.byref(d), int(direction))
     if n == 0:
         raise _lib.RcvError("rcv_conv_packed_bytes", -1, _lib.load().rcv_last_error().decode())
@@ -131,14 +135,15 @@ def conv_engine(g: ConvGeom, n: int, h: int, w: int, direction: int = PACK_FWD, 
     return int(e)
 
 
-def conv_pack(g: ConvGeom, w, direction: int, out=None, math: int = MATH_AUTO):
-    """Weight panel of the tensor-core engine for `w` in math mode `math` (one launch); `out` is reused when given."""
+def conv_pack(g: ConvGeom, w, direction: int, out=None, math: int = MATH_AUTO, nhw=NOMINAL_NHW):
+    """Weight panel of the tensor-core engine for `w` in math mode `math` (one launch); `out` is reused when given.
+    nhw: the input size the panel will be used at (see conv_packed_bytes)."""
     w = _chk(w, name="weight")
     if tuple(w.shape) != g.weight_shape():
         raise ValueError(f"conv_pack: w {tuple(w.shape)} does not match geometry")
     if out is None:
-        out = torch.empty(conv_packed_bytes(g, direction, math), device=w.device, dtype=torch.uint8)
-    d = g.desc(1, 16, 16, EPI_NONE, math)
+        out = torch.empty(conv_packed_bytes(g, direction, math, nhw), device=w.device, dtype=torch.uint8)
+    d = g.desc(*nhw, EPI_NONE, math)
     _call("rcv_conv_pack", 1, C.byref(d), int(direction), _ptr(w), _ptr(out), _stream())
     return out
 
@@ -147,11 +152,13 @@ class PackTable:
     """Device-resident job table that re-packs the weight panels of many layers in one launch
     (rcv_conv_pack_table_*).  Valid while every weight / panel pointer it was built from is."""
 
-    def __init__(self, jobs, math: int = MATH_AUTO):
-        """jobs: list of (ConvGeom, direction, weight tensor, packed uint8 tensor)."""
+    def __init__(self, jobs, math: int = MATH_AUTO, sizes=None):
+        """jobs: list of (ConvGeom, direction, weight tensor, packed uint8 tensor); sizes: the (N, H, W) each panel is
+        used at (see conv_packed_bytes), nominal when omitted."""
         n = len(jobs)
         lib = _lib.load()
-        descs = (ConvDesc * n)(*[g.desc(1, 16, 16, EPI_NONE, math) for g, _, _, _ in jobs])
+        sizes = sizes or [NOMINAL_NHW] * n
+        descs = (ConvDesc * n)(*[g.desc(*sz, EPI_NONE, math) for (g, _, _, _), sz in zip(jobs, sizes)])
         dirs = (C.c_int32 * n)(*[int(d) for _, d, _, _ in jobs])
         ws = (C.c_void_p * n)(*[w.data_ptr() for _, _, w, _ in jobs])
         ps = (C.c_void_p * n)(*[pk.data_ptr() for _, _, _, pk in jobs])
@@ -370,6 +377,50 @@ def maxpool2x2_bwd(dy, code, in_hw):
     h, w = in_hw
     dx = torch.empty((n, c, h, w), device=dy.device, dtype=torch.float32)
     _call("rcv_maxpool2x2_bwd", 1, n, c, h, w, _ptr(dy), _ptr(code), _ptr(dx), _stream())
+    return dx
+
+
+def maxunpool2x2(y, idx=None, code=None, skip=None):
+    """F.max_unpool2d(y, idx, 2, 2) (+ skip) from the int64 indices or the uint8 window codes of maxpool2x2_fwd."""
+    y = _chk(y, name="y")
+    if idx is None and code is None:
+        raise ValueError("maxunpool2x2: needs idx or code")
+    n, c, ho, wo = y.shape
+    out = torch.empty((n, c, 2 * ho, 2 * wo), device=y.device, dtype=torch.float32)
+    if skip is not None:
+        skip = _chk(skip, name="skip")
+        if skip.shape != out.shape:
+            raise ValueError("maxunpool2x2: skip shape mismatch")
+    _call("rcv_maxunpool2x2_fwd", 1, n, c, 2 * ho, 2 * wo, _ptr(y), _ptr(idx), _ptr(code), _ptr(skip), _ptr(out), _stream())
+    return out
+
+
+def maxunpool2x2_bwd(dout, idx=None, code=None):
+    dout = _chk(dout, name="dout")
+    n, c, h, w = dout.shape
+    dy = torch.empty((n, c, h // 2, w // 2), device=dout.device, dtype=torch.float32)
+    _call("rcv_maxunpool2x2_bwd", 1, n, c, h, w, _ptr(dout), _ptr(idx), _ptr(code), _ptr(dy), _stream())
+    return dy
+
+
+def upsample_bilinear2x(x, skip=None):
+    """F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False) (+ skip)."""
+    x = _chk(x, name="x")
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, 2 * h, 2 * w), device=x.device, dtype=torch.float32)
+    if skip is not None:
+        skip = _chk(skip, name="skip")
+        if skip.shape != out.shape:
+            raise ValueError("upsample_bilinear2x: skip shape mismatch")
+    _call("rcv_upsample_bilinear2x_fwd", 1, n, c, h, w, _ptr(x), _ptr(skip), _ptr(out), _stream())
+    return out
+
+
+def upsample_bilinear2x_bwd(dout):
+    dout = _chk(dout, name="dout")
+    n, c, h2, w2 = dout.shape
+    dx = torch.empty((n, c, h2 // 2, w2 // 2), device=dout.device, dtype=torch.float32)
+    _call("rcv_upsample_bilinear2x_bwd", 1, n, c, h2 // 2, w2 // 2, _ptr(dout), _ptr(dx), _stream())
     return dx
 
 

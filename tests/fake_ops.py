@@ -10,6 +10,7 @@ from robocupvision_b200 import ops as real
 from robocupvision_b200.ops import *  # noqa: F401,F403  (constants: EPI_*, MATH_*, PACK_*)
 from robocupvision_b200.ops import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_NONE, EPI_RELU, EPI_RELU_AFFINE)
 
+NOMINAL_NHW = real.NOMINAL_NHW
 calls = []  # (name, detail) log, for assertions about the schedule
 
 

@@ -23,7 +23,7 @@ from util import assert_close
 pytestmark = pytest.mark.gpu
 
 # mode -> (logit tolerance relative to max|ref|, allowed argmax flip fraction, gradient tolerance)
-TOL = {"tf32": (4e-3, 2e-3, 2e-2), "bf16": (1.5e-2, 6e-3, 5e-2)}
+TOL = {"tf32": (2e-3, 1e-3, 5e-2), "bf16": (6e-3, 2e-3, 1e-1)}
 
 
 def _round_tf32(t):
@@ -52,7 +52,7 @@ def test_fast_conv_is_the_conv_of_rounded_operands(mode, cin, cout, dil, nhw):
     b = torch.randn(cout, generator=gen)
     g = ops.ConvGeom(cin, cout, 3, 1, dil, dil, False)
     assert ops.conv_engine(g, n, h, w_, ops.PACK_FWD, math) == ops.ENGINE_UMMA
-    wp = ops.conv_pack(g, wt.cuda(), ops.PACK_FWD, math=math)
+    wp = ops.conv_pack(g, wt.cuda(), ops.PACK_FWD, math=math, nhw=(n, h, w_))
     got = ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), epilogue=ops.EPI_RELU, math=math, wpacked=wp)
     # the bf16 operand format applies where the reduced channel count is a multiple of 64 (halo-staged kernel);
     # other tensor-core layers of that mode run single-pass tf32
@@ -66,7 +66,7 @@ def test_fast_conv_is_the_conv_of_rounded_operands(mode, cin, cout, dil, nhw):
 
     # input gradient and weight gradient in the same mode
     dy = torch.randn(n, cout, h, w_, generator=gen)
-    wpd = ops.conv_pack(g, wt.cuda(), ops.PACK_DGRAD, math=math)
+    wpd = ops.conv_pack(g, wt.cuda(), ops.PACK_DGRAD, math=math, nhw=(n, h, w_))
     dx = ops.conv_dgrad(g, dy.cuda(), wt.cuda(), (h, w_), math=math, wpacked=wpd)
     dx_ref = torch.nn.grad.conv2d_input(x.shape, wt, dy, 1, dil, dil)
     dw, _ = ops.conv_wgrad(g, x.cuda(), dy.cuda(), math=math)
@@ -143,8 +143,8 @@ def test_robo_unet_fast_modes_eval(mode):
 
 @pytest.mark.parametrize("mode", ["tf32", "bf16"])
 def test_robo_unet_fast_modes_gradients(mode):
-    """One training step's gradients in a fast mode against CPU autograd over the oracle (per tensor, relative to the
-    tensor's largest gradient, floor 1e-3 of the net's largest)."""
+    """One training step's gradients in a fast mode against CPU autograd over the oracle (relative L2 per tensor, floor
+    1e-3 of the net's largest gradient norm)."""
     from robocupvision_b200.model import CrossEntropyLoss2d, ROBO_UNet
     sd, kw, okw = robo_state("robo_default")
     m = ROBO_UNet(**kw)
@@ -164,17 +164,16 @@ def test_robo_unet_fast_modes_gradients(mode):
     ltol, _, gtol = TOL[mode]
     assert_close(f"{mode} train logits", pred, pred_ref, ltol)
     assert abs(float(loss.detach()) - float(loss_ref)) <= ltol * max(1.0, abs(float(loss_ref)))
-    gmax = max(float(v.grad.abs().max()) for v in osd.values() if v.grad is not None)
-    worst = 0.0
+    gmax = max(float(v.grad.norm()) for v in osd.values() if v.grad is not None)
+    worst = (0.0, "")
     for k, p in m.named_parameters():
         gref = osd[k].grad
         if gref is None:
             continue
-        scale = max(float(gref.abs().max()), 1e-3 * gmax)
-        err = float((p.grad.cpu() - gref).abs().max()) / scale
-        worst = max(worst, err)
-        assert err <= gtol, f"{mode}: grad {k} rel err {err:.3e}"
-    print(f"{mode}: worst grad rel err {worst:.2e}")
+        err = float((p.grad.cpu() - gref).norm()) / max(float(gref.norm()), 1e-3 * gmax)
+        worst = max(worst, (err, k))
+        assert err <= gtol, f"{mode}: grad {k} relative L2 {err:.3e}"
+    print(f"{mode}: worst gradient relative L2 {worst[0]:.2e} ({worst[1]})")
 
 
 @pytest.mark.parametrize("mode", ["tf32", "bf16"])

@@ -374,6 +374,78 @@ def test_maxpool(shape):
     assert torch.equal(dx.cpu(), xr.grad)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 8, 12), (3, 8, 120, 160), (1, 1, 2, 2), (2, 16, 30, 40)])
+@pytest.mark.parametrize("use_code", [False, True])
+def test_maxunpool_pair(shape, use_code):
+    """The pool-index / unpool pair: rcv_maxunpool2x2_fwd/bwd on the indices (or 2-bit codes) of rcv_maxpool2x2_fwd
+    against F.max_unpool2d and its autograd, bit-exact (pure data movement), with and without the fused skip add."""
+    from robocupvision_b200 import ops
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(shape, generator=gen)
+    y_ref, idx_ref = F.max_pool2d(x, 2, 2, return_indices=True)
+    y, idx, code = ops.maxpool2x2_fwd(x.cuda(), want_idx=True, want_code=True)
+    assert torch.equal(idx.cpu(), idx_ref)
+    v = torch.randn(y_ref.shape, generator=gen).requires_grad_(True)
+    up_ref = F.max_unpool2d(v, idx_ref, 2, 2)
+    dout = torch.randn(shape, generator=gen)
+    up_ref.backward(dout)
+    kw = dict(code=code) if use_code else dict(idx=idx)
+    up = ops.maxunpool2x2(v.detach().cuda(), **kw)
+    assert torch.equal(up.cpu(), up_ref.detach())
+    skip = torch.randn(shape, generator=gen)
+    up2 = ops.maxunpool2x2(v.detach().cuda(), skip=skip.cuda(), **kw)
+    assert torch.equal(up2.cpu(), up_ref.detach() + skip)
+    dv = ops.maxunpool2x2_bwd(dout.cuda(), **kw)
+    assert torch.equal(dv.cpu(), v.grad)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 8, 12), (2, 16, 60, 80), (1, 2, 1, 1), (3, 5, 1, 7), (2, 4, 15, 20), (1, 3, 5, 3)])
+def test_bilinear_upsample_2x(shape):
+    """rcv_upsample_bilinear2x_fwd/bwd against F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) and
+    its autograd; tolerance 1e-6 of the output range (the weights 1/4, 3/4 are exact, the sums round)."""
+    from robocupvision_b200 import ops
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(shape, generator=gen, requires_grad=True)
+    ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+    dout = torch.randn(ref.shape, generator=gen)
+    ref.backward(dout)
+    got = ops.upsample_bilinear2x(x.detach().cuda())
+    assert_close("bilinear fwd", got, ref, 1e-6)
+    skip = torch.randn(ref.shape, generator=gen)
+    got2 = ops.upsample_bilinear2x(x.detach().cuda(), skip=skip.cuda())
+    assert_close("bilinear fwd + skip", got2, ref.detach() + skip, 1e-6)
+    dx = ops.upsample_bilinear2x_bwd(dout.cuda())
+    assert_close("bilinear bwd", dx, x.grad, 2e-6)
+
+
+def test_resample_modules_autograd():
+    """PoolWithIndices -> MaxUnpool2x2(+skip) and UpsampleBilinear2x(+skip) as autograd modules against the torch.nn
+    layers they stand for."""
+    from robocupvision_b200.model import MaxUnpool2x2, PoolWithIndices, UpsampleBilinear2x
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 8, 24, 32, generator=gen)
+    s = torch.randn(2, 8, 24, 32, generator=gen)
+    g = torch.randn(2, 8, 24, 32, generator=gen)
+    xr, sr = x.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    yr, ir = F.max_pool2d(xr, 2, 2, return_indices=True)
+    outr = F.max_unpool2d(yr * 2.0, ir, 2, 2) + sr
+    outr.backward(g)
+    xg, sg = x.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+    y, i = PoolWithIndices()(xg)
+    out = MaxUnpool2x2()(y * 2.0, i, sg)
+    out.backward(g.cuda())
+    assert torch.equal(out.detach().cpu(), outr.detach()) and torch.equal(xg.grad.cpu(), xr.grad)
+    assert torch.equal(sg.grad.cpu(), sr.grad)
+    xr2 = x[:, :, :12, :16].clone().requires_grad_(True)
+    r2 = F.interpolate(xr2, scale_factor=2, mode="bilinear", align_corners=False) + sr.detach()
+    r2.backward(g)
+    xg2 = x[:, :, :12, :16].contiguous().cuda().requires_grad_(True)
+    o2 = UpsampleBilinear2x()(xg2, s.cuda())
+    o2.backward(g.cuda())
+    assert_close("module bilinear", o2, r2, 1e-6)
+    assert_close("module bilinear grad", xg2.grad, xr2.grad, 2e-6)
+
+
 @pytest.mark.parametrize("c", [5, 4, 2, 8])
 @pytest.mark.parametrize("weighted", [True, False])
 def test_cross_entropy_argmax_confusion(c, weighted):

@@ -131,30 +131,42 @@ def test_lr_groups_and_cosine_schedule():
 
 
 def _rel_l2_grad_check(tag, model, oracle_fwd, sd, x, y, weights, tol):
-    """Full-size gradient gate: relative L2 per tensor, train-mode logits and loss exact to the
-    usual tolerances.  Element-wise gates at full size trip over ReLU-after-BatchNorm flips within an ulp of zero."""
+    """Full-size gradient gate: train-mode logits and loss against the fp32 oracle to the usual
+    tolerances; gradients per tensor in relative L2 against the oracle evaluated in FLOAT64, with the fp32 oracle's
+    own distance from that float64 result as the yardstick: err_gpu <= tol + 10 * err_ref.  At full size the
+    reference's fp32 gradients sit 4e-4 [ROBO_UNet noScale 240x320] to 2.4e-3 [bestModelSegVGA, BatchNorm gains up to
+    50x] from the float64 ones, worst on the first layer, whose gradients are cancelling sums over every pixel of what
+    the whole backward chain delivered (a conv bias in front of ReLU -> BatchNorm sums a zero-mean tensor over its
+    active pixels).  The factor 10 is the accuracy ratio of the products: the tensor-core layers' 3xTF32 products
+    carry ~3e-6 of the output range against ~3e-7 for a chain of fp32 FMAs.  Element-wise gates at
+    full size trip over ReLU-after-BatchNorm flips within an ulp of zero."""
     from robocupvision_b200.model import CrossEntropyLoss2d
     osd = R.leaf_state_dict(sd)
     pred_ref = oracle_fwd(osd, x)
     loss_ref = R.cross_entropy_2d(pred_ref, y, torch.tensor(weights))
     loss_ref.backward()
+    osd64 = R.leaf_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()})
+    loss64 = R.cross_entropy_2d(oracle_fwd(osd64, x.double()), y, torch.tensor(weights, dtype=torch.float64))
+    loss64.backward()
     model.cuda().train()
     pred = model(x.cuda())
     loss = CrossEntropyLoss2d(torch.tensor(weights)).cuda()(pred, y.cuda())
     loss.backward()
     assert_close(f"{tag} train logits", pred, pred_ref, 1e-4)
-    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
-    gmax = max(float(v.grad.norm()) for v in osd.values() if v.grad is not None)
-    worst = 0.0
+    assert abs(float(loss.detach()) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    gmax = max(float(v.grad.norm()) for v in osd64.values() if v.grad is not None)
+    worst, worst_ref = 0.0, 0.0
     for k, p in model.named_parameters():
-        gref = osd[k].grad
-        if gref is None:
+        g64 = osd64[k].grad
+        if g64 is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
-        err = float((p.grad.cpu() - gref).norm()) / max(float(gref.norm()), 1e-3 * gmax)
-        worst = max(worst, err)
-        assert err <= tol, f"{tag}: grad {k} relative L2 {err:.3e}"
-    print(f"{tag}: worst gradient relative L2 {worst:.2e}")
+        den = max(float(g64.norm()), 1e-3 * gmax)
+        err = float((p.grad.cpu().double() - g64).norm()) / den
+        err_ref = float((osd[k].grad.double() - g64).norm()) / den
+        worst, worst_ref = max(worst, err), max(worst_ref, err_ref)
+        assert err <= tol + 10.0 * err_ref, f"{tag}: grad {k} relative L2 {err:.3e} from float64 (the fp32 reference: {err_ref:.3e})"
+    print(f"{tag}: worst gradient relative L2 from the float64 oracle {worst:.2e} (fp32 reference: {worst_ref:.2e})")
 
 
 def test_robo_noscale_backward():
@@ -216,7 +228,7 @@ def test_comm_path_schedule_matches_plain_step(use_graph):
     from robocupvision_b200.model import ROBO_UNet
     from robocupvision_b200.train import TrainStep
     models, steps = [], []
-    for comm in (False, True):
+    for comm in (False, True, False):  # plain, bucketed comm-stream schedule, and a second plain step as the control
         torch.manual_seed(12345678)
         m = ROBO_UNet().cuda()
         models.append(m)
@@ -231,11 +243,20 @@ def test_comm_path_schedule_matches_plain_step(use_graph):
             ts.step(x, y)
             losses.append(ts.loss_value())
         assert abs(losses[0] - losses[1]) <= 2e-6 * abs(losses[0]), (s, losses)
-    for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
+    # The weight-gradient kernels accumulate with floating-point atomics, so two runs of the SAME schedule differ
+    # too (run-to-run noise, which Adam's normalisation passes on): the comm-stream schedule must stay within the
+    # larger of 1e-4 and three times what the control shows for the same tensor.
+    worst = (0.0, 0.0, "")
+    for (k, a), (_, b), (_, c) in zip(*(m.state_dict().items() for m in models)):
         if a.is_floating_point():
-            assert_close(k, a, b, 1e-4)
+            scale = max(1.0, float(a.abs().max()))
+            noise = float((a - c).abs().max()) / scale
+            err = float((a - b).abs().max()) / scale
+            worst = max(worst, (err, noise, k))
+            assert err <= max(1e-4, 3.0 * noise), f"{k}: comm-path deviation {err:.2e}, control (plain vs plain) {noise:.2e}"
         else:
             assert torch.equal(a, b), k
+    print(f"comm path vs plain: worst deviation {worst[0]:.2e} at {worst[2]} (plain-vs-plain control there: {worst[1]:.2e})")
 
 
 def test_dp_self_check_single_rank_nccl():
