@@ -647,7 +647,9 @@ def dominant_kernel_roofline(model, wl, batch, dev, pk):
     eng = ops.conv_engine(g, batch, best_in[1], best_in[2], ops.PACK_FWD, math)
     on_tc = eng == ops.ENGINE_UMMA
     wp = ops.conv_pack(g, wt, ops.PACK_FWD, math=math, nhw=(batch, best_in[1], best_in[2])) if on_tc else None
-    ms = _time_alone(lambda: ops.conv_fwd(g, x, wt, None, epilogue=ops.EPI_RELU, out=y, math=math, wpacked=wp), dev)
+    ws = plan.workspace((batch, h, w), dev)  # the plan's conv scratch, as the step itself passes it
+    ms = _time_alone(lambda: ops.conv_fwd(g, x, wt, None, epilogue=ops.EPI_RELU, out=y, math=math, wpacked=wp,
+                                          workspace=ws), dev)
     flops = best_fl * batch
     bytes_alg = 4.0 * (x.numel() + y.numel() + wt.numel())
     intensity = flops / bytes_alg

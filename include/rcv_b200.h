@@ -96,6 +96,14 @@ typedef struct rcv_conv_desc {
   int32_t transposed;
   int32_t epilogue;     /* rcv_epilogue (forward only)                    */
   int32_t math;         /* rcv_math                                       */
+  /* Optional scratch for rcv_conv_fwd / rcv_conv_dgrad (NULL / 0: none).  Caller-owned device memory of at least
+   * rcv_conv_workspace_bytes(d, direction) bytes, 128-byte aligned, ZERO-FILLED ONCE by the caller before its first
+   * use (the kernels leave its counter area zeroed again), and used by one stream at a time.  With it the
+   * halo-staged tensor-core kernel splits the reduction of the pixel tiles that do not fill a whole wave of SMs
+   * across several CTAs (and of every tile when the layer has far fewer tiles than SMs: small batches);
+   * without it, or when it is too small, the same layer runs unsplit -- results agree to accumulation order. */
+  void* workspace;
+  uint64_t workspace_bytes;
 } rcv_conv_desc;
 
 int rcv_version(void);
@@ -125,6 +133,8 @@ size_t rcv_conv_packed_bytes(const rcv_conv_desc* d, int direction);
  * the tensor cores under d->math when given packed weights, else 0: lets the
  * caller skip packing layers that stay on CUDA cores under RCV_MATH_AUTO. */
 int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction);
+/* Bytes of scratch rcv_conv_fwd / rcv_conv_dgrad can use for this layer at this size (d->workspace; 0: none). */
+size_t rcv_conv_workspace_bytes(const rcv_conv_desc* d, int direction);
 int rcv_conv_pack(const rcv_conv_desc* d, int direction, const float* w,
                   void* packed, void* stream);
 

@@ -38,7 +38,8 @@ ENGINE_SIMT, ENGINE_DIRECT, ENGINE_UMMA, ENGINE_NARROW = 0, 1, 2, 3
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
-        "N", "Cin", "H", "W", "Cout", "ksize", "stride", "pad", "dil", "transposed", "epilogue", "math")]
+        "N", "Cin", "H", "W", "Cout", "ksize", "stride", "pad", "dil", "transposed", "epilogue", "math")] + [
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
 
 _p = C.c_void_p
@@ -53,6 +54,7 @@ SIGNATURES = {
     "rcv_conv_out_hw": [C.POINTER(ConvDesc), C.POINTER(_i32), C.POINTER(_i32)],
     "rcv_conv_packed_bytes": [C.POINTER(ConvDesc), C.c_int],
     "rcv_conv_uses_tensor_cores": [C.POINTER(ConvDesc), C.c_int],
+    "rcv_conv_workspace_bytes": [C.POINTER(ConvDesc), C.c_int],
     "rcv_conv_pack": [C.POINTER(ConvDesc), C.c_int, _p, _p, _p],
     "rcv_conv_engine": [C.POINTER(ConvDesc), C.c_int],
     "rcv_conv_pack_table_bytes": [_i32],
@@ -95,7 +97,7 @@ SIGNATURES = {
     "rcv_sgd_step": [_i64, _p, _p, _p, _p, _f32, _f32, _f32, _f32, C.c_int, _f32, _p, _p, _p],
     "rcv_zero": [_p, C.c_size_t, _p],
 }
-_RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t,
+_RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t, "rcv_conv_workspace_bytes": C.c_size_t,
              "rcv_conv_pack_table_bytes": C.c_size_t}
 PACK_FWD, PACK_DGRAD = 0, 1
 ABI_VERSION = 3

@@ -129,6 +129,8 @@ void fwd_problem(const rcv_conv_desc* d, RcvIgemm* pp) {
   p.Hin = d->H; p.Win = d->W; p.Hout = Ho; p.Wout = Wo;
   p.epilogue = d->epilogue;
   p.math = d->math;
+  p.ws = d->workspace;
+  p.ws_bytes = d->workspace_bytes;
   const int kk = d->ksize * d->ksize;
   if (!d->transposed) {
     p.Hg = Ho; p.Wg = Wo; p.gs = d->stride; p.ostep = 1; p.nclass = 1;
@@ -153,6 +155,8 @@ int dgrad_problem(const rcv_conv_desc* d, RcvIgemm* pp) {
   p.Hin = Ho; p.Win = Wo; p.Hout = d->H; p.Wout = d->W;
   p.epilogue = RCV_EPI_NONE;
   p.math = d->math;
+  p.ws = d->workspace;
+  p.ws_bytes = d->workspace_bytes;
   const int kk = d->ksize * d->ksize;
   if (d->transposed) {
     // dx[ci,i,j] = sum dy[co, 2i+ky-1, 2j+kx-1] * w[ci,co,ky,kx]: a stride-2 conv over dy
@@ -203,6 +207,13 @@ extern "C" int rcv_conv_uses_tensor_cores(const rcv_conv_desc* d, int direction)
   RcvIgemm p;
   if (pack_problem(d, direction, &p, "rcv_conv_uses_tensor_cores")) return 0;
   return rcv_pick_engine(p, true) == RCV_ENGINE_UMMA ? 1 : 0;
+}
+
+extern "C" size_t rcv_conv_workspace_bytes(const rcv_conv_desc* d, int direction) {
+  RcvIgemm p;
+  if (pack_problem(d, direction, &p, "rcv_conv_workspace_bytes")) return 0;
+  if (rcv_pick_engine(p, true) != RCV_ENGINE_UMMA) return 0;
+  return rcv_umma_workspace_bytes(p);
 }
 
 namespace {

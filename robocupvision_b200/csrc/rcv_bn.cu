@@ -193,10 +193,18 @@ __global__ void __launch_bounds__(NT) bn_bwd_kernel(int N, int C, int64_t HW, in
   const float sc = scale[c], sft = shift[c], mean = save_mean[c], invstd = save_invstd[c];
   const int64_t E = (int64_t)N * HW;  // elements of this channel
   const double cnt = (double)E;
-  float m1 = 0.f, m2 = 0.f;
+  // The two channel means the apply pass subtracts are kept as fp32 hi + lo pairs of their fp64 values.  Where the
+  // incoming gradient is almost all common mode (|g - mean g| << |g|: measured ~1/4000 at the decoder's first
+  // blocks), a mean rounded to fp32 leaves the SAME offset on every pixel of the channel, which the next input
+  // and weight gradients sum coherently: 10x the error of the fp32 reference, whose CPU kernel does this
+  // subtraction in double (tools/grad_accuracy.py).
+  float m1 = 0.f, m2 = 0.f, m1l = 0.f, m2l = 0.f;
   if (PASS == 1) {
-    m1 = (float)(sums[c] / cnt);
-    m2 = (float)(sums[C + c] / cnt);
+    const double m1d = sums[c] / cnt, m2d = sums[C + c] / cnt;
+    m1 = (float)m1d;
+    m1l = (float)(m1d - (double)m1);
+    m2 = (float)m2d;
+    m2l = (float)(m2d - (double)m2);
   }
   const bool vec = (HW & 3) == 0;
   const int64_t per = (E + gridDim.y - 1) / gridDim.y;
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(NT) bn_bwd_kernel(int N, int C, int64_t HW, in
       fs1 += g;
       fs2 += g * xh;
     } else {
-      float d = sc * (g - m1 - xh * m2);
+      float d = sc * fmaf(-xh, m2l, fmaf(-xh, m2, (g - m1) - m1l));
       if (order == RCV_EPI_RELU_AFFINE) d = zz > 0.f ? d : 0.f;
       out = d;
       fs1 += d;

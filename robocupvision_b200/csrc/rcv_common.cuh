@@ -98,6 +98,9 @@ struct RcvIgemm {
   const float* in_scale;
   const float* in_shift;
   int32_t in_relu;
+  // optional caller-owned scratch (rcv_conv_desc::workspace): split-reduction partial tiles + arrival counters
+  void* ws;
+  unsigned long long ws_bytes;
   int32_t N, CA, CB;
   int32_t Hin, Win, Hout, Wout, Hg, Wg;
   int32_t gs, ostep;
@@ -155,6 +158,8 @@ int rcv_pick_engine(const RcvIgemm& p, bool have_packed);      // rcv_engine tha
 int rcv_launch_igemm_umma(const RcvIgemm& p, cudaStream_t st);  // tcgen05 3xTF32, TMEM accumulators
 bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb);    // stride-1 3x3, halo-staged A operand (rcv_umma_halo.cu)
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st);
+size_t rcv_umma_workspace_bytes(const RcvIgemm& p);          // scratch the tensor-core engine can use for this problem (0: none)
+size_t rcv_umma_halo_workspace_bytes(const RcvIgemm& p, int bn);
 bool rcv_umma_halo_bf16_ok(const RcvIgemm& p, int bn);        // RCV_MATH_BF16: would that kernel take bf16 operands (bf16 panel layout)
 bool rcv_umma_takes_input_transform(const RcvIgemm& p);      // would rcv_launch_igemm_umma run the halo-staged kernel
 bool rcv_umma_wgrad_takes_input_transform(const RcvWgrad& p);  // tensor-core weight gradient with the quad gather

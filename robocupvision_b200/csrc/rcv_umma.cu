@@ -652,6 +652,12 @@ int rcv_launch_umma_pack_multi(const RcvPackJob* dev_jobs, int njobs, long long 
   return RCV_OK;
 }
 
+size_t rcv_umma_workspace_bytes(const RcvIgemm& p) {
+  const int bn = umma_bn(p.CB);
+  if (!(rcv_umma_halo_ok(p, bn, umma_kb(p.CB)) || rcv_umma_halo_bf16_ok(p, bn))) return 0;
+  return rcv_umma_halo_workspace_bytes(p, bn);
+}
+
 bool rcv_umma_takes_input_transform(const RcvIgemm& p) {
   return rcv_umma_halo_ok(p, umma_bn(p.CB), umma_kb(p.CB)) || rcv_umma_halo_bf16_ok(p, umma_bn(p.CB));
 }

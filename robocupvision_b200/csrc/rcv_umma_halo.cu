@@ -31,8 +31,12 @@ constexpr int MAXL = 256;  // staged rows per channel block: one per producer th
 
 struct HaloGeo {
   int32_t d, PW, HP, S, L, Lpad, nkc, kbmax, nbs;  // nbs: B ring depth (2..4), as many stages as fit beside the patch
+  // split reduction (needs RcvIgemm::ws): pixel tiles [0, tfull) run whole; every later tile is handled by nsplit
+  // CTAs that each reduce a contiguous share of the channel blocks, leave their partial accumulator in the
+  // workspace and count themselves in; the last one to arrive sums the partials in share order and runs the epilogue
+  int32_t tfull, nsplit;
   int64_t Mh;
-  int8_t dy[9], dx[9];
+  int32_t tsign;  // tap t reads offset tsign * d * ((t / 3 - 1) * PW + (t % 3 - 1)): +1 forward order, -1 flipped (input gradient)
 };
 
 template <int KBB>
@@ -117,6 +121,69 @@ __device__ __forceinline__ bool decode_pos(long long q, const HaloGeo& g, int N,
   return n < N && i < H;
 }
 
+// Split reduction, epilogue side (kept out of line: its registers must not weigh on the kernel's hot loops).
+// Leaves this share's partial accumulator (main + correction) in the workspace as [column][row] (lanes = rows:
+// coalesced), counts the share in, and returns true in the ONE CTA that arrived last -- after summing all shares
+// in share order (the result does not depend on who arrived last) back over its main accumulator in TMEM.
+template <int BN>
+__device__ __noinline__ bool split_exchange(void* ws, int slot, int part, int nsplit, uint32_t trow, int ncols, int grp,
+                                            int row, int tid, bool fast, uint32_t* s_arrived) {
+  uint32_t* counters = reinterpret_cast<uint32_t*>(ws);
+  float* base_part = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(ws) + 1024) +
+                     (size_t)slot * nsplit * (BN * BM);
+  float* mine = base_part + (size_t)part * (BN * BM);
+#pragma unroll 1
+  for (int c0 = grp * 16; c0 < BN; c0 += 32) {
+    if (c0 >= ncols) break;
+    uint32_t rm[16];
+    tmem_ld16_nowait(trow + c0, rm);
+    if (!fast) {
+      uint32_t rc[16];
+      tmem_ld16_nowait(trow + BN + c0, rc);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) rm[j] = __float_as_uint(__uint_as_float(rm[j]) + __uint_as_float(rc[j]));
+    } else {
+      tmem_ld_wait();
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) __stcg(mine + (size_t)(c0 + j) * BM + row, __uint_as_float(rm[j]));
+  }
+  __threadfence();
+  asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+  if (tid == 0) *s_arrived = atomicAdd(counters + slot, 1u);
+  asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+  if (*s_arrived != (uint32_t)(nsplit - 1)) return false;
+  __threadfence();
+  if (tid == 0) counters[slot] = 0u;  // every share has arrived: leave the counter ready for the next launch
+#pragma unroll 1
+  for (int c0 = grp * 16; c0 < BN; c0 += 32) {
+    if (c0 >= ncols) break;
+    // all shares' loads of the chunk in flight at once (up to 64 per thread), then summed in share order
+    float v[4][16];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u < nsplit) {
+        const float* src = base_part + (size_t)u * (BN * BM) + (size_t)c0 * BM + row;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[u][j] = __ldcg(src + (size_t)j * BM);
+      }
+    }
+    uint32_t a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float t = v[0][j];
+#pragma unroll
+      for (int u = 1; u < 4; ++u)
+        if (u < nsplit) t += v[u][j];
+      a[j] = __float_as_uint(t);
+    }
+    tmem_st16(trow + c0, a);
+  }
+  tmem_st_wait();
+  return true;
+}
+
 template <int BN, int KBB, bool BF>
 __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, const HaloGeo g) {
   rcv_pdl_enter();
@@ -134,6 +201,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
   unsigned char* misc = gen + NPATCH * patch_bytes + NBS * C::B_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // patch_full, patch_empty, done, bfull[NBS], bempty[NBS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 120);
+  uint32_t* s_arrived = reinterpret_cast<uint32_t*>(misc + 124);  // split reduction: shares that arrived before this CTA
   float* s_cst = reinterpret_cast<float*>(misc + 256);
   float* s_in = s_cst + 3 * BN;  // [2][CA] input scale, shift (normalise-on-load)
   const uint32_t bar_pfull = smem_u32(bars), bar_pempty = bar_pfull + 8, bar_done = bar_pfull + 16;
@@ -142,9 +210,16 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int CA = p.CA, H = p.Hin, W = p.Win, HW = H * W;
-  const long long q0 = (long long)blockIdx.x * BM;
+  int tile = blockIdx.x, part = -1, cb0 = 0, cb1 = g.nkc;
+  if (tile >= g.tfull) {
+    const int r = tile - g.tfull;
+    tile = g.tfull + r / g.nsplit;
+    part = r - (r / g.nsplit) * g.nsplit;
+    cb0 = part * g.nkc / g.nsplit;
+    cb1 = (part + 1) * g.nkc / g.nsplit;
+  }
+  const long long q0 = (long long)tile * BM;
   const int n0 = blockIdx.y * BN;
-  const int nkc = g.nkc;
   const bool fast = BF || p.math >= RCV_MATH_TF32;  // one MMA per product: no lo halves, no correction accumulator
 
   for (int c = tid; c < BN; c += NT) {
@@ -184,7 +259,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
                                 ((size_t)blockIdx.y * g.kbmax) * C::B_STAGE;
       const int kper = BF ? CA / 64 : CA / KBB;  // B K-blocks per tap in the pack (K = tap-major, then channel)
       int it = 0;
-      for (int cb = 0; cb < nkc; ++cb)
+      for (int cb = cb0; cb < cb1; ++cb)
         for (int t = 0; t < 9; ++t)
           for (int sub = 0; sub < SUB; ++sub, ++it) {
             const int st = it % NBS, u = it / NBS;
@@ -201,11 +276,13 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
       constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc(BM, BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       int it = 0;
-      for (int cb = 0; cb < nkc; ++cb) {
-        mbar_wait(bar_pfull, (uint32_t)(cb & 1));
+      for (int cb = cb0; cb < cb1; ++cb) {
+        mbar_wait(bar_pfull, (uint32_t)((cb - cb0) & 1));
         tc_fence_after();
+#pragma unroll 1
         for (int t = 0; t < 9; ++t) {
-          const uint32_t roff = (uint32_t)(g.S + g.dy[t] * g.PW + g.dx[t]) * 128u;
+          const int ty = t / 3 - 1, tx = t - (t / 3) * 3 - 1;
+          const uint32_t roff = (uint32_t)(g.S + g.tsign * g.d * (ty * g.PW + tx)) * 128u;
           const uint64_t a_hi = make_desc(a_hi_s + roff), a_lo = make_desc(a_lo_s + roff);
 #pragma unroll
           for (int sub = 0; sub < SUB; ++sub, ++it) {
@@ -244,7 +321,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
     const char* inb = reinterpret_cast<const char*>(p.in);
     const uint32_t boff0 = 4u * (uint32_t)((pn * CA) * HW + pi * W + pj);
     const uint32_t cstride = 4u * (uint32_t)HW;
-    for (int cb = 0; cb < nkc; ++cb) {
+    for (int cb = cb0; cb < cb1; ++cb) {
       if (BF) {
         // 64 channels of this position as bf16: two half blocks of 32 loads each, four 16-byte chunks per half
         uint32_t pk[32];
@@ -266,7 +343,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[hf * 16 + i] = pack_bf16x2(va[2 * i], va[2 * i + 1]);
         }
-        if (cb > 0) mbar_wait(bar_pempty, (uint32_t)((cb - 1) & 1));
+        if (cb > cb0) mbar_wait(bar_pempty, (uint32_t)((cb - cb0 - 1) & 1));
         if (has_row) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -288,7 +365,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
           va[i] = rl ? fmaxf(t, 0.f) : t;
         }
       }
-      if (cb > 0) mbar_wait(bar_pempty, (uint32_t)((cb - 1) & 1));
+      if (cb > cb0) mbar_wait(bar_pempty, (uint32_t)((cb - cb0 - 1) & 1));
       if (has_row) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -313,19 +390,29 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
     tc_fence_after();
     const int row = tid & (BM - 1);
     const int grp = tid / BM;  // column half
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    // Split reduction: leave this share's partial accumulator (main + correction) in the workspace as
+    // [column][row] (lanes = rows: coalesced), count in, and go on only if every other share has arrived; the
+    // finishing CTA sums all shares in share order (so the result does not depend on who arrived last), writes
+    // the sums back over its main accumulator in TMEM and runs the ordinary epilogue on them.
+    bool finish = true, skip_corr = fast;
+    if (part >= 0) {
+      finish = split_exchange<BN>(p.ws, (tile - g.tfull) * gridDim.y + blockIdx.y, part, g.nsplit, trow, p.CB - n0, grp,
+                                  row, tid, fast, s_arrived);
+      skip_corr = true;
+    }
     int en = 0, ei = 0, ej = 0;
     const bool mrow = decode_pos(q0 + row, g, p.N, H, W, en, ei, ej);
     const int epi = p.epilogue;
     const int HWo = p.Hout * p.Wout;
     const size_t obase = mrow ? (size_t)en * p.CB * HWo + (size_t)ei * p.Wout + ej : 0;
-    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const bool has_res = p.residual != nullptr, has_stats = p.stats != nullptr;
 #pragma unroll 1
-    for (int c0 = grp * 16; c0 < BN; c0 += 32) {
+    for (int c0 = grp * 16; c0 < BN && finish; c0 += 32) {
       if (n0 + c0 >= p.CB) break;
       uint32_t rm[16], rc[16];
       tmem_ld16_nowait(trow + c0, rm);
-      if (!fast) {
+      if (!skip_corr) {
         tmem_ld16_nowait(trow + BN + c0, rc);
       } else {
 #pragma unroll
@@ -389,16 +476,13 @@ bool geometry(const RcvIgemm& p, HaloGeo* out) {
     d = b > d ? b : d;
   }
   if (d != 1 && d != 2) return false;
-  bool seen[9] = {false};
+  // the nine taps must be the {-d, 0, d}^2 grid in row-major order, as it is (forward) or point-reflected (input
+  // gradient): the issuer derives each tap's row shift from its index
+  const int sgn = p.taps[0].dy[0] < 0 ? 1 : -1;
   for (int t = 0; t < 9; ++t) {
-    const int dy = p.taps[0].dy[t], dx = p.taps[0].dx[t];
-    if ((dy != -d && dy != 0 && dy != d) || (dx != -d && dx != 0 && dx != d)) return false;
-    const int k = (dy / d + 1) * 3 + (dx / d + 1);
-    if (seen[k]) return false;
-    seen[k] = true;
-    g.dy[t] = (int8_t)dy;
-    g.dx[t] = (int8_t)dx;
+    if (p.taps[0].dy[t] != sgn * (t / 3 - 1) * d || p.taps[0].dx[t] != sgn * (t % 3 - 1) * d) return false;
   }
+  g.tsign = sgn;
   g.d = d;
   g.PW = p.Win + d;
   g.HP = p.Hin + d;
@@ -426,6 +510,38 @@ int ring_depth(const HaloGeo& g, int bn, int kbb, int ca, bool bf, size_t* smem)
   return 0;
 }
 
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// Split-reduction plan of a layer (HaloGeo::tfull / nsplit) and the workspace it needs.  nkc = channel blocks of
+// the kernel variant that will run.  Two cases pay: (a) a grid slightly larger than a whole number of SM waves --
+// at batch 64 the 15x20 layers are 169 tiles on 148 SMs, so 21 SMs carry two tiles while 127 wait: the left-over
+// tiles are cut into up to four shares that run as second CTAs beside whole tiles; (b) a grid far smaller than
+// the machine (small batches, batch-1 latency): every tile is cut.
+size_t split_plan(const RcvIgemm& p, int bn, int nkc, int64_t Mh, int* tfull, int* nsplit) {
+  static const int on = getenv("RCV_UMMA_SPLIT") ? atoi(getenv("RCV_UMMA_SPLIT")) : 1;
+  const int T = rcv_cdiv(Mh, BM), ny = rcv_cdiv(p.CB, bn), S = sm_count();
+  *tfull = T;
+  *nsplit = 1;
+  const int parts = nkc < 4 ? nkc : 4;
+  if (!on || parts < 2) return 0;
+  int tf = T;
+  if ((int64_t)T * ny * 2 <= S) tf = 0;
+  else if (ny == 1 && T > S && (T % S) * 2 <= S) tf = T - T % S;
+  if (tf == T || (int64_t)(T - tf) * ny > 256) return 0;  // 256 arrival counters
+  *tfull = tf;
+  *nsplit = parts;
+  return 1024 + (size_t)(T - tf) * ny * parts * ((size_t)bn * BM * 4);
+}
+
 template <int BN, int KBB, bool BF = false>
 int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
   if (BF) {
@@ -449,7 +565,13 @@ int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
                          cudaSharedmemCarveoutMaxShared);
     attr_done = true;
   }
-  dim3 grid(rcv_cdiv(g.Mh, BM), rcv_cdiv(p.CB, BN), 1);
+  const int T = rcv_cdiv(g.Mh, BM);
+  const size_t need = split_plan(p, BN, g.nkc, g.Mh, &g.tfull, &g.nsplit);
+  if (need == 0 || p.ws == nullptr || p.ws_bytes < need || ((uintptr_t)p.ws & 127) != 0) {
+    g.tfull = T;  // no (or too small a) workspace: every tile whole
+    g.nsplit = 1;
+  }
+  dim3 grid(g.tfull + (T - g.tfull) * g.nsplit, rcv_cdiv(p.CB, BN), 1);
   rcv_launch(umma_halo_kernel<BN, KBB, BF>, dim3(grid), dim3(NT), smem, st, p, g);
   RCV_CHECK_LAUNCH("umma_halo_kernel");
   return RCV_OK;
@@ -474,6 +596,13 @@ bool rcv_umma_halo_bf16_ok(const RcvIgemm& p, int bn) {
   HaloGeo g;
   if (!on || !halo_on || p.math != RCV_MATH_BF16 || (p.CA % 64) != 0 || bn < 32 || !geometry(p, &g)) return false;
   return ring_depth(g, bn, 32, p.CA, true, nullptr) >= 2;
+}
+
+size_t rcv_umma_halo_workspace_bytes(const RcvIgemm& p, int bn) {
+  HaloGeo g;
+  if (!geometry(p, &g)) return 0;
+  int tfull, nsplit;
+  return split_plan(p, bn, rcv_umma_halo_bf16_ok(p, bn) ? p.CA / 64 : g.nkc, g.Mh, &tfull, &nsplit);
 }
 
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st) {

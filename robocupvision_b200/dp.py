@@ -79,7 +79,7 @@ def allreduce_buckets(flat, buckets: Sequence[Tuple[int, int, int]], group=None)
 
 def self_check(model_ctor, class_weights, batch: int, cin: int, h: int, w: int, steps: int = 3, group=None,
                lr: float = 1e-3, l1_decay: float = 1e-6, seed: int = 777, use_graph: bool = True,
-               force_comm_path: bool = True, tol: float = 2e-4) -> dict:
+               force_comm_path: bool = True, tol: float = 5e-4) -> dict:
     """Numerical check of the data-parallel product path on THIS job's ranks (bench.py emits it as `dp_check`).
 
     Every rank trains `steps` steps of TrainStep (bucketed all-reduce + optimiser on the comm stream, captured in a
@@ -89,6 +89,10 @@ def self_check(model_ctor, class_weights, batch: int, cin: int, h: int, w: int, 
     The single-GPU path is pinned against the CPU oracle by tests/, so agreement here extends that pin to N ranks.
     Adam runs with eps = 1e-3 on both sides (with torch's default 1e-8 a gradient that is analytically zero moves
     its weight by +-lr according to the sign of rounding noise; see tests/test_gpu_models.py::test_step_async).
+    Gate: weights within `tol` = 5e-4 of the largest weight after `steps` steps.  Two runs of the SAME schedule differ
+    by up to ~1e-4 here (floating-point atomics in the weight-gradient kernels, passed on by Adam's normalisation:
+    the control in tests/test_gpu_train.py::test_comm_path_schedule_matches_plain_step); a missing or mis-scaled
+    all-reduce, or an optimiser pass racing a gradient, moves weights by the order of lr = 1e-3 per step.
 
     -> {"ok", "world", "steps", "max_weight_err", "max_loss_err", "weights_identical_across_ranks"}"""
     import copy

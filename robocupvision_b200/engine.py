@@ -160,6 +160,8 @@ class Plan:
                 self._consumers.setdefault(nd.skip, []).append((t, "skip"))
         self._defer_cache = {}
         self._size_cache = {}
+        self._workspace = None   # scratch of the tensor-core convs (ops.new_workspace), sized for the largest need seen
+        self._ws_need = {}
         self.n_stats = 0
         self._sum_off = {}
         for t, nd in enumerate(self.nodes):
@@ -178,6 +180,28 @@ class Plan:
                 hw.append((ih // 2, iw // 2) if nd.kind == "pool" else nd.geom.out_hw(ih, iw))
             hit = self._size_cache[key] = [(n, *hw[nd.src]) for nd in self.nodes]
         return hit
+
+    def workspace(self, nhw, dev) -> Optional[torch.Tensor]:
+        """The plan's conv scratch for a plan input of size nhw = (N, H, W): one buffer, shared by every tensor-core
+        layer and direction (they run one after the other on the plan's main stream), zero-filled when allocated
+        (the kernels leave it ready for the next launch).  None when no layer can use one."""
+        key = (nhw, self.math)
+        need = self._ws_need.get(key)
+        if need is None:
+            need = 0
+            if self.math != MATH_FP32:
+                for nd, (n, h, w) in zip(self.nodes, self._in_sizes(*nhw)):
+                    if nd.kind == "conv":
+                        for d in (PACK_FWD, PACK_DGRAD):
+                            if nd.uses_tc(d, self.math):
+                                need = max(need, ops.conv_workspace_bytes(nd.geom, n, h, w, d, self.math))
+            self._ws_need[key] = need
+        if need == 0:
+            return None
+        ws = self._workspace
+        if ws is None or ws.device != dev or ws.numel() < need:
+            ws = self._workspace = ops.new_workspace(need, dev)
+        return ws
 
     def _ensure_packed(self, directions, fresh: bool, x_requires_grad: bool, nhw):
         """Weight panels of every tensor-core layer, re-packed in ONE launch when `fresh` (training:
@@ -233,8 +257,9 @@ class Plan:
         soff = 0
         if training:
             self.epoch += 1
-        self._ensure_packed((PACK_FWD, PACK_DGRAD) if save else (PACK_FWD,), training, x.requires_grad,
-                            (x.shape[0], x.shape[2], x.shape[3]))
+        nhw = (x.shape[0], x.shape[2], x.shape[3])
+        self._ensure_packed((PACK_FWD, PACK_DGRAD) if save else (PACK_FWD,), training, x.requires_grad, nhw)
+        ws = self.workspace(nhw, dev)
         for t, nd in enumerate(self.nodes):
             src = acts[nd.src]
             if nd.kind == "pool":
@@ -249,7 +274,8 @@ class Plan:
             wp = nd._pack[PACK_FWD] if nd.uses_tc(PACK_FWD, self.math) else None
             ina = lazy.get(nd.src)  # the producer's BatchNorm, applied on load
             if bn is None:
-                y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, math=self.math, wpacked=wp, in_affine=ina)
+                y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, math=self.math, wpacked=wp, in_affine=ina,
+                                 workspace=ws)
                 saved[t] = (y if nd.order == EPI_RELU else None,)
             elif training and bn.training:
                 if stats_arena is None:
@@ -257,7 +283,7 @@ class Plan:
                 stats = stats_arena[soff:soff + 2 * g.cout]
                 soff += 2 * g.cout
                 z = ops.conv_fwd(g, src, w, b, epilogue=EPI_RELU if nd.order == EPI_RELU_AFFINE else EPI_NONE,
-                                 stats=stats, math=self.math, wpacked=wp, in_affine=ina)
+                                 stats=stats, math=self.math, wpacked=wp, in_affine=ina, workspace=ws)
                 count = z.numel() // g.cout
                 if bn.momentum is None:
                     momentum = 1.0 / float(int(bn.num_batches_tracked) + 1)
@@ -280,7 +306,7 @@ class Plan:
             else:
                 scale, shift = nd.folded(self.epoch)
                 y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, scale=scale, shift=shift, residual=skip,
-                                 math=self.math, wpacked=wp, in_affine=ina)
+                                 math=self.math, wpacked=wp, in_affine=ina, workspace=ws)
             if nd.skip >= 0 and nd.skip_mode == "partial":
                 y[:, :nd.skip_ch] += acts[nd.skip]
             elif nd.skip >= 0 and nd.skip_mode == "cat":
@@ -380,8 +406,10 @@ class Plan:
             wg_bias = grad_views[id(conv.bias)] if has_bias else None
         if nd.src != 0 or x_needs_grad:
             wp = nd._pack[PACK_DGRAD] if nd.uses_tc(PACK_DGRAD, self.math) else None
+            x0 = acts[0]
             grads[nd.src] = ops.conv_dgrad(geom, dconv, w, in_hw, residual=grads[nd.src], math=self.math,
-                                           wpacked=wp)
+                                           wpacked=wp, workspace=self.workspace(
+                                               (x0.shape[0], x0.shape[2], x0.shape[3]), x0.device))
         la = lazy.get(nd.src) if lazy else None
         if la is not None and WGRAD_ON_LOAD and ops.conv_wgrad_normalises_on_load(
                 geom, src.shape[0], src.shape[2], src.shape[3], self.math):

@@ -18,7 +18,7 @@ from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_A
                    PACK_FWD, ConvDesc)
 
 __all__ = [
-    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
+    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_workspace_bytes", "new_workspace", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "maxunpool2x2", "maxunpool2x2_bwd", "upsample_bilinear2x", "upsample_bilinear2x_bwd", "ce_fwd", "ce_bwd",
     "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "zero_", "zeros", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
@@ -121,6 +121,25 @@ def conv_packed_bytes(g: ConvGeom, direction: int, math: int = MATH_AUTO, nhw=NO
     return int(n)
 
 
+def conv_workspace_bytes(g: ConvGeom, n: int, h: int, w: int, direction: int = PACK_FWD, math: int = MATH_AUTO) -> int:
+    """Bytes of scratch conv_fwd / conv_dgrad can use for this layer at this size (0: none); see `workspace`."""
+    d = g.desc(n, h, w, EPI_NONE, math)
+    return int(_lib.load().rcv_conv_workspace_bytes(C.byref(d), int(direction)))
+
+
+def new_workspace(nbytes: int, device) -> torch.Tensor:
+    """A zero-filled scratch buffer for the `workspace` argument of conv_fwd / conv_dgrad (rcv_conv_desc::workspace:
+    zero-filled once by the caller, then owned by ONE stream of convolution launches at a time)."""
+    return torch.zeros(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+
+
+def _with_ws(d: ConvDesc, workspace):
+    if workspace is not None:
+        d.workspace = workspace.data_ptr()
+        d.workspace_bytes = workspace.numel() * workspace.element_size()
+    return d
+
+
 def conv_uses_tensor_cores(g: ConvGeom, direction: int, math: int = MATH_AUTO) -> bool:
     d = g.desc(1, 2, 2, EPI_NONE, math)
     return bool(_lib.load().rcv_conv_uses_tensor_cores(C.byref(d), int(direction)))
@@ -203,7 +222,7 @@ def conv_normalises_on_load(g: ConvGeom, n: int, h: int, w: int, math: int = MAT
 
 
 def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=None, residual=None,
-             stats=None, math=MATH_FP32, out=None, wpacked=None, in_affine=None):
+             stats=None, math=MATH_FP32, out=None, wpacked=None, in_affine=None, workspace=None):
     x = _chk(x, name="x")
     w = _chk(w, name="weight")
     wpacked = _packed_for(g, w, wpacked, math, PACK_FWD)
@@ -221,7 +240,7 @@ def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=
             raise ValueError(f"conv_fwd: bad {nm}")
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 2 * g.cout):
         raise ValueError("conv_fwd: stats must be float64[2*Cout]")
-    d = g.desc(n, h, wd, epilogue, math)
+    d = _with_ws(g.desc(n, h, wd, epilogue, math), workspace)
     if in_affine is not None:
         # (in_scale, in_shift, relu): the BatchNorm of the block that produced x, applied on load (rcv_conv_fwd_nl)
         isc, ish, irelu = in_affine
@@ -236,7 +255,7 @@ def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=
 
 
 def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=MATH_FP32, out=None,
-               wpacked=None):
+               wpacked=None, workspace=None):
     """Input gradient; `residual` (shape of dx; may be `out`) is the gradient the same tensor
     receives from a second consumer and is added in the kernel epilogue."""
     dy = _chk(dy, name="dy")
@@ -246,7 +265,7 @@ def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=M
     h, wd = in_hw
     if tuple(dy.shape[1:]) != (g.cout, *g.out_hw(h, wd)):
         raise ValueError(f"conv_dgrad: dy {tuple(dy.shape)} does not match geometry for input {in_hw}")
-    d = g.desc(n, h, wd, EPI_NONE, math)
+    d = _with_ws(g.desc(n, h, wd, EPI_NONE, math), workspace)
     dx = out if out is not None else torch.empty((n, g.cin, h, wd), device=dy.device, dtype=torch.float32)
     if residual is not None:
         residual = _chk(residual, name="residual")

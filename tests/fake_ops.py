@@ -41,8 +41,12 @@ def _conv(g, x, w, b):
     return F.conv2d(x, w, b, g.stride, g.pad, g.dil)
 
 
+def conv_workspace_bytes(g, n, h, w, direction=0, math=real.MATH_AUTO):
+    return 0
+
+
 def conv_fwd(g, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=None, residual=None, stats=None,
-             math=real.MATH_FP32, out=None, wpacked=None, in_affine=None):
+             math=real.MATH_FP32, out=None, wpacked=None, in_affine=None, workspace=None):
     calls.append(("conv_fwd", in_affine is not None))
     if in_affine is not None:
         n, _, h, wd = x.shape
@@ -68,7 +72,7 @@ def conv_fwd(g, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=None, resi
     return v
 
 
-def conv_dgrad(g, dy, w, in_hw, residual=None, math=real.MATH_FP32, out=None, wpacked=None):
+def conv_dgrad(g, dy, w, in_hw, residual=None, math=real.MATH_FP32, out=None, wpacked=None, workspace=None):
     n = dy.shape[0]
     x = torch.zeros(n, g.cin, *in_hw, requires_grad=True)
     with torch.enable_grad():

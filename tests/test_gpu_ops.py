@@ -76,6 +76,53 @@ def test_conv_wide_channel_tiles():
     assert_close("conv_fwd 40->200 tc", got, ref, 8e-6)
 
 
+@pytest.mark.parametrize("math", [1, 3, 4])  # RCV_MATH_TF32X3, RCV_MATH_TF32, RCV_MATH_BF16
+@pytest.mark.parametrize("cin,cout,dil,nhw", [(128, 128, 1, (64, 15, 20)),   # 169 tiles on 148 SMs: left-over tiles split
+                                              (64, 64, 1, (64, 15, 20)), (128, 64, 2, (64, 15, 20)),
+                                              (128, 128, 1, (1, 15, 20)),    # 3 tiles: every tile split
+                                              (64, 128, 2, (2, 15, 20)), (40, 200, 1, (1, 9, 11))])
+def test_conv_split_reduction_workspace(cin, cout, dil, nhw, math):
+    """rcv_conv_desc::workspace: the halo-staged kernel splits the reduction of left-over / few tiles across CTAs
+    (partials through the workspace, last arriver runs the epilogue).  With and without the workspace the layer must
+    agree to accumulation order, the workspace must be reusable without re-zeroing, and the fused epilogue (bias,
+    ReLU, residual, BatchNorm statistics) must see every element exactly once."""
+    from robocupvision_b200 import ops
+    n, h, w_ = nhw
+    g = ops.ConvGeom(cin, cout, 3, 1, dil, dil, False)
+    gen = torch.Generator().manual_seed(cin * 7 + cout + n)
+    x = torch.randn(n, cin, h, w_, generator=gen).cuda()
+    wt = (torch.randn(cout, cin, 3, 3, generator=gen) / (cin * 9) ** 0.5).cuda()
+    b = torch.randn(cout, generator=gen).cuda()
+    res = torch.randn(n, cout, h, w_, generator=gen).cuda()
+    need = ops.conv_workspace_bytes(g, n, h, w_, ops.PACK_FWD, math)
+    if cin % 32 == 0 and cin // (64 if math == 4 and cin % 64 == 0 else 32) >= 2:
+        assert need > 0, "this geometry is expected to use the split reduction"
+    ws = ops.new_workspace(max(need, 1024), x.device)
+    wp = ops.conv_pack(g, wt, ops.PACK_FWD, math=math, nhw=nhw)
+    outs = []
+    for wsp in (None, ws, ws):
+        stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+        y = ops.conv_fwd(g, x, wt, b, epilogue=ops.EPI_RELU, residual=res, stats=stats, math=math, wpacked=wp,
+                         workspace=wsp)
+        outs.append((y, stats))
+    torch.cuda.synchronize()
+    assert int(ws[:1024].view(torch.int32).abs().sum()) == 0, "arrival counters must be left zeroed"
+    for y, st in outs[1:]:
+        assert_close("split vs whole", y, outs[0][0], 2e-6)
+        assert_close("split stats", st, outs[0][1], 1e-6, atol=1e-3)
+    assert torch.equal(outs[1][0], outs[2][0]), "same shares, same order: bitwise reproducible"
+    if math == 1:
+        ref = F.relu(F.conv2d(x.cpu(), wt.cpu(), b.cpu(), 1, dil, dil)) + res.cpu()
+        assert_close("split vs fp32", outs[1][0], ref, 8e-6)
+    # input gradient through the same path
+    dy = torch.randn(n, cout, h, w_, generator=gen).cuda()
+    wpd = ops.conv_pack(g, wt, ops.PACK_DGRAD, math=math, nhw=nhw)
+    ws2 = ops.new_workspace(max(ops.conv_workspace_bytes(g, n, h, w_, ops.PACK_DGRAD, math), 1024), x.device)
+    d0 = ops.conv_dgrad(g, dy, wt, (h, w_), math=math, wpacked=wpd)
+    d1 = ops.conv_dgrad(g, dy, wt, (h, w_), math=math, wpacked=wpd, workspace=ws2)
+    assert_close("split dgrad", d1, d0, 4e-6)
+
+
 def test_pack_table_matches_single_packs():
     """rcv_conv_pack_table_* (all layers in one launch) writes the same panels as rcv_conv_pack."""
     from robocupvision_b200 import ops
