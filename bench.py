@@ -371,12 +371,13 @@ def run_workload(job: Job, key: str, batch: int, steps: int, warmup: int, headli
     ms_total = job.max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / steps
     extra_steps = 0
-    if headline and job.sampler is not None:
+    if headline:
         # a timed region shorter than a few sampling periods: keep the same load running (untimed) until three
-        # samples have been taken under it, and say so
+        # samples have been taken under it, and say so.  Every rank runs this loop (rank 0, which owns the poller,
+        # decides; the decision travels through the all-reduce)
         per_round = max(8, int(200.0 / max(ms_step, 1e-3)))  # ~0.2 s of steps
         for _ in range(8):
-            need = 1 if (job.sampler.proc and job.sampler.mark() - row0 < 3) else 0
+            need = 1 if (job.sampler is not None and job.sampler.proc and job.sampler.mark() - row0 < 3) else 0
             need = int(job.max_over_ranks(float(need)))
             if not need:
                 break

