@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RCV_ABI_VERSION 3
+#define RCV_ABI_VERSION 4
 
 typedef enum rcv_status {
   RCV_OK = 0,

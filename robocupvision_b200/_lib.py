@@ -100,7 +100,7 @@ SIGNATURES = {
 _RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t, "rcv_conv_workspace_bytes": C.c_size_t,
              "rcv_conv_pack_table_bytes": C.c_size_t}
 PACK_FWD, PACK_DGRAD = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _lib = None
 

@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
   if (warp == NPROD / 32 + 1) {
     // ================================ B LOADER ========================================
     // one bulk copy of a packed weight block per ring stage, as soon as the stage is free
-    if (lane == 0 && !(p.debug & 16)) {
+    if (elect_one() && !(p.debug & 16)) {
       const int kbmax = (CA * max_taps(p) + BK - 1) / BK;  // K blocks per (class, N tile) in the pack
       const unsigned char* gB = reinterpret_cast<const unsigned char*>(p.wpacked) +
                                 ((size_t)(cls * gridDim.y + blockIdx.y) * kbmax) * C::B_STAGE;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
     }
   } else if (warp == NPROD / 32) {
     // ================================ MMA ISSUER ======================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       mbar_wait(bar_full, 0);

@@ -80,7 +80,7 @@ struct HCfg {
   static constexpr int CBLK = BF ? 64 : 32;           // channels per staged block
   static constexpr int BROWB = BF ? 128 : KBB * 4;    // bytes per B row
   static constexpr int B_STAGE = BF ? BN * 128 : BN * BROWB * 2;  // fp32: hi rows then lo rows
-  static constexpr int MAXBS = 4;                     // deepest B ring
+  static constexpr int MAXBS = 12;                    // deepest B ring
   static constexpr int SUB = BF ? 1 : 32 / KBB;       // B K-blocks per (tap, channel block)
   static constexpr int KSTEPS = BF ? 4 : KBB / 8;     // MMAs (32 bytes of K each) per B K-block
   static constexpr int TCOLS = BF ? (BN < 32 ? 32 : BN) : (2 * BN < 32 ? 32 : 2 * BN);
@@ -200,13 +200,13 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
   const uint32_t a_hi_s = base, a_lo_s = base + patch_bytes, b_s = base + NPATCH * patch_bytes;
   unsigned char* misc = gen + NPATCH * patch_bytes + NBS * C::B_STAGE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // patch_full, patch_empty, done, bfull[NBS], bempty[NBS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 120);
-  uint32_t* s_arrived = reinterpret_cast<uint32_t*>(misc + 124);  // split reduction: shares that arrived before this CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 240);
+  uint32_t* s_arrived = reinterpret_cast<uint32_t*>(misc + 244);  // split reduction: shares that arrived before this CTA
   float* s_cst = reinterpret_cast<float*>(misc + 256);
   float* s_in = s_cst + 3 * BN;  // [2][CA] input scale, shift (normalise-on-load)
   const uint32_t bar_pfull = smem_u32(bars), bar_pempty = bar_pfull + 8, bar_done = bar_pfull + 16;
   const uint32_t bar_bfull = bar_pfull + 24, bar_bempty = bar_bfull + 8 * C::MAXBS;
-  static_assert(24 + 16 * C::MAXBS <= 120, "barrier area");
+  static_assert(24 + 16 * C::MAXBS <= 240, "barrier area");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int CA = p.CA, H = p.Hin, W = p.Win, HW = H * W;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
 
   if (warp == NPROD / 32 + 1) {
     // ================================ B LOADER ========================================
-    if (lane == 0) {
+    if (elect_one()) {
       const unsigned char* gB = reinterpret_cast<const unsigned char*>(p.wpacked) +
                                 ((size_t)blockIdx.y * g.kbmax) * C::B_STAGE;
       const int kper = BF ? CA / 64 : CA / KBB;  // B K-blocks per tap in the pack (K = tap-major, then channel)
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
     }
   } else if (warp == NPROD / 32) {
     // ================================ MMA ISSUER ======================================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc(BM, BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       int it = 0;
@@ -498,11 +498,16 @@ bool geometry(const RcvIgemm& p, HaloGeo* out) {
 }
 
 // B ring depth that fits beside the patch in a two-CTAs-per-SM shared-memory budget (0: nothing fits)
+size_t smem_budget() {  // RCV_HALO_SMEM_KB (experiments): 113 = two CTAs per SM (default), up to 227 = one
+  static const int kb = getenv("RCV_HALO_SMEM_KB") ? atoi(getenv("RCV_HALO_SMEM_KB")) : 113;
+  return (size_t)(kb < 48 ? 48 : kb > 227 ? 227 : kb) * 1024;
+}
+
 int ring_depth(const HaloGeo& g, int bn, int kbb, int ca, bool bf, size_t* smem) {
-  const size_t budget = 113 * 1024;
+  const size_t budget = smem_budget();
   const size_t fixed = 1024 + (bf ? 1 : 2) * (size_t)g.Lpad * 128 + 256 + 3 * (size_t)bn * 4 + 2 * (size_t)ca * 4;
   const size_t stage = bf ? (size_t)bn * 128 : (size_t)bn * kbb * 8;
-  for (int nbs = 4; nbs >= 2; --nbs)
+  for (int nbs = 12; nbs >= 2; --nbs)
     if (fixed + nbs * stage <= budget) {
       if (smem) *smem = fixed + nbs * stage;
       return nbs;
@@ -532,7 +537,9 @@ size_t split_plan(const RcvIgemm& p, int bn, int nkc, int64_t Mh, int* tfull, in
   *tfull = T;
   *nsplit = 1;
   const int parts = nkc < 4 ? nkc : 4;
-  if (!on || parts < 2) return 0;
+  // the fast modes issue a third (tf32) or a sixth (bf16) of the MMA work: measured, the exchange then costs more
+  // than the balance gains (bf16 128->128 @15x20 batch 64: 19.6 us whole, 21.7 us split)
+  if (!on || parts < 2 || p.math >= RCV_MATH_TF32) return 0;
   int tf = T;
   if ((int64_t)T * ny * 2 <= S) tf = 0;
   else if (ny == 1 && T > S && (T % S) * 2 <= S) tf = T - T % S;
@@ -556,7 +563,7 @@ int launch_h(const RcvIgemm& p, HaloGeo g, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(umma_halo_kernel<BN, KBB, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         113 * 1024);
+                                         (int)smem_budget());
     if (e != cudaSuccess) {
       rcv_set_error("umma_halo: cannot reserve shared memory: %s", cudaGetErrorString(e));
       return RCV_ERR_CUDA;

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
 
   if (warp == NPROD / 32) {
     // ================================ MMA ISSUER ======================================
-    if (lane == 0 && nchunks > 0) {
+    if (elect_one() && nchunks > 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       mbar_wait(bar_full, 0);
