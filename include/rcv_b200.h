@@ -342,6 +342,13 @@ int rcv_ce_bwd(int32_t N, int32_t C, int64_t HW, const float* logits,
 int rcv_confusion(int32_t N, int32_t C, int64_t HW, const int64_t* pred,
                   const int64_t* target, int64_t* conf, void* stream);
 
+/* The tail of the validation loops (train.py:148-163) on the device: iou_sum[c] (double[C], overwritten) = sum over
+ * the N images of inter/union per class from the per-image confusion counts conf int64[N,C,C] (union = row + column
+ * - diagonal; an image without the class counts 1, train.py:152-153), and *loss (double, may be NULL) =
+ * loss_sums[0] / loss_sums[1] of rcv_ce_fwd.  One launch, no host round trip (the reference does 25*B .item() calls). */
+int rcv_metric_tail(int32_t N, int32_t C, const int64_t* conf, const double* loss_sums,
+                    double* iou_sum, double* loss, void* stream);
+
 /* ---- input-side label ops of the callers --------------------------------- */
 /* labels[i] = lut[labels[i]] in place for 0 <= labels[i] < nlut (nlut <= 64): maskLabel,
  * transform.py:26-49 (the class-drop relabel is a permutation-with-merges of 0..4). */

@@ -86,6 +86,7 @@ SIGNATURES = {
     "rcv_ce_fwd": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_ce_bwd": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p],
     "rcv_confusion": [_i32, _i32, _i64, _p, _p, _p, _p],
+    "rcv_metric_tail": [_i32, _i32, _p, _p, _p, _p, _p],
     "rcv_label_lut": [_i64, _p, _i32, _p, _p],
     "rcv_label_to_pred": [_i64, _i32, _i64, _p, _p, _p],
     "rcv_lp_assemble": [_i64, _i32, _i64, _p, _p, _p, _p, _p, _p, _p],

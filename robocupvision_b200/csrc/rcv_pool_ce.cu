@@ -278,6 +278,46 @@ extern "C" int rcv_ce_bwd(int32_t N, int32_t C, int64_t HW, const float* logits,
   return RCV_OK;
 }
 
+namespace {
+// The per-image IoU rule of the validation loops (train.py:148-153) from per-image confusion counts, and the
+// weighted mean loss, in one tiny launch: iou_sum[c] = sum over images of inter / union (1 where union == 0),
+// union = row + column - diagonal; loss = loss_sums[0] / loss_sums[1].  One warp per class.
+__global__ void __launch_bounds__(256) metric_tail_kernel(int N, int C, const long long* __restrict__ conf,
+                                                         const double* __restrict__ loss_sums, double* iou_sum,
+                                                         double* loss) {
+  rcv_pdl_enter();
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (c < C) {
+    double acc = 0.0;
+    for (int n = lane; n < N; n += 32) {
+      const long long* m = conf + (size_t)n * C * C;
+      long long row = 0, col = 0;
+      for (int k = 0; k < C; ++k) {
+        row += m[c * C + k];
+        col += m[k * C + c];
+      }
+      const long long inter = m[c * C + c], uni = row + col - inter;
+      acc += uni == 0 ? 1.0 : (double)inter / (double)uni;
+    }
+    // fixed-order tree: the sum does not depend on scheduling
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) iou_sum[c] = acc;
+  }
+  if (threadIdx.x == 0 && loss && loss_sums) *loss = loss_sums[0] / loss_sums[1];
+}
+}  // namespace
+
+extern "C" int rcv_metric_tail(int32_t N, int32_t C, const int64_t* conf, const double* loss_sums, double* iou_sum,
+                               double* loss, void* stream) {
+  RCV_REQUIRE(N > 0 && conf && iou_sum, RCV_ERR_BAD_ARG, "metric_tail: bad arg");
+  RCV_REQUIRE(C >= 1 && C <= CMAX, RCV_ERR_UNSUPPORTED, "metric_tail: C=%d (supported 1..8)", C);
+  rcv_launch(metric_tail_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, (int)N, (int)C,
+             reinterpret_cast<const long long*>(conf), loss_sums, iou_sum, loss);
+  RCV_CHECK_LAUNCH("metric_tail");
+  return RCV_OK;
+}
+
 extern "C" int rcv_confusion(int32_t N, int32_t C, int64_t HW, const int64_t* pred,
                              const int64_t* target, int64_t* conf, void* stream) {
   RCV_REQUIRE(N > 0 && HW > 0 && pred && target && conf, RCV_ERR_BAD_ARG, "confusion: bad arg");

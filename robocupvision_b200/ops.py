@@ -20,7 +20,7 @@ from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_A
 __all__ = [
     "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_workspace_bytes", "new_workspace", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "maxunpool2x2", "maxunpool2x2_bwd", "upsample_bilinear2x", "upsample_bilinear2x_bwd", "ce_fwd", "ce_bwd",
-    "confusion", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "zero_", "zeros", "counter_add", "launch_count", "reset_launch_count",
+    "confusion", "metric_tail", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "zero_", "zeros", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
     "MATH_FP32", "MATH_TF32X3", "MATH_AUTO", "MATH_TF32", "MATH_BF16", "ENGINE_SIMT", "ENGINE_DIRECT", "ENGINE_UMMA", "ENGINE_NARROW",
 ]
@@ -491,6 +491,17 @@ def confusion(pred, target, num_classes: int):
     conf = zeros((n, num_classes, num_classes), torch.int64, pred.device)
     _call("rcv_confusion", 1, n, num_classes, hw, _ptr(pred), _ptr(target), _ptr(conf), _stream())
     return conf
+
+
+def metric_tail(conf, loss_sums=None):
+    """-> (iou_sum float64[C], loss float64[] | None) from per-image confusion counts int64[N,C,C] and the loss sums of
+    ce_fwd: the validation loops' per-image IoU rule and the mean loss in one launch (rcv_metric_tail)."""
+    conf = _chk(conf, torch.int64, "conf")
+    n, c = conf.shape[0], conf.shape[1]
+    out = torch.empty(c + 1, dtype=torch.float64, device=conf.device)
+    _call("rcv_metric_tail", 1, n, c, _ptr(conf), _ptr(loss_sums), _ptr(out), _ptr(out[c:]) if loss_sums is not None else None,
+          _stream())
+    return out[:c], (out[c] if loss_sums is not None else None)
 
 
 # --------------------------------------------------------------------------- input-side label ops

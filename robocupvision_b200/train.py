@@ -457,8 +457,8 @@ class EvalStep:
             self.model.train(was_training)
         sums, am, conf, corr = ops.ce_fwd(logits, y, self.class_w, want_argmax=True, want_conf=True,
                                           want_correct=True)
-        return {"logits": logits, "loss": sums[0] / sums[1], "argmax": am, "conf": conf, "correct": corr,
-                "iou_sum": iou_sums(conf)}
+        iou, loss = ops.metric_tail(conf, sums)
+        return {"logits": logits, "loss": loss, "argmax": am, "conf": conf, "correct": corr, "iou_sum": iou}
 
     def _state_key(self):
         """Anything a captured forward bakes in: folded BatchNorm constants and packed weight panels are
@@ -501,6 +501,8 @@ class EvalStep:
 def iou_sums(conf: torch.Tensor) -> torch.Tensor:
     """Sum over images of per-class IoU from per-image confusion [N,C,C] with the reference's
     union==0 -> 1 rule (train.py:148-153): union_c = row_c + col_c - conf[c,c]."""
+    if conf.is_cuda:
+        return ops.metric_tail(conf)[0]
     confd = conf.to(torch.float64)
     inter = torch.diagonal(confd, dim1=1, dim2=2)
     union = confd.sum(2) + confd.sum(1) - inter
