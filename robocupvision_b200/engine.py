@@ -206,8 +206,9 @@ class Plan:
     def _ensure_packed(self, directions, fresh: bool, x_requires_grad: bool, nhw):
         """Weight panels of every tensor-core layer, re-packed in ONE launch when `fresh` (training:
         the weights change every step) or when any weight tensor / the plan epoch changed.  nhw: the plan input's
-        (N, H, W) -- the bf16 fast mode's panel layout follows the kernel each layer runs on at its input size."""
-        sizes = self._in_sizes(*nhw) if self.math == MATH_BF16 else [ops.NOMINAL_NHW] * len(self.nodes)
+        (N, H, W) -- a panel's layout follows the kernel the layer runs on at its input size (bf16 panels of the
+        fast mode, and any future size-dependent layout)."""
+        sizes = self._in_sizes(*nhw)  # panel layouts follow the kernel each layer runs on at its input size
         jobs = [(nd, d, sz) for nd, sz in zip(self.nodes, sizes) if nd.kind == "conv" for d in directions
                 if nd.uses_tc(d, self.math) and not (d == PACK_DGRAD and nd.src == 0 and not x_requires_grad)]
         if not jobs:

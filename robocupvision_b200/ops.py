@@ -110,10 +110,10 @@ NOMINAL_NHW = (1, 16, 16)
 
 
 def conv_packed_bytes(g: ConvGeom, direction: int, math: int = MATH_AUTO, nhw=NOMINAL_NHW) -> int:
-    """Bytes of the layer's weight panel.  The panel layout depends on the math mode: RCV_MATH_BF16 panels are bf16
-    for the layers the halo-staged kernel runs AT THE INPUT SIZE `nhw` = (N, H, W) (long rows or deep dilation fall
-    to the single-pass tf32 kernels and their fp32 panels), so that mode must be given the real size; the other
-    modes' panels do not depend on it."""
+    """Bytes of the layer's weight panel.  The panel layout follows the kernel the layer runs on AT THE INPUT SIZE
+    `nhw` = (N, H, W): RCV_MATH_BF16 panels are bf16 for the layers the halo-staged kernel runs at that size (rows too
+    long for the kernel's patch fall to the single-pass tf32 kernels and their fp32 panels).  Pass the real size; the
+    nominal default is only good outside the bf16 mode."""
     d = g.desc(*nhw, EPI_NONE, math)
     n = _lib.load().rcv_conv_packed_bytes(C.byref(d), int(direction))
     if n == 0:
@@ -209,9 +209,9 @@ def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum
     return y, buf[0], buf[1], buf[2], buf[3]
 
 
-def _packed_for(g, w, wpacked, math, direction):
+def _packed_for(g, w, wpacked, math, direction, nhw):
     if wpacked is None and math == MATH_TF32X3:
-        wpacked = conv_pack(g, w, direction, math=math)
+        wpacked = conv_pack(g, w, direction, math=math, nhw=nhw)
     return wpacked
 
 
@@ -225,8 +225,8 @@ def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=
              stats=None, math=MATH_FP32, out=None, wpacked=None, in_affine=None, workspace=None):
     x = _chk(x, name="x")
     w = _chk(w, name="weight")
-    wpacked = _packed_for(g, w, wpacked, math, PACK_FWD)
     n, cin, h, wd = x.shape
+    wpacked = _packed_for(g, w, wpacked, math, PACK_FWD, (n, h, wd))
     if cin != g.cin or tuple(w.shape) != g.weight_shape():
         raise ValueError(f"conv_fwd: x {tuple(x.shape)} / w {tuple(w.shape)} do not match geometry")
     ho, wo = g.out_hw(h, wd)
@@ -260,9 +260,9 @@ def conv_dgrad(g: ConvGeom, dy, w, in_hw: Tuple[int, int], residual=None, math=M
     receives from a second consumer and is added in the kernel epilogue."""
     dy = _chk(dy, name="dy")
     w = _chk(w, name="weight")
-    wpacked = _packed_for(g, w, wpacked, math, PACK_DGRAD)
     n = dy.shape[0]
     h, wd = in_hw
+    wpacked = _packed_for(g, w, wpacked, math, PACK_DGRAD, (n, h, wd))
     if tuple(dy.shape[1:]) != (g.cout, *g.out_hw(h, wd)):
         raise ValueError(f"conv_dgrad: dy {tuple(dy.shape)} does not match geometry for input {in_hw}")
     d = _with_ws(g.desc(n, h, wd, EPI_NONE, math), workspace)

@@ -99,10 +99,10 @@ def test_conv_kernels_for_the_new_families(geom, cin, cout):
     wc = w.detach().cuda()
     tc_f, tc_d = (ops.conv_uses_tensor_cores(g, d, ops.MATH_AUTO) for d in (ops.PACK_FWD, ops.PACK_DGRAD))
     got = ops.conv_fwd(g, x.detach().cuda(), wc, b.detach().cuda(), math=ops.MATH_AUTO,
-                       wpacked=ops.conv_pack(g, wc, ops.PACK_FWD) if tc_f else None)
+                       wpacked=ops.conv_pack(g, wc, ops.PACK_FWD, nhw=(3, 12, 20)) if tc_f else None)
     assert_close(f"fwd {geom} {cin}->{cout}", got, y.detach(), 8e-6)
     dx = ops.conv_dgrad(g, dy.cuda(), wc, (12, 20), math=ops.MATH_AUTO,
-                        wpacked=ops.conv_pack(g, wc, ops.PACK_DGRAD) if tc_d else None)
+                        wpacked=ops.conv_pack(g, wc, ops.PACK_DGRAD, nhw=(3, 12, 20)) if tc_d else None)
     assert_close(f"dgrad {geom} {cin}->{cout}", dx, x.grad, 1.2e-5)
     dw, db = ops.conv_wgrad(g, x.detach().cuda(), dy.cuda(), want_bias=True, math=ops.MATH_AUTO)
     assert_close(f"wgrad {geom} {cin}->{cout}", dw, w.grad, 1e-5)

@@ -173,7 +173,7 @@ def test_full_size_adjoint_identities(geom, cin, cout, h, w):
     x2 = torch.randn(n, cin, h, w, device="cuda", generator=gen)
     wt = torch.randn((cin, cout, 3, 3) if tr else (cout, cin, k, k), device="cuda", generator=gen) / (cin * k * k) ** 0.5
     eng = [ops.conv_engine(g, n, h, w, dd, ops.MATH_AUTO) for dd in (0, 1, 2)]
-    wp = {dd: ops.conv_pack(g, wt, dd) for dd in (0, 1) if eng[dd] == ops.ENGINE_UMMA}
+    wp = {dd: ops.conv_pack(g, wt, dd, nhw=(n, h, w)) for dd in (0, 1) if eng[dd] == ops.ENGINE_UMMA}
     y = ops.conv_fwd(g, x, wt, None, math=ops.MATH_AUTO, wpacked=wp.get(0))
     dy = torch.randn(y.shape, device="cuda", generator=gen)
     dx = ops.conv_dgrad(g, dy, wt, (h, w), math=ops.MATH_AUTO, wpacked=wp.get(1))

@@ -125,12 +125,46 @@ def test_conv_split_reduction_workspace(cin, cout, dil, nhw, math):
     assert_close("split dgrad", d1, d0, 4e-6)
 
 
+@pytest.mark.parametrize("cin,cout,nhw", [(16, 32, (64, 60, 80)), (32, 64, (64, 30, 40)), (32, 32, (8, 60, 80)),
+                                          (64, 64, (4, 30, 40)), (128, 128, (2, 30, 40)), (16, 32, (2, 6, 8))])
+@pytest.mark.parametrize("math", [1, 3])  # RCV_MATH_TF32X3 (parity), RCV_MATH_TF32 (fast)
+def test_stride2_conv_at_real_sizes(cin, cout, nhw, math):
+    """Stride-2 3x3 convs on the tensor-core engine at the nets' real sizes: forward with the fused epilogue and
+    BatchNorm statistics against F.conv2d, and the transposed convolution's input gradient (the same problem)."""
+    from robocupvision_b200 import ops
+    n, h, w_ = nhw
+    g = ops.ConvGeom(cin, cout, 3, 2, 1, 1, False)
+    gen = torch.Generator().manual_seed(cin * 3 + cout)
+    x = torch.randn(n, cin, h, w_, generator=gen)
+    wt = torch.randn(cout, cin, 3, 3, generator=gen) / (cin * 9) ** 0.5
+    b = torch.randn(cout, generator=gen)
+    assert ops.conv_engine(g, n, h, w_, ops.PACK_FWD, math) == ops.ENGINE_UMMA
+    wp = ops.conv_pack(g, wt.cuda(), ops.PACK_FWD, math=math, nhw=nhw)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    got = ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), epilogue=ops.EPI_RELU, stats=stats, math=math, wpacked=wp)
+    ref = F.relu(F.conv2d(x, wt, b, 2, 1))
+    tol = 8e-6 if math == 1 else 2e-3
+    assert_close(f"s2 conv {cin}->{cout} {nhw}", got, ref, tol)
+    assert_close("s2 stats", stats[:cout], ref.double().sum((0, 2, 3)), tol, atol=1e-2)
+    # ConvTranspose2d(cout -> cin)'s input gradient is a stride-2 conv over dy with the transposed weight layout
+    gt = ops.ConvGeom(cout, cin, 3, 2, 1, 1, True)
+    wtt = torch.randn(cout, cin, 3, 3, generator=gen) / (cin * 9) ** 0.5          # (Cin_T = cout, Cout_T = cin, 3, 3)
+    xt = torch.randn(n, cout, h // 2, w_ // 2, generator=gen, requires_grad=True)
+    yt = F.conv_transpose2d(xt, wtt, None, stride=2, padding=1, output_padding=1)
+    dyt = torch.randn(yt.shape, generator=gen)
+    yt.backward(dyt)
+    if ops.conv_engine(gt, n, h // 2, w_ // 2, ops.PACK_DGRAD, math) == ops.ENGINE_UMMA:
+        wpd = ops.conv_pack(gt, wtt.cuda(), ops.PACK_DGRAD, math=math, nhw=(n, h // 2, w_ // 2))
+        dx = ops.conv_dgrad(gt, dyt.cuda(), wtt.cuda(), (h // 2, w_ // 2), math=math, wpacked=wpd)
+        assert_close(f"convT dgrad {cout}->{cin}", dx, xt.grad, 1.2e-5 if math == 1 else 3e-3)
+
+
 def test_pack_table_matches_single_packs():
     """rcv_conv_pack_table_* (all layers in one launch) writes the same panels as rcv_conv_pack."""
     from robocupvision_b200 import ops
     jobs, singles = [], []
     for i, (geom, cin, cout, d) in enumerate([("k3s1d1", 128, 128, 0), ("k3s1d1", 128, 128, 1), ("convT", 64, 32, 0),
-                                              ("k3s2", 16, 32, 1), ("k3s1d2", 24, 40, 0), ("k1", 16, 5, 0)]):
+                                              ("k3s2", 16, 32, 1), ("k3s2", 16, 32, 0), ("k3s2", 64, 128, 0), ("k3s1d2", 24, 40, 0), ("k1", 16, 5, 0)]):
         g, x, w, b = _mk(geom, cin, cout, 1, 4, 4, seed=20 + i)
         w = w.cuda()
         singles.append(ops.conv_pack(g, w, d))
@@ -197,7 +231,7 @@ def test_conv_fwd_normalise_on_load(geom, cin, cout, nhw, relu):
         xn = F.relu(xn)
     ref = F.relu(_ref_conv(geom, xn, w, b))
     stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
-    wp = ops.conv_pack(g, w.cuda(), ops.PACK_FWD)
+    wp = ops.conv_pack(g, w.cuda(), ops.PACK_FWD, nhw=(n, h, w_))
     got = ops.conv_fwd(g, x.cuda(), w.cuda(), b.cuda(), epilogue=ops.EPI_RELU, stats=stats, math=ops.MATH_AUTO,
                        wpacked=wp, in_affine=(sc.cuda(), sh.cuda(), relu))
     assert_close(f"conv_fwd_nl {geom} {cin}->{cout} relu={relu}", got, ref, 8e-6)

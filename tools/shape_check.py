@@ -31,12 +31,12 @@ for geom, cin, cout, div in layers:
     dy = torch.randn(v.shape, generator=gen)
     v.backward(dy)
     eng = ops.conv_engine(g, N, h, w, ops.PACK_FWD, ops.MATH_AUTO)
-    wp = ops.conv_pack(g, wt.cuda(), ops.PACK_FWD) if eng == 2 else None
+    wp = ops.conv_pack(g, wt.cuda(), ops.PACK_FWD, nhw=(N, h, w)) if eng == 2 else None
     got = ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), epilogue=ops.EPI_RELU_AFFINE, scale=sc.cuda(), shift=sh.cuda(),
                        residual=res.cuda(), math=ops.MATH_AUTO, wpacked=wp)
     ef = float((got.cpu() - ref).abs().max()) / max(1.0, float(ref.abs().max()))
     engd = ops.conv_engine(g, N, h, w, ops.PACK_DGRAD, ops.MATH_AUTO)
-    wpd = ops.conv_pack(g, wt.cuda(), ops.PACK_DGRAD) if engd == 2 else None
+    wpd = ops.conv_pack(g, wt.cuda(), ops.PACK_DGRAD, nhw=(N, h, w)) if engd == 2 else None
     dx = ops.conv_dgrad(g, dy.cuda(), wt.cuda(), (h, w), math=ops.MATH_AUTO, wpacked=wpd)
     ed = float((dx.cpu() - xr.grad).abs().max()) / max(1.0, float(xr.grad.abs().max()))
     engw = ops.conv_engine(g, N, h, w, 2, ops.MATH_AUTO)
