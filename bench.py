@@ -60,12 +60,15 @@ WORKLOADS = {
                         name="LabelProp two-frame training, 16 samples = 8 frame pairs per GPU (BASELINE configs[4])",
                         batch=16),
 }
-# the extra records of a default run: (workload, batch, latency mode, checkpoint override)
-EXTRAS_1GPU = [("infer", 256, False, None), ("infer", 1, True, None),
-               ("infer_pbfcn", 256, False, "bestModelSegFinetunedPruned"), ("infer_pbfcn", 1, True, "bestModelSeg"),
-               ("infer_vga", 8, False, None), ("infer_vga", 1, True, None),
-               ("train_vga", 8, False, None), ("train_unet", 64, False, None), ("train_lp", 16, False, None)]
-EXTRAS_NGPU = [("train_unet", 64, False, None), ("train_lp", 16, False, None)]
+# the extra records of a default run: (workload, batch, latency mode, checkpoint override, math mode override)
+EXTRAS_1GPU = [("infer", 256, False, None, None), ("infer", 1, True, None, None),
+               ("infer_pbfcn", 256, False, "bestModelSegFinetunedPruned", None), ("infer_pbfcn", 1, True, "bestModelSeg", None),
+               ("infer_vga", 8, False, None, None), ("infer_vga", 1, True, None, None),
+               ("train_vga", 8, False, None, None), ("train_unet", 64, False, None, None), ("train_lp", 16, False, None, None),
+               # the FAST math modes, stated separately from the fp32-parity records above (their own dtype)
+               ("train", 64, False, None, "bf16"), ("infer", 256, False, None, "bf16"), ("infer", 256, False, None, "tf32"),
+               ("infer_pbfcn", 256, False, "bestModelSegFinetunedPruned", "bf16")]
+EXTRAS_NGPU = [("train_unet", 64, False, None, None), ("train_lp", 16, False, None, None)]
 ENGINE_NAMES = {0: "igemm (fp32 FFMA)", 1: "direct_conv (fp32 FFMA)",
                 2: "umma_halo / umma_igemm (tcgen05, TMEM accumulators, halo-staged A operand for stride-1 3x3)",
                 3: "narrow_conv (TMA halo staging + FFMA2)"}  # rcv_engine
@@ -332,13 +335,16 @@ class Job:
 
 
 def run_workload(job: Job, key: str, batch: int, steps: int, warmup: int, headline: bool, latency: bool = False,
-                 ckpt: str = None, cpu_budget_s: float = 3.0):
+                 ckpt: str = None, cpu_budget_s: float = 3.0, math: str = None):
     """One workload on this job's ranks -> record (dict).  Also returns the model for the headline's kernel rooflines."""
     from robocupvision_b200 import _lib, ops
     from robocupvision_b200.train import EvalStep, TrainStep
     args, dev, world, rank = job.args, job.dev, job.world, job.rank
     wl = WORKLOADS[key]
     model, ckpt_used = build_model(wl, dev, ckpt or wl.get("ckpt"))
+    if math:
+        model.set_math(math)
+    mode = math or args.math
     cw = class_weights(wl)
     nbatches = 8  # rotate distinct input batches; the per-step activation working set is >> L2 except at batch 1
     xs_host = [synth.images(batch, wl["cin"], wl["h"], wl["w"], seed=1234 + 17 * rank + i).pin_memory() for i in range(nbatches)]
@@ -424,7 +430,8 @@ def run_workload(job: Job, key: str, batch: int, steps: int, warmup: int, headli
     roof_step["frac"] = roof_step["achieved"] / roof_step["peak"]
     rec = {"workload": wl["name"], "key": key, "value": value, "unit": "samples/s" if key == "train_lp" else UNIT,
            "n_gpus": world, "batch_per_gpu": batch, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
-           "dtype": MATH_DTYPE[args.math], "weights": f"released checkpoint {ckpt_used}" if ckpt_used else "random init, seed 12345678",
+           "dtype": MATH_DTYPE[mode], "math": mode,
+           "weights": f"released checkpoint {ckpt_used}" if ckpt_used else "random init, seed 12345678",
            "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches), "roofline_whole_step": roof_step,
@@ -453,7 +460,10 @@ def run_workload(job: Job, key: str, batch: int, steps: int, warmup: int, headli
         for i in range(n):
             EvalStep.wait_host(ev.run_async(xs_host[i % nbatches], ys_host[i % nbatches]))
         rec["latency_ms_host_to_host"] = (time.perf_counter() - t0) * 1e3 / n / batch
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if math:
+        rec["key"] = f"{key}_{math}"
+        rec["note"] = "fast math mode, stated separately from the fp32-parity record of the same workload (tests/test_gpu_fast_math.py holds its tolerances)"
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not math:
         # bounded sample: at most 64 frames per CPU step, a few seconds of steps
         cb = min(batch, 64)
         fps, ms, threads, kind, n = cpu_reference(wl, cb, 12 if headline else 6, 1, ckpt or wl.get("ckpt"),
@@ -568,10 +578,12 @@ def main():
             line["dp_check"] = {"ok": False, "error": repr(e)}
     if not args.no_extras and args.workload == "train":
         line["extra"] = []
-        for key, b, lat, ck in (EXTRAS_1GPU if world == 1 else EXTRAS_NGPU):
+        for key, b, lat, ck, mth in (EXTRAS_1GPU if world == 1 else EXTRAS_NGPU):
+            if mth and args.math != "parity":
+                continue
             torch.cuda.empty_cache()
             try:
-                r, m = run_workload(job, key, b, args.extra_steps, 5, headline=False, latency=lat, ckpt=ck)
+                r, m = run_workload(job, key, b, args.extra_steps, 5, headline=False, latency=lat, ckpt=ck, math=mth)
                 del m
             except Exception as e:  # noqa: BLE001
                 r = {"workload": WORKLOADS[key]["name"], "key": key, "batch_per_gpu": b, "error": repr(e)}
