@@ -195,6 +195,33 @@ def test_robo_noscale_backward():
     _rel_l2_grad_check("robo_noscale 240x320", m2, fwd, sd, x, synth.labels_learnable(x), synth.CLASS_WEIGHTS, 2e-3)
 
 
+@pytest.mark.parametrize("tag,batch", [("robo_default", 64), ("robo_unet_pool", 32)])
+def test_robo_full_size_backward(tag, batch):
+    """BASELINE configs[1] / configs[4] at their real size (batch x 3 x 120 x 160): one forward / backward of the
+    drop-in module against CPU autograd over the oracle evaluated in float64 (relative L2, `_rel_l2_grad_check`)."""
+    from robocupvision_b200.model import ROBO_UNet
+    sd, kw, okw = robo_state(tag)
+    m = ROBO_UNet(**kw)
+    m.load_state_dict(sd)
+    x = synth.images(batch, 3, 120, 160, seed=9)
+    _rel_l2_grad_check(f"{tag} {batch}x3x120x160", m, lambda s, xx: R.robo_unet_forward(s, xx, training=True, **okw), sd, x,
+                       synth.labels_learnable(x), synth.CLASS_WEIGHTS, 2e-3)
+
+
+def test_labelprop_full_size_backward():
+    """BASELINE configs[4]: the label-propagation net at 16 x 8 x 120 x 160 from its released checkpoint."""
+    from robocupvision_b200.model import LabelProp, load_legacy_state_dict
+    from util import load_ckpt
+    raw = load_ckpt("bestModelLPFinetunedPruned")
+    m = LabelProp(5, 32, 0)
+    load_legacy_state_dict(m, raw)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    x = synth.images(16, 8, 120, 160, seed=10)
+    y = synth.labels_random(16, 120, 160, seed=11)
+    _rel_l2_grad_check("labelprop 16x8x120x160", m, lambda s, xx: R.labelprop_forward(s, xx, training=True), sd, x, y,
+                       synth.LP_CLASS_WEIGHTS, 3e-3, tol_each=2e-2)
+
+
 def test_pb_fcn_vga_training_step():
     """BASELINE configs[3] training: PB_FCN(32,5,1,noScale=True) from pth/bestModelSegVGA.pth at 2x3x480x640 --
     forward/backward against CPU autograd over the oracle (relative L2 per tensor), then two fused SGD steps
