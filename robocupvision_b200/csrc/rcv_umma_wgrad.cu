@@ -25,6 +25,21 @@
 
 using namespace rcv_umma;
 
+// Phase-timing instrumentation (tools/umma_phases.py wgrad): compiled in only with -DRCV_PROF=1
+#ifndef RCV_PROF
+#define RCV_PROF 0
+#endif
+#if RCV_PROF
+#define WPROF_ON(cond) (p.prof && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (cond))
+#define WPROF_I(e) do { if (WPROF_ON(c < 128)) p.prof[2048 + c * 4 + (e)] = clock64(); } while (0)
+#define WPROF_P(e) do { if (WPROF_ON(gt == 0 && c < 128)) p.prof[c * 8 + (e)] = clock64(); } while (0)
+#define WPROF_E(e) do { if (WPROF_ON(gt == 0)) p.prof[4000 + grp * 4 + (e)] = clock64(); } while (0)
+#else
+#define WPROF_I(e) do { } while (0)
+#define WPROF_P(e) do { } while (0)
+#define WPROF_E(e) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;        // (channel, tap) rows per tile (MMA M)
@@ -137,6 +152,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
         for (int st = 0; st < G; ++st) {
           const int c = c0 + st;
           if (c < nchunks) {
+            WPROF_I(0);
             tc_fence_after();
             const uint32_t base = tiles + st * C::STAGE;
             const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + C::A_TILE);
@@ -154,9 +170,12 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
               }
               umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
             }
+            WPROF_I(1);
             if (c + 1 < nchunks) mbar_wait(bar_full + 8 * ((st + 1) % G), st + 1 == G ? par ^ 1u : par);
+            WPROF_I(2);
             umma_commit(bar_empty + 8 * st);
             if (c == nchunks - 1) umma_commit(bar_done);
+            WPROF_I(3);
           }
         }
       }
@@ -179,6 +198,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
 
     for (int c = grp, use = 0; c < nchunks; c += G, ++use) {
       const int mc = mbeg + c * BK;
+      WPROF_P(0);
       // ---- B: dense tensor, rows = channels, float4 along pixels ----
       float4 rb[C::BROWS];
       {
@@ -308,7 +328,9 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
         }
       }
       }
+      WPROF_P(1);
       if (use > 0) mbar_wait(my_empty, (uint32_t)((use - 1) & 1));
+      WPROF_P(2);
 #pragma unroll
       for (int i = 0; i < C::BROWS; ++i) {
         const int rowc = br0 + 16 * i;
@@ -365,9 +387,12 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
         if (!fast) *reinterpret_cast<float*>(st + C::A_TILE + off) = l;
       }
       }
+      WPROF_P(3);
       fence_proxy_async_smem();
+      WPROF_P(4);
       __syncwarp();
       if (lane == 0) mbar_arrive(my_full);
+      WPROF_P(5);
     }
 
     if (do_bias) {
@@ -386,7 +411,9 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
     // ================================ EPILOGUE ========================================
     // thread = accumulator row = one weight offset; consecutive lanes hit consecutive addresses
     if (nchunks > 0) {
+      WPROF_E(0);
       mbar_wait(bar_done, 0);
+      WPROF_E(1);
       tc_fence_after();
       const int lrow = (warp & 3) * 32 + lane;
       const int wo = s_wo[lrow];
@@ -410,6 +437,7 @@ __global__ void __launch_bounds__(WCfg<BN>::NT, 1) umma_wgrad_kernel(const RcvWg
             if (cb0 + c0 + j < p.CB) atomicAdd(dst + (size_t)j * p.wsB, __uint_as_float(rm[j]) + __uint_as_float(rc[j]));
         }
       }
+      WPROF_E(2);
     }
   }
 
@@ -486,6 +514,7 @@ bool rcv_umma_wgrad_takes_input_transform(const RcvWgrad& p) {
 }
 
 int rcv_launch_wgrad_umma(RcvWgrad p, cudaStream_t st) {
+  p.prof = g_rcv_prof;
   const int64_t M = (int64_t)p.N * p.Hg * p.Wg;
   RCV_REQUIRE(M < (1ll << 31), RCV_ERR_UNSUPPORTED, "wgrad: problem too large");
   RCV_REQUIRE(p.taps.n >= 1 && p.taps.n <= MAXT, RCV_ERR_UNSUPPORTED, "wgrad: %d taps", p.taps.n);
