@@ -31,7 +31,9 @@ def cold(fn, n=12):
 for cin, cout, dil, n, h, w in [(128, 128, 1, 64, 15, 20), (64, 64, 1, 64, 15, 20), (128, 64, 1, 64, 15, 20),
                                 (64, 128, 1, 64, 15, 20), (32, 32, 1, 64, 30, 40), (128, 128, 1, 256, 15, 20),
                                 (128, 128, 1, 1, 15, 20), (128, 128, 2, 1, 15, 20), (128, 128, 1, 8, 15, 20),
-                                (64, 64, 1, 1, 15, 20), (32, 32, 1, 1, 30, 40)]:
+                                (64, 64, 1, 1, 15, 20), (32, 32, 1, 1, 30, 40),
+                                (128, 128, 2, 8, 30, 40), (64, 128, 2, 8, 30, 40), (128, 128, 2, 1, 30, 40),
+                                (128, 128, 1, 32, 15, 20), (128, 128, 1, 40, 15, 20)]:
     g = ops.ConvGeom(cin, cout, 3, 1, dil, dil, False)
     x = torch.randn(n, cin, h, w, device="cuda")
     wt = torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5
