@@ -529,6 +529,23 @@ def test_resample_modules_autograd():
     assert_close("module bilinear grad", xg2.grad, xr2.grad, 2e-6)
 
 
+@pytest.mark.parametrize("n,c", [(1, 5), (7, 5), (70, 5), (3, 2), (5, 8)])
+def test_metric_tail_matches_reference_rule(n, c):
+    """rcv_metric_tail: the validation loops' per-image IoU rule (train.py:148-153: inter / union per class, an image
+    without the class counts 1) and the mean loss, against the oracle's restatement; counts are exact integers."""
+    from robocupvision_b200 import ops
+    from oracle import ref_metrics
+    gen = torch.Generator().manual_seed(n * 10 + c)
+    conf = torch.randint(0, 5000, (n, c, c), generator=gen, dtype=torch.int64)
+    conf[0, :, 0] = 0
+    conf[0, 0, :] = 0          # class 0 absent from image 0: union == 0 -> counts 1
+    sums = torch.tensor([123.456, 78.9], dtype=torch.float64)
+    iou, loss = ops.metric_tail(conf.cuda(), sums.cuda())
+    ref = ref_metrics.iou_sums(conf.numpy())
+    assert torch.allclose(iou.cpu(), torch.as_tensor(ref, dtype=torch.float64), rtol=0, atol=1e-12)
+    assert abs(float(loss) - 123.456 / 78.9) < 1e-15
+
+
 @pytest.mark.parametrize("c", [5, 4, 2, 8])
 @pytest.mark.parametrize("weighted", [True, False])
 def test_cross_entropy_argmax_confusion(c, weighted):

@@ -321,3 +321,41 @@ def test_dp_self_check_single_rank_nccl():
     r = json.loads(line[0][8:])
     print(r)
     assert r["ok"], r
+
+
+def _cuda_kernel_names(fn):
+    """Names of the CUDA kernels fn() launches (torch.profiler / CUPTI)."""
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    return [e.key for e in prof.key_averages() if getattr(e, "device_type", None) is not None and "Memcpy" not in e.key
+            and "Memset" not in e.key]
+
+
+def test_hot_path_launches_only_library_kernels():
+    """north_star: "no Triton, no cuDNN dispatch, no CPU fallback" -- and no eager PyTorch kernel either: every kernel
+    a graph-replayed training step and an EvalStep call launch belongs to librcv_b200.so (memsets / copies of the
+    accumulators and inputs aside)."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import EvalStep, TrainStep
+    torch.manual_seed(12345678)
+    m = ROBO_UNet().cuda()
+    ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, use_graph=True)
+    x = synth.images(8, 3, 120, 160, seed=3).cuda()
+    y = synth.labels_random(8, 120, 160, seed=4).cuda()
+    for _ in range(3):
+        ts.step(x, y)
+    names = _cuda_kernel_names(lambda: ts.step(x, y))
+    assert len(names) >= 20, names
+    foreign = [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()
+               or "cutlass" in n.lower()]
+    assert not foreign, f"non-library kernels inside a training step: {foreign}"
+    ev = EvalStep(m, synth.CLASS_WEIGHTS, use_graph=True)
+    for _ in range(2):
+        ev(x, y)
+    names = _cuda_kernel_names(lambda: ev(x, y))
+    foreign = [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()
+               or "cutlass" in n.lower()]
+    assert len(names) >= 10 and not foreign, f"non-library kernels inside an EvalStep call: {foreign}"
