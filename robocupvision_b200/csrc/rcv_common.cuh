@@ -160,6 +160,8 @@ bool rcv_umma_halo_ok(const RcvIgemm& p, int bn, int kbb);    // stride-1 3x3, h
 int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t st);
 size_t rcv_umma_workspace_bytes(const RcvIgemm& p);          // scratch the tensor-core engine can use for this problem (0: none)
 size_t rcv_umma_halo_workspace_bytes(const RcvIgemm& p, int bn);
+bool rcv_umma_c16_ok(const RcvIgemm& p);                       // 16 -> <= 16 stride-1 3x3: persistent tensor-core kernel (KB = 16 panel)
+int rcv_launch_igemm_umma_c16(const RcvIgemm& p, cudaStream_t st);
 bool rcv_umma_halo_bf16_ok(const RcvIgemm& p, int bn);        // RCV_MATH_BF16: would that kernel take bf16 operands (bf16 panel layout)
 bool rcv_umma_takes_input_transform(const RcvIgemm& p);      // would rcv_launch_igemm_umma run the halo-staged kernel
 bool rcv_umma_wgrad_takes_input_transform(const RcvWgrad& p);  // tensor-core weight gradient with the quad gather

@@ -305,6 +305,8 @@ int rcv_pick_engine(const RcvIgemm& p, bool have_packed) {
   static const int use_narrow = env_flag("RCV_NARROW", 1);
   static const int use_direct = env_flag("RCV_DIRECT", 1);
   if (p.math == RCV_MATH_TF32X3) return RCV_ENGINE_UMMA;
+  // 16 -> <= 16 stride-1 3x3: the persistent tensor-core kernel (rcv_umma_halo.cu) beats the FFMA2 kernel
+  if (rcv_math_auto(p.math) && have_packed && rcv_umma_c16_ok(p)) return RCV_ENGINE_UMMA;
   // <= 16 output channels: TMA-staged FFMA2 direct convolution (exact fp32), whatever the reduction length
   if (use_narrow && rcv_narrow_supported(p)) return RCV_ENGINE_NARROW;
   if (rcv_math_auto(p.math) && have_packed && rcv_umma_pays(p)) return RCV_ENGINE_UMMA;

@@ -596,14 +596,17 @@ bool rcv_umma_supported(const RcvIgemm& p) {
 }
 
 // panel layout of a layer: K-block width in elements (64 = the bf16 layout of RCV_MATH_BF16 halo layers)
-static int panel_kb(const RcvIgemm& p) { return rcv_umma_halo_bf16_ok(p, umma_bn(p.CB)) ? 64 : umma_kb(p.CB); }
+static int panel_kb(const RcvIgemm& p) {
+  if (rcv_umma_c16_ok(p)) return 16;  // the persistent 16-channel kernel keeps the whole 9 x [16 rows x 64 B] panel resident
+  return rcv_umma_halo_bf16_ok(p, umma_bn(p.CB)) ? 64 : umma_kb(p.CB);
+}
 
 size_t rcv_umma_packed_bytes(const RcvIgemm& p) {
   if (panel_kb(p) == 64) {
     const int BN = umma_bn(p.CB);
     return (size_t)rcv_cdiv(p.CB, BN) * (p.CA * 9 / 64) * BN * 128;
   }
-  const int BN = umma_bn(p.CB), KB = umma_kb(p.CB);
+  const int BN = umma_bn(p.CB), KB = panel_kb(p);
   const int ntiles = rcv_cdiv(p.CB, BN);
   const int kbmax = rcv_cdiv((int64_t)p.CA * max_taps(p), KB);
   return (size_t)p.nclass * ntiles * kbmax * BN * KB * 8;
@@ -678,6 +681,7 @@ int rcv_launch_igemm_umma(const RcvIgemm& p_in, cudaStream_t st) {
   RCV_REQUIRE(((uintptr_t)p.wpacked & 127) == 0, RCV_ERR_BAD_ARG, "packed weights must be 128-byte aligned");
   // Ring depth = producer groups.  Long reductions: 3-4 stages, one CTA per SM.  Short ones (a few
   // K blocks per tile): 2 stages so that 2 CTAs share an SM and overlap prologue / epilogue.
+  if (rcv_umma_c16_ok(p)) return rcv_launch_igemm_umma_c16(p, st);
   const int bn = umma_bn(p.CB);
   const bool deep = g_force_g > 0 ? g_force_g >= 3 : (int64_t)p.CA * max_taps(p) > 10 * BK;
   // stride-1 3x3 layers: nine tap-shifted descriptors over one staged patch instead of nine gathers

@@ -628,3 +628,283 @@ int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t 
   rcv_set_error("umma_halo: no configuration for BN=%d, K block %d", bn, kbb);
   return RCV_ERR_UNSUPPORTED;
 }
+
+// =====================================================================================================================
+// 16-channel layers (16 -> <= 16, stride-1 3x3, dilation 1: ROBO_UNet Level1.Conv1, the second conv of every --UNet
+// level-1 block, and their input gradients) on the tensor cores: a PERSISTENT kernel.
+//
+// A tile of 128 positions of such a layer is only 54 small MMAs (9 taps x 16 channels = 18 K steps x 3 products,
+// N = 16), ~2 k cycles -- less than the fixed cost of a CTA of the kernel above (barrier init, TMEM allocation,
+// first load, epilogue), which is why these layers ran as FFMA2 direct convolutions at 50 % of the FP32 pipe
+// (narrow_conv_kernel<16,0,1>, 46 us at batch 64).  Here every CTA allocates once and loops over its tiles
+// (blockIdx.x, + gridDim.x, ...) with everything double-buffered:
+//   * the whole weight panel (9 taps x 16 rows x 64 B, hi + lo = 18 KB) stays in shared memory for the CTA's lifetime;
+//   * 8 producer warps stage the patch of tile t+1 (64-byte rows = 16 channels, SWIZZLE_64B, hi / lo copies, tap
+//     shifts by descriptor start as above; up to two positions per thread) while
+//   * the MMA warp runs the 54 MMAs of tile t into one of two TMEM accumulator pairs and
+//   * 4 epilogue warps drain tile t-1 (fused bias / ReLU / affine / residual / BatchNorm statistics, NCHW stores).
+namespace {
+
+constexpr int C16_NPROD = 256;                  // producer threads (warps 0-7)
+constexpr int C16_NEPI = 128;                   // epilogue threads (warps 9-12: TMEM lane quarters 1, 2, 3, 0)
+constexpr int C16_NT = C16_NPROD + 32 + C16_NEPI;
+constexpr int C16_WB = 9 * 16 * 64 * 2;         // resident weight panel bytes (hi rows then lo rows per tap block)
+
+bool geometry16(const RcvIgemm& p, HaloGeo* out) {
+  if (p.nclass != 1 || p.gs != 1 || p.ostep != 1 || p.taps[0].n != 9 || p.in_scale != nullptr) return false;
+  if (p.Hout != p.Hin || p.Wout != p.Win || p.Hg != p.Hin || p.Wg != p.Win) return false;
+  if (p.CA != 16 || p.CB > 16 || p.CB < 1) return false;
+  const int sgn = p.taps[0].dy[0] < 0 ? 1 : -1;
+  for (int t = 0; t < 9; ++t)
+    if (p.taps[0].dy[t] != sgn * (t / 3 - 1) || p.taps[0].dx[t] != sgn * (t % 3 - 1)) return false;  // dilation 1
+  HaloGeo g;
+  memset(&g, 0, sizeof(g));
+  g.tsign = sgn;
+  g.d = 1;
+  g.PW = p.Win + 1;
+  g.HP = p.Hin + 1;
+  g.S = g.PW + 1;
+  g.L = BM + 2 * g.S;
+  g.Lpad = (g.L + 7) & ~7;
+  g.nkc = 1;
+  g.Mh = ((int64_t)p.N * g.HP + 1) * g.PW;
+  if (g.L > 2 * C16_NPROD) return false;
+  if ((int64_t)p.N * p.CA * p.Hin * p.Win >= (1ll << 30) || g.Mh >= (1ll << 31)) return false;
+  *out = g;
+  return true;
+}
+
+size_t c16_smem(const HaloGeo& g) { return 1024 + 4 * (size_t)g.Lpad * 64 + C16_WB + 512; }
+
+__global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, const HaloGeo g, int ntiles) {
+  rcv_pdl_enter();
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gen = smem_raw + (base - raw);
+  const uint32_t patch_bytes = (uint32_t)g.Lpad * 64u;   // one copy (hi or lo) of one buffer
+  const uint32_t buf_bytes = 2u * patch_bytes;
+  const uint32_t wb_s = base + 2u * buf_bytes;           // resident weight panel
+  unsigned char* misc = gen + 2u * buf_bytes + C16_WB;
+  // barriers: pfull[2], pempty[2], tfull[2], tempty[2], wfull
+  const uint32_t bars = smem_u32(misc);
+  const uint32_t bar_pfull = bars, bar_pempty = bars + 16, bar_tfull = bars + 32, bar_tempty = bars + 48, bar_wfull = bars + 64;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 80);
+  float* s_cst = reinterpret_cast<float*>(misc + 128);   // bias, scale, shift [3][16]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.Hin, W = p.Win, HW = H * W;
+  const bool fast = p.math >= RCV_MATH_TF32;
+
+  if (tid < 16) {
+    const bool in = tid < p.CB;
+    s_cst[tid] = (in && p.bias) ? __ldg(p.bias + tid) : 0.f;
+    s_cst[16 + tid] = (in && p.scale) ? __ldg(p.scale + tid) : 1.f;
+    s_cst[32 + tid] = (in && p.shift) ? __ldg(p.shift + tid) : 0.f;
+  }
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_pfull + 8 * b, C16_NPROD / 32);
+      mbar_init(bar_pempty + 8 * b, 1);
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, C16_NEPI / 32);
+    }
+    mbar_init(bar_wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == C16_NPROD / 32) tmem_alloc(smem_u32(tmem_slot), 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == C16_NPROD / 32) {
+    // ================================ WEIGHTS + MMA ISSUER =============================
+    if (elect_one()) {
+      mbar_expect_tx(bar_wfull, C16_WB);
+      bulk_g2s(wb_s, p.wpacked, C16_WB, bar_wfull);
+      mbar_wait(bar_wfull, 0);
+      constexpr uint32_t idesc = make_idesc(BM, 16);
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int buf = lt & 1;
+        const uint32_t ph = (uint32_t)((lt >> 1) & 1);
+        const uint32_t d_main = tmem_base + buf * 32, d_corr = d_main + 16;
+        if (lt >= 2) mbar_wait(bar_tempty + 8 * buf, ph ^ 1u);  // the epilogue has drained this accumulator pair
+        mbar_wait(bar_pfull + 8 * buf, ph);
+        tc_fence_after();
+        const uint32_t a_hi_s = base + buf * buf_bytes, a_lo_s = a_hi_s + patch_bytes;
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+          const int ty = t / 3 - 1, tx = t - (t / 3) * 3 - 1;
+          const uint32_t roff = (uint32_t)(g.S + g.tsign * (ty * g.PW + tx)) * 64u;
+          const uint64_t a_hi = make_desc_b<16>(a_hi_s + roff), a_lo = make_desc_b<16>(a_lo_s + roff);
+          const uint32_t bb = wb_s + t * (16 * 64 * 2);
+          const uint64_t b_hi = make_desc_b<16>(bb), b_lo = make_desc_b<16>(bb + 16 * 64);
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t acc = (t == 0 && ks == 0) ? 0u : 1u;
+            if (!fast) {
+              umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, acc);
+              umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+            }
+            umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
+          }
+        }
+        umma_commit(bar_pempty + 8 * buf);  // the patch buffer may be overwritten once these MMAs have read it
+        umma_commit(bar_tfull + 8 * buf);   // ... and the accumulators are complete
+      }
+    }
+  } else if (warp < C16_NPROD / 32) {
+    // ================================ PRODUCERS =======================================
+    const char* inb = reinterpret_cast<const char*>(p.in);
+    const uint32_t cstride = 4u * (uint32_t)HW;
+    const bool two = tid + C16_NPROD < g.L;  // a second staged position for this thread (L > 256)
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int buf = lt & 1;
+      const long long q0 = (long long)((int)blockIdx.x + lt * (int)gridDim.x) * BM;
+      int n0, i0, j0, n1 = 0, i1 = 0, j1 = 0;
+      const bool v0 = tid < g.L && decode_pos(q0 - g.S + tid, g, p.N, H, W, n0, i0, j0);
+      const bool v1 = two && decode_pos(q0 - g.S + tid + C16_NPROD, g, p.N, H, W, n1, i1, j1);
+      float va[16], vb[16];
+      {
+        const uint32_t b0 = v0 ? 4u * (uint32_t)((n0 * 16) * HW + i0 * W + j0) : 0u;
+        const uint32_t b1 = v1 ? 4u * (uint32_t)((n1 * 16) * HW + i1 * W + j1) : 0u;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) va[i] = v0 ? __ldg(reinterpret_cast<const float*>(inb + (b0 + (uint32_t)i * cstride))) : 0.f;
+        if (two) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vb[i] = v1 ? __ldg(reinterpret_cast<const float*>(inb + (b1 + (uint32_t)i * cstride))) : 0.f;
+        }
+      }
+      if (lt >= 2) mbar_wait(bar_pempty + 8 * buf, (uint32_t)(((lt >> 1) - 1) & 1));
+      unsigned char* dst = gen + buf * buf_bytes;
+      if (tid < g.L) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 h, l;
+          split_tf32(va[4 * c + 0], h.x, l.x);
+          split_tf32(va[4 * c + 1], h.y, l.y);
+          split_tf32(va[4 * c + 2], h.z, l.z);
+          split_tf32(va[4 * c + 3], h.w, l.w);
+          const int off = tid * 64 + ((c ^ ((tid >> 1) & 3)) << 4);  // SWIZZLE_64B of the absolute address
+          *reinterpret_cast<float4*>(dst + off) = h;
+          if (!fast) *reinterpret_cast<float4*>(dst + patch_bytes + off) = l;
+        }
+      }
+      if (two) {
+        const int r2 = tid + C16_NPROD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float4 h, l;
+          split_tf32(vb[4 * c + 0], h.x, l.x);
+          split_tf32(vb[4 * c + 1], h.y, l.y);
+          split_tf32(vb[4 * c + 2], h.z, l.z);
+          split_tf32(vb[4 * c + 3], h.w, l.w);
+          const int off = r2 * 64 + ((c ^ ((r2 >> 1) & 3)) << 4);
+          *reinterpret_cast<float4*>(dst + off) = h;
+          if (!fast) *reinterpret_cast<float4*>(dst + patch_bytes + off) = l;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_pfull + 8 * buf);
+    }
+  } else {
+    // ================================ EPILOGUE ========================================
+    // thread = one accumulator row; warps 9..12 own TMEM lane quarters (warp % 4)
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    const int epi = p.epilogue;
+    const int HWo = p.Hout * p.Wout;
+    const bool has_res = p.residual != nullptr, has_stats = p.stats != nullptr;
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int buf = lt & 1;
+      const long long q0 = (long long)((int)blockIdx.x + lt * (int)gridDim.x) * BM;
+      int en = 0, ei = 0, ej = 0;
+      const bool mrow = decode_pos(q0 + row, g, p.N, H, W, en, ei, ej);
+      const size_t obase = mrow ? (size_t)en * p.CB * HWo + (size_t)ei * p.Wout + ej : 0;
+      float res[16];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) res[j] = (mrow && j < p.CB) ? __ldg(p.residual + obase + (size_t)j * HWo) : 0.f;
+      }
+      mbar_wait(bar_tfull + 8 * buf, (uint32_t)((lt >> 1) & 1));
+      tc_fence_after();
+      uint32_t rm[16], rc[16];
+      tmem_ld16_nowait(tmem_base + tlane + buf * 32, rm);
+      if (!fast) {
+        tmem_ld16_nowait(tmem_base + tlane + buf * 32 + 16, rc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rc[j] = 0u;
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);  // the accumulator pair is free for tile lt + 2
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float acc = __uint_as_float(rm[j]) + __uint_as_float(rc[j]) + s_cst[j];
+        float y = apply_epi(acc, epi, s_cst[16 + j], s_cst[32 + j]);
+        if (has_res) y += res[j];
+        v[j] = (mrow && j < p.CB) ? y : 0.f;
+      }
+      if (mrow) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < p.CB) p.out[obase + (size_t)j * HWo] = v[j];
+      }
+      if (has_stats) {
+        float s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s2[j] = v[j] * v[j];
+        warp_transpose_reduce16(v, lane);
+        warp_transpose_reduce16(s2, lane);
+        const int co = lane >> 1;
+        if ((lane & 1) == 0 && co < p.CB) {
+          atomicAdd(p.stats + co, (double)v[0]);
+          atomicAdd(p.stats + p.CB + co, (double)s2[0]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == C16_NPROD / 32) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+}  // namespace
+
+bool rcv_umma_c16_ok(const RcvIgemm& p) {
+  static const int on = getenv("RCV_UMMA_C16") ? atoi(getenv("RCV_UMMA_C16")) : 1;
+  HaloGeo g;
+  return on && geometry16(p, &g) && c16_smem(g) <= 113 * 1024;
+}
+
+int rcv_launch_igemm_umma_c16(const RcvIgemm& p, cudaStream_t st) {
+  HaloGeo g;
+  RCV_REQUIRE(geometry16(p, &g), RCV_ERR_UNSUPPORTED, "umma_c16: geometry outside the kernel's limits");
+  const size_t smem = c16_smem(g);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(umma_c16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+    if (e != cudaSuccess) {
+      rcv_set_error("umma_c16: cannot reserve shared memory: %s", cudaGetErrorString(e));
+      return RCV_ERR_CUDA;
+    }
+    cudaFuncSetAttribute(umma_c16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_done = true;
+  }
+  const int ntiles = rcv_cdiv(g.Mh, BM);
+  const int slots = 2 * sm_count();
+  const int grid = ntiles < slots ? ntiles : slots;
+  rcv_launch(umma_c16_kernel, dim3(grid), dim3(C16_NT), smem, st, p, g, ntiles);
+  RCV_CHECK_LAUNCH("umma_c16_kernel");
+  return RCV_OK;
+}

@@ -280,7 +280,7 @@ def test_engine_dispatch_table_without_gpu():
     table = [  # geom, cin, cout, h, w -> (fwd, dgrad, wgrad)
         (("k3s1d1", 3, 8, 120, 160), (N, N, N)),
         (("k3s2", 8, 16, 120, 160), (N, N, N)),
-        (("k3s1d1", 16, 16, 60, 80), (N, N, N)),
+        (("k3s1d1", 16, 16, 60, 80), (U, U, N)),   # persistent 16-channel tensor-core kernel; weight gradient narrow
         (("k3s2", 16, 32, 60, 80), (U, N, U)),
         (("k3s1d1", 32, 32, 30, 40), (U, U, U)),
         (("k3s1d1", 128, 128, 15, 20), (U, U, U)),

@@ -23,7 +23,7 @@ from util import assert_close
 pytestmark = pytest.mark.gpu
 
 # mode -> (logit tolerance relative to max|ref|, allowed argmax flip fraction, gradient tolerance)
-TOL = {"tf32": (2e-3, 1e-3, 5e-2), "bf16": (6e-3, 2e-3, 1e-1)}
+TOL = {"tf32": (2e-3, 1e-3, 8e-2), "bf16": (6e-3, 2e-3, 1.5e-1)}
 
 
 def _round_tf32(t):

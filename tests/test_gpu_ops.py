@@ -159,6 +159,44 @@ def test_stride2_conv_at_real_sizes(cin, cout, nhw, math):
         assert_close(f"convT dgrad {cout}->{cin}", dx, xt.grad, 1.2e-5 if math == 1 else 3e-3)
 
 
+@pytest.mark.parametrize("math", [2, 3])  # RCV_MATH_AUTO (parity: 3xTF32), RCV_MATH_TF32 (fast)
+@pytest.mark.parametrize("cout", [16, 8, 5])
+@pytest.mark.parametrize("nhw", [(64, 60, 80), (3, 12, 20), (5, 30, 40), (2, 9, 7), (1, 1, 1), (300, 6, 8)])
+def test_conv16_persistent_tensor_core_kernel(nhw, cout, math):
+    """16 -> <= 16 stride-1 3x3 layers on the persistent tensor-core kernel (resident weight panel, double-buffered
+    patch and accumulators): forward with every fused epilogue piece (bias, ReLU, residual, BatchNorm statistics)
+    and the input gradient, against ATen; many tiles per CTA (300 images), odd widths, a single pixel."""
+    from robocupvision_b200 import ops
+    n, h, w_ = nhw
+    g = ops.ConvGeom(16, cout, 3, 1, 1, 1, False)
+    gen = torch.Generator().manual_seed(n + cout)
+    x = torch.randn(n, 16, h, w_, generator=gen)
+    wt = torch.randn(cout, 16, 3, 3, generator=gen) / 12.0
+    b = torch.randn(cout, generator=gen)
+    res = torch.randn(n, cout, h, w_, generator=gen)
+    assert ops.conv_engine(g, n, h, w_, ops.PACK_FWD, math) == ops.ENGINE_UMMA
+    wp = ops.conv_pack(g, wt.cuda(), ops.PACK_FWD, math=math, nhw=nhw)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device="cuda")
+    got = ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), epilogue=ops.EPI_RELU, residual=res.cuda(), stats=stats,
+                       math=math, wpacked=wp)
+    ref = F.relu(F.conv2d(x, wt, b, 1, 1)) + res
+    tol = 8e-6 if math == 2 else 2e-3
+    assert_close(f"conv16 fwd -> {cout} {nhw}", got, ref, tol)
+    rd = ref.double()
+    assert_close("conv16 stats sum", stats[:cout], rd.sum((0, 2, 3)), tol, atol=1e-2)
+    assert_close("conv16 stats sumsq", stats[cout:], (rd * rd).sum((0, 2, 3)), tol, atol=1e-2)
+    # the input gradient of a (cout' -> 16) layer reduces over 16 channels as well: take cin = cout
+    g2 = ops.ConvGeom(cout, 16, 3, 1, 1, 1, False)
+    w2 = torch.randn(16, cout, 3, 3, generator=gen) / 12.0
+    dy = torch.randn(n, 16, h, w_, generator=gen)
+    if ops.conv_engine(g2, n, h, w_, ops.PACK_DGRAD, math) == ops.ENGINE_UMMA:
+        wpd = ops.conv_pack(g2, w2.cuda(), ops.PACK_DGRAD, math=math, nhw=nhw)
+        prev = torch.randn(n, cout, h, w_, generator=gen)
+        dx = ops.conv_dgrad(g2, dy.cuda(), w2.cuda(), (h, w_), residual=prev.cuda(), math=math, wpacked=wpd)
+        dref = torch.nn.grad.conv2d_input((n, cout, h, w_), w2, dy, 1, 1) + prev
+        assert_close(f"conv16 dgrad {nhw}", dx, dref, 1.2e-5 if math == 2 else 3e-3)
+
+
 def test_pack_table_matches_single_packs():
     """rcv_conv_pack_table_* (all layers in one launch) writes the same panels as rcv_conv_pack."""
     from robocupvision_b200 import ops
