@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
     // ================================ MMA ISSUER ======================================
     if (elect_one()) {
       constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc(BM, BN);
+      constexpr uint32_t idesc2 = make_idesc(BM, 2 * BN);  // fp32 parity mode: main | correction in one instruction
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       int it = 0;
       for (int cb = cb0; cb < cb1; ++cb) {
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
             mbar_wait(bar_bfull + 8 * st, (uint32_t)((it / NBS) & 1));
             tc_fence_after();
             const uint32_t bb = b_s + st * C::B_STAGE;
-            const uint64_t b_hi = BF ? make_desc(bb) : make_desc_b<KBB>(bb), b_lo = make_desc_b<KBB>(bb + BN * C::BROWB);
+            const uint64_t b_hi = BF ? make_desc(bb) : make_desc_b<KBB>(bb);
 #pragma unroll
             for (int ks = 0; ks < C::KSTEPS; ++ks) {
               const int ka = sub * C::KSTEPS + ks;  // K step (32 bytes) inside the 128-byte A row
@@ -300,10 +301,14 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
                 continue;
               }
               if (!fast) {
-                umma_tf32(d_corr, a_lo + 2 * ka, b_hi + 2 * ks, idesc, first);
-                umma_tf32(d_corr, a_hi + 2 * ka, b_lo + 2 * ks, idesc, 1u);
+                // Two MMAs per K step instead of three: a B stage holds the BN hi rows and then the BN lo rows, so
+                // ONE instruction with N = 2*BN computes a_hi * [b_hi | b_lo] into the adjacent main and correction
+                // accumulators; the second adds a_lo * b_hi to the correction accumulator.
+                umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc2, first);
+                umma_tf32(d_corr, a_lo + 2 * ka, b_hi + 2 * ks, idesc, 1u);
+              } else {
+                umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc, first);
               }
-              umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc, first);
             }
             umma_commit(bar_bempty + 8 * st);
           }
@@ -645,8 +650,9 @@ int rcv_launch_igemm_umma_halo(const RcvIgemm& p, int bn, int kbb, cudaStream_t 
 //   * 4 epilogue warps drain tile t-1 (fused bias / ReLU / affine / residual / BatchNorm statistics, NCHW stores).
 namespace {
 
-constexpr int C16_NPROD = 256;                  // producer threads (warps 0-7)
-constexpr int C16_NEPI = 128;                   // epilogue threads (warps 9-12: TMEM lane quarters 1, 2, 3, 0)
+constexpr int C16_GT = 160;                     // threads of one producer group: group g stages the tiles lt = g (mod 2)
+constexpr int C16_NPROD = 2 * C16_GT;           // producer threads (warps 0-9)
+constexpr int C16_NEPI = 128;                   // epilogue threads (warps 11-14: TMEM lane quarters 3, 0, 1, 2)
 constexpr int C16_NT = C16_NPROD + 32 + C16_NEPI;
 constexpr int C16_WB = 9 * 16 * 64 * 2;         // resident weight panel bytes (hi rows then lo rows per tap block)
 
@@ -668,7 +674,7 @@ bool geometry16(const RcvIgemm& p, HaloGeo* out) {
   g.Lpad = (g.L + 7) & ~7;
   g.nkc = 1;
   g.Mh = ((int64_t)p.N * g.HP + 1) * g.PW;
-  if (g.L > 2 * C16_NPROD) return false;
+  if (g.L > 2 * C16_GT) return false;  // at most two staged positions per producer thread
   if ((int64_t)p.N * p.CA * p.Hin * p.Win >= (1ll << 30) || g.Mh >= (1ll << 31)) return false;
   *out = g;
   return true;
@@ -704,7 +710,7 @@ __global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, c
   }
   if (tid == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_pfull + 8 * b, C16_NPROD / 32);
+      mbar_init(bar_pfull + 8 * b, C16_GT / 32);
       mbar_init(bar_pempty + 8 * b, 1);
       mbar_init(bar_tfull + 8 * b, 1);
       mbar_init(bar_tempty + 8 * b, C16_NEPI / 32);
@@ -725,7 +731,11 @@ __global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, c
       mbar_expect_tx(bar_wfull, C16_WB);
       bulk_g2s(wb_s, p.wpacked, C16_WB, bar_wfull);
       mbar_wait(bar_wfull, 0);
-      constexpr uint32_t idesc = make_idesc(BM, 16);
+      // Two MMAs per K step instead of three: the tap block holds the hi rows and then the lo rows of the weights,
+      // so ONE N = 32 instruction computes a_hi * [b_hi | b_lo] into the adjacent main and correction columns, and
+      // a second, N = 16, adds a_lo * b_hi to the correction columns.  At N <= 32 an MMA costs its A-operand fetch
+      // (~64 cycles measured), so this is a third off the MMA phase.
+      constexpr uint32_t idesc = make_idesc(BM, 16), idesc32 = make_idesc(BM, 32);
       for (int lt = 0; lt < my_tiles; ++lt) {
         const int buf = lt & 1;
         const uint32_t ph = (uint32_t)((lt >> 1) & 1);
@@ -740,15 +750,16 @@ __global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, c
           const uint32_t roff = (uint32_t)(g.S + g.tsign * (ty * g.PW + tx)) * 64u;
           const uint64_t a_hi = make_desc_b<16>(a_hi_s + roff), a_lo = make_desc_b<16>(a_lo_s + roff);
           const uint32_t bb = wb_s + t * (16 * 64 * 2);
-          const uint64_t b_hi = make_desc_b<16>(bb), b_lo = make_desc_b<16>(bb + 16 * 64);
+          const uint64_t b_hi = make_desc_b<16>(bb);
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint32_t acc = (t == 0 && ks == 0) ? 0u : 1u;
             if (!fast) {
-              umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, acc);
-              umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+              umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc32, acc);  // main | correction (a_hi * b_lo)
+              umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+            } else {
+              umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
             }
-            umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
           }
         }
         umma_commit(bar_pempty + 8 * buf);  // the patch buffer may be overwritten once these MMAs have read it
@@ -757,29 +768,29 @@ __global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, c
     }
   } else if (warp < C16_NPROD / 32) {
     // ================================ PRODUCERS =======================================
+    // Two groups of 5 warps; group grp stages the tiles lt = grp, grp + 2, ... into patch buffer grp, so one group's
+    // load round trip runs under the other group's stores (a single group exposed one round trip per tile).
     const char* inb = reinterpret_cast<const char*>(p.in);
     const uint32_t cstride = 4u * (uint32_t)HW;
-    const bool two = tid + C16_NPROD < g.L;  // a second staged position for this thread (L > 256)
-    for (int lt = 0; lt < my_tiles; ++lt) {
-      const int buf = lt & 1;
+    const int grp = tid / C16_GT, gt = tid - grp * C16_GT;
+    const bool one = gt < g.L, two = gt + C16_GT < g.L;  // staged positions gt and gt + 160 of the tile's patch
+    unsigned char* dst = gen + grp * buf_bytes;
+    for (int lt = grp, use = 0; lt < my_tiles; lt += 2, ++use) {
       const long long q0 = (long long)((int)blockIdx.x + lt * (int)gridDim.x) * BM;
       int n0, i0, j0, n1 = 0, i1 = 0, j1 = 0;
-      const bool v0 = tid < g.L && decode_pos(q0 - g.S + tid, g, p.N, H, W, n0, i0, j0);
-      const bool v1 = two && decode_pos(q0 - g.S + tid + C16_NPROD, g, p.N, H, W, n1, i1, j1);
+      const bool v0 = one && decode_pos(q0 - g.S + gt, g, p.N, H, W, n0, i0, j0);
+      const bool v1 = two && decode_pos(q0 - g.S + gt + C16_GT, g, p.N, H, W, n1, i1, j1);
       float va[16], vb[16];
       {
         const uint32_t b0 = v0 ? 4u * (uint32_t)((n0 * 16) * HW + i0 * W + j0) : 0u;
         const uint32_t b1 = v1 ? 4u * (uint32_t)((n1 * 16) * HW + i1 * W + j1) : 0u;
 #pragma unroll
         for (int i = 0; i < 16; ++i) va[i] = v0 ? __ldg(reinterpret_cast<const float*>(inb + (b0 + (uint32_t)i * cstride))) : 0.f;
-        if (two) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) vb[i] = v1 ? __ldg(reinterpret_cast<const float*>(inb + (b1 + (uint32_t)i * cstride))) : 0.f;
-        }
+        for (int i = 0; i < 16; ++i) vb[i] = v1 ? __ldg(reinterpret_cast<const float*>(inb + (b1 + (uint32_t)i * cstride))) : 0.f;
       }
-      if (lt >= 2) mbar_wait(bar_pempty + 8 * buf, (uint32_t)(((lt >> 1) - 1) & 1));
-      unsigned char* dst = gen + buf * buf_bytes;
-      if (tid < g.L) {
+      if (use >= 1) mbar_wait(bar_pempty + 8 * grp, (uint32_t)((use - 1) & 1));
+      if (one) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float4 h, l;
@@ -787,13 +798,13 @@ __global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, c
           split_tf32(va[4 * c + 1], h.y, l.y);
           split_tf32(va[4 * c + 2], h.z, l.z);
           split_tf32(va[4 * c + 3], h.w, l.w);
-          const int off = tid * 64 + ((c ^ ((tid >> 1) & 3)) << 4);  // SWIZZLE_64B of the absolute address
+          const int off = gt * 64 + ((c ^ ((gt >> 1) & 3)) << 4);  // SWIZZLE_64B of the absolute address
           *reinterpret_cast<float4*>(dst + off) = h;
           if (!fast) *reinterpret_cast<float4*>(dst + patch_bytes + off) = l;
         }
       }
       if (two) {
-        const int r2 = tid + C16_NPROD;
+        const int r2 = gt + C16_GT;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float4 h, l;
@@ -808,11 +819,11 @@ __global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, c
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pfull + 8 * buf);
+      if (lane == 0) mbar_arrive(bar_pfull + 8 * grp);
     }
   } else {
     // ================================ EPILOGUE ========================================
-    // thread = one accumulator row; warps 9..12 own TMEM lane quarters (warp % 4)
+    // thread = one accumulator row; the four epilogue warps own TMEM lane quarters (warp % 4)
     const int row = (warp & 3) * 32 + lane;
     const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
     const int epi = p.epilogue;
