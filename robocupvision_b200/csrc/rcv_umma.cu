@@ -248,6 +248,9 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
     // ================================ MMA ISSUER ======================================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
+      // parity mode: a_hi * [b_hi | b_lo] in ONE instruction (N = 2*BN: the stage holds the hi rows then the lo rows,
+      // the correction accumulator follows the main one), then a_lo * b_hi -- two MMAs per K step instead of three
+      constexpr uint32_t idesc2 = make_idesc(BM, BN < 128 ? 2 * BN : BN);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       mbar_wait(bar_full, 0);
       for (int kb0 = 0; kb0 < nkb; kb0 += G) {
@@ -260,24 +263,27 @@ __global__ void __launch_bounds__(Cfg<BN, G, KB>::NT, Cfg<BN, G, KB>::CTAS) umma
             tc_fence_after();
             const uint32_t abase = tiles + st * C::STAGE, bbase = abase + C::A_STAGE;
             const uint64_t a_hi = make_desc_kb<KB>(abase), a_lo = make_desc_kb<KB>(abase + C::A_BYTES);
-            const uint64_t b_hi = make_desc_kb<KB>(bbase), b_lo = make_desc_kb<KB>(bbase + BN * C::ROWB);
+            const uint64_t b_hi = make_desc_kb<KB>(bbase);
             const int krem = K - kb * BK;
             const int ksteps = krem >= BK ? BK / 8 : (krem + 7) / 8;
             if (!(p.debug & 1)) {
               // 8 tf32 = 32 B = 2 x 16 B along K inside the swizzled row per step
-              if (!fast) {
-                umma_tf32(d_corr, a_lo, b_hi, idesc, kb != 0);
-                umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
-              }
-              umma_tf32(d_main, a_hi, b_hi, idesc, kb != 0);
+              constexpr bool FUSE = BN < 128;  // BN = 128 tiles are throughput-bound: they keep three instructions
+              const uint64_t b_lo = make_desc_kb<KB>(bbase + BN * C::ROWB);
 #pragma unroll
-              for (int ks = 1; ks < BK / 8; ++ks) {
+              for (int ks = 0; ks < BK / 8; ++ks) {
                 if (ks < ksteps) {
-                  if (!fast) {
+                  const uint32_t acc = ks == 0 ? (uint32_t)(kb != 0) : 1u;
+                  if (fast) {
+                    umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
+                  } else if (FUSE) {
+                    umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc2, acc);
                     umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, 1u);
+                  } else {
+                    umma_tf32(d_corr, a_lo + 2 * ks, b_hi + 2 * ks, idesc, acc);
                     umma_tf32(d_corr, a_hi + 2 * ks, b_lo + 2 * ks, idesc, 1u);
+                    umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, acc);
                   }
-                  umma_tf32(d_main, a_hi + 2 * ks, b_hi + 2 * ks, idesc, 1u);
                 }
               }
             }

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
     // ================================ MMA ISSUER ======================================
     if (elect_one()) {
       constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc(BM, BN);
-      constexpr uint32_t idesc2 = make_idesc(BM, 2 * BN);  // fp32 parity mode: main | correction in one instruction
+      constexpr uint32_t idesc2 = make_idesc(BM, BN < 128 ? 2 * BN : BN);  // fp32 parity mode: main | correction in one instruction
       const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
       int it = 0;
       for (int cb = cb0; cb < cb1; ++cb) {
@@ -304,8 +304,16 @@ __global__ void __launch_bounds__(NT, 2) umma_halo_kernel(const RcvIgemm p, cons
                 // Two MMAs per K step instead of three: a B stage holds the BN hi rows and then the BN lo rows, so
                 // ONE instruction with N = 2*BN computes a_hi * [b_hi | b_lo] into the adjacent main and correction
                 // accumulators; the second adds a_lo * b_hi to the correction accumulator.
-                umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc2, first);
-                umma_tf32(d_corr, a_lo + 2 * ka, b_hi + 2 * ks, idesc, 1u);
+                // (neutral at BN = 128, whose tiles are throughput-bound: those keep the three-instruction form)
+                if (BN < 128) {
+                  umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc2, first);
+                  umma_tf32(d_corr, a_lo + 2 * ka, b_hi + 2 * ks, idesc, 1u);
+                } else {
+                  const uint64_t b_lo = make_desc_b<KBB>(bb + BN * C::BROWB);
+                  umma_tf32(d_corr, a_lo + 2 * ka, b_hi + 2 * ks, idesc, first);
+                  umma_tf32(d_corr, a_hi + 2 * ka, b_lo + 2 * ks, idesc, 1u);
+                  umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc, first);
+                }
               } else {
                 umma_tf32(d_main, a_hi + 2 * ka, b_hi + 2 * ks, idesc, first);
               }
