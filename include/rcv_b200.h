@@ -273,6 +273,14 @@ int rcv_bn_bwd_apply(int32_t N, int32_t C, int64_t HW, int order,
                      float* dconv, float* dgamma, float* dbeta, float* dbias,
                      void* stream);
 
+/* rcv_bn_bwd_reduce + rcv_bn_bwd_apply as ONE call: a single launch (one thread-block cluster per channel, the
+ * partial sums exchanged through distributed shared memory and added in rank order: bitwise reproducible) where the
+ * channels split into <= 8 CTA-sized slices, else the two passes.  sums is only touched by the two-pass form. */
+int rcv_bn_bwd_is_fused(int32_t N, int32_t C, int64_t HW);   /* host query: 1 = one launch, 0 = two */
+int rcv_bn_bwd(int32_t N, int32_t C, int64_t HW, int order, const float* dy, const float* z,
+               const float* scale, const float* shift, const float* save_mean, const float* save_invstd,
+               double* sums, float* dconv, float* dgamma, float* dbeta, float* dbias, void* stream);
+
 /* dx = dy * [y > 0] (threshold_backward for a stored ReLU output y). */
 int rcv_relu_bwd(int64_t n, const float* dy, const float* y, float* dx,
                  void* stream);

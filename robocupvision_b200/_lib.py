@@ -75,6 +75,8 @@ SIGNATURES = {
                               _p, _p, _p],
     "rcv_bn_bwd_reduce": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_bn_bwd_apply": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "rcv_bn_bwd_is_fused": [_i32, _i32, _i64],
+    "rcv_bn_bwd": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_relu_bwd": [_i64, _p, _p, _p, _p],
     "rcv_channel_sum": [_i32, _i32, _i64, _p, _p, _p],
     "rcv_maxpool2x2_fwd": [_i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],

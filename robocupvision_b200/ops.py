@@ -354,9 +354,9 @@ def bn_bwd(order: int, dy, z, scale, shift, mean, invstd, dgamma=None, dbeta=Non
             dbias = small[2]
     dconv = torch.empty_like(z)
     st = _stream()
-    _call("rcv_bn_bwd_reduce", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
-          _ptr(invstd), _ptr(sums), st)
-    _call("rcv_bn_bwd_apply", 1, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
+    # one cluster launch where the tensor suits it, else reduce + apply (the library decides; either way <= 2 kernels)
+    fused = bool(_lib.load().rcv_bn_bwd_is_fused(n, c, hw)) and not ((dy.data_ptr() | z.data_ptr()) & 15)
+    _call("rcv_bn_bwd", 1 if fused else 2, n, c, hw, order, _ptr(dy), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean),
           _ptr(invstd), _ptr(sums), _ptr(dconv), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), st)
     return dconv, dgamma, dbeta, dbias
 
