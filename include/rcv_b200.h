@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RCV_ABI_VERSION 4
+#define RCV_ABI_VERSION 5
 
 typedef enum rcv_status {
   RCV_OK = 0,
@@ -104,6 +104,10 @@ typedef struct rcv_conv_desc {
    * without it, or when it is too small, the same layer runs unsplit -- results agree to accumulation order. */
   void* workspace;
   uint64_t workspace_bytes;
+  /* rcv_conv_fwd: channels of the `residual` tensor (0 = Cout).  A value below Cout adds residual[N, res_channels,
+   * Ho, Wo] to the FIRST res_channels output channels only -- the partial skip of LabelProp, `x[:, 0:8] += top`
+   * (model.py:565) -- and is taken by the narrow-layer engine only (RCV_ERR_UNSUPPORTED elsewhere). */
+  int32_t res_channels;
 } rcv_conv_desc;
 
 int rcv_version(void);
@@ -235,10 +239,11 @@ int rcv_bn_fold(int32_t C, const float* gamma, const float* beta,
                 float* shift, void* stream);
 
 /* y = act(scale_c*z + shift_c) [+ residual], act = relu if relu!=0.
- * z,y: [N,C,HW]. */
+ * z,y: [N,C,HW].  res_channels: channels of residual (0 = C); below C, residual[N,res_channels,HW] is added to the
+ * first res_channels channels only (LabelProp's partial skip, model.py:565). */
 int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z,
                  const float* scale, const float* shift, int relu,
-                 const float* residual, float* y, void* stream);
+                 const float* residual, int32_t res_channels, float* y, void* stream);
 
 /* rcv_bn_finalize + rcv_bn_apply in one launch (the train-mode forward of a BatchNorm node):
  * every block derives scale/shift from stats; block 0 also writes scale, shift, save_mean,
@@ -247,7 +252,7 @@ int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z,
 int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const double* stats,
                           const float* gamma, const float* beta, float* running_mean,
                           float* running_var, float momentum, float eps, const float* z,
-                          int relu, const float* residual, float* y, float* scale,
+                          int relu, const float* residual, int32_t res_channels, float* y, float* scale,
                           float* shift, float* save_mean, float* save_invstd,
                           int64_t* num_batches_tracked, void* stream);
 

@@ -39,7 +39,7 @@ ENGINE_SIMT, ENGINE_DIRECT, ENGINE_UMMA, ENGINE_NARROW = 0, 1, 2, 3
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "N", "Cin", "H", "W", "Cout", "ksize", "stride", "pad", "dil", "transposed", "epilogue", "math")] + [
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("res_channels", C.c_int32)]
 
 
 _p = C.c_void_p
@@ -70,8 +70,8 @@ SIGNATURES = {
     "rcv_conv_wgrad_nl": [C.POINTER(ConvDesc), _p, _p, _p, C.c_int, _p, _p, _p, _p],
     "rcv_bn_finalize": [_i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, _p, _p, _p, _p, _p],
     "rcv_bn_fold": [_i32, _p, _p, _p, _p, _f32, _p, _p, _p],
-    "rcv_bn_apply": [_i32, _i32, _i64, _p, _p, _p, C.c_int, _p, _p, _p],
-    "rcv_bn_finalize_apply": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, C.c_int, _p, _p, _p, _p, _p,
+    "rcv_bn_apply": [_i32, _i32, _i64, _p, _p, _p, C.c_int, _p, _i32, _p, _p],
+    "rcv_bn_finalize_apply": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _f32, _f32, _p, C.c_int, _p, _i32, _p, _p, _p, _p,
                               _p, _p, _p],
     "rcv_bn_bwd_reduce": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_bn_bwd_apply": [_i32, _i32, _i64, C.c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
@@ -103,7 +103,7 @@ SIGNATURES = {
 _RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t, "rcv_conv_workspace_bytes": C.c_size_t,
              "rcv_conv_pack_table_bytes": C.c_size_t}
 PACK_FWD, PACK_DGRAD = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _lib = None
 

@@ -47,6 +47,8 @@ int validate(const rcv_conv_desc* d, const char* who) {
   }
   RCV_REQUIRE(d->math >= RCV_MATH_FP32 && d->math <= RCV_MATH_BF16, RCV_ERR_BAD_ARG, "%s: bad math mode %d", who,
               d->math);
+  RCV_REQUIRE(d->res_channels >= 0 && d->res_channels <= d->Cout, RCV_ERR_BAD_ARG, "%s: res_channels %d outside [0, %d]",
+              who, d->res_channels, d->Cout);
   return RCV_OK;
 }
 
@@ -131,6 +133,7 @@ void fwd_problem(const rcv_conv_desc* d, RcvIgemm* pp) {
   p.math = d->math;
   p.ws = d->workspace;
   p.ws_bytes = d->workspace_bytes;
+  p.res_C = d->res_channels > 0 ? d->res_channels : d->Cout;
   const int kk = d->ksize * d->ksize;
   if (!d->transposed) {
     p.Hg = Ho; p.Wg = Wo; p.gs = d->stride; p.ostep = 1; p.nclass = 1;
@@ -157,6 +160,7 @@ int dgrad_problem(const rcv_conv_desc* d, RcvIgemm* pp) {
   p.math = d->math;
   p.ws = d->workspace;
   p.ws_bytes = d->workspace_bytes;
+  p.res_C = d->Cin;
   const int kk = d->ksize * d->ksize;
   if (d->transposed) {
     // dx[ci,i,j] = sum dy[co, 2i+ky-1, 2j+kx-1] * w[ci,co,ky,kx]: a stride-2 conv over dy

@@ -69,36 +69,44 @@ __global__ void bn_fold_kernel(int C, const float* __restrict__ gamma, const flo
   shift[c] = b - mean[c] * sc;
 }
 
+// index into a residual tensor that has only the first RC of the C channels ([N, RC, HW]; RC == C: the same index):
+// i = element (or float4) index in [N, C, HW], plane = i / HW = n * C + c
+__device__ __forceinline__ int64_t res_index(int64_t i, int64_t plane, int64_t hw, int C, int RC) {
+  return RC == C ? i : i - (plane / C) * (int64_t)(C - RC) * hw;
+}
+
 // y = act(sc*z+sh) + residual ; flat float4 grid-stride
 template <bool VEC>
 __global__ void __launch_bounds__(NT) bn_apply_kernel(int64_t total, int C, int64_t HW,
                                                        const float* __restrict__ z,
                                                        const float* __restrict__ scale,
                                                        const float* __restrict__ shift, int relu,
-                                                       const float* __restrict__ residual,
+                                                       const float* __restrict__ residual, int RC,
                                                        float* __restrict__ y) {
   rcv_pdl_enter();
   const int64_t stride = (int64_t)gridDim.x * NT;
   if (VEC) {
     const int64_t hw4 = HW >> 2, tot4 = total >> 2;
     for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < tot4; i += stride) {
-      const int c = (int)((i / hw4) % C);
+      const int64_t plane = i / hw4;
+      const int c = (int)(plane % C);
       const float sc = __ldg(scale + c), sh = __ldg(shift + c);
       float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
       v.x = fmaf(sc, v.x, sh); v.y = fmaf(sc, v.y, sh); v.z = fmaf(sc, v.z, sh); v.w = fmaf(sc, v.w, sh);
       if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      if (residual) {
-        const float4 r = __ldg(reinterpret_cast<const float4*>(residual) + i);
+      if (residual && c < RC) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(residual) + res_index(i, plane, hw4, C, RC));
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
       }
       reinterpret_cast<float4*>(y)[i] = v;
     }
   } else {
     for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
-      const int c = (int)((i / HW) % C);
+      const int64_t plane = i / HW;
+      const int c = (int)(plane % C);
       float v = fmaf(__ldg(scale + c), z[i], __ldg(shift + c));
       if (relu) v = fmaxf(v, 0.f);
-      if (residual) v += residual[i];
+      if (residual && c < RC) v += residual[res_index(i, plane, HW, C, RC)];
       y[i] = v;
     }
   }
@@ -111,7 +119,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
     int64_t total, int C, int64_t HW, double count, const double* __restrict__ stats,
     const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean, float* running_var,
-    float momentum, float eps, const float* __restrict__ z, int relu, const float* __restrict__ residual,
+    float momentum, float eps, const float* __restrict__ z, int relu, const float* __restrict__ residual, int RC,
     float* __restrict__ y, float* scale_out, float* shift_out, float* save_mean, float* save_invstd,
     long long* nbt) {
   rcv_pdl_enter();
@@ -150,11 +158,12 @@ __global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
       float4 v = __ldg(reinterpret_cast<const float4*>(z) + i);
       float4 w = two ? __ldg(reinterpret_cast<const float4*>(z) + i2) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f), q = r;
+      const int64_t pl = i / hw4, pl2 = two ? i2 / hw4 : pl;
+      const int c = (int)(pl % C), c2 = (int)(pl2 % C);
       if (residual) {
-        r = __ldg(reinterpret_cast<const float4*>(residual) + i);
-        if (two) q = __ldg(reinterpret_cast<const float4*>(residual) + i2);
+        if (c < RC) r = __ldg(reinterpret_cast<const float4*>(residual) + res_index(i, pl, hw4, C, RC));
+        if (two && c2 < RC) q = __ldg(reinterpret_cast<const float4*>(residual) + res_index(i2, pl2, hw4, C, RC));
       }
-      const int c = (int)((i / hw4) % C), c2 = two ? (int)((i2 / hw4) % C) : c;
       const float sc = s_ss[c], sh = s_ss[C + c], sc2 = s_ss[c2], sh2 = s_ss[C + c2];
       v.x = fmaf(sc, v.x, sh); v.y = fmaf(sc, v.y, sh); v.z = fmaf(sc, v.z, sh); v.w = fmaf(sc, v.w, sh);
       w.x = fmaf(sc2, w.x, sh2); w.y = fmaf(sc2, w.y, sh2); w.z = fmaf(sc2, w.z, sh2); w.w = fmaf(sc2, w.w, sh2);
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(NT) bn_finalize_apply_kernel(
       const int c = (int)((i / HW) % C);
       float v = fmaf(s_ss[c], z[i], s_ss[C + c]);
       if (relu) v = fmaxf(v, 0.f);
-      if (residual) v += residual[i];
+      if (residual && c < RC) v += residual[res_index(i, i / HW, HW, C, RC)];
       y[i] = v;
     }
   }
@@ -550,24 +559,27 @@ extern "C" int rcv_bn_fold(int32_t C, const float* gamma, const float* beta, con
 }
 
 extern "C" int rcv_bn_apply(int32_t N, int32_t C, int64_t HW, const float* z, const float* scale,
-                            const float* shift, int relu, const float* residual, float* y,
+                            const float* shift, int relu, const float* residual, int32_t res_channels, float* y,
                             void* stream) {
   RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && z && scale && shift && y, RCV_ERR_BAD_ARG,
               "bn_apply: bad arg");
   const int64_t total = (int64_t)N * C * HW;
+  RCV_REQUIRE(res_channels >= 0 && res_channels <= C, RCV_ERR_BAD_ARG, "bn_apply: res_channels %d outside [0, %d]", res_channels, C);
+  const int rc_ = res_channels > 0 ? res_channels : C;
   if ((HW & 3) == 0)
     rcv_launch(bn_apply_kernel<true>, dim3(ew_blocks(total / 4)), dim3(NT), 0, (cudaStream_t)stream, total, C, HW, z,
-               scale, shift, relu, residual, y);
+               scale, shift, relu, residual, rc_, y);
   else
     rcv_launch(bn_apply_kernel<false>, dim3(ew_blocks(total)), dim3(NT), 0, (cudaStream_t)stream, total, C, HW, z,
-               scale, shift, relu, residual, y);
+               scale, shift, relu, residual, rc_, y);
   RCV_CHECK_LAUNCH("bn_apply");
   return RCV_OK;
 }
 
 extern "C" int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const double* stats, const float* gamma,
                                      const float* beta, float* running_mean, float* running_var, float momentum,
-                                     float eps, const float* z, int relu, const float* residual, float* y,
+                                     float eps, const float* z, int relu, const float* residual,
+                                     int32_t res_channels, float* y,
                                      float* scale, float* shift, float* save_mean, float* save_invstd,
                                      int64_t* num_batches_tracked, void* stream) {
   RCV_REQUIRE(N > 0 && C > 0 && HW > 0 && stats && z && y && scale && shift, RCV_ERR_BAD_ARG,
@@ -576,13 +588,16 @@ extern "C" int rcv_bn_finalize_apply(int32_t N, int32_t C, int64_t HW, const dou
   const int64_t total = (int64_t)N * C * HW;
   const double count = (double)N * (double)HW;
   const size_t smem = (size_t)2 * C * sizeof(float);
+  RCV_REQUIRE(res_channels >= 0 && res_channels <= C, RCV_ERR_BAD_ARG, "bn_finalize_apply: res_channels %d outside [0, %d]",
+              res_channels, C);
+  const int rc_ = res_channels > 0 ? res_channels : C;
   if ((HW & 3) == 0)
     rcv_launch(bn_finalize_apply_kernel<true>, dim3(fa_blocks(total / 4)), dim3(NT), smem, (cudaStream_t)stream,
                total, C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual,
-               y, scale, shift, save_mean, save_invstd, reinterpret_cast<long long*>(num_batches_tracked));
+               rc_, y, scale, shift, save_mean, save_invstd, reinterpret_cast<long long*>(num_batches_tracked));
   else
     rcv_launch(bn_finalize_apply_kernel<false>, dim3(ew_blocks(total)), dim3(NT), smem, (cudaStream_t)stream, total,
-               C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, y,
+               C, HW, count, stats, gamma, beta, running_mean, running_var, momentum, eps, z, relu, residual, rc_, y,
                scale, shift, save_mean, save_invstd, reinterpret_cast<long long*>(num_batches_tracked));
   RCV_CHECK_LAUNCH("bn_finalize_apply");
   return RCV_OK;

@@ -101,6 +101,7 @@ struct RcvIgemm {
   // optional caller-owned scratch (rcv_conv_desc::workspace): split-reduction partial tiles + arrival counters
   void* ws;
   unsigned long long ws_bytes;
+  int32_t res_C;  // channels of `residual` (== CB unless a partial skip: added to the first res_C channels only; narrow engine)
   int32_t N, CA, CB;
   int32_t Hin, Win, Hout, Wout, Hg, Wg;
   int32_t gs, ostep;

@@ -318,6 +318,9 @@ int rcv_launch_igemm(const RcvIgemm& p, cudaStream_t st) {
   const int eng = rcv_pick_engine(p, p.wpacked != nullptr);
   RCV_REQUIRE(p.in_scale == nullptr || eng == RCV_ENGINE_UMMA, RCV_ERR_UNSUPPORTED,
               "normalise-on-load is a feature of the halo-staged tensor-core kernel only");
+  RCV_REQUIRE(p.residual == nullptr || p.res_C == p.CB || eng == RCV_ENGINE_NARROW, RCV_ERR_UNSUPPORTED,
+              "a residual with fewer channels than the output (res_channels %d < %d) is taken by the narrow-layer engine only",
+              p.res_C, p.CB);
   switch (eng) {
     case RCV_ENGINE_UMMA: return rcv_launch_igemm_umma(p, st);
     case RCV_ENGINE_NARROW: return rcv_launch_narrow(p, st);

@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__((CBP <= 8 ||
     // output row 2*gi+z, slot q is column parity: 8 consecutive floats interleaving the two slots
     bool vq[2];
     size_t ob[2];
+    // the residual tensor may hold only the first res_C channels (partial skip): its batch stride differs
+    const size_t rshift = (size_t)n * (size_t)(p.CB - p.res_C) * HWo;
     if (par) {
       vq[0] = active; vq[1] = false;  // one row, both slots written together
       ob[0] = (size_t)n * p.CB * HWo + (size_t)(2 * gi + z) * p.Wout + 2 * gj;
@@ -369,9 +371,9 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__((CBP <= 8 ||
               float* o = p.out + ob[0] + (size_t)cb * HWo;
               float4 a = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
               float4 b = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
-              if (has_res) {
-                const float4 ra = __ldg(reinterpret_cast<const float4*>(p.residual + ob[0] + (size_t)cb * HWo));
-                const float4 rb = __ldg(reinterpret_cast<const float4*>(p.residual + ob[0] + (size_t)cb * HWo) + 1);
+              if (has_res && cb < p.res_C) {
+                const float4 ra = __ldg(reinterpret_cast<const float4*>(p.residual + (ob[0] - rshift) + (size_t)cb * HWo));
+                const float4 rb = __ldg(reinterpret_cast<const float4*>(p.residual + (ob[0] - rshift) + (size_t)cb * HWo) + 1);
                 a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
                 b.x += rb.x; b.y += rb.y; b.z += rb.z; b.w += rb.w;
               }
@@ -385,8 +387,8 @@ __global__ void __launch_bounds__(CBP <= 8 ? 256 : 128) __maxnreg__((CBP <= 8 ||
             for (int q = 0; q < SLOTS; ++q) {
               if (!vq[q]) continue;
               float4 a = make_float4(v[q][0], v[q][1], v[q][2], v[q][3]);
-              if (has_res) {
-                const float4 ra = __ldg(reinterpret_cast<const float4*>(p.residual + ob[q] + (size_t)cb * HWo));
+              if (has_res && cb < p.res_C) {
+                const float4 ra = __ldg(reinterpret_cast<const float4*>(p.residual + (ob[q] - rshift) + (size_t)cb * HWo));
                 a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
               }
               *reinterpret_cast<float4*>(p.out + ob[q] + (size_t)cb * HWo) = a;

@@ -272,6 +272,16 @@ class Plan:
             w = conv.weight.detach()
             b = conv.bias.detach() if conv.bias is not None else None
             skip = acts[nd.skip] if (nd.skip >= 0 and nd.skip_mode == "add") else None
+            # partial skip (LabelProp, model.py:565: x[:, 0:8] += top): the train-mode BatchNorm apply pass adds it to
+            # the first channels itself, and so does the narrow-layer engine's epilogue in eval mode
+            partial_fused = False
+            if nd.skip >= 0 and nd.skip_mode == "partial":
+                if bn is not None and training and bn.training:
+                    partial_fused = not self._defer_bn_apply(t, src.shape[0], *g.out_hw(src.shape[2], src.shape[3]))
+                else:
+                    partial_fused = ops.conv_takes_partial_residual(g, src.shape[0], src.shape[2], src.shape[3], self.math)
+                if partial_fused:
+                    skip = acts[nd.skip]
             wp = nd._pack[PACK_FWD] if nd.uses_tc(PACK_FWD, self.math) else None
             ina = lazy.get(nd.src)  # the producer's BatchNorm, applied on load
             if bn is None:
@@ -308,7 +318,7 @@ class Plan:
                 scale, shift = nd.folded(self.epoch)
                 y = ops.conv_fwd(g, src, w, b, epilogue=nd.order, scale=scale, shift=shift, residual=skip,
                                  math=self.math, wpacked=wp, in_affine=ina, workspace=ws)
-            if nd.skip >= 0 and nd.skip_mode == "partial":
+            if nd.skip >= 0 and nd.skip_mode == "partial" and not partial_fused:
                 y[:, :nd.skip_ch] += acts[nd.skip]
             elif nd.skip >= 0 and nd.skip_mode == "cat":
                 y = torch.cat([y, acts[nd.skip]], 1)

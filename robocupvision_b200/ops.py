@@ -18,7 +18,7 @@ from ._lib import (ENGINE_DIRECT, ENGINE_NARROW, ENGINE_SIMT, ENGINE_UMMA, EPI_A
                    PACK_FWD, ConvDesc)
 
 __all__ = [
-    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_workspace_bytes", "new_workspace", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
+    "ConvGeom", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_pack", "conv_packed_bytes", "conv_workspace_bytes", "new_workspace", "conv_takes_partial_residual", "conv_uses_tensor_cores", "conv_engine", "conv_normalises_on_load", "PackTable", "bn_finalize_apply", "PACK_FWD", "PACK_DGRAD", "bn_finalize", "bn_fold", "bn_apply",
     "bn_bwd", "relu_bwd", "channel_sum", "maxpool2x2_fwd", "maxpool2x2_bwd", "maxunpool2x2", "maxunpool2x2_bwd", "upsample_bilinear2x", "upsample_bilinear2x_bwd", "ce_fwd", "ce_bwd",
     "confusion", "metric_tail", "mask_label_lut", "mask_label_", "label_to_pred", "lp_assemble", "augment", "color_jitter_params", "dice_fwd", "dice_bwd", "adam_l1_step", "sgd_step", "zero_", "zeros", "counter_add", "launch_count", "reset_launch_count",
     "EPI_NONE", "EPI_RELU", "EPI_RELU_AFFINE", "EPI_AFFINE_RELU", "EPI_AFFINE",
@@ -140,6 +140,12 @@ def _with_ws(d: ConvDesc, workspace):
     return d
 
 
+def conv_takes_partial_residual(g: ConvGeom, n: int, h: int, w: int, math: int = MATH_AUTO) -> bool:
+    """Can conv_fwd add a residual that has fewer channels than the output (rcv_conv_desc::res_channels)?  Only the
+    narrow-layer engine does."""
+    return conv_engine(g, n, h, w, PACK_FWD, math) == ENGINE_NARROW
+
+
 def conv_uses_tensor_cores(g: ConvGeom, direction: int, math: int = MATH_AUTO) -> bool:
     d = g.desc(1, 2, 2, EPI_NONE, math)
     return bool(_lib.load().rcv_conv_uses_tensor_cores(C.byref(d), int(direction)))
@@ -193,9 +199,20 @@ class PackTable:
         _call("rcv_conv_pack_table_run", 1, _ptr(self.table), self.n, self.total, _stream())
 
 
+def _res_channels(residual, c):
+    """Channels of a residual tensor for the `res_channels` arguments: 0 = all; fewer = a partial skip (added to the
+    first channels only, LabelProp model.py:565)."""
+    if residual is None or residual.shape[1] == c:
+        return 0
+    if residual.shape[1] > c:
+        raise ValueError("residual has more channels than the output")
+    return int(residual.shape[1])
+
+
 def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum, eps, relu, residual=None,
                       num_batches_tracked=None):
-    """Train-mode BatchNorm forward in one launch -> (y, scale, shift, mean, invstd)."""
+    """Train-mode BatchNorm forward in one launch -> (y, scale, shift, mean, invstd).  A residual with fewer channels
+    than z is added to the first channels only."""
     z = _chk(z, name="z")
     n, c = z.shape[0], z.shape[1]
     hw = z.numel() // (n * c)
@@ -204,7 +221,8 @@ def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum
     if residual is not None:
         residual = _chk(residual, name="residual")
     _call("rcv_bn_finalize_apply", 1, n, c, hw, _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(running_mean),
-          _ptr(running_var), float(momentum), float(eps), _ptr(z), 1 if relu else 0, _ptr(residual), _ptr(y),
+          _ptr(running_var), float(momentum), float(eps), _ptr(z), 1 if relu else 0, _ptr(residual),
+          _res_channels(residual, c), _ptr(y),
           _ptr(buf[0]), _ptr(buf[1]), _ptr(buf[2]), _ptr(buf[3]), _ptr(num_batches_tracked), _stream())
     return y, buf[0], buf[1], buf[2], buf[3]
 
@@ -233,14 +251,17 @@ def conv_fwd(g: ConvGeom, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=
     y = out if out is not None else torch.empty((n, g.cout, ho, wo), device=x.device, dtype=torch.float32)
     if residual is not None:
         residual = _chk(residual, name="residual")
-        if residual.shape != y.shape:
-            raise ValueError(f"conv_fwd: residual {tuple(residual.shape)} != output {tuple(y.shape)}")
+        # fewer channels than the output = a partial skip (first channels only; narrow-layer engine, see
+        # conv_takes_partial_residual)
+        if (residual.shape[0], *residual.shape[2:]) != (y.shape[0], *y.shape[2:]) or residual.shape[1] > y.shape[1]:
+            raise ValueError(f"conv_fwd: residual {tuple(residual.shape)} does not fit output {tuple(y.shape)}")
     for t, nm in ((bias, "bias"), (scale, "scale"), (shift, "shift")):
         if t is not None and (t.numel() != g.cout or not t.is_cuda or t.dtype != torch.float32):
             raise ValueError(f"conv_fwd: bad {nm}")
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != 2 * g.cout):
         raise ValueError("conv_fwd: stats must be float64[2*Cout]")
     d = _with_ws(g.desc(n, h, wd, epilogue, math), workspace)
+    d.res_channels = _res_channels(residual, g.cout)
     if in_affine is not None:
         # (in_scale, in_shift, relu): the BatchNorm of the block that produced x, applied on load (rcv_conv_fwd_nl)
         isc, ish, irelu = in_affine
@@ -332,7 +353,7 @@ def bn_apply(z, scale, shift, relu: bool, residual=None, out=None):
     if residual is not None:
         residual = _chk(residual, name="residual")
     _call("rcv_bn_apply", 1, n, c, hw, _ptr(z), _ptr(scale), _ptr(shift), 1 if relu else 0, _ptr(residual),
-          _ptr(y), _stream())
+          _res_channels(residual, c), _ptr(y), _stream())
     return y
 
 

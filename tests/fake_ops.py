@@ -27,6 +27,19 @@ conv_normalises_on_load = real.conv_normalises_on_load              # host logic
 conv_wgrad_normalises_on_load = real.conv_wgrad_normalises_on_load
 
 
+def _add_res(v, residual):
+    """+ residual; a residual with fewer channels goes to the first channels only (rcv_*::res_channels)."""
+    if residual.shape[1] == v.shape[1]:
+        return v + residual
+    v = v.clone()
+    v[:, :residual.shape[1]] += residual
+    return v
+
+
+def conv_takes_partial_residual(g, n, h, w, math=real.MATH_AUTO):
+    return True
+
+
 def _affine_in(x, in_affine):
     if in_affine is None:
         return x
@@ -63,7 +76,7 @@ def conv_fwd(g, x, w, bias=None, epilogue=EPI_NONE, scale=None, shift=None, resi
     elif epilogue == EPI_AFFINE:
         v = A * v + B
     if residual is not None:
-        v = v + residual
+        v = _add_res(v, residual)
     if stats is not None:
         c = v.shape[1]
         d = v.double()
@@ -129,7 +142,7 @@ def bn_apply(z, scale, shift, relu, residual=None, out=None):
     y = z * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     if relu:
         y = F.relu(y)
-    return y if residual is None else y + residual
+    return y if residual is None else _add_res(y, residual)
 
 
 def bn_finalize_apply(z, stats, gamma, beta, running_mean, running_var, momentum, eps, relu, residual=None,

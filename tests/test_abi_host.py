@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in rcv_b200.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.rcv_version() == 4
+    assert lib.rcv_version() == 5
 
 
 def test_validation_without_gpu():

@@ -567,6 +567,51 @@ def test_resample_modules_autograd():
     assert_close("module bilinear grad", xg2.grad, xr2.grad, 2e-6)
 
 
+@pytest.mark.parametrize("hw", [(12, 16), (5, 3)])   # float4 path and the scalar path
+def test_partial_channel_residual(hw):
+    """rcv_*::res_channels: a residual with fewer channels than the output is added to the FIRST channels only --
+    LabelProp's `x[:, 0:8] += top` (model.py:565) -- in the BatchNorm apply passes and in the narrow-layer engine's
+    epilogue; the other engines refuse it."""
+    from robocupvision_b200 import _lib, ops
+    h, w_ = hw
+    gen = torch.Generator().manual_seed(h * w_)
+    n, c, rc = 3, 16, 8
+    z = torch.randn(n, c, h, w_, generator=gen)
+    sc, sh = torch.randn(c, generator=gen), torch.randn(c, generator=gen)
+    top = torch.randn(n, rc, h, w_, generator=gen)
+    ref = F.relu(sc.view(1, -1, 1, 1) * z + sh.view(1, -1, 1, 1))
+    ref[:, :rc] += top
+    got = ops.bn_apply(z.cuda(), sc.cuda(), sh.cuda(), True, residual=top.cuda())
+    assert_close("bn_apply partial residual", got, ref, 1e-6)
+    # train-mode finalize + apply
+    stats = torch.stack([z.double().sum((0, 2, 3)), (z.double() ** 2).sum((0, 2, 3))]).reshape(-1).cuda()
+    gam, bet = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
+    y, *_ = ops.bn_finalize_apply(z.cuda(), stats, gam.cuda(), bet.cuda(), None, None, 0.1, 1e-5, relu=True,
+                                  residual=top.cuda())
+    bn_ref = F.relu(F.batch_norm(z, None, None, gam, bet, True, 0.1, 1e-5))
+    bn_ref[:, :rc] += top
+    assert_close("bn_finalize_apply partial residual", y, bn_ref, 2e-6)
+    if w_ % 4 == 0:
+        # transposed conv 16 -> 16 on the narrow engine (LabelProp upConv3), eval-mode epilogue + partial skip
+        g = ops.ConvGeom(16, 16, 3, 2, 1, 1, True)
+        x = torch.randn(n, 16, h, w_, generator=gen)
+        wt = torch.randn(16, 16, 3, 3, generator=gen) / 12.0
+        b = torch.randn(16, generator=gen)
+        topT = torch.randn(n, rc, 2 * h, 2 * w_, generator=gen)
+        assert ops.conv_takes_partial_residual(g, n, h, w_)
+        out = ops.conv_fwd(g, x.cuda(), wt.cuda(), b.cuda(), epilogue=ops.EPI_AFFINE_RELU, scale=sc.cuda(), shift=sh.cuda(),
+                           residual=topT.cuda(), math=ops.MATH_AUTO)
+        cref = F.relu(sc.view(1, -1, 1, 1) * F.conv_transpose2d(x, wt, b, stride=2, padding=1, output_padding=1) + sh.view(1, -1, 1, 1))
+        cref[:, :rc] += topT
+        assert_close("narrow convT partial residual", out, cref, 3e-6)
+        # a tensor-core layer refuses
+        g2 = ops.ConvGeom(64, 64, 3, 1, 1, 1, False)
+        x2 = torch.randn(2, 64, h, w_, generator=gen).cuda()
+        w2 = torch.randn(64, 64, 3, 3, generator=gen).cuda()
+        with pytest.raises(_lib.RcvError):
+            ops.conv_fwd(g2, x2, w2, None, residual=torch.zeros(2, 8, h, w_, device="cuda"), math=ops.MATH_TF32X3)
+
+
 @pytest.mark.parametrize("n,c", [(1, 5), (7, 5), (70, 5), (3, 2), (5, 8)])
 def test_metric_tail_matches_reference_rule(n, c):
     """rcv_metric_tail: the validation loops' per-image IoU rule (train.py:148-153: inter / union per class, an image

@@ -359,3 +359,14 @@ def test_hot_path_launches_only_library_kernels():
     foreign = [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()
                or "cutlass" in n.lower()]
     assert len(names) >= 10 and not foreign, f"non-library kernels inside an EvalStep call: {foreign}"
+    # LabelProp: the partial skip (`x[:, 0:8] += top`, model.py:565) is added by the producing layer's epilogue
+    from robocupvision_b200.model import LabelProp
+    lp = LabelProp(5, 32, 0).cuda()
+    evl = EvalStep(lp, synth.LP_CLASS_WEIGHTS, use_graph=True)
+    x8 = synth.images(4, 8, 120, 160, seed=5).cuda()
+    y8 = synth.labels_random(4, 120, 160, seed=6).cuda()
+    for _ in range(2):
+        evl(x8, y8)
+    names = _cuda_kernel_names(lambda: evl(x8, y8))
+    foreign = [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()]
+    assert len(names) >= 8 and not foreign, f"non-library kernels inside a LabelProp EvalStep call: {foreign}"
