@@ -333,6 +333,13 @@ int rcv_upsample_bilinear2x_fwd(int32_t N, int32_t C, int32_t H, int32_t W,
 int rcv_upsample_bilinear2x_bwd(int32_t N, int32_t C, int32_t H, int32_t W,
                                 const float* dout, float* dx, void* stream);
 
+/* dst[n, dst_offset + c, :] = src[n, src_offset + c, :] for c < count; src [N,src_channels,HW], dst
+ * [N,dst_channels,HW].  The channel moves of the skip wiring that no producer can fold: ROBO_UNet --v2's
+ * torch.cat([layer(up), downs[-(i+2)]], 1) (model.py:507; two calls fill the concatenated tensor), the gradient
+ * halves autograd slices back out of it, and the gradient of LabelProp's partial skip (model.py:565). */
+int rcv_channel_copy(int64_t N, int64_t HW, int32_t count, const float* src, int32_t src_channels,
+                     int32_t src_offset, float* dst, int32_t dst_channels, int32_t dst_offset, void* stream);
+
 /* ---- weighted softmax cross-entropy + argmax + confusion ----------------- */
 /* CrossEntropyLoss2d (model.py:76-82), torch.max(pred,1) (train.py:70,128) and
  * the per-image confusion loop (train.py:133-153) in one pass over the logits.

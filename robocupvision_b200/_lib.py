@@ -85,6 +85,7 @@ SIGNATURES = {
     "rcv_maxunpool2x2_bwd": [_i32, _i32, _i32, _i32, _p, _p, _p, _p, _p],
     "rcv_upsample_bilinear2x_fwd": [_i32, _i32, _i32, _i32, _p, _p, _p, _p],
     "rcv_upsample_bilinear2x_bwd": [_i32, _i32, _i32, _i32, _p, _p, _p],
+    "rcv_channel_copy": [_i64, _i64, _i32, _p, _i32, _i32, _p, _i32, _i32, _p],
     "rcv_ce_fwd": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_ce_bwd": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p],
     "rcv_confusion": [_i32, _i32, _i64, _p, _p, _p, _p],

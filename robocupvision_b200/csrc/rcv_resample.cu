@@ -154,6 +154,21 @@ __global__ void __launch_bounds__(NT) bilinear2x_bwd_kernel(int64_t total, int H
   }
 }
 
+// dst[n, dst_off + c, :] = src[n, src_off + c, :], c < count: the channel slice / concat copy (VEC = 4: float4 rows)
+template <int VEC>
+__global__ void __launch_bounds__(NT) channel_copy_kernel(int64_t total, int64_t row, int count, const float* __restrict__ src,
+                                                           int64_t src_batch, float* __restrict__ dst, int64_t dst_batch) {
+  rcv_pdl_enter();
+  const int64_t per = (int64_t)count * row;  // elements (of VEC floats) one image moves
+  const int64_t stride = (int64_t)gridDim.x * NT;
+  for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < total; i += stride) {
+    const int64_t n = i / per, r = i - n * per;
+    if (VEC == 4)
+      reinterpret_cast<float4*>(dst + n * dst_batch)[r] = __ldg(reinterpret_cast<const float4*>(src + n * src_batch) + r);
+    else
+      dst[n * dst_batch + r] = __ldg(src + n * src_batch + r);
+  }
+}
 }  // namespace
 
 extern "C" int rcv_maxunpool2x2_fwd(int32_t N, int32_t C, int32_t H, int32_t W, const float* y, const int64_t* idx,
@@ -195,5 +210,29 @@ extern "C" int rcv_upsample_bilinear2x_bwd(int32_t N, int32_t C, int32_t H, int3
   rcv_launch(bilinear2x_bwd_kernel, dim3(blocks_for(total, 148 * 16)), dim3(NT), 0, (cudaStream_t)stream, total, H, W,
              dout, dx);
   RCV_CHECK_LAUNCH("upsample_bilinear2x_bwd");
+  return RCV_OK;
+}
+
+extern "C" int rcv_channel_copy(int64_t N, int64_t HW, int32_t count, const float* src, int32_t src_channels,
+                                int32_t src_offset, float* dst, int32_t dst_channels, int32_t dst_offset, void* stream) {
+  RCV_REQUIRE(N > 0 && HW > 0 && count > 0 && src && dst, RCV_ERR_BAD_ARG, "channel_copy: bad arg");
+  RCV_REQUIRE(src_offset >= 0 && dst_offset >= 0 && src_offset + count <= src_channels &&
+                  dst_offset + count <= dst_channels,
+              RCV_ERR_BAD_ARG, "channel_copy: channels [%d,+%d) of %d -> [%d,+%d) of %d", src_offset, count,
+              src_channels, dst_offset, count, dst_channels);
+  const float* s0 = src + (int64_t)src_offset * HW;
+  float* d0 = dst + (int64_t)dst_offset * HW;
+  const int64_t sb = (int64_t)src_channels * HW, db = (int64_t)dst_channels * HW;
+  const bool v4 = (HW % 4 == 0) && (((uintptr_t)s0 | (uintptr_t)d0) % 16 == 0);
+  if (v4) {
+    const int64_t total = N * count * (HW / 4);
+    rcv_launch(channel_copy_kernel<4>, dim3(blocks_for(total, 148 * 16)), dim3(NT), 0, (cudaStream_t)stream, total,
+               HW / 4, (int)count, s0, sb, d0, db);
+  } else {
+    const int64_t total = N * count * HW;
+    rcv_launch(channel_copy_kernel<1>, dim3(blocks_for(total, 148 * 16)), dim3(NT), 0, (cudaStream_t)stream, total, HW,
+               (int)count, s0, sb, d0, db);
+  }
+  RCV_CHECK_LAUNCH("channel_copy");
   return RCV_OK;
 }

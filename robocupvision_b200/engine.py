@@ -321,7 +321,7 @@ class Plan:
             if nd.skip >= 0 and nd.skip_mode == "partial" and not partial_fused:
                 y[:, :nd.skip_ch] += acts[nd.skip]
             elif nd.skip >= 0 and nd.skip_mode == "cat":
-                y = torch.cat([y, acts[nd.skip]], 1)
+                y = ops.concat_channels(y, acts[nd.skip])
             acts.append(y)
         outs = [acts[i] for i in self.outputs]
         return outs, ((acts, saved, lazy) if save else None)
@@ -396,10 +396,10 @@ class Plan:
             if nd.skip_mode == "add":
                 add_to(nd.skip, g)
             elif nd.skip_mode == "partial":
-                add_to(nd.skip, g[:, :nd.skip_ch].contiguous())
+                add_to(nd.skip, ops.channel_slice(g, 0, nd.skip_ch))
             else:  # cat
-                add_to(nd.skip, g[:, geom.cout:].contiguous())
-                g = g[:, :geom.cout].contiguous()
+                add_to(nd.skip, ops.channel_slice(g, geom.cout, g.shape[1] - geom.cout))
+                g = ops.channel_slice(g, 0, geom.cout)
         w = conv.weight.detach()
         has_bias = conv.bias is not None
         if bn is not None:

@@ -464,6 +464,29 @@ def upsample_bilinear2x_bwd(dout):
     return dx
 
 
+def channel_slice(x, offset: int, count: int) -> torch.Tensor:
+    """x[:, offset:offset+count] as a dense tensor (the gradient halves of a concatenated skip, the gradient of
+    LabelProp's partial skip)."""
+    x = _chk(x, name="x")
+    n, c, h, w = x.shape
+    out = torch.empty((n, count, h, w), device=x.device, dtype=torch.float32)
+    _call("rcv_channel_copy", 1, n, h * w, count, _ptr(x), c, offset, _ptr(out), count, 0, _stream())
+    return out
+
+
+def concat_channels(a, b) -> torch.Tensor:
+    """torch.cat([a, b], 1) (ROBO_UNet --v2, model.py:507)."""
+    a, b = _chk(a, name="a"), _chk(b, name="b")
+    if a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise ValueError(f"concat_channels: {tuple(a.shape)} vs {tuple(b.shape)}")
+    n, ca, h, w = a.shape
+    cb = b.shape[1]
+    out = torch.empty((n, ca + cb, h, w), device=a.device, dtype=torch.float32)
+    _call("rcv_channel_copy", 1, n, h * w, ca, _ptr(a), ca, 0, _ptr(out), ca + cb, 0, _stream())
+    _call("rcv_channel_copy", 1, n, h * w, cb, _ptr(b), cb, 0, _ptr(out), ca + cb, ca, _stream())
+    return out
+
+
 # --------------------------------------------------------------------------- loss / metrics
 def ce_fwd(logits, target, class_w=None, want_argmax=False, want_conf=False, want_correct=False, sums=None,
            corr=None):

@@ -186,6 +186,14 @@ def bn_bwd(order, dy, z, scale, shift, mean, invstd, dgamma=None, dbeta=None, db
     return dz, dgamma, dbeta, dbias
 
 
+def channel_slice(x, offset, count):
+    return x[:, offset:offset + count].contiguous()
+
+
+def concat_channels(a, b):
+    return torch.cat([a, b], 1)
+
+
 def relu_bwd(dy, y):
     return torch.where(y > 0, dy, torch.zeros_like(dy))
 

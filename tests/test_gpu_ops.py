@@ -567,6 +567,25 @@ def test_resample_modules_autograd():
     assert_close("module bilinear grad", xg2.grad, xr2.grad, 2e-6)
 
 
+@pytest.mark.parametrize("hw", [(12, 16), (5, 3), (15, 20)])   # float4 rows, scalar rows, 300-element planes
+def test_channel_copy(hw):
+    """rcv_channel_copy: torch.cat([a, b], 1) of ROBO_UNet --v2 (model.py:507) and the slices autograd cuts back
+    out of its gradient; bit-exact (a copy)."""
+    from robocupvision_b200 import ops
+    h, w_ = hw
+    gen = torch.Generator().manual_seed(h + w_)
+    a = torch.randn(3, 8, h, w_, generator=gen).cuda()
+    b = torch.randn(3, 5, h, w_, generator=gen).cuda()
+    cat = ops.concat_channels(a, b)
+    assert torch.equal(cat, torch.cat([a, b], 1))
+    assert torch.equal(ops.channel_slice(cat, 8, 5), b)
+    assert torch.equal(ops.channel_slice(cat, 0, 8), a)
+    assert torch.equal(ops.channel_slice(cat, 3, 7), cat[:, 3:10].contiguous())
+    from robocupvision_b200 import _lib
+    with pytest.raises(_lib.RcvError):
+        ops.channel_slice(cat, 10, 5)
+
+
 @pytest.mark.parametrize("hw", [(12, 16), (5, 3)])   # float4 path and the scalar path
 def test_partial_channel_residual(hw):
     """rcv_*::res_channels: a residual with fewer channels than the output is added to the FIRST channels only --

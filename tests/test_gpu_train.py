@@ -334,39 +334,36 @@ def _cuda_kernel_names(fn):
             and "Memset" not in e.key]
 
 
+def _foreign(names):
+    return [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()
+            or "cutlass" in n.lower()]
+
+
 def test_hot_path_launches_only_library_kernels():
     """north_star: "no Triton, no cuDNN dispatch, no CPU fallback" -- and no eager PyTorch kernel either: every kernel
     a graph-replayed training step and an EvalStep call launch belongs to librcv_b200.so (memsets / copies of the
-    accumulators and inputs aside)."""
-    from robocupvision_b200.model import ROBO_UNet
+    accumulators and inputs aside).  Checked for the default ROBO_UNet, for --v2 (its torch.cat, model.py:507, and the
+    gradient slices are rcv_channel_copy launches) and for LabelProp (partial skip model.py:565 added by the
+    producing layer, its gradient slice cut by rcv_channel_copy)."""
+    from robocupvision_b200.model import LabelProp, ROBO_UNet
     from robocupvision_b200.train import EvalStep, TrainStep
     torch.manual_seed(12345678)
-    m = ROBO_UNet().cuda()
-    ts = TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, use_graph=True)
     x = synth.images(8, 3, 120, 160, seed=3).cuda()
     y = synth.labels_random(8, 120, 160, seed=4).cuda()
-    for _ in range(3):
-        ts.step(x, y)
-    names = _cuda_kernel_names(lambda: ts.step(x, y))
-    assert len(names) >= 20, names
-    foreign = [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()
-               or "cutlass" in n.lower()]
-    assert not foreign, f"non-library kernels inside a training step: {foreign}"
-    ev = EvalStep(m, synth.CLASS_WEIGHTS, use_graph=True)
-    for _ in range(2):
-        ev(x, y)
-    names = _cuda_kernel_names(lambda: ev(x, y))
-    foreign = [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()
-               or "cutlass" in n.lower()]
-    assert len(names) >= 10 and not foreign, f"non-library kernels inside an EvalStep call: {foreign}"
-    # LabelProp: the partial skip (`x[:, 0:8] += top`, model.py:565) is added by the producing layer's epilogue
-    from robocupvision_b200.model import LabelProp
-    lp = LabelProp(5, 32, 0).cuda()
-    evl = EvalStep(lp, synth.LP_CLASS_WEIGHTS, use_graph=True)
     x8 = synth.images(4, 8, 120, 160, seed=5).cuda()
     y8 = synth.labels_random(4, 120, 160, seed=6).cuda()
-    for _ in range(2):
-        evl(x8, y8)
-    names = _cuda_kernel_names(lambda: evl(x8, y8))
-    foreign = [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()]
-    assert len(names) >= 8 and not foreign, f"non-library kernels inside a LabelProp EvalStep call: {foreign}"
+    cases = [("ROBO_UNet", ROBO_UNet().cuda(), synth.CLASS_WEIGHTS, x, y),
+             ("ROBO_UNet v2", ROBO_UNet(v2=True).cuda(), synth.CLASS_WEIGHTS, x, y),
+             ("LabelProp", LabelProp(5, 32, 0).cuda(), synth.LP_CLASS_WEIGHTS, x8, y8)]
+    for tag, m, cw, xi, yi in cases:
+        ts = TrainStep(m, cw, lr=1e-3, l1_decay=1e-6, use_graph=True)
+        for _ in range(3):
+            ts.step(xi, yi)
+        names = _cuda_kernel_names(lambda: ts.step(xi, yi))
+        assert len(names) >= 20, names
+        assert not _foreign(names), f"{tag}: non-library kernels inside a training step: {_foreign(names)}"
+        ev = EvalStep(m, cw, use_graph=True)
+        for _ in range(2):
+            ev(xi, yi)
+        names = _cuda_kernel_names(lambda: ev(xi, yi))
+        assert len(names) >= 8 and not _foreign(names), f"{tag}: non-library kernels inside an EvalStep call: {_foreign(names)}"
