@@ -437,6 +437,11 @@ def run_workload(job: Job, key: str, batch: int, steps: int, warmup: int, headli
            "gpu_launches": int(launches), "roofline_whole_step": roof_step,
            "l2": "8 rotating input batches; per-step activation working set >> 126 MB L2" if batch * wl["mb"] > 252
                  else "8 rotating input batches; working set fits the 126 MB L2 (see latency_ms_l2_flushed)"}
+    if wl["train"] and world > 1:
+        # how the gradient buckets are summed: "peer" = rcv_peer_allreduce over NVLink peer memory, "nccl" = dist.all_reduce
+        rec["dp_reduce"] = ts.reduce
+        if ts.peer is not None:
+            ts.peer.check()
     if latency:
         # per-frame latency, the reference's own inference metric (tester.py:142-144): each iteration timed alone with
         # CUDA events; once with the L2 flushed before every iteration (cold weights), once warm
@@ -564,6 +569,10 @@ def main():
             "roofline_hbm_layer": narrow_layer_roofline(model, wl, batch, dev, pk)}
     if "cpu_baseline" in rec:
         line["cpu_baseline"] = rec["cpu_baseline"]
+    if "dp_reduce" in rec:
+        line["config"]["gradient_exchange"] = {
+            "peer": "rcv_peer_allreduce: one kernel per bucket over NVLink peer-mapped gradient arenas",
+            "nccl": "dist.all_reduce (NCCL) per bucket"}[rec["dp_reduce"]]
     del model
     if world > 1 and wl["train"]:
         # numerical check of the N-rank product path (bucketed all-reduce + optimiser on the comm stream, inside a

@@ -441,6 +441,30 @@ int rcv_sgd_step(int64_t n, float* p, const float* g, float* buf,
  * arena (optimizer.zero_grad(), train.py:45), BatchNorm statistics, loss sums. */
 int rcv_zero(void* ptr, size_t bytes, void* stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory ------------- */
+/* The one exchange of batch-sharded training: the sum all-reduce of the flat gradient arena after
+ * `loss.backward()` (train.py:66; what DistributedDataParallel adds to the reference's loop), as ONE kernel per
+ * bucket over peer-mapped arenas instead of a collective-library call: a ready barrier (flags in peer memory), each
+ * rank sums its 1/N share of the range over all ranks' arenas IN RANK ORDER (bitwise the same result whichever rank
+ * computes it) and stores the sums into every arena, then a done barrier.  When the launch completes, the range of
+ * the local arena holds the sums and no peer touches it until the next launch on the same slot.
+ *
+ * Setup, once per rank: rcv_peer_alloc (a zero-filled cudaMalloc block + its 64-byte cudaIpc handle), exchange the
+ * handles through any host channel, rcv_peer_open each peer's handle.  The block holds the arena followed by
+ * rcv_peer_flag_bytes() of flags (16-byte aligned); a rank passes its OWN block for its own index. */
+uint64_t rcv_peer_flag_bytes(void);
+int rcv_peer_alloc(uint64_t bytes, void** ptr, void* handle64);
+int rcv_peer_open(const void* handle64, void** ptr);
+int rcv_peer_close(void* ptr);   /* a pointer rcv_peer_open returned  */
+int rcv_peer_free(void* ptr);    /* a pointer rcv_peer_alloc returned */
+/* arenas[world], flags[world]: HOST arrays of device pointers in rank order (own block included).  slot: 0..15, one
+ * per concurrently outstanding range (every rank must issue the same sequence of launches per slot).  offset, count:
+ * floats, multiples of 4.  status: device int32 in local memory, set to 1 if a peer did not arrive within
+ * RCV_PEER_TIMEOUT_S (default 30) seconds -- the launch then returns without hanging and the sums are invalid.
+ * world = 1 is legal (flags and barriers run, the sums are the gradients themselves). */
+int rcv_peer_allreduce(int32_t world, int32_t rank, int32_t slot, float* const* arenas, uint32_t* const* flags,
+                       int64_t offset, int64_t count, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,12 @@ SIGNATURES = {
     "rcv_upsample_bilinear2x_fwd": [_i32, _i32, _i32, _i32, _p, _p, _p, _p],
     "rcv_upsample_bilinear2x_bwd": [_i32, _i32, _i32, _i32, _p, _p, _p],
     "rcv_channel_copy": [_i64, _i64, _i32, _p, _i32, _i32, _p, _i32, _i32, _p],
+    "rcv_peer_flag_bytes": [],
+    "rcv_peer_alloc": [C.c_uint64, C.POINTER(C.c_void_p), _p],
+    "rcv_peer_open": [_p, C.POINTER(C.c_void_p)],
+    "rcv_peer_close": [_p],
+    "rcv_peer_free": [_p],
+    "rcv_peer_allreduce": [_i32, _i32, _i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64, _i64, _p, _p],
     "rcv_ce_fwd": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_ce_bwd": [_i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p],
     "rcv_confusion": [_i32, _i32, _i64, _p, _p, _p, _p],
@@ -102,7 +108,7 @@ SIGNATURES = {
     "rcv_zero": [_p, C.c_size_t, _p],
 }
 _RESTYPES = {"rcv_last_error": C.c_char_p, "rcv_conv_packed_bytes": C.c_size_t, "rcv_conv_workspace_bytes": C.c_size_t,
-             "rcv_conv_pack_table_bytes": C.c_size_t}
+             "rcv_conv_pack_table_bytes": C.c_size_t, "rcv_peer_flag_bytes": C.c_uint64}
 PACK_FWD, PACK_DGRAD = 0, 1
 ABI_VERSION = 5
 

@@ -79,7 +79,7 @@ def allreduce_buckets(flat, buckets: Sequence[Tuple[int, int, int]], group=None)
 
 def self_check(model_ctor, class_weights, batch: int, cin: int, h: int, w: int, steps: int = 3, group=None,
                lr: float = 1e-3, l1_decay: float = 1e-6, seed: int = 777, use_graph: bool = True,
-               force_comm_path: bool = True, tol: float = 5e-4) -> dict:
+               force_comm_path: bool = True, tol: float = 5e-4, reduce=None) -> dict:
     """Numerical check of the data-parallel product path on THIS job's ranks (bench.py emits it as `dp_check`).
 
     Every rank trains `steps` steps of TrainStep (bucketed all-reduce + optimiser on the comm stream, captured in a
@@ -114,7 +114,7 @@ def self_check(model_ctor, class_weights, batch: int, cin: int, h: int, w: int, 
     emu = copy.deepcopy(model)
     eps = 1e-3
     ts = TrainStep(model, class_weights, lr=lr, l1_decay=l1_decay, eps=eps, use_graph=use_graph,
-                   process_group=group, force_comm_path=force_comm_path)
+                   process_group=group, force_comm_path=force_comm_path, reduce=reduce)
     crit = CrossEntropyLoss2d(torch.tensor(class_weights)).to(dev)
     opt = torch.optim.Adam(emu.parameters(), lr=lr, eps=eps)
     gen = torch.Generator().manual_seed(seed)
@@ -139,6 +139,8 @@ def self_check(model_ctor, class_weights, batch: int, cin: int, h: int, w: int, 
         opt.step()
         emu._get_plan().epoch += 1  # the optimiser wrote the weights behind the plan's caches
     torch.cuda.synchronize()
+    if ts.peer is not None:
+        ts.peer.check()
     max_w = 0.0
     for p, q in zip(model.parameters(), emu.parameters()):
         max_w = max(max_w, float((p.detach() - q.detach()).abs().max()) / max(1.0, float(q.detach().abs().max())))
@@ -155,5 +157,5 @@ def self_check(model_ctor, class_weights, batch: int, cin: int, h: int, w: int, 
     return {"ok": bool(max_w <= tol and max_loss <= 1e-4 and identical), "world": world, "steps": steps,
             "batch_per_rank": batch, "max_weight_err": max_w, "max_loss_err": max_loss,
             "weights_identical_across_ranks": identical, "buckets": [list(b) for b in ts.buckets],
-            "graph": bool(use_graph), "reference": "serial N-shard gradient accumulation on one GPU "
+            "graph": bool(use_graph), "reduce": ts.reduce if world > 1 or ts.peer is not None else "none", "reference": "serial N-shard gradient accumulation on one GPU "
             "(autograd path of the same kernels, pinned against the CPU oracle by tests/)"}

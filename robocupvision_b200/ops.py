@@ -130,7 +130,7 @@ def conv_workspace_bytes(g: ConvGeom, n: int, h: int, w: int, direction: int = P
 def new_workspace(nbytes: int, device) -> torch.Tensor:
     """A zero-filled scratch buffer for the `workspace` argument of conv_fwd / conv_dgrad (rcv_conv_desc::workspace:
     zero-filled once by the caller, then owned by ONE stream of convolution launches at a time)."""
-    return torch.zeros(max(int(nbytes), 1024), dtype=torch.uint8, device=device)
+    return zeros(max(int(nbytes), 1024), torch.uint8, device)
 
 
 def _with_ws(d: ConvDesc, workspace):

@@ -14,6 +14,7 @@ no host round trips.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -21,6 +22,14 @@ import torch.nn as nn
 
 from . import dp, ops
 from .engine import Plan
+
+
+def _zeros(n, dtype, device) -> torch.Tensor:
+    """Zero-filled state buffer: a stream-ordered memset on the GPU (no fill kernel); plain torch on the CPU, where only
+    the host-side meters of the gloo tests live."""
+    if torch.device(device).type == "cuda":
+        return ops.zeros(n, dtype, device)
+    return torch.zeros(n, dtype=dtype, device=device)
 
 
 ARENA_ALIGN = 4  # floats: every parameter's slice starts on a 16-byte boundary (vector loads, TMA, no clones in ops._chk)
@@ -36,7 +45,7 @@ def flatten_parameters(model: nn.Module):
     for p in params:
         offs.append(o)
         o += -(-p.numel() // ARENA_ALIGN) * ARENA_ALIGN
-    arena = torch.zeros(o, device=dev, dtype=torch.float32)
+    arena = _zeros(o, torch.float32, dev)
     table = []
     for p, o in zip(params, offs):
         n = p.numel()
@@ -72,7 +81,7 @@ class TrainStep:
                  masks: Optional[List[torch.Tensor]] = None, optimizer: str = "adam", momentum: float = 0.0,
                  weight_decay: float = 0.0, lr_mults: Optional[Sequence] = None,
                  process_group=None, use_graph: bool = True, overlap_comm: bool = True, n_buckets: int = 3,
-                 force_comm_path: bool = False):
+                 force_comm_path: bool = False, reduce: Optional[str] = None):
         """masks: pruneModelNew-style list of bool tensors for the >1-D parameters, in parameter
         order (train.py:59-65); with masks the L1 term is dropped (train.py:53).
         optimizer: "adam" (train.py:357-363; torch defaults, no weight decay) or "sgd" (trainer.py:182-184:
@@ -80,7 +89,13 @@ class TrainStep:
         lr_mults: [(module_or_param_list, multiplier)] for the reference's 10x group (train.py:357-363).
         n_buckets: data-parallel gradient buckets (cut at plan-node boundaries, dp.plan_buckets); each is
         all-reduced and its optimiser pass run on a side stream as soon as backward has passed its first node.
-        force_comm_path: run the bucketed side-stream schedule even with one rank (tests)."""
+        force_comm_path: run the bucketed side-stream schedule even with one rank (tests).
+        reduce: how the buckets are summed over ranks -- "peer": rcv_peer_allreduce, one kernel per bucket over the
+        ranks' peer-mapped gradient arenas (peer.PeerExchange; the group is only used to exchange the IPC handles);
+        "nccl": dist.all_reduce on the group.  Default: $RCV_B200_DP_REDUCE, else "peer" -- with dist.all_reduce taking
+        over (with a warning, on every rank together) if the GPUs cannot map each other's memory.
+        The optimiser passes of the buckets run on the side stream with one rank too (overlap_comm): they overlap the
+        encoder's backward (+0.5 % on the single-GPU step)."""
         if optimizer not in ("adam", "sgd"):
             raise ValueError(f"TrainStep: optimizer must be 'adam' or 'sgd', got {optimizer!r}")
         if optimizer == "adam" and (weight_decay != 0.0 or momentum != 0.0):
@@ -94,9 +109,40 @@ class TrainStep:
         self.dev = dev
         self.arena, self.table = flatten_parameters(model)
         n = self.arena.numel()
-        self.grads = torch.zeros(n, device=dev)
-        self.m = torch.zeros(n, device=dev)          # Adam exp_avg / SGD momentum buffer
-        self.v = torch.zeros(n, device=dev) if optimizer == "adam" else None
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        force_comm_path = force_comm_path or os.environ.get("RCV_B200_FORCE_COMM_PATH", "") == "1"
+        asked = reduce or os.environ.get("RCV_B200_DP_REDUCE", "")
+        if asked not in ("", "peer", "nccl"):
+            raise ValueError(f"TrainStep: reduce must be 'peer' or 'nccl', got {asked!r}")
+        self.reduce = asked or "peer"
+        self.peer = None
+        self.grads = None
+        if self.reduce == "peer" and (self.world > 1 or force_comm_path):
+            from .peer import PeerExchange, PeerUnavailable
+            try:
+                self.peer = PeerExchange(n, dev, group=process_group)
+                self.grads = self.peer.grads
+            except PeerUnavailable as e:  # raised on every rank or on none
+                if asked == "peer":
+                    raise
+                import warnings
+                warnings.warn(f"robocupvision_b200: peer-memory gradient exchange unavailable ({e}); "
+                              "using dist.all_reduce", RuntimeWarning)
+                self.reduce = "nccl"
+        if self.world == 1 and self.peer is None:
+            self.reduce = "none"
+        if self.grads is None:
+            self.grads = _zeros(n, torch.float32, dev)
+        if self.world > 1 and "RCV_PDL" not in os.environ:
+            # programmatic dependent launch: measured -1.5 % with NCCL kernels inside the step's graph, neutral to
+            # +0.8 % with the peer-memory exchange (2 x B200); single-process runs have it on from _lib.load()
+            from . import _lib
+            _lib.load().rcv_set_pdl(1 if self.peer is not None else 0)
+        self.m = _zeros(n, torch.float32, dev)       # Adam exp_avg / SGD momentum buffer
+        self.v = _zeros(n, torch.float32, dev) if optimizer == "adam" else None
         self.grad_views = {id(p): self.grads[o:o + k].view(p.shape) for p, o, k in self.table}
         self.offsets = {id(p): (o, k) for p, o, k in self.table}
         self.optimizer = optimizer
@@ -105,7 +151,7 @@ class TrainStep:
         self.l1_decay = 0.0 if masks is not None else float(l1_decay)
         self.mask = None
         if masks is not None:
-            self.mask = torch.zeros(n, device=dev, dtype=torch.uint8)
+            self.mask = _zeros(n, torch.uint8, dev)
             i = 0
             for p, o, k in self.table:
                 if p.dim() > 1:
@@ -141,20 +187,16 @@ class TrainStep:
         self.base_lr = lr
         self._lr_host = torch.tensor([lr * r[2] for r in self.ranges], dtype=torch.float32).pin_memory()
         self.lr_dev = self._lr_host.to(dev)
-        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.step_dev = _zeros(1, torch.int32, dev)
         # every small accumulator of a step in ONE buffer (one memset per step):
         # [l1 sum | CE loss sums (2) | correct pixels (int64 view) | BN batch statistics | BN backward sums]
         ns = self.plan.n_stats
-        self._accum = torch.zeros(4 + 2 * ns, device=dev, dtype=torch.float64)
+        self._accum = _zeros(4 + 2 * ns, torch.float64, dev)
         self._acc_l1, self._acc_ce = self._accum[0:1], self._accum[1:3]
         self._acc_corr = self._accum[3:4].view(torch.int64)
         self._acc_stats, self._acc_sums = self._accum[4:4 + ns], self._accum[4 + ns:4 + 2 * ns]
         # distributed
-        self.pg = process_group
-        self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
-        self.comm_path = (overlap_comm and self.world > 1) or force_comm_path
+        self.comm_path = overlap_comm or force_comm_path
         self.comm_stream = torch.cuda.Stream(device=dev) if self.comm_path else None
         # (first plan node, arena start, arena end), in the order backward completes them (arena tail first)
         self.buckets = dp.plan_buckets([[self.offsets[id(p)] for p in nd.params()] for nd in self.plan.nodes],
@@ -193,9 +235,12 @@ class TrainStep:
         f = (1.0 + math.cos(math.pi * epoch / t_max)) / 2.0
         self.set_group_lrs([eta_min + (self.base_lr * r[2] - eta_min) * f for r in self.ranges])
 
-    def _allreduce(self, t: torch.Tensor):
-        if self.world > 1 or self.pg is not None:
-            torch.distributed.all_reduce(t, group=self.pg)
+    def _allreduce(self, a: int, b: int, slot: int = 0):
+        """grads[a:b] <- sum over ranks, on the current stream."""
+        if self.peer is not None:
+            self.peer.allreduce(slot, a, b)
+        elif self.world > 1 or self.pg is not None:
+            torch.distributed.all_reduce(self.grads[a:b], group=self.pg)
 
     def _optim_range(self, a: int, b: int, l1):
         """Optimiser pass over arena[a:b), split at the lr-group boundaries."""
@@ -233,18 +278,18 @@ class TrainStep:
         dl = ops.ce_bwd(logits, y, self.class_w, sums)
         if self.comm_path:
             cur = torch.cuda.current_stream()
-            pending = list(self.buckets)
+            pending = [(k,) + tuple(bk) for k, bk in enumerate(self.buckets)]
 
             def flush(upto):
                 """All-reduce + optimiser pass, on the comm stream, of every bucket whose gradients are final once
                 backward has passed node `upto` (their weights are read by no later backward kernel)."""
-                while pending and pending[0][0] >= upto:
-                    _, a, b = pending.pop(0)
+                while pending and pending[0][1] >= upto:
+                    k, _, a, b = pending.pop(0)
                     self.comm_stream.wait_stream(cur)
                     if self.plan._wgrad_stream is not None:  # weight gradients are produced on the side stream
                         self.comm_stream.wait_stream(self.plan._wgrad_stream)
                     with torch.cuda.stream(self.comm_stream):
-                        self._allreduce(self.grads[a:b])
+                        self._allreduce(a, b, slot=k)
                         self._optim_range(a, b, l1)
             self.plan.backward(saved, [dl], False, self.grad_views, node_done=flush, sums_arena=self._acc_sums)
             flush(-1)
@@ -252,7 +297,7 @@ class TrainStep:
         else:
             self.plan.backward(saved, [dl], False, self.grad_views, sums_arena=self._acc_sums)
             if self.world > 1:
-                self._allreduce(self.grads)
+                self._allreduce(0, self.arena.numel())
             self._optim_range(0, self.arena.numel(), l1)
         self.kernels_per_step = ops.launch_count() - k0
         return sums, l1, corr
@@ -348,8 +393,10 @@ class TrainStep:
 
     def loss_value(self) -> float:
         """Host read (one sync) of the last step's total loss, as train.py:73 accumulates it."""
-        ce = float(self.loss_sums[0] / self.loss_sums[1])
-        return ce + self.l1_decay * float(self.l1_sum)
+        num, den = self.loss_sums.tolist()
+        if self.peer is not None:
+            self.peer.check()
+        return num / den + self.l1_decay * float(self.l1_sum)
 
 
 class _HostPipe:
@@ -385,7 +432,8 @@ class StepResult:
         """Result of a step that ran through step() (first call / device inputs): read now, the
         device scalars are overwritten by the next replay."""
         r = StepResult(None, 0, ts.l1_decay)
-        ce = float(ts.loss_sums[0] / ts.loss_sums[1])
+        num, den = ts.loss_sums.tolist()
+        ce = num / den
         r._ts = (ce, ce + ts.l1_decay * float(ts.l1_sum), int(ts.correct))
         return r
 
@@ -395,7 +443,7 @@ class StepResult:
             return self._ts
         self.pipe.done[self.k].synchronize()
         f = self.pipe.out_f[self.k]
-        ce = float(f[0] / f[1])
+        ce = float(f[0]) / float(f[1])
         return ce, ce + self.l1_decay * float(f[2]), int(self.pipe.out_i[self.k])
 
 
@@ -522,9 +570,9 @@ class ValidationMeter:
         self.nc = num_classes
         self.pg = process_group
         # [conf (nc*nc) | correct | images | pixels | batches]
-        self.ints = torch.zeros(num_classes * num_classes + 4, dtype=torch.int64, device=device)
+        self.ints = _zeros(num_classes * num_classes + 4, torch.int64, device)
         # [iou_sum (nc) | loss sum]
-        self.flts = torch.zeros(num_classes + 1, dtype=torch.float64, device=device)
+        self.flts = _zeros(num_classes + 1, torch.float64, device)
 
     @torch.no_grad()
     def update(self, out: dict, extra_loss=None) -> None:

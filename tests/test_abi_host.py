@@ -386,3 +386,19 @@ def test_host_side_dispatch_is_total_over_random_geometries():
             ops.conv_engine(bad, 2, 12, 16, ops.PACK_FWD, ops.MATH_AUTO)
     assert seen == {ops.ENGINE_SIMT, ops.ENGINE_DIRECT, ops.ENGINE_UMMA, ops.ENGINE_NARROW} or \
         seen == {ops.ENGINE_SIMT, ops.ENGINE_UMMA, ops.ENGINE_NARROW}
+
+
+def test_peer_share_bounds_partition_the_range():
+    """peer.share_bounds (the host statement of peer_allreduce_kernel's split): the ranks' shares are disjoint, in rank
+    order, float4-aligned and cover the range, for every world size the kernel is instantiated for."""
+    from robocupvision_b200.peer import share_bounds
+    for count in (0, 4, 8, 36, 4 * 1001, 4 * 4096):
+        for world in range(1, 9):
+            end = 0
+            for r in range(world):
+                lo, hi = share_bounds(count, world, r)
+                assert lo == end and lo <= hi and lo % 4 == 0 and hi % 4 == 0
+                end = hi
+            assert end == count
+    with pytest.raises(ValueError):
+        share_bounds(6, 2, 0)

@@ -271,8 +271,9 @@ def test_comm_path_schedule_matches_plain_step(use_graph):
         m = ROBO_UNet().cuda()
         models.append(m)
         steps.append(TrainStep(m, synth.CLASS_WEIGHTS, lr=1e-3, l1_decay=1e-6, eps=1e-3, use_graph=use_graph,
-                               force_comm_path=comm))
-    assert len(steps[1].buckets) == 3 and not steps[0].buckets
+                               overlap_comm=comm, force_comm_path=comm))
+    # force_comm_path on one rank also runs the exchange kernel itself (rcv_peer_allreduce, world 1: flags + barriers)
+    assert len(steps[1].buckets) == 3 and not steps[0].buckets and steps[1].peer is not None and steps[0].peer is None
     for s in range(5):
         x = synth.images(8, 3, 120, 160, seed=200 + s).cuda()
         y = synth.labels_learnable(x.cpu()).cuda()
@@ -321,6 +322,86 @@ def test_dp_self_check_single_rank_nccl():
     r = json.loads(line[0][8:])
     print(r)
     assert r["ok"], r
+
+
+_PEER_RANK = r"""
+import json, os, sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import torch.distributed as dist
+rank, world, port, mode = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
+os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = port
+os.environ.setdefault('RCV_PEER_TIMEOUT_S', '20')
+torch.cuda.set_device(0)
+dist.init_process_group('gloo', rank=rank, world_size=world)
+out = {{}}
+if mode == 'kernel':
+    from robocupvision_b200.peer import PeerExchange
+    n = 4 * 50000 + 8
+    px = PeerExchange(n, 'cuda:0')
+    ranges = [(0, n), (8, 408), (400, n), (0, 4)]
+    bad = 0
+    for it in range(4):
+        for slot, (a, b) in enumerate(ranges):
+            data = torch.randn(world, n, generator=torch.Generator().manual_seed(100 * it + slot))
+            px.grads.copy_(data[rank])
+            px.allreduce(slot, a, b)
+            torch.cuda.synchronize()
+            expect = data[rank].clone()
+            acc = data[0, a:b].clone()
+            for q in range(1, world):
+                acc += data[q, a:b]          # rank order, as the kernel adds
+            expect[a:b] = acc
+            bad += int(not torch.equal(px.grads.cpu(), expect))
+            dist.barrier()
+    px.check()
+    out = {{'bad': bad}}
+else:
+    from robocupvision_b200 import dp
+    from robocupvision_b200.model import ROBO_UNet
+    import synth
+    out = dp.self_check(ROBO_UNet, synth.CLASS_WEIGHTS, 4, 3, 48, 64, steps=3, reduce='peer',
+                        use_graph=(mode == 'graph'))
+print('PEER ' + json.dumps(out)); sys.stdout.flush()
+torch.cuda.synchronize(); dist.barrier(); os._exit(0)
+"""
+
+
+def _run_peer_ranks(mode, world=2, port="29683", timeout=240):
+    """`world` processes on THIS GPU (the IPC mapping, flags and barriers of rcv_peer_allreduce do not care that the
+    peers share a device; the GPU time-slices between the ranks' contexts), gloo only for the handle exchange."""
+    import json
+    code = _PEER_RANK.format(root=str(ROOT), tests=str(ROOT / "tests"))
+    procs = [subprocess.Popen([sys.executable, "-c", code, str(r), str(world), port, mode], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = []
+    try:
+        for p in procs:
+            o, e = p.communicate(timeout=timeout)
+            line = [l for l in o.splitlines() if l.startswith("PEER ")]
+            assert line, o[-1500:] + e[-3000:]
+            outs.append(json.loads(line[0][5:]))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    return outs
+
+
+def test_peer_allreduce_two_ranks():
+    """rcv_peer_allreduce: sums over two ranks' peer-mapped arenas equal the rank-order sum bit for bit, outside the
+    range nothing changes; whole arena, interior ranges and a 4-float range, four rounds per slot (flag epochs)."""
+    for r in _run_peer_ranks("kernel"):
+        assert r == {"bad": 0}, r
+
+
+@pytest.mark.parametrize("mode", ["graph", "eager"])
+def test_peer_exchange_train_step(mode):
+    """The product's data-parallel step with reduce="peer" (bucketed rcv_peer_allreduce + optimiser on the comm
+    stream, CUDA graph or eager) on two ranks: dp.self_check against the serial two-shard accumulation, and the
+    ranks' weights bitwise identical."""
+    for r in _run_peer_ranks(mode, port="29684" if mode == "graph" else "29685"):
+        print(r)
+        assert r["ok"] and r["world"] == 2 and r["reduce"] == "peer" and r["weights_identical_across_ranks"], r
 
 
 def _cuda_kernel_names(fn):
