@@ -32,6 +32,10 @@ def _zeros(n, dtype, device) -> torch.Tensor:
     return torch.zeros(n, dtype=dtype, device=device)
 
 
+# diagnostic only (tools/ngpu_ab.sh): ranks run the data-parallel schedule WITHOUT exchanging gradients, which
+# separates the cost of the lock-step from everything else that differs between one process and N
+_SKIP_EXCHANGE = os.environ.get("RCV_B200_DP_SKIP_EXCHANGE", "") == "1"
+
 ARENA_ALIGN = 4  # floats: every parameter's slice starts on a 16-byte boundary (vector loads, TMA, no clones in ops._chk)
 
 
@@ -237,6 +241,8 @@ class TrainStep:
 
     def _allreduce(self, a: int, b: int, slot: int = 0):
         """grads[a:b] <- sum over ranks, on the current stream."""
+        if _SKIP_EXCHANGE:
+            return
         if self.peer is not None:
             self.peer.allreduce(slot, a, b)
         elif self.world > 1 or self.pg is not None:
