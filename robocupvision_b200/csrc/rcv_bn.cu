@@ -526,7 +526,10 @@ int fa_blocks(int64_t quads) {
 }
 
 int chan_splits(int C, int64_t E) {
-  int s = rcv_cdiv(148 * 8, C);
+  // ONE wave: six CTAs of 256 threads are resident per SM (40 registers), so at most 148 * 6 CTAs.  A grid of 148 * 8
+  // ran a second, third-full wave with too few warps per SM to hide the load latency: 42.1 -> 36.4 us for the pair of
+  // passes on 8 channels @120x160, 19.0 -> 17.1 us on 16 channels @60x80 (batch 64; 4, 5, 7 and 12 per SM all slower).
+  int s = (148 * 6) / C;
   const int64_t maxs = (E + NT * 16 - 1) / (NT * 16);
   if (s > maxs) s = (int)maxs;
   if (s < 1) s = 1;
