@@ -837,6 +837,9 @@ __global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, c
     const int epi = p.epilogue;
     const int HWo = p.Hout * p.Wout;
     const bool has_res = p.residual != nullptr, has_stats = p.stats != nullptr;
+    // BatchNorm statistics of this warp's 32 rows, summed over ALL tiles of this persistent CTA and flushed once:
+    // one fp64 atomic pair per channel per tile (2 400 tiles x 4 warps onto 32 addresses) serialised in L2
+    double st1 = 0.0, st2 = 0.0;
     for (int lt = 0; lt < my_tiles; ++lt) {
       const int buf = lt & 1;
       const long long q0 = (long long)((int)blockIdx.x + lt * (int)gridDim.x) * BM;
@@ -881,11 +884,15 @@ __global__ void __launch_bounds__(C16_NT, 2) umma_c16_kernel(const RcvIgemm p, c
         for (int j = 0; j < 16; ++j) s2[j] = v[j] * v[j];
         warp_transpose_reduce16(v, lane);
         warp_transpose_reduce16(s2, lane);
-        const int co = lane >> 1;
-        if ((lane & 1) == 0 && co < p.CB) {
-          atomicAdd(p.stats + co, (double)v[0]);
-          atomicAdd(p.stats + p.CB + co, (double)s2[0]);
-        }
+        st1 += (double)v[0];
+        st2 += (double)s2[0];
+      }
+    }
+    if (has_stats) {
+      const int co = lane >> 1;
+      if ((lane & 1) == 0 && co < p.CB) {
+        atomicAdd(p.stats + co, st1);
+        atomicAdd(p.stats + p.CB + co, st2);
       }
     }
   }

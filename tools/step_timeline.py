@@ -37,3 +37,16 @@ tot = sum(v[1] for v in agg.values())
 print(f"{len(seg)} kernels, sum of durations {tot:.1f} us, first start -> last end {t1 - t0:.1f} us")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"  {k[:60]:60s} {n:3d} {t:8.1f} us {100 * t / tot:5.1f}%  avg {t / n:6.1f}")
+if "--trace" in sys.argv:
+    # the step in start order: offset from the step's first kernel, duration, stream, idle time of that stream before it
+    last_end = {}
+    print("\n  start_us   dur_us  stream  idle_before_us  kernel")
+    for e in seg:
+        st = getattr(e, "stream", None)
+        if st is None:
+            st = getattr(e, "device_resource_id", -1)
+        s, d = e.time_range.start - t0, e.device_time
+        idle = s - last_end.get(st, s)
+        last_end[st] = max(last_end.get(st, 0), e.time_range.end - t0)
+        k = re.sub(r"\(.*", "", e.name.replace("(anonymous namespace)::", "").replace("void ", ""))
+        print(f"  {s:8.1f} {d:8.1f}  {st!s:>6}  {idle:8.1f}        {k[:70]}")
