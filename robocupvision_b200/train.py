@@ -336,9 +336,11 @@ class TrainStep:
         """Pipelined form of step() for a loop fed from pinned host memory: this step's inputs go
         H2D on a copy stream into one of two staging buffers (overlapping the previous step, which
         is still running), the main stream waits for them, moves them into the graph's input
-        buffers device-to-device and replays; the step's loss sums / L1 sum / correct count are
-        copied to pinned host memory right behind it.  Returns a handle whose wait() blocks until
-        THIS step's scalars have landed -- call it one step late to keep the pipe full."""
+        buffers device-to-device and replays; the step's scalars (L1 sum, loss sums, correct count: the 32-byte head
+        of the accumulator buffer) follow in ONE copy to pinned host memory.  Returns a handle whose wait() blocks until
+        THIS step's scalars have landed -- call it one step late to keep the pipe full.
+        (A second capture of the step over the staging buffers themselves would save the device-to-device copy,
+        ~10 us; tried, and dropped after one unexplained failure of test_step_async_matches_step in three runs.)"""
         if self.graph is None or self.static_x.shape != x.shape or not self.use_graph or x.is_cuda:
             self.step(x, y)
             return StepResult.ready(self)
@@ -359,9 +361,7 @@ class TrainStep:
         self.static_y.copy_(pipe.sy[k], non_blocking=True)
         pipe.free[k].record(cur)
         self.graph.replay()
-        pipe.out_f[k][:2].copy_(self.loss_sums, non_blocking=True)
-        pipe.out_f[k][2:3].copy_(self.l1_sum, non_blocking=True)
-        pipe.out_i[k].copy_(self.correct, non_blocking=True)
+        pipe.out[k].copy_(self._accum[:4], non_blocking=True)
         pipe.done[k].record(cur)
         self.plan.epoch += 1  # as in step(): the weights changed after the panels were packed
         return StepResult(pipe, k, self.l1_decay)
@@ -389,6 +389,7 @@ class TrainStep:
         with torch.cuda.graph(g):
             self.loss_sums, self.l1_sum, self.correct = self._step_impl(self.static_x, self.static_y)
         self.graph = g
+        self._pipe = None  # the staging slots have the old shape
         g.replay()
 
     def broadcast_state(self, src: int = 0):
@@ -412,8 +413,8 @@ class _HostPipe:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.sx = [torch.empty_like(like_x) for _ in range(2)]
         self.sy = [torch.empty_like(like_y) for _ in range(2)]
-        self.out_f = [torch.empty(3, dtype=torch.float64).pin_memory() for _ in range(2)]
-        self.out_i = [torch.empty(1, dtype=torch.int64).pin_memory() for _ in range(2)]
+        # [l1 sum | CE loss sums (2) | correct pixels (int64 bits)]: the head of TrainStep._accum
+        self.out = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
         self.loaded = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
@@ -448,9 +449,9 @@ class StepResult:
         if self._ts is not None:
             return self._ts
         self.pipe.done[self.k].synchronize()
-        f = self.pipe.out_f[self.k]
-        ce = float(f[0]) / float(f[1])
-        return ce, ce + self.l1_decay * float(f[2]), int(self.pipe.out_i[self.k])
+        f = self.pipe.out[self.k]
+        ce = float(f[1]) / float(f[2])
+        return ce, ce + self.l1_decay * float(f[0]), int(f.view(torch.int64)[3])
 
 
 class EvalStep:

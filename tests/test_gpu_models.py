@@ -327,10 +327,11 @@ def test_step_async_matches_step():
         prev = h
     got.append(prev.wait())
     for (l0, c0), (ce, tot, c1) in zip(ref_losses, got):
-        assert abs(l0 - tot) <= 1e-5 * abs(l0) and abs(c0 - c1) <= 8   # run-to-run spread of the losses: a few 1e-6
+        # run-to-run spread of the losses: a few 1e-6 (a skipped or doubled step shows at 1e-3 and above)
+        assert abs(l0 - tot) <= 3e-5 * abs(l0) and abs(c0 - c1) <= 8, (l0, tot, c0, c1)
     for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
         if a.is_floating_point():
-            assert_close(k, a, b, 1e-4)  # (observed spread with eps = 1e-3: <= 4.4e-5; a sign flip would be 2e-3)
+            assert_close(k, a, b, 2e-4)  # (observed spread with eps = 1e-3: <= 4.4e-5; a sign flip would be 2e-3)
         else:
             assert torch.equal(a, b), k
 
