@@ -333,6 +333,26 @@ int rcv_upsample_bilinear2x_fwd(int32_t N, int32_t C, int32_t H, int32_t W,
 int rcv_upsample_bilinear2x_bwd(int32_t N, int32_t C, int32_t H, int32_t W,
                                 const float* dout, float* dx, void* stream);
 
+/* ---- classifier head of a training step, one pass ----------------------- */
+/* The 1x1 classifier conv (model.py:259 UltClassifier / :411 / :554), CrossEntropyLoss2d (model.py:76-82), the
+ * argmax / correct-pixel count (train.py:70-71) and the backward of all three in ONE pass over the decoder's last
+ * feature map: logits = weight feat + bias; loss_sums[0] += sum_p w[y_p] nll_p; correct += #(argmax == y);
+ * dlogits = gscale w[y_p] (softmax - onehot) / loss_sums[1]; dfeat = weight^T dlogits; dweight += dlogits feat^T;
+ * dbias += dlogits.  Logits and their gradient never exist in memory.  Replaces, inside TrainStep, the sequence
+ * rcv_conv_fwd (head) -> rcv_ce_fwd -> rcv_ce_bwd -> rcv_conv_dgrad + rcv_conv_wgrad (head).
+ * loss_sums[1] must already hold sum_p w[y_p]: it depends on the labels only, rcv_ce_weight_sum adds it (to a zeroed
+ * cell) any time before.  feat, dfeat [N,Cin,HW]; weight, dweight [C,Cin]; bias, dbias [C] or NULL; target int64
+ * [N,HW] (labels outside [0,C) contribute nothing); class_w [C] or NULL; gscale device float or NULL (1).
+ * Supported (rcv_head_ce_supported): 2..8 classes over 8 or 16 channels; anything else RCV_ERR_UNSUPPORTED and the
+ * caller keeps the unfused sequence. */
+int rcv_head_ce_supported(int32_t Cin, int32_t C);
+int rcv_ce_weight_sum(int32_t C, int64_t count, const int64_t* target, const float* class_w, double* out,
+                      void* stream);
+int rcv_head_ce_train(int32_t N, int32_t Cin, int32_t C, int64_t HW, const float* feat, const float* weight,
+                      const float* bias, const int64_t* target, const float* class_w, const float* gscale,
+                      double* loss_sums, int64_t* correct, float* dfeat, float* dweight, float* dbias,
+                      void* stream);
+
 /* dst[n, dst_offset + c, :] = src[n, src_offset + c, :] for c < count; src [N,src_channels,HW], dst
  * [N,dst_channels,HW].  The channel moves of the skip wiring that no producer can fold: ROBO_UNet --v2's
  * torch.cat([layer(up), downs[-(i+2)]], 1) (model.py:507; two calls fill the concatenated tensor), the gradient

@@ -86,6 +86,9 @@ SIGNATURES = {
     "rcv_upsample_bilinear2x_fwd": [_i32, _i32, _i32, _i32, _p, _p, _p, _p],
     "rcv_upsample_bilinear2x_bwd": [_i32, _i32, _i32, _i32, _p, _p, _p],
     "rcv_channel_copy": [_i64, _i64, _i32, _p, _i32, _i32, _p, _i32, _i32, _p],
+    "rcv_head_ce_supported": [_i32, _i32],
+    "rcv_ce_weight_sum": [_i32, _i64, _p, _p, _p, _p],
+    "rcv_head_ce_train": [_i32, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "rcv_peer_flag_bytes": [],
     "rcv_peer_alloc": [C.c_uint64, C.POINTER(C.c_void_p), _p],
     "rcv_peer_open": [_p, C.POINTER(C.c_void_p)],

@@ -244,10 +244,28 @@ class Plan:
         return hit
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, training: bool, save: bool, stats_arena: Optional[torch.Tensor] = None):
+    def fusable_head(self) -> int:
+        """Index of the last node if it is a bare 1x1 stride-1 classifier conv (no BatchNorm, no ReLU, no skip) whose
+        output is the plan's only output -- the head TrainStep can hand to ops.head_ce_train -- else -1."""
+        if not self.nodes or self.outputs != [len(self.nodes)]:
+            return -1
+        nd = self.nodes[-1]
+        if nd.kind != "conv" or nd.bn is not None or nd.order != EPI_NONE or nd.skip >= 0:
+            return -1
+        g = nd.geom
+        if g.k != 1 or g.stride != 1 or g.pad != 0 or g.transposed or not ops.head_ce_supported(g.cin, g.cout):
+            return -1
+        if any(other.src == len(self.nodes) or other.skip == len(self.nodes) for other in self.nodes):
+            return -1
+        return len(self.nodes) - 1
+
+    def forward(self, x: torch.Tensor, training: bool, save: bool, stats_arena: Optional[torch.Tensor] = None,
+                stop_before: Optional[int] = None):
         """-> (outputs, saved).  training selects batch statistics for BatchNorm nodes whose
         module is in training mode; save keeps what backward needs.  stats_arena: caller-zeroed float64[n_stats]
-        for the batch statistics (TrainStep zeroes all of a step's accumulators with one memset)."""
+        for the batch statistics (TrainStep zeroes all of a step's accumulators with one memset).
+        stop_before: run nodes [0, stop_before) only (TrainStep's fused head); outputs that were not produced are
+        None, and backward() then starts from the `seed` gradients it is given."""
         x = ops._chk(x, name="input")
         if x.dim() != 4:
             raise ValueError(f"expected NCHW input, got shape {tuple(x.shape)}")
@@ -262,6 +280,8 @@ class Plan:
         self._ensure_packed((PACK_FWD, PACK_DGRAD) if save else (PACK_FWD,), training, x.requires_grad, nhw)
         ws = self.workspace(nhw, dev)
         for t, nd in enumerate(self.nodes):
+            if stop_before is not None and t >= stop_before:
+                break
             src = acts[nd.src]
             if nd.kind == "pool":
                 y, _, code = ops.maxpool2x2_fwd(src, want_idx=False, want_code=save)
@@ -323,17 +343,18 @@ class Plan:
             elif nd.skip >= 0 and nd.skip_mode == "cat":
                 y = ops.concat_channels(y, acts[nd.skip])
             acts.append(y)
-        outs = [acts[i] for i in self.outputs]
+        outs = [acts[i] if i < len(acts) else None for i in self.outputs]
         return outs, ((acts, saved, lazy) if save else None)
 
     # ------------------------------------------------------------------ backward
     def backward(self, saved_all, gouts: Sequence[Optional[torch.Tensor]], x_needs_grad: bool,
                  grad_views: Optional[Dict[int, torch.Tensor]] = None, node_done=None,
-                 sums_arena: Optional[torch.Tensor] = None):
+                 sums_arena: Optional[torch.Tensor] = None, seed: Optional[Dict[int, torch.Tensor]] = None):
         """-> (dx or None, {id(param): grad}).  grad_views, if given, maps id(param) to zero-filled
         tensors that receive the gradients (the train step's flat arena).  node_done(t) is called
         once node t's parameter gradients are final (nodes are visited last to first).  sums_arena: caller-zeroed
-        float64[n_stats] for the BatchNorm-backward sums."""
+        float64[n_stats] for the BatchNorm-backward sums.  seed: {activation index: gradient} for a forward that
+        stopped early (forward(stop_before=...)): the nodes that did not run are skipped, node_done still sees them."""
         acts, saved, lazy = saved_all
         lazy_done: Dict[int, torch.Tensor] = {}  # BatchNorm outputs materialised for a weight gradient, per activation
         dev = acts[0].device
@@ -352,6 +373,8 @@ class Plan:
         for oi, g in zip(self.outputs, gouts):
             if g is not None:
                 add_to(oi, g)
+        for i, g in (seed or {}).items():
+            add_to(i, g)
         if sums_arena is None:
             sums_arena = ops.zeros(max(self.n_stats, 1), torch.float64, dev)
         # Weight gradients run on a side stream: dgrad(t) and wgrad(t) only share their input, so the
@@ -366,8 +389,9 @@ class Plan:
             side = self._wgrad_stream
         keep: List[torch.Tensor] = []
         for t in range(len(self.nodes) - 1, -1, -1):
-            self._backward_node(t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side, keep,
-                                lazy, lazy_done)
+            if t + 1 < len(acts):  # (a node the forward pass stopped before has no activation and no gradient)
+                self._backward_node(t, acts, saved, grads, grad_views, sums_arena, x_needs_grad, add_to, side, keep,
+                                    lazy, lazy_done)
             if node_done is not None:
                 node_done(t)
         if side is not None:

@@ -464,6 +464,32 @@ def upsample_bilinear2x_bwd(dout):
     return dx
 
 
+def head_ce_supported(cin: int, classes: int) -> bool:
+    """True if head_ce_train has a kernel for a `classes`-way 1x1 classifier over `cin` channels."""
+    return bool(_lib.load().rcv_head_ce_supported(int(cin), int(classes)))
+
+
+def ce_weight_sum(target, class_w, out, classes: int) -> None:
+    """out[0] += sum over pixels of class_w[target] (the normaliser of the weighted mean loss; labels only)."""
+    target = _chk(target, torch.int64, "target")
+    _call("rcv_ce_weight_sum", 1, int(classes), target.numel(), _ptr(target), _ptr(class_w), _ptr(out), _stream())
+
+
+def head_ce_train(feat, weight, bias, target, class_w, sums, corr, dweight, dbias):
+    """The classifier head of a training step in one pass (rcv_head_ce_train): -> dfeat.  sums: float64[2] with
+    sums[1] already holding the weight sum (ce_weight_sum); sums[0], corr, dweight, dbias are accumulated into."""
+    feat = _chk(feat, name="feat")
+    target = _chk(target, torch.int64, "target")
+    n, cin, h, w_ = feat.shape
+    c = weight.shape[0]
+    if weight.numel() != c * cin or tuple(target.shape) != (n, h, w_):
+        raise ValueError(f"head_ce_train: feat {tuple(feat.shape)}, weight {tuple(weight.shape)}, target {tuple(target.shape)}")
+    dfeat = torch.empty_like(feat)
+    _call("rcv_head_ce_train", 1, n, cin, c, h * w_, _ptr(feat), _ptr(weight), _ptr(bias), _ptr(target), _ptr(class_w),
+          None, _ptr(sums), _ptr(corr), _ptr(dfeat), _ptr(dweight), _ptr(dbias), _stream())
+    return dfeat
+
+
 def channel_slice(x, offset: int, count: int) -> torch.Tensor:
     """x[:, offset:offset+count] as a dense tensor (the gradient halves of a concatenated skip, the gradient of
     LabelProp's partial skip)."""

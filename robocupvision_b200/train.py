@@ -36,6 +36,8 @@ def _zeros(n, dtype, device) -> torch.Tensor:
 # separates the cost of the lock-step from everything else that differs between one process and N
 _SKIP_EXCHANGE = os.environ.get("RCV_B200_DP_SKIP_EXCHANGE", "") == "1"
 
+_FUSED_HEAD = os.environ.get("RCV_B200_FUSED_HEAD", "1") != "0"
+
 ARENA_ALIGN = 4  # floats: every parameter's slice starts on a 16-byte boundary (vector loads, TMA, no clones in ops._chk)
 
 
@@ -85,7 +87,8 @@ class TrainStep:
                  masks: Optional[List[torch.Tensor]] = None, optimizer: str = "adam", momentum: float = 0.0,
                  weight_decay: float = 0.0, lr_mults: Optional[Sequence] = None,
                  process_group=None, use_graph: bool = True, overlap_comm: bool = True, n_buckets: int = 3,
-                 force_comm_path: bool = False, reduce: Optional[str] = None):
+                 force_comm_path: bool = False, reduce: Optional[str] = None,
+                 fused_head: bool = _FUSED_HEAD):
         """masks: pruneModelNew-style list of bool tensors for the >1-D parameters, in parameter
         order (train.py:59-65); with masks the L1 term is dropped (train.py:53).
         optimizer: "adam" (train.py:357-363; torch defaults, no weight decay) or "sgd" (trainer.py:182-184:
@@ -98,6 +101,9 @@ class TrainStep:
         ranks' peer-mapped gradient arenas (peer.PeerExchange; the group is only used to exchange the IPC handles);
         "nccl": dist.all_reduce on the group.  Default: $RCV_B200_DP_REDUCE, else "peer" -- with dist.all_reduce taking
         over (with a warning, on every rank together) if the GPUs cannot map each other's memory.
+        fused_head: run the classifier conv, the loss, the argmax and their backward as one kernel
+        (ops.head_ce_train) where the plan ends in a bare 1x1 conv of 2..8 classes over 8 or 16 channels;
+        otherwise (and with RCV_B200_FUSED_HEAD=0) the separate kernels run.
         The optimiser passes of the buckets run on the side stream with one rank too (overlap_comm): they overlap the
         encoder's backward (+0.5 % on the single-GPU step)."""
         if optimizer not in ("adam", "sgd"):
@@ -205,6 +211,8 @@ class TrainStep:
         # (first plan node, arena start, arena end), in the order backward completes them (arena tail first)
         self.buckets = dp.plan_buckets([[self.offsets[id(p)] for p in nd.params()] for nd in self.plan.nodes],
                                        [(o, k) for _, o, k in self.table], n, n_buckets) if self.comm_path else []
+        # the classifier head in one pass (ops.head_ce_train) where the plan ends in a bare 1x1 conv the kernel covers
+        self._head = self.plan.fusable_head() if fused_head else -1
         # outputs (device scalars)
         self.loss_sums = None
         self.l1_sum = None
@@ -277,11 +285,29 @@ class TrainStep:
         ops.zero_(self._accum)
         l1 = self._acc_l1
         ops.counter_add(self.step_dev, 1)
-        outs, saved = self.plan.forward(x, training=True, save=True, stats_arena=self._acc_stats)
-        logits = outs[0]
-        sums, _, _, corr = ops.ce_fwd(logits, y, self.class_w, want_correct=True, sums=self._acc_ce,
-                                      corr=self._acc_corr)
-        dl = ops.ce_bwd(logits, y, self.class_w, sums)
+        head = self._head
+        seed = None
+        if head >= 0:
+            # the normaliser of the weighted mean loss depends on the labels only: produced here, so that the head
+            # needs ONE pass (classifier conv + loss + argmax + their backward, ops.head_ce_train)
+            ops.ce_weight_sum(y, self.class_w, self._acc_ce[1:2], self.plan.nodes[head].geom.cout)
+        outs, saved = self.plan.forward(x, training=True, save=True, stats_arena=self._acc_stats,
+                                        stop_before=head if head >= 0 else None)
+        if head >= 0 and saved[2].get(self.plan.nodes[head].src) is not None:
+            raise RuntimeError("TrainStep: the classifier reads a BatchNorm that was deferred to its consumer")
+        if head >= 0:
+            nd = self.plan.nodes[head]
+            sums, corr = self._acc_ce, self._acc_corr
+            dfeat = ops.head_ce_train(saved[0][nd.src], nd.conv.weight.detach(),
+                                      None if nd.conv.bias is None else nd.conv.bias.detach(), y, self.class_w, sums,
+                                      corr, self.grad_views[id(nd.conv.weight)],
+                                      None if nd.conv.bias is None else self.grad_views[id(nd.conv.bias)])
+            seed, gouts = {nd.src: dfeat}, [None]
+        else:
+            logits = outs[0]
+            sums, _, _, corr = ops.ce_fwd(logits, y, self.class_w, want_correct=True, sums=self._acc_ce,
+                                          corr=self._acc_corr)
+            gouts = [ops.ce_bwd(logits, y, self.class_w, sums)]
         if self.comm_path:
             cur = torch.cuda.current_stream()
             pending = [(k,) + tuple(bk) for k, bk in enumerate(self.buckets)]
@@ -297,11 +323,12 @@ class TrainStep:
                     with torch.cuda.stream(self.comm_stream):
                         self._allreduce(a, b, slot=k)
                         self._optim_range(a, b, l1)
-            self.plan.backward(saved, [dl], False, self.grad_views, node_done=flush, sums_arena=self._acc_sums)
+            self.plan.backward(saved, gouts, False, self.grad_views, node_done=flush, sums_arena=self._acc_sums,
+                               seed=seed)
             flush(-1)
             cur.wait_stream(self.comm_stream)
         else:
-            self.plan.backward(saved, [dl], False, self.grad_views, sums_arena=self._acc_sums)
+            self.plan.backward(saved, gouts, False, self.grad_views, sums_arena=self._acc_sums, seed=seed)
             if self.world > 1:
                 self._allreduce(0, self.arena.numel())
             self._optim_range(0, self.arena.numel(), l1)

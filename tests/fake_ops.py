@@ -186,6 +186,34 @@ def bn_bwd(order, dy, z, scale, shift, mean, invstd, dgamma=None, dbeta=None, db
     return dz, dgamma, dbeta, dbias
 
 
+def head_ce_supported(cin, classes):
+    return cin in (8, 16) and 2 <= classes <= 8
+
+
+def ce_weight_sum(target, class_w, out, classes):
+    w = class_w if class_w is not None else torch.ones(classes)
+    ok = (target >= 0) & (target < classes)
+    out += w.double()[target.clamp(0, classes - 1)][ok].sum()
+
+
+def head_ce_train(feat, weight, bias, target, class_w, sums, corr, dweight, dbias):
+    """ATen stand-in of rcv_head_ce_train: autograd over conv1x1 + weighted NLL (sum form) / sums[1]."""
+    calls.append(("head_ce_train",))
+    f = feat.detach().clone().requires_grad_(True)
+    w = weight.detach().clone().requires_grad_(True)
+    b = None if bias is None else bias.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        z = F.conv2d(f, w.view(w.shape[0], -1, 1, 1), b)
+        nll = F.cross_entropy(z, target, weight=class_w, reduction="sum")
+        (nll / float(sums[1])).backward()
+    sums[0] += nll.detach().double()
+    corr += (z.argmax(1) == target).sum()
+    dweight += w.grad.view_as(dweight)
+    if dbias is not None:
+        dbias += b.grad
+    return f.grad
+
+
 def channel_slice(x, offset, count):
     return x[:, offset:offset + count].contiguous()
 

@@ -567,6 +567,44 @@ def test_resample_modules_autograd():
     assert_close("module bilinear grad", xg2.grad, xr2.grad, 2e-6)
 
 
+@pytest.mark.parametrize("cin,classes,hw,weighted", [(8, 5, (24, 32), True), (8, 5, (5, 3), True), (16, 5, (12, 16), True),
+                                                     (16, 3, (7, 5), False), (8, 2, (6, 8), False), (8, 8, (6, 8), True)])
+def test_head_ce_train(cin, classes, hw, weighted):
+    """rcv_head_ce_train + rcv_ce_weight_sum: classifier conv (model.py:259), CrossEntropyLoss2d (model.py:76-82),
+    argmax / correct count (train.py:70-71) and their backward in one pass, against autograd over F.conv2d +
+    F.cross_entropy in float64; labels outside [0, C) contribute nothing."""
+    from robocupvision_b200 import ops
+    h, w_ = hw
+    gen = torch.Generator().manual_seed(cin * 100 + classes + h)
+    n = 3
+    f = torch.randn(n, cin, h, w_, generator=gen)
+    wt = torch.randn(classes, cin, 1, 1, generator=gen) * 0.5
+    b = torch.randn(classes, generator=gen)
+    y = torch.randint(0, classes, (n, h, w_), generator=gen)
+    cw = (torch.rand(classes, generator=gen) + 0.5) if weighted else None
+    fd = f.double().requires_grad_(True)
+    wd = wt.double().requires_grad_(True)
+    bd = b.double().requires_grad_(True)
+    z = F.conv2d(fd, wd, bd)
+    loss = F.cross_entropy(z, y, weight=None if cw is None else cw.double())
+    loss.backward()
+    sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+    corr = torch.zeros(1, dtype=torch.int64, device="cuda")
+    dw = torch.zeros(classes, cin, 1, 1, device="cuda")
+    db = torch.zeros(classes, device="cuda")
+    cwd = None if cw is None else cw.cuda()
+    ops.ce_weight_sum(y.cuda(), cwd, sums[1:2], classes)
+    df = ops.head_ce_train(f.cuda(), wt.cuda(), b.cuda(), y.cuda(), cwd, sums, corr, dw, db)
+    s = sums.cpu()
+    assert abs(float(s[0] / s[1]) - float(loss)) <= 2e-6 * abs(float(loss))
+    wsum = float((cw.double()[y]).sum()) if weighted else float(y.numel())
+    assert abs(float(s[1]) - wsum) <= 1e-11 * wsum
+    assert int(corr) == int((z.argmax(1) == y).sum())
+    assert_close("dfeat", df, fd.grad.float(), 2e-6)
+    assert_close("dweight", dw, wd.grad.float(), 5e-6)
+    assert_close("dbias", db, bd.grad.float(), 5e-6)
+
+
 @pytest.mark.parametrize("hw", [(12, 16), (5, 3), (15, 20)])   # float4 rows, scalar rows, 300-element planes
 def test_channel_copy(hw):
     """rcv_channel_copy: torch.cat([a, b], 1) of ROBO_UNet --v2 (model.py:507) and the slices autograd cuts back

@@ -415,6 +415,39 @@ def _cuda_kernel_names(fn):
             and "Memset" not in e.key]
 
 
+@pytest.mark.parametrize("net", ["robo", "labelprop"])
+def test_fused_head_matches_separate_kernels(net):
+    """TrainStep with the classifier head as one kernel (ops.head_ce_train) against the same steps with conv forward ->
+    ce_fwd -> ce_bwd -> conv dgrad / wgrad: losses, correct counts and weights after five steps (Adam eps = 1e-3, as in
+    test_step_async_matches_step: with 1e-8 the sign of rounding noise decides where a zero gradient moves a weight)."""
+    from robocupvision_b200.model import LabelProp, ROBO_UNet
+    from robocupvision_b200.train import TrainStep
+    models, steps = [], []
+    for fused in (True, False):
+        torch.manual_seed(12345678)
+        m = (ROBO_UNet() if net == "robo" else LabelProp(5, 32, 0)).cuda()
+        models.append(m)
+        steps.append(TrainStep(m, synth.CLASS_WEIGHTS if net == "robo" else synth.LP_CLASS_WEIGHTS, lr=1e-3,
+                               l1_decay=1e-6, eps=1e-3, use_graph=True, fused_head=fused))
+    assert steps[0]._head == len(steps[0].plan.nodes) - 1 and steps[1]._head == -1
+    assert steps[0].kernels_per_step == 0
+    cin = 3 if net == "robo" else 8
+    for s in range(5):
+        x = synth.images(4, cin, 48, 64, seed=300 + s).cuda()
+        y = synth.labels_random(4, 48, 64, seed=400 + s).cuda()
+        got = []
+        for ts in steps:
+            ts.step(x, y)
+            got.append((ts.loss_value(), int(ts.correct)))
+        assert abs(got[0][0] - got[1][0]) <= 3e-5 * abs(got[1][0]) and abs(got[0][1] - got[1][1]) <= 8, (s, got)
+    assert steps[0].kernels_per_step < steps[1].kernels_per_step - 2
+    for (k, a), (_, b) in zip(models[0].state_dict().items(), models[1].state_dict().items()):
+        if a.is_floating_point():
+            assert_close(k, a, b, 2e-4)
+        else:
+            assert torch.equal(a, b), k
+
+
 def _foreign(names):
     return [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()
             or "cutlass" in n.lower()]

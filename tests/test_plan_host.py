@@ -5,6 +5,7 @@ import copy
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 import synth
 from oracle import ref_model as R
@@ -404,3 +405,53 @@ def test_engine_backward_side_stream_code_path_on_cpu(cpu_engine, monkeypatch):
     n_conv = sum(1 for nd in plan.nodes if nd.kind == "conv")
     assert waits.count(("wait", False, True)) == n_conv      # side waits for main before every weight gradient
     assert waits.count(("wait", True, False)) == 1 and waits[-1] == ("wait", True, False)   # one join, at the end
+
+
+@pytest.mark.parametrize("tag", ["robo_default", "labelprop"])
+def test_fused_head_wiring_on_cpu(tag, cpu_engine):
+    """TrainStep's fused classifier head: Plan.forward(stop_before=head) + ops.head_ce_train + Plan.backward(seed=...)
+    give the gradients of the full plan fed with the cross-entropy gradient (same stand-in kernels on both sides)."""
+    if tag not in _cases():
+        pytest.skip(f"no case {tag}")
+    engine, fake = cpu_engine
+    make, oracle, cin = _cases()[tag]
+    torch.manual_seed(12345678)
+    m = make().train()
+    plan = m._get_plan()
+    head = plan.fusable_head()
+    assert head == len(plan.nodes) - 1
+    x = synth.images(2, cin, 24, 32, seed=5)
+    y = synth.labels_learnable(x[:, :3])
+    cw = torch.tensor(synth.CLASS_WEIGHTS)
+    bufs = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        outs, saved = plan.forward(x, training=True, save=True)
+        lg = outs[0].detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            loss = F.cross_entropy(lg, y, weight=cw)
+            loss.backward()
+        _, gv = plan.backward(saved, [lg.grad], x_needs_grad=False)
+        ref = {id(p): gv[id(p)].clone() for p in plan.params}
+        m.load_state_dict(bufs)  # the running statistics moved; same starting point for the second pass
+        sums = torch.zeros(2, dtype=torch.float64)
+        corr = torch.zeros(1, dtype=torch.int64)
+        fake.ce_weight_sum(y, cw, sums[1:2], plan.nodes[head].geom.cout)
+        outs2, saved2 = plan.forward(x, training=True, save=True, stop_before=head)
+        assert outs2 == [None] and len(saved2[0]) == len(plan.nodes)
+        nd = plan.nodes[head]
+        total = sum(p.numel() for p in plan.params)
+        flat = torch.zeros(total)
+        views, o = {}, 0
+        for p in plan.params:
+            views[id(p)] = flat[o:o + p.numel()].view(p.shape)
+            o += p.numel()
+        dfeat = fake.head_ce_train(saved2[0][nd.src], nd.conv.weight.detach(), nd.conv.bias.detach(), y, cw, sums, corr,
+                                   views[id(nd.conv.weight)], views[id(nd.conv.bias)])
+        seen = []
+        plan.backward(saved2, [None], False, views, node_done=seen.append, seed={nd.src: dfeat})
+    assert seen == list(range(len(plan.nodes) - 1, -1, -1))
+    assert abs(float(sums[0] / sums[1]) - float(loss)) <= 1e-6 * abs(float(loss))
+    assert int(corr) == int((outs[0].argmax(1) == y).sum())
+    for p in plan.params:
+        a, b = views[id(p)], ref[id(p)]
+        assert float((a - b).abs().max()) <= 1e-5 * max(1e-3, float(b.abs().max())), (tag, tuple(p.shape))
