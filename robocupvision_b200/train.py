@@ -442,6 +442,8 @@ class _HostPipe:
         self.sy = [torch.empty_like(like_y) for _ in range(2)]
         # [l1 sum | CE loss sums (2) | correct pixels (int64 bits)]: the head of TrainStep._accum
         self.out = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
+        self.out_f = self.out  # EvalStep.run_async: [loss | - | - | -] and the correct count beside it
+        self.out_i = [torch.empty(1, dtype=torch.int64).pin_memory() for _ in range(2)]
         self.loaded = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]

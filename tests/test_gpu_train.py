@@ -448,6 +448,31 @@ def test_fused_head_matches_separate_kernels(net):
             assert torch.equal(a, b), k
 
 
+def test_eval_step_run_async_matches_call():
+    """EvalStep.run_async (pinned host inputs through the two-slot pipe, scalars read back with wait_host) returns what
+    EvalStep.__call__ returns on device inputs, batch after batch (bench.py's end-to-end inference loop)."""
+    from robocupvision_b200.model import ROBO_UNet
+    from robocupvision_b200.train import EvalStep
+    torch.manual_seed(12345678)
+    m = ROBO_UNet().cuda()
+    ev = EvalStep(m, synth.CLASS_WEIGHTS, use_graph=True)
+    xs = [synth.images(4, 3, 48, 64, seed=500 + i) for i in range(4)]
+    ys = [synth.labels_random(4, 48, 64, seed=600 + i) for i in range(4)]
+    want = []
+    for x, y in zip(xs, ys):
+        out = ev(x.cuda(), y.cuda())
+        want.append((float(out["loss"]), int(out["correct"])))
+    pending, got = None, []
+    for x, y in zip(xs, ys):
+        out = ev.run_async(x.pin_memory(), y.pin_memory())
+        if pending is not None:
+            got.append(EvalStep.wait_host(pending))
+        pending = out
+    got.append(EvalStep.wait_host(pending))
+    for (l0, c0), (l1, c1) in zip(want, got):
+        assert abs(l0 - l1) <= 1e-6 * abs(l0) and c0 == c1, (want, got)
+
+
 def _foreign(names):
     return [n for n in names if "at::" in n or "cudnn" in n.lower() or "cublas" in n.lower() or "triton" in n.lower()
             or "cutlass" in n.lower()]
