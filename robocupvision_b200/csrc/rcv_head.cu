@@ -4,8 +4,10 @@
 //   dlogits = w_y (softmax - onehot) / sum_p w_{y_p}   (the backward of the mean-reduced weighted NLL)
 //   dfeat = W^T dlogits, dW += dlogits f^T, db += dlogits
 // instead of conv forward -> ce_fwd -> ce_bwd -> conv dgrad (+ conv wgrad on the side stream): the logits and their
-// gradient (2 x N x C x HW floats, written once and read two / three times) never exist in memory.  HBM-bound:
-// algorithmic bytes per pixel = 4 Cin (features) + 8 (label) + 4 Cin (feature gradient).
+// gradient (2 x N x C x HW floats, written once and read two / three times) never exist in memory.  Algorithmic
+// bytes per pixel = 4 Cin (features) + 8 (label) + 4 Cin (feature gradient).  Measured (ncu, ROBO_UNet batch 64):
+// 28.6 us = 3.1 TB/s algorithmic, 0.47 of the HBM peak; issue-bound (62 % issue slots at 16 warps per SM: 128
+// registers for the C x Cin weight-gradient sums), DRAM itself at 24 % -- the feature gradient stays in L2.
 // The normaliser sum_p w_{y_p} depends on the labels only and is produced beforehand by rcv_ce_weight_sum into
 // loss_sums[1] (the same cell ce_fwd accumulates it into), so one pass suffices.
 #include <math.h>
