@@ -73,8 +73,8 @@ class PeerExchange:
                 hbuf = (C.c_ubyte * 64)()
                 _lib.call("rcv_peer_alloc", C.c_uint64(self.arena_bytes + self.flag_bytes), C.byref(base), hbuf)
             self._own, handle = base.value, bytes(hbuf)
-        except _lib.RcvError as e:
-            why = str(e)
+        except Exception as e:  # noqa: BLE001  (whatever went wrong here, the other ranks must hear of it)
+            why = f"{type(e).__name__}: {e}"
         every = sorted(gather((self.rank, handle, why)), key=lambda t: t[0])
         if any(h is None for _, h, _ in every):
             self._release()
@@ -90,8 +90,8 @@ class PeerExchange:
                     _lib.call("rcv_peer_open", (C.c_ubyte * 64).from_buffer_copy(h), C.byref(ptr))
                     self._opened.append(ptr.value)
                     bases.append(ptr.value)
-        except _lib.RcvError as e:
-            why = str(e)
+        except Exception as e:  # noqa: BLE001  (whatever went wrong here, the other ranks must hear of it)
+            why = f"{type(e).__name__}: {e}"
         outcome = gather((self.rank, why))
         if any(w for _, w in outcome):
             self._release()
