@@ -102,25 +102,33 @@ class PeerExchange:
         self.grads = torch.as_tensor(self._raw, device=self.dev).view(torch.float32)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         # one real exchange before anything depends on it: rank r contributes r + 1, everyone must read N(N+1)/2
-        with torch.cuda.device(self.dev):
-            self.grads[:4] = float(self.rank + 1)
-            self.allreduce(SLOTS - 1, 0, 4)
-            got = self.grads[:4].tolist()
-            bad = int(self.status.item()) != 0 or got != [self.world * (self.world + 1) / 2.0] * 4
-            self.grads[:4] = 0.0
-            torch.cuda.synchronize()
-        outcome = gather((self.rank, f"self-test read {got}" if bad else ""))
+        why = ""
+        try:
+            with torch.cuda.device(self.dev):
+                self.grads[:4] = float(self.rank + 1)
+                self.allreduce(SLOTS - 1, 0, 4)
+                got = self.grads[:4].tolist()
+                if int(self.status.item()) != 0 or got != [self.world * (self.world + 1) / 2.0] * 4:
+                    why = f"self-test read {got}"
+                self.grads[:4] = 0.0
+                torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            why = f"{type(e).__name__}: {e}"
+        outcome = gather((self.rank, why))
         if any(w for _, w in outcome):
             self._release()
             raise PeerUnavailable("; ".join(f"rank {r}: {w}" for r, w in outcome if w))
 
     def _release(self) -> None:
-        with torch.cuda.device(self.dev):
-            torch.cuda.synchronize()
-            for p in self._opened:
-                _lib.call("rcv_peer_close", C.c_void_p(p))
-            if self._own is not None:
-                _lib.call("rcv_peer_free", C.c_void_p(self._own))
+        try:
+            with torch.cuda.device(self.dev):
+                torch.cuda.synchronize()
+                for p in self._opened:
+                    _lib.call("rcv_peer_close", C.c_void_p(p))
+                if self._own is not None:
+                    _lib.call("rcv_peer_free", C.c_void_p(self._own))
+        except Exception:  # noqa: BLE001  (clean-up on a failure path: the failure itself is what gets reported)
+            pass
         self._opened, self._own, self.grads = [], None, None
 
     def allreduce(self, slot: int, a: int, b: int) -> None:

@@ -402,3 +402,38 @@ def test_peer_share_bounds_partition_the_range():
             assert end == count
     with pytest.raises(ValueError):
         share_bounds(6, 2, 0)
+
+
+def _peer_fail_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from robocupvision_b200.peer import PeerExchange, PeerUnavailable
+    try:
+        PeerExchange(64, "cuda:0")
+        out.put((rank, "constructed"))
+    except PeerUnavailable as e:
+        out.put((rank, str(e)))
+    dist.barrier()  # both ranks got here: nobody was left waiting in a gather
+
+
+def test_peer_exchange_unavailable_is_collective_gloo():
+    """world_size-2 gloo, no GPU: the peer-memory exchange cannot be set up, and BOTH ranks learn it the same way --
+    PeerUnavailable naming every rank's reason -- so TrainStep's fall-back to dist.all_reduce is taken by all ranks
+    together (a rank raising on its own would leave the others waiting in the handle exchange)."""
+    if torch.cuda.is_available():
+        pytest.skip("the failure path needs a box without a GPU")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_fail_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict(q.get(timeout=5) for _ in range(2))
+    assert set(got) == {0, 1}
+    for r, msg in got.items():
+        assert "rank 0:" in msg and "rank 1:" in msg, (r, msg)
